@@ -1,0 +1,113 @@
+// common.cu -- error string, pinned scalar page, optional per-kernel event profiler.
+#include "common.cuh"
+#include "prof.cuh"
+
+#include <stdarg.h>
+
+namespace hkcsa {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void *pinned_page()
+{
+    static void *page = nullptr;
+    if (!page) {
+        cudaError_t e = cudaHostAlloc(&page, 4096, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            set_error("cudaHostAlloc(4096) -> %s", cudaGetErrorString(e));
+            page = nullptr;
+        }
+    }
+    return page;
+}
+
+// ---------------------------------------------------------------- profiler
+namespace prof {
+static bool g_on = false;
+struct Rec {
+    cudaEvent_t a, b;
+    int cls;
+    uint64_t bytes;
+};
+static Rec g_rec[MAX_RECORDS];
+static int g_created = 0;
+static int g_used = 0;
+static const char *g_names[NUM_CLASSES] = {
+    "byte_hist", "sa_pack0", "sa_keybuild", "radix_scan", "onesweep_u64", "seg_reduce", "seg_scan",
+    "seg_apply", "bwt_gather", "wt_partition", "wt_pack", "wt_dir", "count", "locate", "ssa_build", "other"};
+
+bool enabled() { return g_on; }
+
+Scope::Scope(cudaStream_t st, int cls, uint64_t bytes) : st_(st), slot_(-1)
+{
+    if (!g_on || g_used >= MAX_RECORDS) return;
+    if (g_used >= g_created) {
+        if (cudaEventCreate(&g_rec[g_created].a) != cudaSuccess) return;
+        if (cudaEventCreate(&g_rec[g_created].b) != cudaSuccess) return;
+        ++g_created;
+    }
+    slot_ = g_used++;
+    g_rec[slot_].cls = cls;
+    g_rec[slot_].bytes = bytes;
+    cudaEventRecord(g_rec[slot_].a, st_);
+}
+Scope::~Scope()
+{
+    if (slot_ >= 0) cudaEventRecord(g_rec[slot_].b, st_);
+}
+}  // namespace prof
+}  // namespace hkcsa
+
+using namespace hkcsa;
+
+extern "C" int hkcsa_abi_version(void) { return HKCSA_ABI_VERSION; }
+extern "C" const char *hkcsa_last_error(void) { return g_err; }
+
+extern "C" size_t hkcsa_struct_size(int which)
+{
+    switch (which) {
+        case 0: return sizeof(hkcsa_sa_stats);
+        case 1: return sizeof(hkcsa_wt_plan);
+        case 2: return sizeof(hkcsa_ssa_plan);
+        case 3: return sizeof(hkcsa_prof_entry);
+        default: return 0;
+    }
+}
+
+extern "C" int hkcsa_prof_enable(int on)
+{
+    prof::g_on = (on != 0);
+    return HKCSA_OK;
+}
+extern "C" int hkcsa_prof_reset(void)
+{
+    prof::g_used = 0;
+    return HKCSA_OK;
+}
+extern "C" int hkcsa_prof_read(hkcsa_prof_entry *h_out, int max_entries, int *h_n)
+{
+    HK_REQUIRE(h_out && h_n && max_entries >= prof::NUM_CLASSES, HKCSA_EINVAL, "need room for every class");
+    for (int c = 0; c < prof::NUM_CLASSES; ++c) {
+        memset(&h_out[c], 0, sizeof(hkcsa_prof_entry));
+        strncpy(h_out[c].name, prof::g_names[c], sizeof(h_out[c].name) - 1);
+    }
+    for (int i = 0; i < prof::g_used; ++i) {
+        HK_CUDA(cudaEventSynchronize(prof::g_rec[i].b));
+        float ms = 0.f;
+        HK_CUDA(cudaEventElapsedTime(&ms, prof::g_rec[i].a, prof::g_rec[i].b));
+        hkcsa_prof_entry &e = h_out[prof::g_rec[i].cls];
+        e.launches += 1;
+        e.ms += ms;
+        e.alg_bytes += prof::g_rec[i].bytes;
+    }
+    *h_n = prof::NUM_CLASSES;
+    return HKCSA_OK;
+}

@@ -1,0 +1,297 @@
+// fm_search.cu -- K4: batched FM-index backward search (count) and locate.
+//
+// Replaces EnhancedFMIndex.find_range / .rank / .find (reference
+// csa/enhanced_fm_index.py:15-40).  occ[c][i] of build_occ (utils/utils.py:
+// 26-32) is answered by a rank walk over the wavelet tree; C[] and the node
+// tables live in shared memory; every rank step reads one 32-byte block.
+#include "common.cuh"
+#include "prof.cuh"
+#include "radix_sort.cuh"
+#include "wavelet.cuh"
+
+namespace hkcsa {
+
+int build_bitvector(const uint8_t *d_sym, uint64_t len, const uint8_t *d_lut_bit, RankBlock *d_blocks,
+                    uint64_t *d_super, uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones,
+                    cudaStream_t st);
+
+constexpr int COUNT_THREADS = 256;
+
+// One lane per pattern; a warp owns groups of 32 consecutive patterns, dealt
+// round-robin over all resident warps.  find_range (csa/enhanced_fm_index.py:
+// 21-32) in half-open form:
+//   l = 0, r = n;  per symbol from the end: l = C[c] + occ(c, l), r = C[c] + occ(c, r);
+//   l >= r -> (-1, -1).  Result (l, r-1).
+__global__ void __launch_bounds__(COUNT_THREADS)
+fm_count_kernel(WtDev wt, const uint8_t *__restrict__ pat, const int64_t *__restrict__ off, uint64_t P,
+                int64_t *__restrict__ out_lo, int64_t *__restrict__ out_hi)
+{
+    __shared__ WtSmem s;
+    wt_smem_load(s, wt);
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    const uint32_t n = (uint32_t)wt.n;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t base = warp * 32; base < P; base += nwarps * 32) {
+        const uint64_t p = base + lane;
+        if (p >= P) continue;
+        const int64_t b = off[p], e = off[p + 1];
+        uint32_t l = 0, r = n;
+        bool miss = false;
+        for (int64_t k = e - 1; k >= b; --k) {
+            const uint32_t code = s.code_of_sym[pat[k]];
+            if (code == 0xFFFFu) { miss = true; break; }   // symbol absent: rank 0, C 0 -> empty
+            if (wt.sigma > 1) wt_rank_code2(s, wt, code, l, r);
+            const uint32_t c0 = s.C[code];
+            l += c0;
+            r += c0;
+            if (l >= r) { miss = true; break; }
+        }
+        out_lo[p] = miss ? -1 : (int64_t)l;
+        out_hi[p] = miss ? -1 : (int64_t)r - 1;
+    }
+}
+
+// rows[off[p] + k] = lo[p] + k: one warp per pattern
+__global__ void expand_ranges_kernel(const int64_t *__restrict__ lo, const int64_t *__restrict__ hi,
+                                     const int64_t *__restrict__ out_off, uint64_t P, uint32_t *__restrict__ rows)
+{
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = lane_id();
+    for (uint64_t p = warp; p < P; p += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
+        const int64_t l = lo[p], h = hi[p];
+        if (l < 0) continue;
+        const int64_t o = out_off[p];
+        for (int64_t k = lane; k <= h - l; k += 32) rows[o + k] = (uint32_t)(l + k);
+    }
+}
+
+__global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ rows, uint64_t m,
+                                  uint32_t *__restrict__ out)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < m) out[q] = src[rows[q]];
+}
+
+// flag[j] = (SA[j] % rate == 0)
+__global__ void ssa_mark_kernel(const uint32_t *__restrict__ sa, uint64_t n, uint32_t rate, uint8_t *__restrict__ flag)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) flag[j] = (sa[j] % rate == 0) ? 1 : 0;
+}
+// samples[rank1(marks, j)] = SA[j] / rate for marked rows
+__global__ void ssa_fill_kernel(const uint32_t *__restrict__ sa, uint64_t n, uint32_t rate, BitVec marks,
+                                uint32_t *__restrict__ samples)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t v = sa[j];
+    if (v % rate == 0) samples[bv_rank(marks, j)] = v / rate;
+}
+
+// position of row j: walk LF until a marked row, pos = sample * rate + steps.
+// LF(j) = C[c] + occ(c, j) with c = bwt[j], both from one wavelet descent.
+__global__ void __launch_bounds__(256)
+locate_rows_kernel(WtDev wt, BitVec marks, const uint32_t *__restrict__ samples, uint32_t rate,
+                   const uint32_t *__restrict__ rows, uint64_t m, uint32_t *__restrict__ out)
+{
+    __shared__ WtSmem s;
+    wt_smem_load(s, wt);
+    __syncthreads();
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    uint32_t j = rows[q];
+    uint32_t steps = 0;
+    while (true) {
+        const uint64_t g = j / HKCSA_BLOCK_BITS;
+        const uint32_t o = j - (uint32_t)g * HKCSA_BLOCK_BITS;
+        const RankBlock b = load_block(marks.blocks + g);
+        if (block_bit(b, o)) {
+            const uint64_t r = marks.super[g / HKCSA_SUPER_BLOCKS] + (uint32_t)(b.w[0] & 0xFFFFFFFFu) + block_rank(b, o);
+            out[q] = samples[r] * rate + steps;
+            return;
+        }
+        uint32_t occ;
+        const uint32_t code = wt_access_rank(s, wt, j, occ);
+        j = s.C[code] + occ;
+        ++steps;
+    }
+}
+
+__global__ void identity_lut_kernel(uint8_t *lut)
+{
+    lut[threadIdx.x] = (uint8_t)(threadIdx.x & 1u);
+}
+
+__global__ void symbol_lut_kernel(uint8_t *lut, uint32_t *base, const uint64_t *__restrict__ hist, uint64_t *start)
+{
+    // single CTA of 256 threads: bucket = byte value, base = exclusive prefix of the histogram
+    __shared__ uint64_t s_h[256];
+    const uint32_t t = threadIdx.x;
+    s_h[t] = hist[t];
+    __syncthreads();
+    uint64_t pre = 0;
+    for (uint32_t c = 0; c < t; ++c) pre += s_h[c];
+    lut[t] = (uint8_t)t;
+    base[t] = (uint32_t)pre;
+    start[t] = pre;
+    if (t == 255) start[256] = pre + s_h[255];
+}
+
+}  // namespace hkcsa
+
+using namespace hkcsa;
+
+extern "C" int hkcsa_count_batch(const void *d_blob, const hkcsa_wt_plan *h_plan, const uint8_t *d_pat,
+                                 const int64_t *d_off, uint64_t P, int64_t *d_lo, int64_t *d_hi, void *stream)
+{
+    HK_REQUIRE(h_plan && d_blob, HKCSA_EINVAL, "null pointer");
+    if (P == 0) return HKCSA_OK;
+    HK_REQUIRE(d_off && d_lo && d_hi, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(h_plan->n >= 1, HKCSA_EINVAL, "empty index");
+    cudaStream_t st = as_stream(stream);
+    WtDev wt = make_wt_dev(d_blob, h_plan);
+    const int blocks = (int)std::min<uint64_t>((P + COUNT_THREADS - 1) / COUNT_THREADS, (uint64_t)num_sms() * 8);
+    prof::Scope ps(st, prof::COUNT, 0);
+    fm_count_kernel<<<blocks, COUNT_THREADS, 0, st>>>(wt, d_pat, d_off, P, d_lo, d_hi);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_ssa_plan_make(uint64_t n, uint32_t rate, hkcsa_ssa_plan *p)
+{
+    HK_REQUIRE(p && rate >= 1, HKCSA_EINVAL, "bad argument");
+    HK_REQUIRE(n <= HKCSA_MAX_N, HKCSA_ERANGE, "n exceeds HKCSA_MAX_N");
+    memset(p, 0, sizeof(*p));
+    p->n = n;
+    p->rate = rate;
+    p->n_samples = (n + rate - 1) / rate;
+    uint64_t off = 0;
+    p->off_blocks = off;
+    off = align_up(off + rank_blocks_for(n) * sizeof(RankBlock), 256);
+    p->off_super = off;
+    off = align_up(off + super_for(n) * sizeof(uint64_t), 256);
+    p->off_samples = off;
+    off = align_up(off + (p->n_samples + 1) * sizeof(uint32_t), 256);
+    p->blob_bytes = off;
+    Carver c(nullptr);
+    c.take<uint8_t>(n + 16);
+    const uint64_t tiles = rank_blocks_for(n) / 64 + 2;
+    c.take<uint32_t>(tiles);
+    c.take<uint64_t>(tiles);
+    c.take<uint64_t>(8);
+    c.take<uint32_t>(select_samples_for(n));
+    c.take<uint8_t>(256);
+    p->scratch_bytes = c.total();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_ssa_build(const uint32_t *d_sa, const hkcsa_ssa_plan *p, void *d_blob, void *d_scratch,
+                               size_t scratch_bytes, void *stream)
+{
+    HK_REQUIRE(p && d_blob && d_scratch && (d_sa || p->n == 0), HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(p->scratch_bytes <= scratch_bytes, HKCSA_ESCRATCH, "sampled-SA scratch too small");
+    HK_REQUIRE((reinterpret_cast<uintptr_t>(d_blob) & 31) == 0, HKCSA_EINVAL, "blob must be 32-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const uint64_t n = p->n;
+    if (n == 0) return HKCSA_OK;
+    Carver c(d_scratch);
+    uint8_t *d_flag = c.take<uint8_t>(n + 16);
+    const uint64_t tiles = rank_blocks_for(n) / 64 + 2;
+    uint32_t *d_agg = c.take<uint32_t>(tiles);
+    uint64_t *d_carry = c.take<uint64_t>(tiles);
+    uint64_t *d_ones = c.take<uint64_t>(8);
+    uint32_t *d_sel = c.take<uint32_t>(select_samples_for(n));
+    uint8_t *d_lut = c.take<uint8_t>(256);
+    uint8_t *blob = static_cast<uint8_t *>(d_blob);
+    prof::Scope ps(st, prof::SSA_BUILD, n * 10);
+    const uint32_t grid = (uint32_t)((n + 255) / 256);
+    identity_lut_kernel<<<1, 256, 0, st>>>(d_lut);
+    ssa_mark_kernel<<<grid, 256, 0, st>>>(d_sa, n, p->rate, d_flag);
+    HK_LAUNCH_CHECK();
+    BitVec marks;
+    marks.blocks = reinterpret_cast<const RankBlock *>(blob + p->off_blocks);
+    marks.super = reinterpret_cast<const uint64_t *>(blob + p->off_super);
+    marks.len = n;
+    int rc = build_bitvector(d_flag, n, d_lut, reinterpret_cast<RankBlock *>(blob + p->off_blocks),
+                             reinterpret_cast<uint64_t *>(blob + p->off_super), d_sel, d_agg, d_carry, d_ones, st);
+    if (rc != HKCSA_OK) return rc;
+    ssa_fill_kernel<<<grid, 256, 0, st>>>(d_sa, n, p->rate, marks, reinterpret_cast<uint32_t *>(blob + p->off_samples));
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_expand_ranges(const int64_t *d_lo, const int64_t *d_hi, const int64_t *d_out_off, uint64_t P,
+                                   uint32_t *d_rows, void *stream)
+{
+    if (P == 0) return HKCSA_OK;
+    HK_REQUIRE(d_lo && d_hi && d_out_off, HKCSA_EINVAL, "null pointer");
+    const int blocks = (int)std::min<uint64_t>((P * 32 + 255) / 256, (uint64_t)num_sms() * 16);
+    expand_ranges_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_lo, d_hi, d_out_off, P, d_rows);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_gather_u32(const uint32_t *d_src, const uint32_t *d_rows, uint64_t m, uint32_t *d_out,
+                                void *stream)
+{
+    if (m == 0) return HKCSA_OK;
+    HK_REQUIRE(d_src && d_rows && d_out, HKCSA_EINVAL, "null pointer");
+    gather_u32_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, as_stream(stream)>>>(d_src, d_rows, m, d_out);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_locate_rows(const void *d_wt_blob, const hkcsa_wt_plan *h_plan, const void *d_ssa_blob,
+                                 const hkcsa_ssa_plan *h_ssa, const uint32_t *d_rows, uint64_t m,
+                                 uint32_t *d_out_pos, void *stream)
+{
+    if (m == 0) return HKCSA_OK;
+    HK_REQUIRE(d_wt_blob && h_plan && d_ssa_blob && h_ssa && d_rows && d_out_pos, HKCSA_EINVAL, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    WtDev wt = make_wt_dev(d_wt_blob, h_plan);
+    const uint8_t *sb = static_cast<const uint8_t *>(d_ssa_blob);
+    BitVec marks;
+    marks.blocks = reinterpret_cast<const RankBlock *>(sb + h_ssa->off_blocks);
+    marks.super = reinterpret_cast<const uint64_t *>(sb + h_ssa->off_super);
+    marks.len = h_ssa->n;
+    prof::Scope ps(st, prof::LOCATE, 0);
+    locate_rows_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(
+        wt, marks, reinterpret_cast<const uint32_t *>(sb + h_ssa->off_samples), h_ssa->rate, d_rows, m, d_out_pos);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_symbol_positions(const uint8_t *d_bwt, uint64_t n, uint32_t *d_pos, uint64_t *d_start,
+                                      void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    HK_REQUIRE(d_start && d_scratch, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(n <= HKCSA_MAX_N, HKCSA_ERANGE, "n exceeds HKCSA_MAX_N");
+    cudaStream_t st = as_stream(stream);
+    Carver c(d_scratch);
+    uint64_t *d_hist = c.take<uint64_t>(256);
+    uint8_t *d_lut = c.take<uint8_t>(256);
+    uint32_t *d_base = c.take<uint32_t>(256);
+    uint8_t *d_sorted = c.take<uint8_t>(n + 16);
+    SortScratch ss = carve_sort_scratch(c, n);
+    HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "scratch too small");
+    HK_CUDA(hkcsa_byte_hist(d_bwt, n, d_hist, stream) == HKCSA_OK ? cudaSuccess : cudaErrorUnknown);
+    symbol_lut_kernel<<<1, 256, 0, st>>>(d_lut, d_base, d_hist, d_start);
+    HK_LAUNCH_CHECK();
+    if (n == 0) return HKCSA_OK;
+    HK_REQUIRE(d_bwt && d_pos, HKCSA_EINVAL, "null pointer");
+    HK_CUDA(radix_partition_bytes(d_bwt, d_sorted, d_pos, (uint32_t)n, d_lut, d_base, ss, st));
+    return HKCSA_OK;
+}
+
+extern "C" size_t hkcsa_symbol_positions_scratch_bytes(uint64_t n)
+{
+    Carver c(nullptr);
+    c.take<uint64_t>(256);
+    c.take<uint8_t>(256);
+    c.take<uint32_t>(256);
+    c.take<uint8_t>(n + 16);
+    carve_sort_scratch(c, n);
+    return c.total();
+}

@@ -1,0 +1,322 @@
+// radix_sort.cu -- onesweep LSD radix sort kernels (see radix_sort.cuh).
+#include "radix_sort.cuh"
+#include "prof.cuh"
+
+namespace hkcsa {
+
+// VAL_MODE: 0 = keys only, 1 = values loaded from vin, 2 = value = source index.
+template <typename KeyT, int VAL_MODE, int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS)
+onesweep_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint32_t *__restrict__ vin,
+                uint32_t *__restrict__ vout, uint32_t n, int shift, const uint8_t *__restrict__ lut,
+                const uint32_t *__restrict__ digit_base, uint32_t *lookback, uint32_t *ticket)
+{
+    constexpr int TILE = THREADS * IPT;
+    constexpr int WARPS = THREADS / 32;
+    constexpr bool BYTE_KEYS = (sizeof(KeyT) == 1);
+    static_assert(THREADS >= RADIX, "one thread per digit is required");
+    static_assert(WARPS <= 32, "warp totals live in s_misc");
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *s_whist = reinterpret_cast<uint32_t *>(smem_raw);   // [WARPS][RADIX]
+    uint32_t *s_gbase = s_whist + WARPS * RADIX;                  // [RADIX]
+    uint32_t *s_misc = s_gbase + RADIX;                           // [64]
+    uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_misc + 64);    // [256]
+    KeyT *s_keys = reinterpret_cast<KeyT *>(s_lut + 256);         // [TILE]
+    uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_lut + 256); // [TILE] (aliases s_keys)
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
+    for (int i = tid; i < WARPS * RADIX; i += THREADS) s_whist[i] = 0;
+    if (BYTE_KEYS && tid < 256) s_lut[tid] = lut[tid];
+    __syncthreads();
+
+    const uint32_t tile = s_misc[0];
+    const uint32_t tile_base = tile * (uint32_t)TILE;
+    const uint32_t nvalid = min((uint32_t)TILE, n - tile_base);
+
+    auto digit_of = [&](KeyT k) -> uint32_t {
+        if constexpr (BYTE_KEYS) return s_lut[k];
+        else return (uint32_t)(k >> shift) & 0xFFu;
+    };
+
+    // ---- load (warp-striped: lane l, item k <-> tile offset warp*32*IPT + k*32 + l)
+    KeyT key[IPT];
+    uint32_t val[IPT];
+    uint16_t rnk[IPT];
+    const uint32_t wbase = warp * 32u * IPT + lane;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const uint32_t local = wbase + k * 32u;
+        const bool valid = local < nvalid;
+        key[k] = valid ? kin[tile_base + local] : (KeyT)(~(KeyT)0);
+        if (VAL_MODE == 1) val[k] = valid ? vin[tile_base + local] : 0u;
+        if (VAL_MODE == 2) val[k] = tile_base + local;
+    }
+
+    // ---- rank inside the warp: match.any groups equal digits, the group's
+    //      first lane bumps the warp's private counter.
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const bool valid = (wbase + k * 32u) < nvalid;
+        const uint32_t d = valid ? digit_of(key[k]) : 255u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t before = 0;
+        uint32_t *cnt = &s_whist[warp * RADIX + d];
+        if (lane == leader) {
+            before = *cnt;
+            *cnt = before + __popc(peers);
+        }
+        before = __shfl_sync(0xffffffffu, before, leader);
+        rnk[k] = (uint16_t)(before + __popc(peers & lanemask_lt()));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive prefix over warps, tile count, publish aggregate
+    uint32_t bt = 0;
+    if (tid < RADIX) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = s_whist[w * RADIX + tid];
+            s_whist[w * RADIX + tid] = run;
+            run += c;
+        }
+        bt = run;
+        st_volatile_u32(&lookback[(size_t)tile * RADIX + tid], (tile == 0 ? LB_INC : LB_AGG) | bt);
+    }
+    uint32_t wtotal;
+    const uint32_t ex = warp_excl_sum(bt, wtotal);
+    if (lane == 0) s_misc[1 + warp] = wtotal;
+    __syncthreads();
+    uint32_t wprefix = 0;
+    for (uint32_t w = 0; w < warp; ++w) wprefix += s_misc[1 + w];
+    const uint32_t bexcl = ex + wprefix;   // first slot of digit `tid` inside the sorted tile
+    if (tid < RADIX) {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) s_whist[w * RADIX + tid] += bexcl;
+    }
+    __syncthreads();
+
+    // ---- stage keys in digit order
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const bool valid = (wbase + k * 32u) < nvalid;
+        const uint32_t d = valid ? digit_of(key[k]) : 255u;
+        const uint32_t slot = s_whist[warp * RADIX + d] + rnk[k];
+        rnk[k] = (uint16_t)slot;
+        s_keys[slot] = key[k];
+    }
+
+    // ---- decoupled look-back: exclusive count of this digit in earlier tiles
+    if (tid < RADIX) {
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                const uint32_t v = ld_volatile_u32(&lookback[(size_t)t * RADIX + tid]);
+                const uint32_t flag = v >> 30;
+                if (flag == 0) continue;
+                excl += v & LB_VAL;
+                if (flag == 2) break;
+                --t;
+            }
+            st_volatile_u32(&lookback[(size_t)tile * RADIX + tid], LB_INC | (excl + bt));
+        }
+        s_gbase[tid] = digit_base[tid] + excl - bexcl;
+    }
+    __syncthreads();
+
+    // ---- coalesced write-out: consecutive threads take consecutive sorted slots
+    uint32_t gpos[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const uint32_t i = k * THREADS + tid;
+        gpos[k] = 0;
+        if (i < nvalid) {
+            const KeyT kk = s_keys[i];
+            gpos[k] = s_gbase[digit_of(kk)] + i;
+            kout[gpos[k]] = kk;
+        }
+    }
+    if (VAL_MODE != 0) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) s_vals[rnk[k]] = val[k];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const uint32_t i = k * THREADS + tid;
+            if (i < nvalid) vout[gpos[k]] = s_vals[i];
+        }
+    }
+}
+
+template <typename KeyT, int VAL_MODE, int THREADS, int IPT>
+static constexpr size_t onesweep_smem()
+{
+    constexpr size_t fixed = (size_t)(THREADS / 32) * RADIX * 4 + RADIX * 4 + 64 * 4 + 256;
+    constexpr size_t elem = (VAL_MODE != 0 && sizeof(KeyT) < 4) ? 4 : sizeof(KeyT);
+    return fixed + elem * (size_t)THREADS * IPT;
+}
+
+__global__ void radix_hist_kernel(const uint64_t *__restrict__ keys, uint32_t n, int passes,
+                                  uint32_t *__restrict__ ghist)
+{
+    __shared__ uint32_t s_hist[8 * RADIX];
+    hist_zero(s_hist, passes);
+    __syncthreads();
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const bool valid = i < n;
+        const uint64_t key = valid ? keys[i] : 0ULL;
+        hist_add_key(s_hist, key, passes, valid);
+    }
+    __syncthreads();
+    hist_flush(s_hist, ghist, passes);
+}
+
+// block p: exclusive scan of hist[p][0..255] -> base[p][0..255]
+__global__ void radix_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ base)
+{
+    __shared__ uint32_t s_w[8];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t v = hist[blockIdx.x * RADIX + tid];
+    uint32_t total;
+    const uint32_t ex = warp_excl_sum(v, total);
+    if ((tid & 31u) == 0) s_w[tid >> 5] = total;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (uint32_t w = 0; w < (tid >> 5); ++w) pre += s_w[w];
+    base[blockIdx.x * RADIX + tid] = ex + pre;
+}
+
+size_t sort_scratch_words(uint64_t n)
+{
+    const uint64_t tiles = (n + SORT64_TILE - 1) / SORT64_TILE + 1;
+    return 8 * RADIX * 2 + 64 + tiles * RADIX + 256;
+}
+
+SortScratch carve_sort_scratch(Carver &c, uint64_t n)
+{
+    SortScratch s;
+    const uint64_t tiles = (n + SORT64_TILE - 1) / SORT64_TILE + 1;
+    s.hist = c.take<uint32_t>(8 * RADIX);
+    s.base = c.take<uint32_t>(8 * RADIX);
+    s.ticket = c.take<uint32_t>(64);
+    s.lookback_words = tiles * RADIX;
+    s.lookback = c.take<uint32_t>(s.lookback_words);
+    return s;
+}
+
+cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, const SortScratch &s,
+                                cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(s.hist, 0, 8 * RADIX * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    int blocks = (int)std::min<uint64_t>((n + 1023) / 1024, (uint64_t)num_sms() * 8);
+    radix_hist_kernel<<<blocks, 256, 0, st>>>(d_keys, n, passes, s.hist);
+    return cudaGetLastError();
+}
+
+cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n,
+                                 int passes, const SortScratch &s, cudaStream_t st)
+{
+    if (n == 0 || passes <= 0) return cudaSuccess;
+    constexpr size_t smem = onesweep_smem<uint64_t, 1, SORT64_THREADS, SORT64_IPT>();
+    auto kern = onesweep_kernel<uint64_t, 1, SORT64_THREADS, SORT64_IPT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    radix_scan_kernel<<<passes, RADIX, 0, st>>>(s.hist, s.base);
+    cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    const uint32_t tiles = (n + SORT64_TILE - 1) / SORT64_TILE;
+    uint64_t *kin = k0, *kout = k1;
+    uint32_t *vin = v0, *vout = v1;
+    for (int p = 0; p < passes; ++p) {
+        e = cudaMemsetAsync(s.lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        {
+            prof::Scope ps(st, prof::ONESWEEP_U64, (uint64_t)n * 24);
+            kern<<<tiles, SORT64_THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, nullptr, s.base + p * RADIX,
+                                                      s.lookback, s.ticket + p);
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        uint64_t *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t radix_partition_bytes(const uint8_t *d_in, uint8_t *d_out, uint32_t *d_pos_out, uint32_t n,
+                                  const uint8_t *d_lut, const uint32_t *d_bucket_base,
+                                  const SortScratch &s, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const uint32_t tiles = (n + SORT8_TILE - 1) / SORT8_TILE;
+    cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(s.lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (d_pos_out) {
+        constexpr size_t smem = onesweep_smem<uint8_t, 2, SORT8_THREADS, SORT8_IPT>();
+        auto kern = onesweep_kernel<uint8_t, 2, SORT8_THREADS, SORT8_IPT>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        kern<<<tiles, SORT8_THREADS, smem, st>>>(d_in, d_out, nullptr, d_pos_out, n, 0, d_lut, d_bucket_base,
+                                                 s.lookback, s.ticket);
+    } else {
+        constexpr size_t smem = onesweep_smem<uint8_t, 0, SORT8_THREADS, SORT8_IPT>();
+        auto kern = onesweep_kernel<uint8_t, 0, SORT8_THREADS, SORT8_IPT>;
+        kern<<<tiles, SORT8_THREADS, smem, st>>>(d_in, d_out, nullptr, nullptr, n, 0, d_lut, d_bucket_base,
+                                                 s.lookback, s.ticket);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace hkcsa
+
+// ------------------------------------------------------------------ C-ABI
+using namespace hkcsa;
+
+extern "C" size_t hkcsa_sort_scratch_bytes(uint64_t n)
+{
+    Carver c(nullptr);
+    carve_sort_scratch(c, n);
+    return c.total();
+}
+
+extern "C" int hkcsa_sort_pairs_u64(uint64_t *d_keys, uint32_t *d_vals, uint64_t *d_keys_alt,
+                                    uint32_t *d_vals_alt, uint64_t n, int key_bits, void *d_scratch,
+                                    size_t scratch_bytes, void *stream)
+{
+    HK_REQUIRE(n <= HKCSA_MAX_N, HKCSA_ERANGE, "n exceeds HKCSA_MAX_N");
+    HK_REQUIRE(key_bits >= 0 && key_bits <= 64, HKCSA_EINVAL, "key_bits must be in [0,64]");
+    if (n == 0 || key_bits == 0) return HKCSA_OK;
+    HK_REQUIRE(d_keys && d_vals && d_keys_alt && d_vals_alt && d_scratch, HKCSA_EINVAL, "null pointer");
+    Carver c(d_scratch);
+    SortScratch s = carve_sort_scratch(c, n);
+    HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "sort scratch too small");
+    cudaStream_t st = as_stream(stream);
+    const int passes = (key_bits + 7) / 8;
+    HK_CUDA(radix_histogram_u64(d_keys, (uint32_t)n, passes, s, st));
+    HK_CUDA(radix_sort_pairs_u64(d_keys, d_vals, d_keys_alt, d_vals_alt, (uint32_t)n, passes, s, st));
+    if (passes & 1) {
+        HK_CUDA(cudaMemcpyAsync(d_keys, d_keys_alt, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        HK_CUDA(cudaMemcpyAsync(d_vals, d_vals_alt, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    return HKCSA_OK;
+}

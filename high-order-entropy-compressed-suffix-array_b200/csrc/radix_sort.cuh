@@ -1,0 +1,82 @@
+// radix_sort.cuh -- single-pass-per-digit ("onesweep") LSD radix sort for sm_100a.
+//
+// One kernel launch per 8-bit digit.  Each CTA takes a tile through a ticket
+// counter, ranks its keys with warp-level match histograms, publishes its
+// per-digit counts to a look-back table, resolves the per-digit exclusive
+// prefix over the preceding tiles by decoupled look-back, stages the tile in
+// shared memory in digit order and writes it out as coalesced runs.
+// Digit histograms for ALL passes are accumulated up front (they do not depend
+// on element order) by whichever kernel produces the keys.
+//
+// Used for: (uint64 key, uint32 value) pairs in suffix-array construction (K1)
+// and byte keys ranked through a look-up table (node id per symbol) in
+// wavelet-tree level construction (K3) and FMIndex.precompute_rank.
+#pragma once
+#include "common.cuh"
+
+namespace hkcsa {
+
+constexpr int RADIX = 256;
+constexpr uint32_t LB_AGG = 1u << 30;   // tile aggregate available
+constexpr uint32_t LB_INC = 2u << 30;   // inclusive prefix available
+constexpr uint32_t LB_VAL = (1u << 30) - 1u;
+
+constexpr int SORT64_THREADS = 256;
+constexpr int SORT64_IPT = 16;
+constexpr int SORT64_TILE = SORT64_THREADS * SORT64_IPT;   // 4096 pairs per CTA
+
+constexpr int SORT8_THREADS = 256;
+constexpr int SORT8_IPT = 32;
+constexpr int SORT8_TILE = SORT8_THREADS * SORT8_IPT;      // 8192 bytes per CTA
+
+// Adds one key's digits (8 bits each, `passes` of them from bit 0) to a CTA's
+// shared histogram hist[pass][256].  Lanes holding the same digit are merged
+// with match.any so sorted / low-entropy digits do not serialise on one bank.
+__device__ __forceinline__ void hist_add_key(uint32_t *s_hist, uint64_t key, int passes, bool valid)
+{
+    const uint32_t lane = lane_id();
+    for (int p = 0; p < passes; ++p) {
+        const uint32_t d = valid ? (uint32_t)((key >> (8 * p)) & 0xFFu) : 0x100u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[p * RADIX + d], __popc(peers));
+    }
+}
+__device__ __forceinline__ void hist_zero(uint32_t *s_hist, int passes)
+{
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) s_hist[i] = 0;
+}
+__device__ __forceinline__ void hist_flush(const uint32_t *s_hist, uint32_t *g_hist, int passes)
+{
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(&g_hist[i], v);
+    }
+}
+
+struct SortScratch {
+    uint32_t *hist;      // [8][256] digit histograms (filled by the key producer)
+    uint32_t *base;      // [8][256] exclusive digit offsets
+    uint32_t *lookback;  // [tiles][256]
+    uint32_t *ticket;    // [8] one per pass
+    size_t lookback_words;
+};
+
+size_t sort_scratch_words(uint64_t n);   // uint32 words needed by carve_sort_scratch
+SortScratch carve_sort_scratch(Carver &c, uint64_t n);
+
+// Histogram-only pass over existing keys (when the producer could not fuse it).
+cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, const SortScratch &s,
+                                cudaStream_t st);
+// Sorts on the low 8*passes bits.  s.hist must hold the digit histograms of the
+// input.  Input in (k0,v0); (k1,v1) is the ping-pong buffer.  The result is in
+// (k0,v0) when passes is even, (k1,v1) when odd.
+cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n,
+                                 int passes, const SortScratch &s, cudaStream_t st);
+// Stable bucket partition of bytes: element x goes to bucket lut[x]; bucket b
+// starts at d_bucket_base[b] in d_out.  No histogram pass (the caller knows the
+// bucket sizes).  If d_pos_out != nullptr the source positions are carried as values.
+cudaError_t radix_partition_bytes(const uint8_t *d_in, uint8_t *d_out, uint32_t *d_pos_out, uint32_t n,
+                                  const uint8_t *d_lut, const uint32_t *d_bucket_base,
+                                  const SortScratch &s, cudaStream_t st);
+
+}  // namespace hkcsa

@@ -1,0 +1,455 @@
+// suffix_array.cu -- K1: suffix-array construction by prefix doubling.
+//
+// Replaces build_suffix_array (reference csa/suffix_array.py:131-134): the
+// permutation that sorts all suffixes in byte order with a proper prefix first.
+//
+// Round 0 packs the first k0 symbols of every suffix (dense codes of b bits,
+// 0 = "past the end", so shorter suffixes sort first) into one 64-bit key and
+// radix-sorts (key, position).  Equal keys form groups; a suffix's rank is the
+// SA position where its group starts.  Round r (depth h = k0 * 2^(r-1)) takes
+// only the suffixes whose group is not yet a singleton, keys them with
+// (group start, rank[i + h] + 1) -- 0 when i + h >= n -- sorts, and refines.
+// Suffixes that became unique leave the working set (their SA slot is final).
+#include "common.cuh"
+#include "prof.cuh"
+#include "radix_sort.cuh"
+
+namespace hkcsa {
+
+constexpr int SEG_THREADS = 256;
+constexpr int SEG_IPT = 8;
+constexpr int SEG_TILE = SEG_THREADS * SEG_IPT;
+
+struct CodeMap {
+    uint16_t code[256];  // byte -> dense code + 1 (0 for bytes that do not occur)
+};
+
+// ---------------------------------------------------------------- byte histogram
+__global__ void byte_hist_kernel(const uint8_t *__restrict__ text, uint64_t n, unsigned long long *__restrict__ ghist)
+{
+    __shared__ uint32_t s_h[8][256];   // one private histogram per warp
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 8 * 256; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    // 16-byte vector loads over the aligned middle; CTA 0 takes the ragged ends
+    const uint64_t mis = (16 - (reinterpret_cast<uintptr_t>(text) & 15)) & 15;
+    const uint64_t pre = mis < n ? mis : n;
+    const uint64_t nvec = (n - pre) / 16;
+    const uint4 *v = reinterpret_cast<const uint4 *>(text + pre);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 q = v[i];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&s_h[warp][w[j] & 0xFFu], 1u);
+            atomicAdd(&s_h[warp][(w[j] >> 8) & 0xFFu], 1u);
+            atomicAdd(&s_h[warp][(w[j] >> 16) & 0xFFu], 1u);
+            atomicAdd(&s_h[warp][w[j] >> 24], 1u);
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (uint64_t i = tid; i < pre; i += blockDim.x) atomicAdd(&s_h[warp][text[i]], 1u);
+        for (uint64_t i = pre + nvec * 16 + tid; i < n; i += blockDim.x) atomicAdd(&s_h[warp][text[i]], 1u);
+    }
+    __syncthreads();
+    if (tid < 256) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_h[w][tid];
+        if (s) atomicAdd(&ghist[tid], (unsigned long long)s);
+    }
+}
+
+cudaError_t byte_hist(const uint8_t *d_text, uint64_t n, uint64_t *d_hist, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint64_t), st);
+    if (e != cudaSuccess || n == 0) return e;
+    const int blocks = (int)std::min<uint64_t>((n + 65535) / 65536, (uint64_t)num_sms() * 4);
+    prof::Scope ps(st, prof::BYTE_HIST, n);
+    byte_hist_kernel<<<std::max(blocks, 1), 256, 0, st>>>(d_text, n, reinterpret_cast<unsigned long long *>(d_hist));
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- round 0: pack
+// key[i] = code(T[i]) code(T[i+1]) ... code(T[i+k0-1]) MSB first, b bits each.
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_IPT = 8;
+constexpr int PACK_TILE = PACK_THREADS * PACK_IPT;
+
+__global__ void __launch_bounds__(PACK_THREADS)
+sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, CodeMap map, int b, int k0, int passes,
+                uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, uint32_t *__restrict__ ghist)
+{
+    __shared__ uint16_t s_code[256];
+    __shared__ uint16_t s_sym[PACK_TILE + 64];
+    __shared__ uint32_t s_hist[8 * RADIX];
+    const uint32_t tid = threadIdx.x;
+    s_code[tid] = map.code[tid];
+    hist_zero(s_hist, passes);
+    __syncthreads();
+    const uint32_t base = blockIdx.x * PACK_TILE;
+    for (uint32_t j = tid; j < PACK_TILE + 64; j += PACK_THREADS) {
+        const uint32_t g = base + j;
+        s_sym[j] = (g < n) ? s_code[text[g]] : (uint16_t)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < PACK_IPT; ++e) {
+        const uint32_t j = e * PACK_THREADS + tid;
+        const uint32_t g = base + j;
+        uint64_t key = 0;
+        for (int t = 0; t < k0; ++t) key = (key << b) | s_sym[j + t];
+        const bool valid = g < n;
+        if (valid) {
+            keys[g] = key;
+            idx[g] = g;
+        }
+        hist_add_key(s_hist, key, passes, valid);
+    }
+    __syncthreads();
+    hist_flush(s_hist, ghist, passes);
+}
+
+// ---------------------------------------------------------------- later rounds: key build
+// key[j] = (group start << b2) | (rank[idx + h] + 1), low part 0 when idx + h >= n.
+__global__ void __launch_bounds__(256)
+sa_keybuild_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp,
+                   const uint32_t *__restrict__ rank, uint32_t n, uint32_t h, int b2, uint32_t m, int passes,
+                   uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist)
+{
+    __shared__ uint32_t s_hist[8 * RADIX];
+    hist_zero(s_hist, passes);
+    __syncthreads();
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < m; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t j = base + threadIdx.x;
+        const bool valid = j < m;
+        uint64_t key = 0;
+        if (valid) {
+            const uint32_t i = cidx[j];
+            const uint64_t t = (uint64_t)i + h;
+            const uint32_t k2 = (t < n) ? (rank[t] + 1u) : 0u;
+            key = ((uint64_t)cgrp[j] << b2) | k2;
+            keys[j] = key;
+        }
+        hist_add_key(s_hist, key, passes, valid);
+    }
+    __syncthreads();
+    hist_flush(s_hist, ghist, passes);
+}
+
+// ---------------------------------------------------------------- segmented rank update
+// After a sort, over the m working elements (sorted keys skey, suffix ids sidx,
+// SA slots pos -- identity in round 0):
+//   head[j]   = j == 0 || skey[j] != skey[j-1]
+//   single[j] = head[j] && (j == m-1 || head[j+1])
+//   grp[j]    = pos[last head <= j]            (max-scan)
+//   SA[pos[j]] = sidx[j];  rank[sidx[j]] = grp[j]
+//   non-singletons are compacted into (cpos, cidx, cgrp) for the next round.
+// Three phases (tile reduce, scan of tile aggregates, apply) -- no spinning.
+
+__device__ __forceinline__ void seg_flags(const uint64_t *__restrict__ skey, uint32_t m, uint32_t j0,
+                                          bool head[SEG_IPT], bool single[SEG_IPT])
+{
+    // thread owns j0 .. j0+SEG_IPT-1 (blocked); needs skey[j0-1] and skey[j0+SEG_IPT]
+    uint64_t k[SEG_IPT + 2];
+#pragma unroll
+    for (int e = 0; e < SEG_IPT + 2; ++e) {
+        const int64_t j = (int64_t)j0 + e - 1;
+        k[e] = (j >= 0 && j < (int64_t)m) ? skey[j] : 0ULL;
+    }
+#pragma unroll
+    for (int e = 0; e < SEG_IPT; ++e) {
+        const uint32_t j = j0 + e;
+        const bool in = j < m;
+        const bool hd = in && (j == 0 || k[e + 1] != k[e]);
+        const bool next_head = (j + 1 >= m) || (k[e + 2] != k[e + 1]);
+        head[e] = hd;
+        single[e] = hd && next_head;
+    }
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+seg_reduce_kernel(const uint64_t *__restrict__ skey, uint32_t m, uint32_t *__restrict__ agg_head,
+                  uint32_t *__restrict__ agg_keep)
+{
+    __shared__ uint32_t s_h[SEG_THREADS / 32], s_k[SEG_THREADS / 32];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t j0 = blockIdx.x * SEG_TILE + tid * SEG_IPT;
+    bool head[SEG_IPT], single[SEG_IPT];
+    seg_flags(skey, m, j0, head, single);
+    uint32_t lasthead = 0, keep = 0;   // lasthead = (index of last head) + 1, 0 = none
+#pragma unroll
+    for (int e = 0; e < SEG_IPT; ++e) {
+        if (head[e]) lasthead = j0 + e + 1;
+        if (j0 + e < m && !single[e]) ++keep;
+    }
+    lasthead = __reduce_max_sync(0xffffffffu, lasthead);
+    keep = __reduce_add_sync(0xffffffffu, keep);
+    if ((tid & 31u) == 0) { s_h[tid >> 5] = lasthead; s_k[tid >> 5] = keep; }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t h = 0, k = 0;
+        for (int w = 0; w < SEG_THREADS / 32; ++w) { h = max(h, s_h[w]); k += s_k[w]; }
+        agg_head[blockIdx.x] = h;
+        agg_keep[blockIdx.x] = k;
+    }
+}
+
+// single CTA: exclusive (max, sum) scan over tile aggregates, in place; total keep -> *out_m
+__global__ void __launch_bounds__(1024)
+seg_scan_kernel(uint32_t *__restrict__ agg_head, uint32_t *__restrict__ agg_keep, uint32_t tiles,
+                uint32_t *__restrict__ out_m)
+{
+    __shared__ uint32_t s_h[32], s_k[32];
+    __shared__ uint32_t s_carry_h, s_carry_k;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) { s_carry_h = 0; s_carry_k = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < tiles; base += 1024) {
+        const uint32_t t = base + tid;
+        const uint32_t h = (t < tiles) ? agg_head[t] : 0u;
+        const uint32_t k = (t < tiles) ? agg_keep[t] : 0u;
+        const uint32_t ih = warp_incl_max(h);
+        uint32_t wk_total;
+        const uint32_t ek = warp_excl_sum(k, wk_total);
+        const uint32_t eh = __shfl_up_sync(0xffffffffu, ih, 1);
+        const uint32_t excl_h_in_warp = lane ? eh : 0u;
+        if (lane == 31) { s_h[warp] = ih; s_k[warp] = wk_total; }
+        __syncthreads();
+        uint32_t ph = s_carry_h, pk = s_carry_k;
+        for (uint32_t w = 0; w < warp; ++w) { ph = max(ph, s_h[w]); pk += s_k[w]; }
+        if (t < tiles) {
+            agg_head[t] = max(ph, excl_h_in_warp);
+            agg_keep[t] = pk + ek;
+        }
+        __syncthreads();
+        if (tid == 1023) {
+            s_carry_h = max(ph, ih);
+            s_carry_k = pk + ek + k;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *out_m = s_carry_k;
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+seg_apply_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sidx,
+                 const uint32_t *__restrict__ pos /* nullptr = identity */, uint32_t m,
+                 const uint32_t *__restrict__ carry_head, const uint32_t *__restrict__ carry_keep,
+                 uint32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint32_t *__restrict__ cpos,
+                 uint32_t *__restrict__ cidx, uint32_t *__restrict__ cgrp)
+{
+    __shared__ uint32_t s_h[SEG_THREADS / 32], s_k[SEG_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t j0 = blockIdx.x * SEG_TILE + tid * SEG_IPT;
+    bool head[SEG_IPT], single[SEG_IPT];
+    seg_flags(skey, m, j0, head, single);
+    uint32_t lasthead = 0, keep = 0;
+#pragma unroll
+    for (int e = 0; e < SEG_IPT; ++e) {
+        if (head[e]) lasthead = j0 + e + 1;
+        if (j0 + e < m && !single[e]) ++keep;
+    }
+    // block-wide exclusive (max, sum) scan over threads
+    const uint32_t ih = warp_incl_max(lasthead);
+    uint32_t wk_total;
+    const uint32_t ek = warp_excl_sum(keep, wk_total);
+    uint32_t eh = __shfl_up_sync(0xffffffffu, ih, 1);
+    if (lane == 0) eh = 0;
+    if (lane == 31) { s_h[warp] = ih; s_k[warp] = wk_total; }
+    __syncthreads();
+    uint32_t ph = carry_head[blockIdx.x], pk = carry_keep[blockIdx.x];
+    for (uint32_t w = 0; w < warp; ++w) { ph = max(ph, s_h[w]); pk += s_k[w]; }
+    uint32_t cur_head = max(ph, eh);   // (index of governing head) + 1 before this thread's first element
+    uint32_t slot = pk + ek;
+    uint32_t cur_grp = 0;
+    bool grp_valid = false;
+#pragma unroll
+    for (int e = 0; e < SEG_IPT; ++e) {
+        const uint32_t j = j0 + e;
+        if (j >= m) break;
+        if (head[e]) { cur_head = j + 1; grp_valid = false; }
+        if (!grp_valid) {
+            cur_grp = pos ? pos[cur_head - 1] : (cur_head - 1);
+            grp_valid = true;
+        }
+        const uint32_t p = pos ? pos[j] : j;
+        const uint32_t s = sidx[j];
+        sa[p] = s;
+        rank[s] = cur_grp;
+        if (!single[e]) {
+            cpos[slot] = p;
+            cidx[slot] = s;
+            cgrp[slot] = cur_grp;
+            ++slot;
+        }
+    }
+}
+
+}  // namespace hkcsa
+
+// ------------------------------------------------------------------ host driver
+using namespace hkcsa;
+
+namespace {
+struct SaBuffers {
+    uint64_t *key[2];
+    uint32_t *val[2];
+    uint32_t *pos[2];
+    uint32_t *grp;
+    uint32_t *rank;
+    uint32_t *agg_head, *agg_keep;
+    uint32_t *counter;
+    uint64_t *hist64;
+    SortScratch sort;
+};
+
+SaBuffers carve_sa(Carver &c, uint64_t n)
+{
+    SaBuffers b;
+    const uint64_t tiles = (n + SEG_TILE - 1) / SEG_TILE + 1;
+    b.key[0] = c.take<uint64_t>(n);
+    b.key[1] = c.take<uint64_t>(n);
+    b.val[0] = c.take<uint32_t>(n);
+    b.val[1] = c.take<uint32_t>(n);
+    b.pos[0] = c.take<uint32_t>(n);
+    b.pos[1] = c.take<uint32_t>(n);
+    b.grp = c.take<uint32_t>(n);
+    b.rank = c.take<uint32_t>(n);
+    b.agg_head = c.take<uint32_t>(tiles);
+    b.agg_keep = c.take<uint32_t>(tiles);
+    b.counter = c.take<uint32_t>(64);
+    b.hist64 = c.take<uint64_t>(256);
+    b.sort = carve_sort_scratch(c, n);
+    return b;
+}
+}  // namespace
+
+extern "C" size_t hkcsa_sa_scratch_bytes(uint64_t n)
+{
+    Carver c(nullptr);
+    carve_sa(c, n);
+    return c.total();
+}
+
+extern "C" int hkcsa_byte_hist(const uint8_t *d_sym, uint64_t n, uint64_t *d_hist, void *stream)
+{
+    HK_REQUIRE(d_hist != nullptr && (d_sym != nullptr || n == 0), HKCSA_EINVAL, "null pointer");
+    HK_CUDA(byte_hist(d_sym, n, d_hist, as_stream(stream)));
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, void *d_scratch,
+                              size_t scratch_bytes, void *stream, hkcsa_sa_stats *h_stats)
+{
+    hkcsa_sa_stats stats;
+    memset(&stats, 0, sizeof(stats));
+    if (h_stats) *h_stats = stats;
+    if (n == 0) return HKCSA_OK;   // build_suffix_array("") == []
+    HK_REQUIRE(n <= HKCSA_MAX_N, HKCSA_ERANGE, "n exceeds HKCSA_MAX_N");
+    HK_REQUIRE(d_text && d_sa && d_scratch, HKCSA_EINVAL, "null pointer");
+    Carver c(d_scratch);
+    SaBuffers B = carve_sa(c, n);
+    HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "SA scratch too small");
+    cudaStream_t st = as_stream(stream);
+    uint8_t *pin = static_cast<uint8_t *>(pinned_page());
+    HK_REQUIRE(pin != nullptr, HKCSA_ECUDA, "pinned page allocation failed");
+    uint64_t *h_hist = reinterpret_cast<uint64_t *>(pin);           // 2048 bytes
+    uint32_t *h_m = reinterpret_cast<uint32_t *>(pin + 2048);
+
+    // ---- alphabet: dense codes 1..sigma in byte order, 0 = past the end
+    HK_CUDA(byte_hist(d_text, n, B.hist64, st));
+    HK_CUDA(cudaMemcpyAsync(h_hist, B.hist64, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    HK_CUDA(cudaStreamSynchronize(st));
+    CodeMap map;
+    memset(&map, 0, sizeof(map));
+    uint32_t sigma = 0;
+    for (int ch = 0; ch < 256; ++ch)
+        if (h_hist[ch]) map.code[ch] = (uint16_t)(++sigma);
+    const int b = (int)bits_for(sigma);      // codes 0..sigma (9 bits when all 256 bytes occur)
+    const int k0 = 64 / b;
+    const int bits0 = b * k0;
+    const int passes0 = (bits0 + 7) / 8;
+    stats.sigma = sigma;
+    stats.bits_per_symbol = (uint32_t)b;
+    stats.k0 = (uint32_t)k0;
+
+    const uint32_t N = (uint32_t)n;
+    HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
+    {
+        const uint32_t blocks = (N + PACK_TILE - 1) / PACK_TILE;
+        prof::Scope ps(st, prof::SA_PACK0, (uint64_t)N * 13);
+        sa_pack0_kernel<<<blocks, PACK_THREADS, 0, st>>>(d_text, N, map, b, k0, passes0, B.key[0], B.val[0],
+                                                        B.sort.hist);
+        HK_LAUNCH_CHECK();
+    }
+    HK_CUDA(radix_sort_pairs_u64(B.key[0], B.val[0], B.key[1], B.val[1], N, passes0, B.sort, st));
+    int cur = passes0 & 1;             // buffer holding the sorted (key, idx)
+    uint32_t m = N;
+    int pcur = 0;                      // pos buffer describing the current working set (round 0: identity)
+    const uint32_t *pos = nullptr;
+    uint64_t h = (uint64_t)k0;
+    const int b2 = (int)bits_for(n);           // rank + 1 <= n
+    const int b1 = (int)bits_for(n - 1);       // group start <= n - 1
+    uint32_t round = 0;
+    stats.round_elems[0] = m;
+    stats.round_passes[0] = (uint32_t)passes0;
+    stats.sort_elem_passes = (uint64_t)m * passes0;
+    stats.alg_bytes = (uint64_t)n * 13 + (uint64_t)m * (24ull * passes0);
+
+    while (true) {
+        // ---- refine ranks from the sorted keys
+        const uint32_t tiles = (m + SEG_TILE - 1) / SEG_TILE;
+        {
+            prof::Scope ps(st, prof::SEG_REDUCE, (uint64_t)m * 8);
+            seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.key[cur], m, B.agg_head, B.agg_keep);
+            HK_LAUNCH_CHECK();
+        }
+        {
+            prof::Scope ps(st, prof::SEG_SCAN, (uint64_t)tiles * 16);
+            seg_scan_kernel<<<1, 1024, 0, st>>>(B.agg_head, B.agg_keep, tiles, B.counter);
+            HK_LAUNCH_CHECK();
+        }
+        uint32_t *cpos = B.pos[pcur ^ 1];
+        uint32_t *cidx = B.val[cur ^ 1];
+        {
+            prof::Scope ps(st, prof::SEG_APPLY, (uint64_t)m * 24);
+            seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.key[cur], B.val[cur], pos, m, B.agg_head, B.agg_keep,
+                                                           d_sa, B.rank, cpos, cidx, B.grp);
+            HK_LAUNCH_CHECK();
+        }
+        HK_CUDA(cudaMemcpyAsync(h_m, B.counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        HK_CUDA(cudaStreamSynchronize(st));
+        stats.alg_bytes += (uint64_t)m * (8 + 8 + 4 + 4 + 4 + 4);
+        ++round;
+        const uint32_t m_next = *h_m;
+        if (m_next == 0) break;
+        HK_REQUIRE(h < n, HKCSA_EINVAL, "internal: groups remain after depth >= n");
+        HK_REQUIRE(round < 40, HKCSA_EINVAL, "internal: too many doubling rounds");
+        // ---- next round on the compacted working set
+        m = m_next;
+        pcur ^= 1;
+        pos = B.pos[pcur];
+        const int in = cur ^ 1;        // cidx lives in val[in]; keys are written to key[in]
+        const int bits = b1 + b2;
+        const int passes = (bits + 7) / 8;
+        HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
+        {
+            const int blocks = (int)std::min<uint64_t>(((uint64_t)m + 255) / 256, (uint64_t)num_sms() * 16);
+            prof::Scope ps(st, prof::SA_KEYBUILD, (uint64_t)m * 20);
+            sa_keybuild_kernel<<<blocks, 256, 0, st>>>(B.val[in], B.grp, B.rank, N, (uint32_t)std::min<uint64_t>(h, n), b2,
+                                                       m, passes, B.key[in], B.sort.hist);
+            HK_LAUNCH_CHECK();
+        }
+        HK_CUDA(radix_sort_pairs_u64(B.key[in], B.val[in], B.key[in ^ 1], B.val[in ^ 1], m, passes, B.sort, st));
+        cur = (passes & 1) ? (in ^ 1) : in;
+        stats.round_elems[round] = m;
+        stats.round_passes[round] = (uint32_t)passes;
+        stats.sort_elem_passes += (uint64_t)m * passes;
+        stats.alg_bytes += (uint64_t)m * (20ull + 24ull * passes);
+        h *= 2;
+    }
+    stats.rounds = round;
+    if (h_stats) *h_stats = stats;
+    return HKCSA_OK;
+}

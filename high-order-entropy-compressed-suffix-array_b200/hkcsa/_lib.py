@@ -1,0 +1,158 @@
+"""ctypes binding of libhkcsa.so (include/hkcsa.h).
+
+The CUDA library is the only compute path: if it is missing or fails to load
+this module raises -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhkcsa.so")
+
+MAX_LEVELS = 8
+MAX_N = (1 << 30) - 2
+BLOCK_BITS = 224
+SUPER_BLOCKS = 65536
+SELECT_SAMPLE = 4096
+PROF_CLASSES = 16
+
+OK, EINVAL, ECUDA, ESCRATCH, ERANGE = 0, -1, -2, -3, -4
+
+
+class HkcsaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libhkcsa error {code}: {msg}")
+        self.code = code
+
+
+class SaStats(C.Structure):
+    _fields_ = [
+        ("rounds", C.c_uint32),
+        ("bits_per_symbol", C.c_uint32),
+        ("k0", C.c_uint32),
+        ("sigma", C.c_uint32),
+        ("sort_elem_passes", C.c_uint64),
+        ("alg_bytes", C.c_uint64),
+        ("round_elems", C.c_uint64 * 40),
+        ("round_passes", C.c_uint32 * 40),
+    ]
+
+
+class WtPlan(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint64),
+        ("sigma", C.c_uint32),
+        ("levels", C.c_uint32),
+        ("sym_of_code", C.c_uint8 * 256),
+        ("code_of_sym", C.c_uint16 * 256),
+        ("cnt", C.c_uint64 * 256),
+        ("C", C.c_uint64 * 257),
+        ("depth", C.c_uint8 * 256),
+        ("level_len", C.c_uint64 * MAX_LEVELS),
+        ("level_nodes", C.c_uint32 * MAX_LEVELS),
+        ("off_tables", C.c_uint64),
+        ("off_blocks", C.c_uint64 * MAX_LEVELS),
+        ("off_super", C.c_uint64 * MAX_LEVELS),
+        ("off_select", C.c_uint64 * MAX_LEVELS),
+        ("level_ones", C.c_uint64 * MAX_LEVELS),
+        ("blob_bytes", C.c_uint64),
+        ("scratch_bytes", C.c_uint64),
+        ("node_start", (C.c_uint32 * 256) * MAX_LEVELS),
+        ("node_bit", (C.c_uint8 * 256) * MAX_LEVELS),
+        ("node_id", (C.c_uint8 * 256) * MAX_LEVELS),
+    ]
+
+
+class SsaPlan(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint64),
+        ("rate", C.c_uint32),
+        ("n_samples", C.c_uint64),
+        ("off_blocks", C.c_uint64),
+        ("off_super", C.c_uint64),
+        ("off_samples", C.c_uint64),
+        ("blob_bytes", C.c_uint64),
+        ("scratch_bytes", C.c_uint64),
+    ]
+
+
+class ProfEntry(C.Structure):
+    _fields_ = [
+        ("name", C.c_char * 32),
+        ("launches", C.c_uint64),
+        ("ms", C.c_double),
+        ("alg_bytes", C.c_uint64),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/hkcsa.h declares
+_vp, _u64, _u32, _i32, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_size_t
+SIGNATURES = {
+    "hkcsa_abi_version": (_i32, []),
+    "hkcsa_last_error": (C.c_char_p, []),
+    "hkcsa_struct_size": (_sz, [_i32]),
+    "hkcsa_gen_text": (_i32, [_i32, _u64, _u64, _vp, _vp]),
+    "hkcsa_gen_pattern_lengths": (_i32, [_u64, _u64, _u32, _u32, _u64, _vp, _vp]),
+    "hkcsa_gen_pattern_bytes": (_i32, [_u64, _u64, _vp, _u64, _vp, _u32, _vp, _vp, _vp]),
+    "hkcsa_sa_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_sa_build": (_i32, [_vp, _u64, _vp, _vp, _sz, _vp, C.POINTER(SaStats)]),
+    "hkcsa_sort_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_sort_pairs_u64": (_i32, [_vp, _vp, _vp, _vp, _u64, _i32, _vp, _sz, _vp]),
+    "hkcsa_bwt": (_i32, [_vp, _vp, _u64, _vp, _vp]),
+    "hkcsa_byte_hist": (_i32, [_vp, _u64, _vp, _vp]),
+    "hkcsa_wt_plan_from_hist": (_i32, [C.POINTER(_u64), C.POINTER(WtPlan)]),
+    "hkcsa_wt_build": (_i32, [_vp, C.POINTER(WtPlan), _vp, _vp, _sz, _vp]),
+    "hkcsa_bv_rank_batch": (_i32, [_vp, C.POINTER(WtPlan), _u32, _vp, _u64, _vp, _vp]),
+    "hkcsa_bv_select_batch": (_i32, [_vp, C.POINTER(WtPlan), _u32, _vp, _u64, _vp, _vp]),
+    "hkcsa_bv_unpack": (_i32, [_vp, C.POINTER(WtPlan), _u32, _u64, _u64, _vp, _vp]),
+    "hkcsa_bv_rank_range": (_i32, [_vp, C.POINTER(WtPlan), _u32, _u64, _u64, _vp, _vp]),
+    "hkcsa_wt_rank_batch": (_i32, [_vp, C.POINTER(WtPlan), _vp, _vp, _u64, _vp, _vp]),
+    "hkcsa_wt_access_batch": (_i32, [_vp, C.POINTER(WtPlan), _vp, _u64, _vp, _vp]),
+    "hkcsa_golomb_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_golomb_encode": (_i32, [_vp, C.POINTER(WtPlan), _u32, _u64, _u32, _vp, _u64, C.POINTER(_u64), _vp,
+                                   _sz, _vp]),
+    "hkcsa_count_batch": (_i32, [_vp, C.POINTER(WtPlan), _vp, _vp, _u64, _vp, _vp, _vp]),
+    "hkcsa_ssa_plan_make": (_i32, [_u64, _u32, C.POINTER(SsaPlan)]),
+    "hkcsa_ssa_build": (_i32, [_vp, C.POINTER(SsaPlan), _vp, _vp, _sz, _vp]),
+    "hkcsa_expand_ranges": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
+    "hkcsa_gather_u32": (_i32, [_vp, _vp, _u64, _vp, _vp]),
+    "hkcsa_locate_rows": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(SsaPlan), _vp, _u64, _vp, _vp]),
+    "hkcsa_symbol_positions_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_symbol_positions": (_i32, [_vp, _u64, _vp, _vp, _vp, _sz, _vp]),
+    "hkcsa_prof_enable": (_i32, [_i32]),
+    "hkcsa_prof_reset": (_i32, []),
+    "hkcsa_prof_read": (_i32, [C.POINTER(ProfEntry), _i32, C.POINTER(_i32)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libhkcsa.so; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)     # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if L.hkcsa_abi_version() != 1:
+        raise ImportError("libhkcsa.so ABI version mismatch")
+    for idx, st in enumerate((SaStats, WtPlan, SsaPlan, ProfEntry)):
+        if L.hkcsa_struct_size(idx) != C.sizeof(st):
+            raise ImportError(f"struct layout mismatch for {st.__name__}: "
+                              f"C {L.hkcsa_struct_size(idx)} vs ctypes {C.sizeof(st)}")
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise HkcsaError(rc, load().hkcsa_last_error().decode("utf-8", "replace"))

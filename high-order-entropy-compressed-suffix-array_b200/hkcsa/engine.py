@@ -1,0 +1,368 @@
+"""Host-side engine over libhkcsa: device buffers, streams and the build / query
+pipelines.  PyTorch is used for device memory, streams and (in dist.py)
+torch.distributed only -- every computation is a libhkcsa kernel.
+
+Pipeline (reference call stack, csa/enhanced_fm_index.py:8-13):
+    text (+ '$') -> K1 suffix array -> K2 BWT -> byte histogram / C[] ->
+    K3 wavelet tree + rank directories (replaces build_occ) [-> sampled SA]
+Queries: K4 count (find_range), locate via the full SA (find) or via LF walks
+to a sampled SA (CompressedSuffixArray.locate).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HkcsaError, SaStats, SsaPlan, WtPlan, check
+
+ENG96, DNA4 = 0, 1
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("hkcsa needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t: torch.Tensor | None) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _empty(n: int, dtype, device) -> torch.Tensor:
+    return torch.empty(max(int(n), 0), dtype=dtype, device=device)
+
+
+def _scratch(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def to_device_u8(data, device=None) -> torch.Tensor:
+    """str (latin-1: utils/data_loader.py:4) / bytes / numpy / tensor -> contiguous uint8 CUDA tensor."""
+    device = device or _require_cuda()
+    if isinstance(data, torch.Tensor):
+        if data.dtype != torch.uint8:
+            raise TypeError("text tensors must be uint8")
+        return data.to(device).contiguous()
+    if isinstance(data, str):
+        data = data.encode("latin-1")
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        arr = np.frombuffer(data, dtype=np.uint8)
+    else:
+        arr = np.ascontiguousarray(data, dtype=np.uint8)
+    if arr.size == 0:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.from_numpy(arr.copy() if not arr.flags.writeable else arr).to(device)
+
+
+# ------------------------------------------------------------------ workload
+def gen_text(kind: int, seed: int, n: int, device=None) -> torch.Tensor:
+    device = device or _require_cuda()
+    out = _empty(n, torch.uint8, device)
+    check(_lib.load().hkcsa_gen_text(kind, seed, n, _ptr(out), _stream()))
+    return out
+
+
+def gen_patterns(seed: int, P: int, text: torch.Tensor, alphabet: torch.Tensor, min_len: int = 8, max_len: int = 64):
+    """Seeded substring patterns (half with one substitution): (bytes uint8[sum m], offsets int64[P+1])."""
+    L = _lib.load()
+    dev = text.device
+    n = text.numel()
+    lens = _empty(P, torch.int32, dev)
+    check(L.hkcsa_gen_pattern_lengths(seed, P, min_len, max_len, n, _ptr(lens), _stream()))
+    off = torch.zeros(P + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(lens, 0, dtype=torch.int64)   # plumbing: CSR offsets
+    total = int(off[-1].item()) if P else 0
+    out = _empty(total, torch.uint8, dev)
+    check(L.hkcsa_gen_pattern_bytes(seed, P, _ptr(text), n, _ptr(alphabet), alphabet.numel(), _ptr(off), _ptr(out),
+                                    _stream()))
+    return out, off
+
+
+# ------------------------------------------------------------------ K1 / K2
+def suffix_array(text: torch.Tensor, stats: SaStats | None = None) -> torch.Tensor:
+    """build_suffix_array (csa/suffix_array.py:131-134) on a device uint8 tensor -> int32[n]."""
+    L = _lib.load()
+    n = text.numel()
+    if n > _lib.MAX_N:
+        raise HkcsaError(_lib.ERANGE, f"text of {n} symbols exceeds the single-GPU limit {_lib.MAX_N}")
+    sa = _empty(n, torch.int32, text.device)
+    if n == 0:
+        return sa
+    nbytes = L.hkcsa_sa_scratch_bytes(n)
+    scratch = _scratch(nbytes, text.device)
+    st = stats if stats is not None else SaStats()
+    check(L.hkcsa_sa_build(_ptr(text), n, _ptr(sa), _ptr(scratch), nbytes, _stream(), C.byref(st)))
+    return sa
+
+
+def bwt(text: torch.Tensor, sa: torch.Tensor) -> torch.Tensor:
+    """bwt_transform (csa/bwt.py:3-13) -> uint8[n]."""
+    n = text.numel()
+    if sa.numel() != n:
+        raise IndexError("suffix array and text lengths differ")   # the reference would raise IndexError
+    out = _empty(n, torch.uint8, text.device)
+    check(_lib.load().hkcsa_bwt(_ptr(text), _ptr(sa), n, _ptr(out), _stream()))
+    return out
+
+
+def byte_hist(sym: torch.Tensor) -> np.ndarray:
+    """Counts per byte value (host uint64[256]); the histogram under build_count (utils/utils.py:16-24)."""
+    h = torch.empty(256, dtype=torch.int64, device=sym.device)
+    check(_lib.load().hkcsa_byte_hist(_ptr(sym), sym.numel(), _ptr(h), _stream()))
+    return h.cpu().numpy().astype(np.uint64)
+
+
+def sort_pairs_u64(keys: torch.Tensor, vals: torch.Tensor, key_bits: int = 64):
+    """In-place LSD onesweep radix sort of (int64-as-uint64 key, int32 value) pairs."""
+    L = _lib.load()
+    n = keys.numel()
+    k2, v2 = torch.empty_like(keys), torch.empty_like(vals)
+    nbytes = L.hkcsa_sort_scratch_bytes(n)
+    scratch = _scratch(nbytes, keys.device)
+    check(L.hkcsa_sort_pairs_u64(_ptr(keys), _ptr(vals), _ptr(k2), _ptr(v2), n, key_bits, _ptr(scratch), nbytes,
+                                 _stream()))
+    return keys, vals
+
+
+def symbol_positions(bwt_sym: torch.Tensor):
+    """FMIndex.precompute_rank (csa/csa.py:13-19): (positions int32[n] grouped by byte, start uint64[257] host)."""
+    L = _lib.load()
+    n = bwt_sym.numel()
+    pos = _empty(n, torch.int32, bwt_sym.device)
+    start = torch.zeros(257, dtype=torch.int64, device=bwt_sym.device)
+    nbytes = L.hkcsa_symbol_positions_scratch_bytes(n)
+    scratch = _scratch(nbytes, bwt_sym.device)
+    check(L.hkcsa_symbol_positions(_ptr(bwt_sym), n, _ptr(pos), _ptr(start), _ptr(scratch), nbytes, _stream()))
+    return pos, start.cpu().numpy().astype(np.uint64)
+
+
+# ------------------------------------------------------------------ K3
+class DeviceWaveletTree:
+    """Level-wise wavelet tree with rank/select directories, resident in one device blob."""
+
+    def __init__(self, sym: torch.Tensor, hist: np.ndarray | None = None):
+        L = _lib.load()
+        self.device = sym.device
+        self.n = sym.numel()
+        hist = byte_hist(sym) if hist is None else np.ascontiguousarray(hist, dtype=np.uint64)
+        self.hist = hist
+        self.plan = WtPlan()
+        check(L.hkcsa_wt_plan_from_hist(hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(self.plan)))
+        self.blob = torch.zeros(int(self.plan.blob_bytes), dtype=torch.uint8, device=self.device)
+        scratch = _scratch(self.plan.scratch_bytes, self.device)
+        check(L.hkcsa_wt_build(_ptr(sym), C.byref(self.plan), _ptr(self.blob), _ptr(scratch),
+                               int(self.plan.scratch_bytes), _stream()))
+
+    # -- shape
+    @property
+    def levels(self) -> int:
+        return int(self.plan.levels)
+
+    @property
+    def sigma(self) -> int:
+        return int(self.plan.sigma)
+
+    @property
+    def alphabet(self) -> bytes:
+        return bytes(self.plan.sym_of_code[: self.sigma])
+
+    def level_len(self, level: int) -> int:
+        return int(self.plan.level_len[level])
+
+    def level_ones(self, level: int) -> int:
+        return int(self.plan.level_ones[level])
+
+    def count_table(self) -> dict:
+        """C[] as build_count returns it: {chr(byte): number of smaller symbols} (utils/utils.py:16-24)."""
+        return {chr(self.plan.sym_of_code[c]): int(self.plan.C[c]) for c in range(self.sigma)}
+
+    # -- bit-vector queries on one level
+    def _u64(self, x) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=torch.int64).contiguous()
+        return torch.as_tensor(np.asarray(x, dtype=np.int64), device=self.device)
+
+    def bv_rank(self, level: int, pos) -> torch.Tensor:
+        pos = self._u64(pos)
+        out = torch.empty_like(pos)
+        check(_lib.load().hkcsa_bv_rank_batch(_ptr(self.blob), C.byref(self.plan), level, _ptr(pos), pos.numel(),
+                                              _ptr(out), _stream()))
+        return out
+
+    def bv_select(self, level: int, k) -> torch.Tensor:
+        k = self._u64(k)
+        out = torch.empty_like(k)
+        check(_lib.load().hkcsa_bv_select_batch(_ptr(self.blob), C.byref(self.plan), level, _ptr(k), k.numel(),
+                                                _ptr(out), _stream()))
+        return out
+
+    def bv_bits(self, level: int, begin: int, count: int) -> torch.Tensor:
+        out = _empty(count, torch.uint8, self.device)
+        check(_lib.load().hkcsa_bv_unpack(_ptr(self.blob), C.byref(self.plan), level, begin, count, _ptr(out),
+                                          _stream()))
+        return out
+
+    def bv_rank_range(self, level: int, begin: int, count: int) -> torch.Tensor:
+        out = _empty(count, torch.int32, self.device)
+        check(_lib.load().hkcsa_bv_rank_range(_ptr(self.blob), C.byref(self.plan), level, begin, count, _ptr(out),
+                                              _stream()))
+        return out
+
+    # -- symbol-level queries
+    def rank(self, sym, pos) -> torch.Tensor:
+        """occ[c][i] (utils/utils.py:26-32): occurrences of byte sym[q] before position pos[q]."""
+        pos = self._u64(pos)
+        if isinstance(sym, torch.Tensor):
+            sym = sym.to(device=self.device, dtype=torch.uint8).contiguous()
+        else:
+            sym = torch.as_tensor(np.asarray(sym, dtype=np.uint8), device=self.device)
+        if sym.numel() != pos.numel():
+            raise ValueError("sym and pos must have the same length")
+        out = torch.empty_like(pos)
+        check(_lib.load().hkcsa_wt_rank_batch(_ptr(self.blob), C.byref(self.plan), _ptr(sym), _ptr(pos), pos.numel(),
+                                              _ptr(out), _stream()))
+        return out
+
+    def access(self, pos) -> torch.Tensor:
+        pos = self._u64(pos)
+        out = _empty(pos.numel(), torch.uint8, self.device)
+        check(_lib.load().hkcsa_wt_access_batch(_ptr(self.blob), C.byref(self.plan), _ptr(pos), pos.numel(),
+                                                _ptr(out), _stream()))
+        return out
+
+    def golomb(self, level: int, nbits: int, m: int) -> torch.Tensor:
+        """GolombRiceEncoder.encode (csa/wavelet_tree.py:40-63) of bits [0, nbits) of a level -> uint8 0/1."""
+        L = _lib.load()
+        nbytes = L.hkcsa_golomb_scratch_bytes(nbits)
+        scratch = _scratch(nbytes, self.device)
+        total = C.c_uint64(0)
+        check(L.hkcsa_golomb_encode(_ptr(self.blob), C.byref(self.plan), level, nbits, m, 0, 0, C.byref(total),
+                                    _ptr(scratch), nbytes, _stream()))
+        out = _empty(total.value, torch.uint8, self.device)
+        if total.value:
+            check(L.hkcsa_golomb_encode(_ptr(self.blob), C.byref(self.plan), level, nbits, m, _ptr(out), total.value,
+                                        C.byref(total), _ptr(scratch), nbytes, _stream()))
+        return out
+
+
+# ------------------------------------------------------------------ K4
+@dataclass
+class SampledSA:
+    plan: SsaPlan
+    blob: torch.Tensor
+
+
+def build_sampled_sa(sa: torch.Tensor, rate: int) -> SampledSA:
+    L = _lib.load()
+    plan = SsaPlan()
+    check(L.hkcsa_ssa_plan_make(sa.numel(), rate, C.byref(plan)))
+    blob = torch.zeros(int(plan.blob_bytes), dtype=torch.uint8, device=sa.device)
+    scratch = _scratch(plan.scratch_bytes, sa.device)
+    check(L.hkcsa_ssa_build(_ptr(sa), C.byref(plan), _ptr(blob), _ptr(scratch), int(plan.scratch_bytes), _stream()))
+    return SampledSA(plan, blob)
+
+
+def pack_patterns(patterns, device=None):
+    """list[str|bytes] -> (uint8[sum m], int64[P+1]) on the device."""
+    device = device or _require_cuda()
+    enc = [p.encode("latin-1") if isinstance(p, str) else bytes(p) for p in patterns]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        np.cumsum([len(e) for e in enc], out=off[1:])
+    flat = np.frombuffer(b"".join(enc), dtype=np.uint8)
+    d_flat = torch.from_numpy(flat.copy()).to(device) if flat.size else torch.empty(0, dtype=torch.uint8, device=device)
+    return d_flat, torch.from_numpy(off).to(device)
+
+
+@dataclass
+class BuildStats:
+    sa: SaStats = field(default_factory=SaStats)
+    n: int = 0
+
+
+class DeviceIndex:
+    """FM index over `text` exactly as given (callers append the sentinel: EnhancedFMIndex adds '$',
+    csa/enhanced_fm_index.py:9).  Everything stays on the device."""
+
+    def __init__(self, text: torch.Tensor, *, sa_sample_rate: int = 0, keep_sa: bool = True,
+                 keep_text: bool = True):
+        _require_cuda()
+        self.device = text.device
+        self.n = text.numel()
+        self.stats = BuildStats(n=self.n)
+        self.sa = suffix_array(text, self.stats.sa)
+        self.bwt = bwt(text, self.sa)
+        self.wt = DeviceWaveletTree(self.bwt)
+        self.ssa = build_sampled_sa(self.sa, sa_sample_rate) if sa_sample_rate > 0 else None
+        self.text = text if keep_text else None
+        if not keep_sa:
+            if self.ssa is None:
+                raise ValueError("dropping the suffix array needs sa_sample_rate > 0")
+            self.sa = None
+
+    # find_range, batched (csa/enhanced_fm_index.py:21-32)
+    def count_batch(self, pat: torch.Tensor, off: torch.Tensor):
+        P = off.numel() - 1
+        lo = _empty(P, torch.int64, self.device)
+        hi = _empty(P, torch.int64, self.device)
+        if self.n == 0:
+            raise ValueError("empty index")
+        check(_lib.load().hkcsa_count_batch(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(pat), _ptr(off), P,
+                                            _ptr(lo), _ptr(hi), _stream()))
+        return lo, hi
+
+    # find, batched (csa/enhanced_fm_index.py:15-19): CSR (offsets, positions in SA order)
+    def locate_batch(self, pat: torch.Tensor, off: torch.Tensor, *, use_samples: bool | None = None):
+        L = _lib.load()
+        lo, hi = self.count_batch(pat, off)
+        P = lo.numel()
+        cnt = torch.where(lo >= 0, hi - lo + 1, torch.zeros_like(lo))       # plumbing: CSR offsets
+        out_off = torch.zeros(P + 1, dtype=torch.int64, device=self.device)
+        out_off[1:] = torch.cumsum(cnt, 0)
+        total = int(out_off[-1].item()) if P else 0
+        rows = _empty(total, torch.int32, self.device)
+        check(L.hkcsa_expand_ranges(_ptr(lo), _ptr(hi), _ptr(out_off), P, _ptr(rows), _stream()))
+        return out_off, self.locate_rows(rows, use_samples=use_samples)
+
+    def locate_rows(self, rows: torch.Tensor, *, use_samples: bool | None = None) -> torch.Tensor:
+        L = _lib.load()
+        if use_samples is None:
+            use_samples = self.sa is None
+        out = _empty(rows.numel(), torch.int32, self.device)
+        if use_samples:
+            if self.ssa is None:
+                raise ValueError("index was built without a sampled suffix array")
+            check(L.hkcsa_locate_rows(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(self.ssa.blob),
+                                      C.byref(self.ssa.plan), _ptr(rows), rows.numel(), _ptr(out), _stream()))
+        else:
+            check(L.hkcsa_gather_u32(_ptr(self.sa), _ptr(rows), rows.numel(), _ptr(out), _stream()))
+        return out
+
+
+# ------------------------------------------------------------------ measurement hook
+def prof_enable(on: bool) -> None:
+    L = _lib.load()
+    check(L.hkcsa_prof_reset())
+    check(L.hkcsa_prof_enable(1 if on else 0))
+
+
+def prof_read() -> dict:
+    L = _lib.load()
+    arr = (_lib.ProfEntry * _lib.PROF_CLASSES)()
+    n = C.c_int(0)
+    check(L.hkcsa_prof_read(arr, _lib.PROF_CLASSES, C.byref(n)))
+    out = {}
+    for i in range(n.value):
+        e = arr[i]
+        if e.launches:
+            out[e.name.decode()] = {"launches": int(e.launches), "ms": float(e.ms), "alg_bytes": int(e.alg_bytes)}
+    check(L.hkcsa_prof_reset())
+    return out

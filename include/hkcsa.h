@@ -1,0 +1,257 @@
+/*
+ * hkcsa.h -- C-ABI of libhkcsa.so: the B200 (sm_100a) hot path of the H_k-CSA
+ * index: suffix array -> BWT -> wavelet tree with rank/select directories, and
+ * batched FM backward search (count / locate).
+ *
+ * The reference (ajaynair710/High-Order-Entropy-Compressed-Suffix-Array) is pure
+ * Python and has no FFI layer of its own: these entry
+ * points are what the reference's Python functions bind to through ctypes when
+ * its csa/*.py modules are swapped for ours (INTEGRATION.md shows the stub).
+ * Each entry point cites the reference function it replaces (file:line relative
+ * to the reference repository root).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes.  No exceptions cross the boundary.
+ *  - Every function returns an int status: HKCSA_OK (0) or a negative HKCSA_E*;
+ *    hkcsa_last_error() returns a thread-local message for the last failure.
+ *  - Pointers prefixed d_ are DEVICE pointers, h_ are HOST pointers.  The
+ *    caller allocates every device buffer, scratch included (sizes come from
+ *    the *_bytes queries); the library allocates no device memory.  Its only
+ *    allocation is one small pinned host page per process for scalar read-backs.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Work is enqueued on that stream.  Functions documented as "syncs" wait on
+ *    the stream because they return scalars to the host; all others are async.
+ *  - Symbols are bytes (latin-1 text: utils/data_loader.py:4), ordered as
+ *    unsigned bytes == Python code-point order.  Text length n <= HKCSA_MAX_N.
+ */
+#ifndef HKCSA_H
+#define HKCSA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HKCSA_OK        0
+#define HKCSA_EINVAL   (-1)  /* bad argument                                   */
+#define HKCSA_ECUDA    (-2)  /* CUDA runtime error (see hkcsa_last_error)      */
+#define HKCSA_ESCRATCH (-3)  /* scratch / output buffer too small              */
+#define HKCSA_ERANGE   (-4)  /* n exceeds HKCSA_MAX_N                          */
+
+#define HKCSA_MAX_N ((uint64_t)((1u << 30) - 2))
+#define HKCSA_MAX_LEVELS 8
+#define HKCSA_ABI_VERSION 1
+
+int         hkcsa_abi_version(void);
+const char *hkcsa_last_error(void);
+/* sizeof of the public structs (0 hkcsa_sa_stats, 1 hkcsa_wt_plan, 2 hkcsa_ssa_plan, */
+/* 3 hkcsa_prof_entry) so a binding can verify its mirror of the layout.              */
+size_t      hkcsa_struct_size(int which);
+
+/* ------------------------------------------------------------------------ */
+/* Workload synthesis (bench/tests; no reference counterpart -- the corpus    */
+/* URLs of tests/dataset_benchmark.py:10-16 are unreachable offline).         */
+/* kind: 0 = ENG96 order-3 Markov English-like, 1 = DNA4 order-5 Markov.      */
+/* ------------------------------------------------------------------------ */
+int hkcsa_gen_text(int kind, uint64_t seed, uint64_t n, uint8_t *d_text, void *stream);
+/* Patterns (semantics of tests/test_patterns.py:3-9, seeded): lengths first,  */
+/* the caller prefix-sums them into d_offsets[P+1], then the bytes.            */
+int hkcsa_gen_pattern_lengths(uint64_t seed, uint64_t P, uint32_t min_len, uint32_t max_len,
+                              uint64_t n, uint32_t *d_len, void *stream);
+int hkcsa_gen_pattern_bytes(uint64_t seed, uint64_t P, const uint8_t *d_text, uint64_t n,
+                            const uint8_t *d_alphabet, uint32_t sigma, const int64_t *d_offsets,
+                            uint8_t *d_out, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* K1  suffix array -- replaces build_suffix_array, csa/suffix_array.py:131-134*/
+/*     (and the intent of ksa, :46-129).  Prefix doubling over packed 64-bit   */
+/*     keys sorted by an LSD onesweep radix sort; suffixes whose rank is       */
+/*     already unique leave the working set.  Proper prefixes sort first.      */
+/* ------------------------------------------------------------------------ */
+typedef struct hkcsa_sa_stats {
+    uint32_t rounds;            /* doubling rounds executed (round 0 included)  */
+    uint32_t bits_per_symbol;   /* b: width of a dense symbol code in round 0   */
+    uint32_t k0;                /* symbols packed per key in round 0            */
+    uint32_t sigma;             /* distinct bytes in the text                   */
+    uint64_t sort_elem_passes;  /* sum over rounds of elements * radix passes   */
+    uint64_t alg_bytes;         /* algorithmic HBM bytes moved   */
+    uint64_t round_elems[40];   /* working-set size per round                   */
+    uint32_t round_passes[40];  /* radix passes per round                       */
+} hkcsa_sa_stats;
+
+size_t hkcsa_sa_scratch_bytes(uint64_t n);
+/* syncs (once per doubling round).  d_sa: uint32[n].  h_stats may be NULL.    */
+int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, void *d_scratch,
+                   size_t scratch_bytes, void *stream, hkcsa_sa_stats *h_stats);
+
+/* LSD onesweep radix sort of (uint64 key, uint32 value) pairs on the low       */
+/* `key_bits` bits -- the primitive under K1, exported for tests/bench.         */
+/* Result lands in (d_keys, d_vals); *_alt are same-sized ping-pong buffers.    */
+size_t hkcsa_sort_scratch_bytes(uint64_t n);
+int hkcsa_sort_pairs_u64(uint64_t *d_keys, uint32_t *d_vals, uint64_t *d_keys_alt, uint32_t *d_vals_alt,
+                         uint64_t n, int key_bits, void *d_scratch, size_t scratch_bytes, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* K2  BWT gather -- replaces bwt_transform, csa/bwt.py:3-13:                   */
+/*     bwt[i] = text[SA[i]-1], text[n-1] when SA[i] == 0.                       */
+/* ------------------------------------------------------------------------ */
+int hkcsa_bwt(const uint8_t *d_text, const uint32_t *d_sa, uint64_t n, uint8_t *d_bwt, void *stream);
+
+/* Byte histogram: the raw counts under build_count, utils/utils.py:16-24.      */
+/* d_hist: uint64[256] (overwritten).                                           */
+int hkcsa_byte_hist(const uint8_t *d_sym, uint64_t n, uint64_t *d_hist, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* K3  wavelet tree -- replaces WaveletTree.build_tree (csa/wavelet_tree.py:    */
+/*     72-100), SuccinctRankSelect.__init__ (:6-12), build_count and build_occ  */
+/*     (utils/utils.py:16-32).  Full level-wise tree with the reference's       */
+/*     alphabet-halving split (mid = lo + (hi-lo)/2 over the sorted alphabet);  */
+/*     the reference's levels are the first node of each level.                 */
+/*                                                                              */
+/*     Level bit-vectors are stored as 32-byte rank blocks (one DRAM sector):   */
+/*       word0 low 32 bits  = ones before this block, relative to its superblock*/
+/*       remaining 224 bits = payload, bit j of the level at (j % 224) + 32     */
+/*     read as four little-endian uint64.  Superblocks (every 2^16 blocks) hold */
+/*     absolute uint64 counts.  Select samples: position of every 4096-th one.  */
+/* ------------------------------------------------------------------------ */
+#define HKCSA_BLOCK_BITS 224u
+#define HKCSA_SUPER_BLOCKS 65536u
+#define HKCSA_SELECT_SAMPLE 4096u
+
+typedef struct hkcsa_wt_plan {
+    uint64_t n;                           /* symbols in the sequence (BWT)      */
+    uint32_t sigma;                       /* distinct symbols                   */
+    uint32_t levels;                      /* tree height (0 when sigma <= 1)    */
+    uint8_t  sym_of_code[256];            /* dense code -> byte (sorted bytes)  */
+    uint16_t code_of_sym[256];            /* byte -> dense code, 0xFFFF absent  */
+    uint64_t cnt[256];                    /* occurrences per dense code         */
+    uint64_t C[257];                      /* C[code] = symbols with smaller code*/
+    uint8_t  depth[256];                  /* levels a code takes part in        */
+    uint64_t level_len[HKCSA_MAX_LEVELS]; /* bits in each level                 */
+    uint32_t level_nodes[HKCSA_MAX_LEVELS];
+    /* byte offsets into the index blob */
+    uint64_t off_tables;                  /* device copy of node tables         */
+    uint64_t off_blocks[HKCSA_MAX_LEVELS];/* rank blocks of level l             */
+    uint64_t off_super[HKCSA_MAX_LEVELS]; /* uint64 superblock counts           */
+    uint64_t off_select[HKCSA_MAX_LEVELS];/* uint32 select samples              */
+    uint64_t level_ones[HKCSA_MAX_LEVELS];/* filled by hkcsa_wt_build           */
+    uint64_t blob_bytes;                  /* total size of the index blob       */
+    uint64_t scratch_bytes;               /* scratch for hkcsa_wt_build         */
+    /* per (level, code): node start in the level, the bit the code takes,      */
+    /* the node id among the level's internal nodes (0xFF = not present)        */
+    uint32_t node_start[HKCSA_MAX_LEVELS][256];
+    uint8_t  node_bit[HKCSA_MAX_LEVELS][256];
+    uint8_t  node_id[HKCSA_MAX_LEVELS][256];
+} hkcsa_wt_plan;
+
+/* Host-only: derive the tree shape and blob layout from a byte histogram.      */
+int hkcsa_wt_plan_from_hist(const uint64_t h_hist[256], hkcsa_wt_plan *h_plan);
+/* Builds every level, its rank blocks, superblocks and select samples into     */
+/* d_blob (plan->blob_bytes, 32-byte aligned).  syncs once at the end to fill   */
+/* plan->level_ones.  d_sym: the sequence as raw bytes (the BWT).               */
+int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *h_plan, void *d_blob, void *d_scratch,
+                   size_t scratch_bytes, void *stream);
+
+/* Bit-vector primitives on one level -- SuccinctRankSelect.rank/select,        */
+/* csa/wavelet_tree.py:14-25.  rank(i) = ones in bits[0:i], i in [0, len];      */
+/* select(k) = smallest p in [0,len] with rank(p) >= k.                         */
+int hkcsa_bv_rank_batch(const void *d_blob, const hkcsa_wt_plan *h_plan, uint32_t level,
+                        const uint64_t *d_pos, uint64_t m, uint64_t *d_out, void *stream);
+int hkcsa_bv_select_batch(const void *d_blob, const hkcsa_wt_plan *h_plan, uint32_t level,
+                          const uint64_t *d_k, uint64_t m, uint64_t *d_out, void *stream);
+/* Unpack bits [begin, begin+count) of a level to one byte per bit (the          */
+/* SuccinctRankSelect.bit_vector view, csa/wavelet_tree.py:8).                  */
+int hkcsa_bv_unpack(const void *d_blob, const hkcsa_wt_plan *h_plan, uint32_t level,
+                    uint64_t begin, uint64_t count, uint8_t *d_out, void *stream);
+/* rank_support[begin .. begin+count) as uint32 (csa/wavelet_tree.py:9-12).     */
+int hkcsa_bv_rank_range(const void *d_blob, const hkcsa_wt_plan *h_plan, uint32_t level,
+                        uint64_t begin, uint64_t count, uint32_t *d_out, void *stream);
+
+/* Symbol-level queries: occ[c][i] of build_occ (utils/utils.py:26-32) ==       */
+/* EnhancedFMIndex.rank (csa/enhanced_fm_index.py:34-40), and access (bwt[i]).  */
+/* d_sym: query bytes; a byte that never occurs answers 0.                      */
+int hkcsa_wt_rank_batch(const void *d_blob, const hkcsa_wt_plan *h_plan, const uint8_t *d_sym,
+                        const uint64_t *d_pos, uint64_t m, uint64_t *d_out, void *stream);
+int hkcsa_wt_access_batch(const void *d_blob, const hkcsa_wt_plan *h_plan, const uint64_t *d_pos,
+                          uint64_t m, uint8_t *d_out, void *stream);
+
+/* Golomb-Rice run code of a level's first node (the reference's                */
+/* tree[l][0]) -- GolombRiceEncoder, csa/wavelet_tree.py:27-63.                 */
+/* Encodes bits [0, nbits) of `level`; m as computed by :33-38.  Two calls:     */
+/* d_out == NULL sizes the output (*h_out_bits), otherwise writes one byte per  */
+/* code bit.  syncs.                                                            */
+int hkcsa_golomb_encode(const void *d_blob, const hkcsa_wt_plan *h_plan, uint32_t level,
+                        uint64_t nbits, uint32_t m, uint8_t *d_out, uint64_t out_capacity,
+                        uint64_t *h_out_bits, void *d_scratch, size_t scratch_bytes, void *stream);
+size_t hkcsa_golomb_scratch_bytes(uint64_t nbits);
+
+/* ------------------------------------------------------------------------ */
+/* K4  FM backward search -- replaces EnhancedFMIndex.find_range / .rank /      */
+/*     .find, csa/enhanced_fm_index.py:15-40.                                   */
+/*     Patterns: concatenated bytes + int64 offsets[P+1].                       */
+/*     count: inclusive SA range (lo, hi); miss = (-1, -1); empty pattern =     */
+/*     (0, n-1).  Same recurrences and miss conventions as :21-32.              */
+/* ------------------------------------------------------------------------ */
+int hkcsa_count_batch(const void *d_blob, const hkcsa_wt_plan *h_plan, const uint8_t *d_pat,
+                      const int64_t *d_off, uint64_t P, int64_t *d_lo, int64_t *d_hi, void *stream);
+
+/* Sampled suffix array for locate: marks rows with SA[j] % rate == 0 (a rank   */
+/* bit-vector in the block format above) and stores SA[j] / rate for them.      */
+typedef struct hkcsa_ssa_plan {
+    uint64_t n;
+    uint32_t rate;
+    uint64_t n_samples;      /* ceil(n / rate)                                  */
+    uint64_t off_blocks;     /* mark bit-vector rank blocks                     */
+    uint64_t off_super;
+    uint64_t off_samples;    /* uint32[n_samples]                               */
+    uint64_t blob_bytes;
+    uint64_t scratch_bytes;
+} hkcsa_ssa_plan;
+
+int hkcsa_ssa_plan_make(uint64_t n, uint32_t rate, hkcsa_ssa_plan *h_plan);
+int hkcsa_ssa_build(const uint32_t *d_sa, const hkcsa_ssa_plan *h_plan, void *d_blob, void *d_scratch,
+                    size_t scratch_bytes, void *stream);
+
+/* locate, step 1: expand SA ranges into rows.  d_out_off: int64[P+1] exclusive */
+/* prefix sums of (hi-lo+1) (0 for misses), computed by the caller.             */
+int hkcsa_expand_ranges(const int64_t *d_lo, const int64_t *d_hi, const int64_t *d_out_off, uint64_t P,
+                        uint32_t *d_rows, void *stream);
+/* locate, step 2a: positions from the full SA (what EnhancedFMIndex.find does,  */
+/* csa/enhanced_fm_index.py:19): out[q] = SA[rows[q]], SA order preserved.       */
+int hkcsa_gather_u32(const uint32_t *d_src, const uint32_t *d_rows, uint64_t m, uint32_t *d_out,
+                     void *stream);
+/* locate, step 2b: positions by LF walk to the next sampled row.               */
+int hkcsa_locate_rows(const void *d_wt_blob, const hkcsa_wt_plan *h_plan, const void *d_ssa_blob,
+                      const hkcsa_ssa_plan *h_ssa, const uint32_t *d_rows, uint64_t m,
+                      uint32_t *d_out_pos, void *stream);
+
+/* FMIndex.precompute_rank, csa/csa.py:13-19: positions of every symbol in the  */
+/* BWT, ascending, grouped by byte value (a stable counting sort).  d_start:    */
+/* uint64[257].  d_scratch: hkcsa_symbol_positions_scratch_bytes(n).                      */
+size_t hkcsa_symbol_positions_scratch_bytes(uint64_t n);
+int hkcsa_symbol_positions(const uint8_t *d_bwt, uint64_t n, uint32_t *d_pos, uint64_t *d_start,
+                           void *d_scratch, size_t scratch_bytes, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* Measurement hook (no reference counterpart; the reference times with       */
+/* time.time(), tests/benchmark.py:30-35).  When enabled, the library brackets */
+/* its own kernel launches with CUDA events on the launching stream;           */
+/* hkcsa_prof_read syncs on them and returns one entry per kernel class.       */
+/* ------------------------------------------------------------------------ */
+typedef struct hkcsa_prof_entry {
+    char     name[32];
+    uint64_t launches;
+    double   ms;          /* summed device time between the bracketing events  */
+    uint64_t alg_bytes;   /* summed algorithmic bytes (per kernel)   */
+} hkcsa_prof_entry;
+#define HKCSA_PROF_CLASSES 16
+int hkcsa_prof_enable(int on);
+int hkcsa_prof_reset(void);
+int hkcsa_prof_read(hkcsa_prof_entry *h_out, int max_entries, int *h_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HKCSA_H */
