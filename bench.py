@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- index build MB/s (SA + BWT + wavelet tree) and batched count / locate
+throughput of the B200 hot path, with the reference's CPU path timed beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm (CPU oracle port)
+
+One step = one full index build of the workload text: byte histogram -> K1 suffix
+array -> K2 BWT -> K3 wavelet tree with rank/select directories and C[] -> sampled
+SA.  Default workload = BASELINE.json configs[1]: 100 MB synthetic DNA (sigma 4,
+order-5 Markov, seed 43) + '$'.  N > 1 (torchrun): N independent replicas, one per
+GPU ("replicas only"), value = N * text bytes / max-over-ranks time;
+the count queries that follow are sharded over the ranks (index replicated).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "high-order-entropy-compressed-suffix-array_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (generator kind, seed, text bytes, description)
+    "c1": (0, 42, 1 << 20, "1 MiB ENG96 order-3 Markov text + '$' (BASELINE configs[0])"),
+    "c2": (1, 43, 100_000_000, "100 MB DNA4 order-5 Markov text + '$' (BASELINE configs[1])"),
+    "c3": (0, 42, 200_000_000, "200 MB ENG96 order-3 Markov text + '$' (BASELINE configs[2])"),
+}
+METRIC = "index build MB/s (SA+BWT+WT)"
+SA_SAMPLE_RATE = 32
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--size", type=int, default=0, help="override the text size in bytes (debug)")
+    ap.add_argument("--patterns", type=int, default=10_000_000, help="count queries after the build (C4 shape)")
+    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="bytes of the workload the CPU baseline builds")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-queries", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------ reference arm / CPU baseline
+def cpu_build_sample(kind, seed, nbytes):
+    """The oracle port of the reference's build path on a bounded sample of the workload:
+    build_suffix_array(text+'$') -> bwt_transform -> WaveletTree(bwt) spine + rank_support + C[]."""
+    from oracle import oracle as O
+    text = O.gen_text(kind, seed, nbytes).tobytes() + b"$"
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    sa = O.build_suffix_array(text, threads=threads)
+    bwt = O.bwt_transform(text, sa)
+    O.build_count(text)
+    _, levels = O.wt_spine(bwt)
+    for bits in levels:
+        O.rank_support(bits)
+    dt = time.perf_counter() - t0
+    return dt, threads, len(text)
+
+
+def run_reference(args):
+    kind, seed, nbytes, desc = WORKLOADS[args.workload]
+    if args.size:
+        nbytes = args.size
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(nbytes, args.cpu_sample)
+    times = []
+    threads = 1
+    for i in range(args.warmup + args.steps):
+        dt, threads, n = cpu_build_sample(kind, seed, sample)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / 1e6 / (ms / 1e3)
+    sample_desc = f"first {sample} bytes of the workload text (+'$'), oracle port of SA+BWT+WT, {threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer", "data": "synthetic",
+        "config": {"workload": desc, "text_bytes": nbytes, "cpu_sample_bytes": sample},
+        "cpu_baseline": {"value": value, "unit": "MB/s", "cores": threads, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from hkcsa import engine as E
+    from hkcsa import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    kind, seed, nbytes, desc = WORKLOADS[args.workload]
+    if args.size:
+        nbytes = args.size
+    L = _lib.load()
+
+    # ---- synthetic text (+ '$'), resident in HBM; pinned host copy for the e2e leg
+    text = torch.empty(nbytes + 1, dtype=torch.uint8, device=dev)
+    E.check(L.hkcsa_gen_text(kind, seed, nbytes, text.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    text[nbytes] = 0x24
+    n = nbytes + 1
+    h_text = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_text.copy_(text)
+    h_sa = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_bwt = torch.empty(n, dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def build_step(src):
+        return E.DeviceIndex(src, sa_sample_rate=SA_SAMPLE_RATE)
+
+    launches0 = L.hkcsa_launch_count()
+    # ---- warm-up
+    idx = None
+    for _ in range(args.warmup):
+        idx = build_step(text)
+    torch.cuda.synchronize()
+    launches_per_step = (L.hkcsa_launch_count() - launches0) // max(1, args.warmup)
+
+    # ---- timed: K device-resident builds, CUDA events per step, L2 flushed between steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    E.prof_enable(True)
+    with ClockSampler(local) as clk:
+        barrier()
+        wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            idx = build_step(text)
+            b.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+    prof = E.prof_read()
+    E.prof_enable(False)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms = max_over_ranks(float(np.mean(step_ms)))
+    value = world * nbytes / 1e6 / (ms / 1e3)
+    stats = idx.stats.sa
+
+    # ---- e2e: host text -> H2D -> build -> D2H of SA + BWT, every step
+    def e2e_step():
+        d = torch.empty(n, dtype=torch.uint8, device=dev)
+        d.copy_(h_text, non_blocking=True)
+        ix = build_step(d)
+        h_sa.copy_(ix.sa, non_blocking=True)
+        h_bwt.copy_(ix.bwt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return ix
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
+    e2e_value = world * nbytes / 1e6 / (e2e_ms / 1e3)
+
+    # ---- dominant kernel roofline: onesweep radix pass, 24 B per (key, value) pair per launch
+    peak, peak_src = measured_peak_gbs()
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+    one = prof.get("onesweep_u64")
+    roofline = None
+    if one and one["ms"] > 0:
+        achieved = one["alg_bytes"] / (one["ms"] / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "onesweep_kernel<u64,u32> (one 8-bit radix pass, 24 B/pair)",
+                    "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "launches": one["launches"], "avg_launch_ms": one["ms"] / one["launches"],
+                    "share_of_step": one["ms"] / max(1e-9, sum(step_ms))}
+
+    # ---- batched count / locate on the index just built (patterns sharded over ranks)
+    queries = None
+    if not args.no_queries and args.patterns > 0:
+        P_total = args.patterns
+        P = P_total // world
+        alpha = torch.from_numpy(np.frombuffer(idx.wt.alphabet, dtype=np.uint8).copy()).to(dev)
+        alpha = alpha[alpha != 0x24]
+        pats, off = E.gen_patterns(44 + rank, P, text[:nbytes], alpha)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            lo, hi = idx.count_batch(pats, off)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        a.record()
+        for _ in range(reps):
+            lo, hi = idx.count_batch(pats, off)
+        b.record()
+        barrier()
+        c_ms = max_over_ranks(a.elapsed_time(b) / reps)
+        hits = sum_over_ranks(float((lo >= 0).sum().item()))
+        # locate a slice of the patterns through the sampled SA (LF walks)
+        PL = min(P, 1_000_000)
+        offL = off[: PL + 1]
+        idx_ssa = idx
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o_off, o_pos = idx_ssa.locate_batch(pats, offL, use_samples=True)
+        torch.cuda.synchronize()
+        a2.record()
+        o_off, o_pos = idx_ssa.locate_batch(pats, offL, use_samples=True)
+        b2.record()
+        barrier()
+        l_ms = max_over_ranks(a2.elapsed_time(b2))
+        occ_total = sum_over_ranks(float(o_pos.numel()))
+        queries = {"count_patterns_per_s": P * world / (c_ms / 1e3), "count_patterns": P * world,
+                   "count_ms": c_ms, "hit_fraction": hits / (P * world), "pattern_len": "uniform 8-64",
+                   "locate_occurrences_per_s": occ_total / (l_ms / 1e3), "locate_patterns": PL * world,
+                   "locate_occurrences": occ_total, "locate_ms": l_ms, "sa_sample_rate": SA_SAMPLE_RATE,
+                   "sharding": "index replicated per rank, patterns split evenly"}
+
+    # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = min(nbytes, args.cpu_sample)
+        dt, threads, _ = cpu_build_sample(kind, seed, sample)
+        cpu = {"value": sample / 1e6 / dt, "unit": "MB/s", "cores": threads, "kind": "port",
+               "sample": f"first {sample} bytes of the workload text (+'$'): oracle port of SA+BWT+WT spine, "
+                         f"{dt:.2f} s on {threads} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 symbols / u32 ranks / u64 keys (integer)", "data": "synthetic",
+            "config": {"workload": desc, "text_bytes": nbytes, "index_symbols": n, "sa_sample_rate": SA_SAMPLE_RATE,
+                       "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "l2": "256 MiB flush buffer written between timed steps; working set >> L2"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "MB/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": n,
+                    "d2h_bytes_per_step": 5 * n,
+                    "what": "pinned host text -> H2D -> build -> D2H of SA (4n) + BWT (n), wall clock incl. sync"},
+            "gpu_launches": int(launches_per_step) * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                            "alg_GBps": (v["alg_bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["alg_bytes"] else None}
+                        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+            "top_kernel": top[0],
+            "sa": {"rounds": int(stats.rounds), "k0": int(stats.k0), "bits_per_symbol": int(stats.bits_per_symbol),
+                   "round_elems": [int(stats.round_elems[i]) for i in range(int(stats.rounds))],
+                   "round_passes": [int(stats.round_passes[i]) for i in range(int(stats.rounds))],
+                   "alg_bytes": int(stats.alg_bytes)},
+            "queries": queries,
+            "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,129 @@
+"""Drop-in for the reference's csa/csa.py on B200: ``FMIndex`` (:6-45 == main.py:6-46) with its
+degenerate search kept as is, plus the ``CompressedSuffixArray(text, epsilon).locate(p)`` class
+the reference's own benchmark imports but never defines (tests/benchmark.py:8,32,47), and a
+``main()`` demo (:48-61).  The reference module cannot even be imported (it asks
+csa.suffix_array for ``optimized_ksa``, :3); this one can.
+"""
+import math
+
+import numpy as np
+
+from csa.bwt import bwt_transform
+from csa.suffix_array import build_suffix_array, optimized_ksa  # noqa: F401  (csa/csa.py:2-3)
+from csa.wavelet_tree import WaveletTree
+from hkcsa import views as _views
+
+
+class FMIndex:
+    """The reference's FMIndex: SA and BWT of the text WITHOUT a sentinel, per-symbol position
+    lists, and a backward search that -- as written in the reference (:21-38) -- ends with
+    (top, bottom) = (0, n-1) for every pattern, so find_pattern returns the whole suffix array."""
+
+    def __init__(self, text):
+        self.text = text
+        self.suffix_array = build_suffix_array(text)          # :9
+        self.bwt = bwt_transform(text, self.suffix_array)     # :10
+        self.rank = self.precompute_rank()                    # :11
+
+    def precompute_rank(self):
+        """rank[c] = ascending positions of c in the BWT, keys in first-appearance order (:13-19).
+        One stable counting-sort kernel (positions grouped by symbol)."""
+        from hkcsa import engine
+        n = len(self.bwt)
+        if n == 0:
+            return {}
+        d_bwt = engine.to_device_u8(self.bwt)
+        pos, start = engine.symbol_positions(d_bwt)
+        first = {}
+        present = [b for b in range(256) if start[b + 1] > start[b]]
+        heads = pos.cpu().numpy() if n <= _views.MATERIALIZE_MAX else None
+        for b in present:
+            first[b] = int(heads[int(start[b])]) if heads is not None else int(pos[int(start[b])].item())
+        rank = {}
+        for b in sorted(present, key=lambda x: first[x]):
+            s, e = int(start[b]), int(start[b + 1])
+            if heads is not None:
+                rank[chr(b)] = heads[s:e].tolist()
+            else:
+                rank[chr(b)] = _views.DeviceSequence(pos[s:e])
+        return rank
+
+    def backward_search(self, pattern):
+        # The reference's loop (:21-38), restated: with n >= 1 the first iteration sets top = 0
+        # ("top > 0" is false) and bottom = len(bwt) (or positions[n-1] = n-1 when the BWT is one
+        # repeated symbol); later iterations keep that; the clamp gives (0, n-1).  An empty
+        # pattern never enters the loop: also (0, n-1).  Empty text: range(0, 0).
+        n = len(self.bwt)
+        return list(range(0, n))
+
+    def find_pattern(self, pattern):
+        matches = self.backward_search(pattern)
+        if isinstance(self.suffix_array, list):
+            return [self.suffix_array[i] for i in matches if i < len(self.suffix_array)]
+        return self.suffix_array.tolist()
+
+
+class CompressedSuffixArray:
+    """The index the reference's benchmark expects (tests/benchmark.py:25-52) and its README
+    describes (README.md:4-11): text + '$', wavelet tree over the BWT for rank, and a suffix
+    array sampled every s = ceil((log2 n)^epsilon) text positions, so ``locate`` walks at most
+    s-1 LF steps per occurrence.  The full suffix array is dropped after sampling."""
+
+    def __init__(self, text, epsilon=0.5, sa_sample_rate=None):
+        from hkcsa import engine
+        self._E = engine
+        self.text = text
+        self.epsilon = epsilon
+        d = engine.to_device_u8(text)
+        import torch
+        d_text = torch.cat([d, torch.tensor([0x24], dtype=torch.uint8, device=d.device)])
+        n = d_text.numel()
+        if sa_sample_rate is None:
+            sa_sample_rate = max(1, math.ceil(max(1.0, math.log2(max(2, n))) ** epsilon))
+        self.sa_sample_rate = int(sa_sample_rate)
+        self._idx = engine.DeviceIndex(d_text, sa_sample_rate=self.sa_sample_rate, keep_sa=False, keep_text=False)
+        self.n = n
+
+    @property
+    def device_index(self):
+        return self._idx
+
+    def count(self, pattern):
+        lo, hi = self._idx.count_batch(*self._E.pack_patterns([pattern], self._idx.device))
+        lo, hi = int(lo.item()), int(hi.item())
+        return 0 if lo < 0 else hi - lo + 1
+
+    def locate(self, pattern):
+        """Sorted text positions of every occurrence of `pattern`."""
+        off, pos = self._idx.locate_batch(*self._E.pack_patterns([pattern], self._idx.device), use_samples=True)
+        return sorted(pos.cpu().tolist())
+
+    def count_batch(self, patterns):
+        lo, hi = self._idx.count_batch(*self._E.pack_patterns(patterns, self._idx.device))
+        lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+        return np.where(lo >= 0, hi - lo + 1, 0)
+
+    def locate_batch(self, patterns):
+        off, pos = self._idx.locate_batch(*self._E.pack_patterns(patterns, self._idx.device), use_samples=True)
+        off, pos = off.cpu().numpy(), pos.cpu().numpy()
+        return [sorted(pos[off[k]:off[k + 1]].tolist()) for k in range(len(off) - 1)]
+
+    def index_bytes(self):
+        """Device bytes held by the index (wavelet tree blob + sampled SA blob)."""
+        return int(self._idx.wt.blob.numel() + self._idx.ssa.blob.numel())
+
+
+def main():
+    text = "this is an example text"
+    fm_index = FMIndex(text)
+    pattern = "example"
+    print(f"Searching for the pattern: '{pattern}'")
+    matches = fm_index.find_pattern(pattern)
+    print(f"Pattern '{pattern}' found at indices: {matches}")
+    wavelet_tree = WaveletTree(text)
+    compressed = wavelet_tree.compress()
+    print(f"Wavelet Tree Compression: {compressed}")
+
+
+if __name__ == "__main__":
+    main()

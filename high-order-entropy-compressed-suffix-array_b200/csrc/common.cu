@@ -7,6 +7,7 @@
 namespace hkcsa {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char *fmt, ...)
 {
@@ -70,6 +71,8 @@ using namespace hkcsa;
 
 extern "C" int hkcsa_abi_version(void) { return HKCSA_ABI_VERSION; }
 extern "C" const char *hkcsa_last_error(void) { return g_err; }
+
+extern "C" unsigned long long hkcsa_launch_count(void) { return g_launches; }
 
 extern "C" size_t hkcsa_struct_size(int which)
 {

@@ -23,7 +23,15 @@ void set_error(const char *fmt, ...);
         }                                                                                  \
     } while (0)
 
-#define HK_LAUNCH_CHECK() HK_CUDA(cudaGetLastError())
+// every kernel launch of the library is counted (bench.py reports gpu_launches)
+extern unsigned long long g_launches;
+static inline void count_launch(unsigned long long k = 1) { g_launches += k; }
+
+#define HK_LAUNCH_CHECK()                                                                  \
+    do {                                                                                   \
+        hkcsa::count_launch();                                                             \
+        HK_CUDA(cudaGetLastError());                                                       \
+    } while (0)
 
 #define HK_REQUIRE(cond, code, msg)                                                        \
     do {                                                                                   \

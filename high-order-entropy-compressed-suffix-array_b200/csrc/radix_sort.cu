@@ -220,6 +220,7 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
     if (n == 0) return cudaSuccess;
     int blocks = (int)std::min<uint64_t>((n + 1023) / 1024, (uint64_t)num_sms() * 8);
     radix_hist_kernel<<<blocks, 256, 0, st>>>(d_keys, n, passes, s.hist);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -236,6 +237,7 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
         attr_done = true;
     }
     radix_scan_kernel<<<passes, RADIX, 0, st>>>(s.hist, s.base);
+    count_launch();
     cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     const uint32_t tiles = (n + SORT64_TILE - 1) / SORT64_TILE;
@@ -248,6 +250,7 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
             prof::Scope ps(st, prof::ONESWEEP_U64, (uint64_t)n * 24);
             kern<<<tiles, SORT64_THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, nullptr, s.base + p * RADIX,
                                                       s.lookback, s.ticket + p);
+            count_launch();
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -284,6 +287,7 @@ cudaError_t radix_partition_bytes(const uint8_t *d_in, uint8_t *d_out, uint32_t 
         kern<<<tiles, SORT8_THREADS, smem, st>>>(d_in, d_out, nullptr, nullptr, n, 0, d_lut, d_bucket_base,
                                                  s.lookback, s.ticket);
     }
+    count_launch();
     return cudaGetLastError();
 }
 

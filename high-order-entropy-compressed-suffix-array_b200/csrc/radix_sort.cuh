@@ -30,15 +30,24 @@ constexpr int SORT8_IPT = 32;
 constexpr int SORT8_TILE = SORT8_THREADS * SORT8_IPT;      // 8192 bytes per CTA
 
 // Adds one key's digits (8 bits each, `passes` of them from bit 0) to a CTA's
-// shared histogram hist[pass][256].  Lanes holding the same digit are merged
-// with match.any so sorted / low-entropy digits do not serialise on one bank.
+// shared histogram hist[pass][256].  When every lane of the warp holds the same
+// digit (sorted high digits of later rounds) one lane adds the whole count;
+// otherwise plain shared-memory atomics.  Must be called by all 32 lanes.
 __device__ __forceinline__ void hist_add_key(uint32_t *s_hist, uint64_t key, int passes, bool valid)
 {
     const uint32_t lane = lane_id();
+    const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+    const uint64_t key0 = __shfl_sync(0xffffffffu, key, 0);
     for (int p = 0; p < passes; ++p) {
-        const uint32_t d = valid ? (uint32_t)((key >> (8 * p)) & 0xFFu) : 0x100u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[p * RADIX + d], __popc(peers));
+        const uint32_t d = (uint32_t)((key >> (8 * p)) & 0xFFu);
+        const uint32_t d0 = (uint32_t)((key0 >> (8 * p)) & 0xFFu);
+        // lanes are valid in a prefix (tail of the array), so lane 0 is valid whenever any lane is
+        const bool uniform = __all_sync(0xffffffffu, !valid || d == d0);
+        if (uniform) {
+            if (lane == 0 && nvalid) atomicAdd(&s_hist[p * RADIX + d0], nvalid);
+        } else if (valid) {
+            atomicAdd(&s_hist[p * RADIX + d], 1u);
+        }
     }
 }
 __device__ __forceinline__ void hist_zero(uint32_t *s_hist, int passes)

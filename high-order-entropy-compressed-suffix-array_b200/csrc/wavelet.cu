@@ -498,3 +498,118 @@ extern "C" int hkcsa_wt_access_batch(const void *d_blob, const hkcsa_wt_plan *h_
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }
+
+// ------------------------------------------------------------------ stand-alone bit-vector
+// SuccinctRankSelect(bitmap) (reference csa/wavelet_tree.py:5-25) outside a tree:
+// a one-level plan whose level 0 is the bitmap, so hkcsa_bv_* apply unchanged.
+namespace hkcsa {
+__global__ void nonzero_lut_kernel(uint8_t *lut) { lut[threadIdx.x] = threadIdx.x ? 1 : 0; }
+}  // namespace hkcsa
+
+extern "C" int hkcsa_bitvec_plan(uint64_t nbits, hkcsa_wt_plan *p)
+{
+    HK_REQUIRE(p, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(nbits <= HKCSA_MAX_N, HKCSA_ERANGE, "n exceeds HKCSA_MAX_N");
+    memset(p, 0, sizeof(*p));
+    memset(p->code_of_sym, 0xFF, sizeof(p->code_of_sym));
+    memset(p->node_id, 0xFF, sizeof(p->node_id));
+    p->n = nbits;
+    p->sigma = 2;
+    p->levels = 1;
+    p->level_len[0] = nbits;
+    p->level_nodes[0] = 1;
+    uint64_t off = 0;
+    p->off_tables = off;
+    off = align_up(off + sizeof(WtTables), 256);
+    for (uint32_t l = 0; l < HKCSA_MAX_LEVELS; ++l) {
+        const uint64_t bits = (l == 0) ? nbits : 0;
+        p->off_blocks[l] = off;
+        off = align_up(off + rank_blocks_for(bits) * sizeof(RankBlock), 256);
+        p->off_super[l] = off;
+        off = align_up(off + super_for(bits) * sizeof(uint64_t), 256);
+        p->off_select[l] = off;
+        off = align_up(off + select_samples_for(bits) * sizeof(uint32_t), 256);
+    }
+    p->blob_bytes = off;
+    Carver c(nullptr);
+    const uint64_t tiles = rank_blocks_for(nbits) / WTP_BLOCKS_PER_CTA + 2;
+    c.take<uint32_t>(tiles);
+    c.take<uint64_t>(tiles);
+    c.take<uint64_t>(8);
+    c.take<uint8_t>(256);
+    p->scratch_bytes = c.total();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_bitvec_build(const uint8_t *d_bits, hkcsa_wt_plan *p, void *d_blob, void *d_scratch,
+                                  size_t scratch_bytes, void *stream)
+{
+    HK_REQUIRE(p && d_blob && d_scratch, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(p->levels == 1 && p->scratch_bytes <= scratch_bytes, HKCSA_ESCRATCH, "bit-vector scratch too small");
+    HK_REQUIRE((reinterpret_cast<uintptr_t>(d_blob) & 31) == 0, HKCSA_EINVAL, "blob must be 32-byte aligned");
+    HK_REQUIRE(d_bits || p->n == 0, HKCSA_EINVAL, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    uint8_t *blob = static_cast<uint8_t *>(d_blob);
+    Carver c(d_scratch);
+    const uint64_t tiles = rank_blocks_for(p->n) / WTP_BLOCKS_PER_CTA + 2;
+    uint32_t *d_agg = c.take<uint32_t>(tiles);
+    uint64_t *d_carry = c.take<uint64_t>(tiles);
+    uint64_t *d_ones = c.take<uint64_t>(8);
+    uint8_t *d_lut = c.take<uint8_t>(256);
+    nonzero_lut_kernel<<<1, 256, 0, st>>>(d_lut);
+    HK_LAUNCH_CHECK();
+    int rc = build_bitvector(d_bits, p->n, d_lut, reinterpret_cast<RankBlock *>(blob + p->off_blocks[0]),
+                             reinterpret_cast<uint64_t *>(blob + p->off_super[0]),
+                             reinterpret_cast<uint32_t *>(blob + p->off_select[0]), d_agg, d_carry, d_ones, st);
+    if (rc != HKCSA_OK) return rc;
+    uint64_t *h_ones = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(pinned_page()) + 3072);
+    HK_CUDA(cudaMemcpyAsync(h_ones, d_ones, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    HK_CUDA(cudaStreamSynchronize(st));
+    p->level_ones[0] = h_ones[0];
+    return HKCSA_OK;
+}
+
+// Stable bucket partition of a byte sequence by a host-supplied byte -> bucket
+// table (255 = drop).  Used for the reference's next_text (the subsequence of
+// symbols in the left half of the alphabet, csa/wavelet_tree.py:92).
+// h_bucket_sizes[256] receives the element count of every bucket.  syncs.
+extern "C" size_t hkcsa_partition_scratch_bytes(uint64_t n)
+{
+    Carver c(nullptr);
+    c.take<uint64_t>(256);
+    c.take<uint8_t>(256);
+    c.take<uint32_t>(256);
+    carve_sort_scratch(c, n);
+    return c.total();
+}
+
+extern "C" int hkcsa_partition_bytes(const uint8_t *d_in, uint64_t n, const uint8_t *h_lut, uint8_t *d_out,
+                                     uint64_t *h_bucket_sizes, void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    HK_REQUIRE(h_lut && h_bucket_sizes && d_scratch, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(n <= HKCSA_MAX_N, HKCSA_ERANGE, "n exceeds HKCSA_MAX_N");
+    memset(h_bucket_sizes, 0, 256 * sizeof(uint64_t));
+    if (n == 0) return HKCSA_OK;
+    HK_REQUIRE(d_in && d_out, HKCSA_EINVAL, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    Carver c(d_scratch);
+    uint64_t *d_hist = c.take<uint64_t>(256);
+    uint8_t *d_lut = c.take<uint8_t>(256);
+    uint32_t *d_base = c.take<uint32_t>(256);
+    SortScratch ss = carve_sort_scratch(c, n);
+    HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "partition scratch too small");
+    int rc = hkcsa_byte_hist(d_in, n, d_hist, stream);
+    if (rc != HKCSA_OK) return rc;
+    uint64_t *h_hist = reinterpret_cast<uint64_t *>(pinned_page());
+    HK_CUDA(cudaMemcpyAsync(h_hist, d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    HK_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < 256; ++b) h_bucket_sizes[h_lut[b]] += h_hist[b];
+    uint32_t base[256];
+    uint64_t run = 0;
+    for (int k = 0; k < 256; ++k) { base[k] = (uint32_t)run; run += h_bucket_sizes[k]; }
+    HK_CUDA(cudaMemcpyAsync(d_lut, h_lut, 256, cudaMemcpyHostToDevice, st));
+    HK_CUDA(cudaMemcpyAsync(d_base, base, sizeof(base), cudaMemcpyHostToDevice, st));
+    HK_CUDA(radix_partition_bytes(d_in, d_out, nullptr, (uint32_t)n, d_lut, d_base, ss, st));
+    HK_CUDA(cudaStreamSynchronize(st));   // base[] lives on this stack frame
+    return HKCSA_OK;
+}

@@ -108,6 +108,10 @@ SIGNATURES = {
     "hkcsa_bv_select_batch": (_i32, [_vp, C.POINTER(WtPlan), _u32, _vp, _u64, _vp, _vp]),
     "hkcsa_bv_unpack": (_i32, [_vp, C.POINTER(WtPlan), _u32, _u64, _u64, _vp, _vp]),
     "hkcsa_bv_rank_range": (_i32, [_vp, C.POINTER(WtPlan), _u32, _u64, _u64, _vp, _vp]),
+    "hkcsa_bitvec_plan": (_i32, [_u64, C.POINTER(WtPlan)]),
+    "hkcsa_bitvec_build": (_i32, [_vp, C.POINTER(WtPlan), _vp, _vp, _sz, _vp]),
+    "hkcsa_partition_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_partition_bytes": (_i32, [_vp, _u64, C.POINTER(C.c_uint8), _vp, C.POINTER(_u64), _vp, _sz, _vp]),
     "hkcsa_wt_rank_batch": (_i32, [_vp, C.POINTER(WtPlan), _vp, _vp, _u64, _vp, _vp]),
     "hkcsa_wt_access_batch": (_i32, [_vp, C.POINTER(WtPlan), _vp, _u64, _vp, _vp]),
     "hkcsa_golomb_scratch_bytes": (_sz, [_u64]),
@@ -121,6 +125,7 @@ SIGNATURES = {
     "hkcsa_locate_rows": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(SsaPlan), _vp, _u64, _vp, _vp]),
     "hkcsa_symbol_positions_scratch_bytes": (_sz, [_u64]),
     "hkcsa_symbol_positions": (_i32, [_vp, _u64, _vp, _vp, _vp, _sz, _vp]),
+    "hkcsa_launch_count": (C.c_ulonglong, []),
     "hkcsa_prof_enable": (_i32, [_i32]),
     "hkcsa_prof_reset": (_i32, []),
     "hkcsa_prof_read": (_i32, [C.POINTER(ProfEntry), _i32, C.POINTER(_i32)]),

@@ -253,6 +253,41 @@ class DeviceWaveletTree:
         return out
 
 
+class DeviceBitVector(DeviceWaveletTree):
+    """Stand-alone rank/select bit-vector (SuccinctRankSelect, csa/wavelet_tree.py:5-25): a one-level
+    plan whose level 0 is the bitmap.  `bits`: uint8 device tensor, one byte per bit."""
+
+    def __init__(self, bits: torch.Tensor):  # noqa: super().__init__ builds a tree; this builds one level
+        L = _lib.load()
+        self.device = bits.device
+        self.n = bits.numel()
+        self.hist = None
+        self.plan = WtPlan()
+        check(L.hkcsa_bitvec_plan(self.n, C.byref(self.plan)))
+        self.blob = torch.zeros(int(self.plan.blob_bytes), dtype=torch.uint8, device=self.device)
+        scratch = _scratch(self.plan.scratch_bytes, self.device)
+        check(L.hkcsa_bitvec_build(_ptr(bits), C.byref(self.plan), _ptr(self.blob), _ptr(scratch),
+                                   int(self.plan.scratch_bytes), _stream()))
+
+    @property
+    def ones(self) -> int:
+        return int(self.plan.level_ones[0])
+
+
+def partition_bytes(seq: torch.Tensor, lut: np.ndarray):
+    """Stable bucket partition of a byte sequence by lut[byte] -> (partitioned uint8[n], sizes uint64[256])."""
+    L = _lib.load()
+    n = seq.numel()
+    lut = np.ascontiguousarray(lut, dtype=np.uint8)
+    out = _empty(n, torch.uint8, seq.device)
+    sizes = np.zeros(256, dtype=np.uint64)
+    nbytes = L.hkcsa_partition_scratch_bytes(n)
+    scratch = _scratch(nbytes, seq.device)
+    check(L.hkcsa_partition_bytes(_ptr(seq), n, lut.ctypes.data_as(C.POINTER(C.c_uint8)), _ptr(out),
+                                  sizes.ctypes.data_as(C.POINTER(C.c_uint64)), _ptr(scratch), nbytes, _stream()))
+    return out, sizes
+
+
 # ------------------------------------------------------------------ K4
 @dataclass
 class SampledSA:
@@ -307,6 +342,21 @@ class DeviceIndex:
             if self.ssa is None:
                 raise ValueError("dropping the suffix array needs sa_sample_rate > 0")
             self.sa = None
+
+    @classmethod
+    def from_parts(cls, n: int, plan: WtPlan, blob: torch.Tensor, ssa: "SampledSA | None"):
+        """A query-only replica assembled from a broadcast wavelet-tree blob (hkcsa.dist)."""
+        self = cls.__new__(cls)
+        self.device = blob.device
+        self.n = n
+        self.stats = BuildStats(n=n)
+        self.sa = None
+        self.bwt = None
+        self.text = None
+        self.wt = DeviceWaveletTree.__new__(DeviceWaveletTree)
+        self.wt.device, self.wt.n, self.wt.hist, self.wt.plan, self.wt.blob = blob.device, n, None, plan, blob
+        self.ssa = ssa
+        return self
 
     # find_range, batched (csa/enhanced_fm_index.py:21-32)
     def count_batch(self, pat: torch.Tensor, off: torch.Tensor):

@@ -169,6 +169,22 @@ int hkcsa_bv_unpack(const void *d_blob, const hkcsa_wt_plan *h_plan, uint32_t le
 int hkcsa_bv_rank_range(const void *d_blob, const hkcsa_wt_plan *h_plan, uint32_t level,
                         uint64_t begin, uint64_t count, uint32_t *d_out, void *stream);
 
+/* Stand-alone bit-vector: SuccinctRankSelect(bitmap) outside a tree              */
+/* (csa/wavelet_tree.py:5-25).  hkcsa_bitvec_plan fills a one-level plan whose    */
+/* level 0 is the bitmap, so the hkcsa_bv_* queries apply with level = 0.         */
+/* d_bits: one byte per bit (non-zero = 1).  hkcsa_bitvec_build syncs.            */
+int hkcsa_bitvec_plan(uint64_t nbits, hkcsa_wt_plan *h_plan);
+int hkcsa_bitvec_build(const uint8_t *d_bits, hkcsa_wt_plan *h_plan, void *d_blob, void *d_scratch,
+                       size_t scratch_bytes, void *stream);
+
+/* Stable bucket partition of a byte sequence by a host byte -> bucket table      */
+/* (bucket 255 sorts last: use it for "drop").  next_text of the reference        */
+/* (csa/wavelet_tree.py:92) is bucket 0 of {left alphabet -> 0, rest -> 255}.     */
+/* h_bucket_sizes: uint64[256] out.  syncs.                                       */
+size_t hkcsa_partition_scratch_bytes(uint64_t n);
+int hkcsa_partition_bytes(const uint8_t *d_in, uint64_t n, const uint8_t *h_lut, uint8_t *d_out,
+                          uint64_t *h_bucket_sizes, void *d_scratch, size_t scratch_bytes, void *stream);
+
 /* Symbol-level queries: occ[c][i] of build_occ (utils/utils.py:26-32) ==       */
 /* EnhancedFMIndex.rank (csa/enhanced_fm_index.py:34-40), and access (bwt[i]).  */
 /* d_sym: query bytes; a byte that never occurs answers 0.                      */
@@ -247,6 +263,8 @@ typedef struct hkcsa_prof_entry {
     uint64_t alg_bytes;   /* summed algorithmic bytes (per kernel)   */
 } hkcsa_prof_entry;
 #define HKCSA_PROF_CLASSES 16
+/* kernels launched by the library so far in this process */
+unsigned long long hkcsa_launch_count(void);
 int hkcsa_prof_enable(int on);
 int hkcsa_prof_reset(void);
 int hkcsa_prof_read(hkcsa_prof_entry *h_out, int max_entries, int *h_n);

@@ -1,0 +1,167 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/hkcsa.h declares (no compute
+calls), struct mirrors match, host-side planning logic, the lazy views, and the drop-in modules'
+API surface."""
+import ctypes as C
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import oracle as O
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "hkcsa.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hkcsa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hkcsa import _lib
+    L = _lib.load()
+    names = _declared_functions()
+    assert len(names) >= 35
+    for name in names:
+        assert hasattr(L, name), f"libhkcsa.so does not export {name}"
+        assert name in _lib.SIGNATURES, f"ctypes binding lacks {name}"
+    assert sorted(_lib.SIGNATURES) == names
+    assert L.hkcsa_abi_version() == 1
+
+
+def test_struct_mirrors_match_c_layout():
+    from hkcsa import _lib
+    L = _lib.load()
+    for idx, st in enumerate((_lib.SaStats, _lib.WtPlan, _lib.SsaPlan, _lib.ProfEntry)):
+        assert L.hkcsa_struct_size(idx) == C.sizeof(st)
+
+
+def test_scratch_queries_are_host_only():
+    from hkcsa import _lib
+    L = _lib.load()
+    n = 1_000_000
+    assert L.hkcsa_sa_scratch_bytes(n) >= 40 * n
+    assert L.hkcsa_sa_scratch_bytes(2 * n) > L.hkcsa_sa_scratch_bytes(n)
+    assert L.hkcsa_sort_scratch_bytes(n) > 0
+    assert L.hkcsa_golomb_scratch_bytes(n) > 0
+
+
+def _plan(seq: bytes):
+    from hkcsa import _lib
+    L = _lib.load()
+    hist = np.bincount(np.frombuffer(seq, dtype=np.uint8), minlength=256).astype(np.uint64)
+    p = _lib.WtPlan()
+    assert L.hkcsa_wt_plan_from_hist(hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(p)) == 0
+    return p
+
+
+@pytest.mark.parametrize("seq", [b"banana", b"abcde", b"abcd", b"this is an example text", b"a", b"",
+                                 bytes(range(256)) * 2, bytes(range(97)) * 3])
+def test_wavelet_plan_matches_reference_split_rule(seq):
+    """Tree shape (host logic of K3): the left-most node of every level must be the reference's
+    alphabet halving (csa/wavelet_tree.py:78-80), checked against the oracle's spine."""
+    p = _plan(seq)
+    alpha, spine = O.wt_spine(seq)
+    sigma = len(alpha)
+    assert p.sigma == sigma and p.n == len(seq)
+    assert bytes(p.sym_of_code[:sigma]) == alpha.tobytes()
+    assert p.levels == (int(np.ceil(np.log2(sigma))) if sigma > 1 else 0)
+    cnt = np.bincount(np.frombuffer(seq, dtype=np.uint8), minlength=256)
+    a = list(range(sigma))
+    for l, bits in enumerate(spine):
+        mid = len(a) // 2
+        for c in a:                                    # left-most node: starts at 0, bit = right half
+            assert p.node_start[l][c] == 0 and p.node_id[l][c] == 0
+            assert p.node_bit[l][c] == (1 if c >= a[mid] else 0)
+        assert sum(int(cnt[alpha[c]]) for c in a) == len(bits)
+        a = a[:mid]
+    for l in range(p.levels):                          # every level: nodes tile the level exactly
+        alive = [c for c in range(sigma) if p.depth[c] > l]
+        assert p.level_len[l] == sum(int(p.cnt[c]) for c in alive)
+    for c in range(sigma):
+        assert p.C[c] == sum(int(p.cnt[k]) for k in range(c))
+        assert p.depth[c] in (p.levels, p.levels - 1)
+
+
+def test_error_codes_without_gpu():
+    from hkcsa import _lib
+    L = _lib.load()
+    p = _lib.SsaPlan()
+    assert L.hkcsa_ssa_plan_make(100, 0, C.byref(p)) == _lib.EINVAL
+    assert b"bad argument" in L.hkcsa_last_error()
+    assert L.hkcsa_ssa_plan_make(_lib.MAX_N + 1, 4, C.byref(p)) == _lib.ERANGE
+    assert L.hkcsa_ssa_plan_make(1000, 8, C.byref(p)) == 0 and p.n_samples == 125
+    with pytest.raises(_lib.HkcsaError):
+        _lib.check(_lib.EINVAL)
+
+
+def test_engine_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hkcsa import engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.to_device_u8(b"banana")
+    from csa.suffix_array import build_suffix_array
+    with pytest.raises(RuntimeError):
+        build_suffix_array("banana")
+
+
+def test_views_list_semantics():
+    from hkcsa import views
+    t = torch.tensor([5, 3, 1, 0, 4, 2], dtype=torch.int32)
+    s = views.DeviceSequence(t)
+    assert len(s) == 6 and s[0] == 5 and s[-1] == 2 and s[1:3] == [3, 1]
+    assert s == [5, 3, 1, 0, 4, 2] and not (s == [5, 3, 1, 0, 4, 3]) and s != [1]
+    assert list(s) == s.tolist() == [5, 3, 1, 0, 4, 2]
+    with pytest.raises(IndexError):
+        s[6]
+    assert views.int_sequence(t) == [5, 3, 1, 0, 4, 2] and isinstance(views.int_sequence(t), list)
+    lz = views.LazyList(lambda: [1, 0, 1])
+    assert lz == [1, 0, 1] and len(lz) == 3 and lz[0] == 1
+    assert views.maybe_lazy(3, lambda: [7]) == [7]
+
+
+def test_dropin_api_surface():
+    """Same public names and signatures as the reference modules."""
+    import csa.suffix_array as sa
+    import csa.bwt as bwt
+    import csa.wavelet_tree as wt
+    import csa.enhanced_fm_index as efm
+    import csa.csa as csa_mod
+    import utils.utils as uu
+    import utils.data_loader as dl
+
+    assert list(inspect.signature(sa.build_suffix_array).parameters) == ["text"]
+    assert list(inspect.signature(sa.ksa).parameters) == ["T"]
+    assert sa.optimized_ksa is sa.ksa
+    assert list(inspect.signature(bwt.bwt_transform).parameters) == ["text", "suffix_array"]
+    assert list(inspect.signature(uu.build_count).parameters) == ["text"]
+    assert list(inspect.signature(uu.build_occ).parameters) == ["bwt"]
+    assert list(inspect.signature(dl.load_text).parameters) == ["path", "size_limit"]
+    for cls, methods in [
+        (wt.SuccinctRankSelect, ["rank", "select"]),
+        (wt.GolombRiceEncoder, ["compute_dynamic_m", "encode"]),
+        (wt.WaveletTree, ["build_tree", "run_length_encode", "level_ordered_encode", "rank", "select",
+                          "compress", "decompress"]),
+        (efm.EnhancedFMIndex, ["find", "find_range", "rank"]),
+        (csa_mod.FMIndex, ["precompute_rank", "backward_search", "find_pattern"]),
+        (csa_mod.CompressedSuffixArray, ["locate"]),
+    ]:
+        for m in methods:
+            assert callable(getattr(cls, m)), f"{cls.__name__}.{m}"
+    assert list(inspect.signature(csa_mod.CompressedSuffixArray.__init__).parameters)[:3] == ["self", "text", "epsilon"]
+    assert sa.text == "banana" and wt.text == "this is an example text"
+    # integer restatement of the Golomb parameter needs no device
+    enc = wt.GolombRiceEncoder.__new__(wt.GolombRiceEncoder)
+    assert [enc.compute_dynamic_m(o, t) for o, t in [(1, 2), (1, 4), (1, 8), (3, 24), (1, 3), (1, 5), (0, 7)]] == \
+        [1, 2, 3, 3, 1, 2, 1]
+
+
+def test_golomb_m_matches_golden(golden):
+    import csa.wavelet_tree as wt
+    enc = wt.GolombRiceEncoder.__new__(wt.GolombRiceEncoder)
+    for ones, total, m in golden.meta["_golomb_m"]:
+        assert enc.compute_dynamic_m(ones, total) == m

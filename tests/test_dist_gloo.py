@@ -1,0 +1,69 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU query path's host logic: pattern sharding by
+total symbols, all-gather of (lo, hi), and index replication.  The per-rank search is stubbed by
+the CPU oracle here (test infrastructure); on the GPU box it is libhkcsa's count kernel."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle as O
+
+
+def test_shard_bounds_balance_by_symbols():
+    from hkcsa.dist import shard_bounds
+    rng = np.random.RandomState(1)
+    lens = rng.randint(8, 65, 10_000)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for world in (1, 2, 3, 8):
+        b = shard_bounds(off, world)
+        assert b[0][0] == 0 and b[-1][1] == 10_000
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        work = [off[e] - off[s] for s, e in b]
+        assert max(work) - min(work) <= 2 * 64
+    assert shard_bounds(np.array([0], dtype=np.int64), 4) == [(0, 0)] * 4
+    assert shard_bounds(np.array([0, 0, 0, 0], dtype=np.int64), 2) == [(0, 1), (1, 3)]   # empty patterns
+    skew = np.array([0, 1000, 1001, 1002, 1003], dtype=np.int64)
+    b = shard_bounds(skew, 2)
+    assert b[0][1] >= 1 and b[-1][1] == 4
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, text, pats, off, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hkcsa.dist import sharded_count
+        t = text + b"$"
+        fm = O.FM(O.bwt_transform(t, O.build_suffix_array(t, threads=1)))
+
+        def count_fn(p, o):     # stand-in for DeviceIndex.count_batch on this rank
+            lo, hi = fm.find_range_batch(p.numpy(), o.numpy(), threads=1)
+            return torch.from_numpy(lo), torch.from_numpy(hi)
+
+        lo, hi = sharded_count(count_fn, torch.from_numpy(pats), torch.from_numpy(off))
+        w_lo, w_hi = fm.find_range_batch(pats, off, threads=1)
+        ok = np.array_equal(lo.numpy(), w_lo) and np.array_equal(hi.numpy(), w_hi)
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_count_gloo(world):
+    text = O.gen_text(O.ENG96, 42, 20_000).tobytes()
+    pats, off = O.gen_patterns(44, 501, np.frombuffer(text, dtype=np.uint8))
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), text, pats, off, out), nprocs=world, join=True)
+    assert dict(out) == {r: 1 for r in range(world)}

@@ -1,0 +1,337 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI (hkcsa.engine -> libhkcsa.so)
+against the CPU oracle and the golden fixtures frozen from the reference."""
+import numpy as np
+import pytest
+
+from conftest import golden_case_names
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = golden_case_names()
+
+
+@pytest.fixture(scope="module")
+def E(cuda):
+    from hkcsa import engine
+    return engine
+
+
+def dev(E, data):
+    return E.to_device_u8(data)
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+# ------------------------------------------------------------------ workload generators
+@pytest.mark.parametrize("kind,seed,n", [(0, 42, 200_001), (1, 43, 200_001), (0, 7, 1), (1, 9, 65536), (0, 42, 65537)])
+def test_textgen_matches_oracle(E, kind, seed, n):
+    got = host(E.gen_text(kind, seed, n))
+    assert np.array_equal(got, O.gen_text(kind, seed, n))
+
+
+def test_patterns_match_oracle(E):
+    import torch
+    text = O.gen_text(O.ENG96, 42, 300_000)
+    d_text = dev(E, text)
+    alpha = np.unique(text)
+    pats, off = E.gen_patterns(44, 5000, d_text, torch.from_numpy(alpha).cuda())
+    w_p, w_o = O.gen_patterns(44, 5000, text)
+    assert np.array_equal(host(off), w_o)
+    assert np.array_equal(host(pats), w_p)
+
+
+# ------------------------------------------------------------------ radix sort primitive
+@pytest.mark.parametrize("n", [1, 2, 31, 100, 4095, 4096, 4097, 100_000, 1_000_003])
+@pytest.mark.parametrize("bits", [8, 20, 64])
+def test_radix_sort_pairs(E, n, bits):
+    import torch
+    rng = np.random.RandomState(n % 1000 + bits)
+    keys = rng.randint(0, 2 ** 63, size=n, dtype=np.int64).astype(np.uint64) * 2 + rng.randint(0, 2, size=n).astype(np.uint64)
+    if bits < 64:
+        keys &= np.uint64((1 << bits) - 1)
+    vals = np.arange(n, dtype=np.int32)
+    dk = torch.from_numpy(keys.view(np.int64)).cuda()
+    dv = torch.from_numpy(vals).cuda()
+    E.sort_pairs_u64(dk, dv, bits)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(host(dk).view(np.uint64), keys[order])
+    assert np.array_equal(host(dv), vals[order])          # stability: equal keys keep input order
+
+
+def test_radix_sort_few_distinct_keys(E):
+    import torch
+    n = 300_000
+    rng = np.random.RandomState(5)
+    keys = (rng.randint(0, 3, size=n).astype(np.uint64) << np.uint64(40)) | rng.randint(0, 2, size=n).astype(np.uint64)
+    dk = torch.from_numpy(keys.view(np.int64)).cuda()
+    dv = torch.arange(n, dtype=torch.int32, device="cuda")
+    E.sort_pairs_u64(dk, dv, 48)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(host(dk).view(np.uint64), keys[order])
+    assert np.array_equal(host(dv), order.astype(np.int32))
+
+
+# ------------------------------------------------------------------ K1 / K2 against the reference's own outputs
+@pytest.mark.parametrize("name", CASES)
+def test_sa_bwt_golden(E, golden, name):
+    text = golden.text(name)
+    d_text = dev(E, text)
+    sa = E.suffix_array(d_text)
+    assert np.array_equal(host(sa).astype(np.uint32), golden.get(f"{name}/sa"))
+    got = E.bwt(d_text, sa)
+    assert host(got).tobytes() == golden.get(f"{name}/bwt").tobytes()
+    if golden.has(f"{name}/fm/sa"):
+        d2 = dev(E, text + b"$")
+        sa2 = E.suffix_array(d2)
+        assert np.array_equal(host(sa2).astype(np.uint32), golden.get(f"{name}/fm/sa"))
+        assert host(E.bwt(d2, sa2)).tobytes() == golden.get(f"{name}/fm/bwt").tobytes()
+
+
+def _texts():
+    rng = np.random.RandomState(2024)
+    yield "all_a_5000", b"a" * 5000
+    yield "ab_period", b"ab" * 4000
+    yield "abc_period_tail", b"abc" * 3000 + b"ab"
+    yield "fib", _fib(16)
+    yield "rand2_100k", bytes(rng.choice(np.frombuffer(b"xy", dtype=np.uint8), 100_000))
+    yield "rand256_50k", bytes(rng.randint(0, 256, 50_000).astype(np.uint8))
+    yield "runs", b"".join(bytes([65 + (i % 3)]) * int(rng.randint(1, 400)) for i in range(300))
+    yield "eng_300k", O.gen_text(O.ENG96, 42, 300_000).tobytes()
+    yield "dna_300k", O.gen_text(O.DNA4, 43, 300_000).tobytes()
+    yield "dna_1m_dollar", O.gen_text(O.DNA4, 43, 1 << 20).tobytes() + b"$"
+    yield "eng_1m_dollar", O.gen_text(O.ENG96, 42, 1 << 20).tobytes() + b"$"
+    yield "repeat_block", O.gen_text(O.ENG96, 1, 5000).tobytes() * 20
+
+
+def _fib(k):
+    a, b = b"a", b"ab"
+    for _ in range(k):
+        a, b = b, b + a
+    return b
+
+
+TEXTS = dict(_texts())
+
+
+@pytest.mark.parametrize("name", list(TEXTS))
+def test_sa_bwt_oracle(E, name):
+    text = TEXTS[name]
+    d_text = dev(E, text)
+    st = E.SaStats()
+    sa = E.suffix_array(d_text, st)
+    want = O.build_suffix_array(text)
+    got = host(sa).astype(np.uint32)
+    assert np.array_equal(got, want), f"first mismatch at {np.flatnonzero(got != want)[:5]}"
+    assert st.rounds >= 1
+    assert host(E.bwt(d_text, sa)).tobytes() == O.bwt_transform(text, want).tobytes()
+
+
+def test_byte_hist(E):
+    rng = np.random.RandomState(3)
+    for n in (0, 1, 15, 16, 17, 100_003):
+        t = rng.randint(0, 256, n).astype(np.uint8)
+        h = E.byte_hist(dev(E, t))
+        assert np.array_equal(h, np.bincount(t, minlength=256).astype(np.uint64))
+    # unaligned view
+    t = rng.randint(0, 256, 4099).astype(np.uint8)
+    d = dev(E, t)[3:]
+    assert np.array_equal(E.byte_hist(d), np.bincount(t[3:], minlength=256).astype(np.uint64))
+
+
+# ------------------------------------------------------------------ K3
+WT_TEXTS = ["banana", "abcd", "abcde", "mississippi", "this is an example text"]
+
+
+def _wt_check(E, seq: bytes, full=True):
+    d = dev(E, seq)
+    wt = E.DeviceWaveletTree(d)
+    alpha, spine = O.wt_spine(seq)
+    assert wt.alphabet == alpha.tobytes()
+    # the full tree is ceil(log2 sigma) deep; the reference's left spine floor(log2 sigma)
+    assert wt.levels == (int(np.ceil(np.log2(len(alpha)))) if len(alpha) > 1 else 0)
+    assert len(spine) <= wt.levels
+    cnt, Ct = O.build_count(seq)
+    assert wt.count_table() == {chr(c): int(Ct[c]) for c in range(256) if cnt[c]}
+    arr = np.frombuffer(seq, dtype=np.uint8)
+    for l, bits in enumerate(spine):
+        n_l = len(bits)
+        assert wt.level_len(l) >= n_l
+        got = host(wt.bv_bits(l, 0, n_l))
+        assert np.array_equal(got, bits), f"level {l}"
+        rs = O.rank_support(bits)
+        assert np.array_equal(host(wt.bv_rank_range(l, 0, n_l + 1)).astype(np.uint32), rs)
+    # every level: rank/select against a plain prefix sum of the unpacked bits
+    rng = np.random.RandomState(11)
+    for l in range(wt.levels):
+        L = wt.level_len(l)
+        bits = host(wt.bv_bits(l, 0, L))
+        rs = np.concatenate([[0], np.cumsum(bits, dtype=np.int64)])
+        assert wt.level_ones(l) == int(rs[-1])
+        pos = np.unique(np.concatenate([rng.randint(0, L + 1, 200), [0, L, max(0, L - 1), min(L, 224), min(L, 223)]]))
+        assert np.array_equal(host(wt.bv_rank(l, pos)), rs[pos])
+        ks = np.unique(np.concatenate([rng.randint(0, int(rs[-1]) + 2, 200), [0, 1, int(rs[-1]), int(rs[-1]) + 1]]))
+        want = np.searchsorted(rs, ks, side="left")
+        want = np.where(ks > rs[-1], L, want)
+        assert np.array_equal(host(wt.bv_select(l, ks)), want), f"select level {l}"
+    if full and len(seq):
+        # occ[c][i] for every symbol at random positions, and access == sequence
+        pos = np.unique(np.concatenate([rng.randint(0, len(seq) + 1, 400), [0, len(seq)]]))
+        for c in np.unique(arr):
+            want = np.concatenate([[0], np.cumsum(arr == c)])[pos]
+            got = host(wt.rank(np.full(len(pos), c, dtype=np.uint8), pos))
+            assert np.array_equal(got, want), f"rank of {c}"
+        absent = [c for c in range(256) if c not in set(arr.tolist())][:1]
+        for c in absent:
+            assert int(host(wt.rank(np.array([c], dtype=np.uint8), np.array([len(seq)])))[0]) == 0
+        ap = np.unique(rng.randint(0, len(seq), 2000))
+        assert np.array_equal(host(wt.access(ap)), arr[ap])
+    return wt
+
+
+@pytest.mark.parametrize("s", WT_TEXTS)
+def test_wavelet_small(E, s):
+    _wt_check(E, s.encode())
+
+
+@pytest.mark.parametrize("name", ["rand256_50k", "eng_300k", "dna_300k", "runs", "rand2_100k", "dna_1m_dollar"])
+def test_wavelet_on_bwt(E, name):
+    text = TEXTS[name]
+    bwt = O.bwt_transform(text, O.build_suffix_array(text)).tobytes()
+    _wt_check(E, bwt)
+
+
+@pytest.mark.parametrize("sigma", [1, 2, 3, 5, 17, 97, 128, 129, 255, 256])
+def test_wavelet_alphabet_sizes(E, sigma):
+    rng = np.random.RandomState(sigma)
+    seq = rng.randint(0, sigma, 30_000).astype(np.uint8)
+    seq[:sigma] = np.arange(sigma)          # every symbol occurs
+    _wt_check(E, seq.tobytes())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_wavelet_golden(E, golden, name):
+    meta = golden.meta[name]
+    if meta["n"] == 0:
+        return
+    text = golden.text(name)
+    wt = E.DeviceWaveletTree(dev(E, text))
+    assert wt.levels >= meta["wt_levels"]
+    for l in range(meta["wt_levels"]):
+        n_l = int(golden.get(f"{name}/wt/{l}/nbits")[0])
+        want = np.unpackbits(golden.get(f"{name}/wt/{l}/bits"))[:n_l]
+        assert np.array_equal(host(wt.bv_bits(l, 0, n_l)), want)
+        if golden.has(f"{name}/wt/{l}/rank_support"):
+            assert np.array_equal(host(wt.bv_rank_range(l, 0, n_l + 1)).astype(np.uint32),
+                                  golden.get(f"{name}/wt/{l}/rank_support"))
+        ones = int(want.sum())
+        m = O.golomb_m(ones, n_l)
+        g_len = int(golden.get(f"{name}/wt/{l}/golomb_len")[0])
+        want_g = np.unpackbits(golden.get(f"{name}/wt/{l}/golomb"))[:g_len]
+        assert np.array_equal(host(wt.golomb(l, n_l, m)), want_g), f"golomb level {l}"
+
+
+def test_golomb_large_m(E):
+    seq = (b"a" * 700 + b"b" * 3 + b"a" * 1300 + b"bbbbbbbbbbbbbbbbbbbbbbb" + b"a" * 5000 + b"b") * 7
+    wt = E.DeviceWaveletTree(dev(E, seq))
+    bits = (np.frombuffer(seq, dtype=np.uint8) == ord("b")).astype(np.uint8)
+    for m in (1, 2, 5, 9):
+        assert np.array_equal(host(wt.golomb(0, len(bits), m)), O.golomb_encode(bits, m))
+    # a prefix that ends inside a run
+    for nb in (701, 702, 2004, 2026, 1792, 1793):
+        assert np.array_equal(host(wt.golomb(0, nb, 3)), O.golomb_encode(bits[:nb], 3))
+
+
+# ------------------------------------------------------------------ K4
+def _fm_check(E, text: bytes, P=3000, seed=44, sample_rates=(1, 4, 32)):
+    import torch
+    t = text + b"$"
+    idx = E.DeviceIndex(dev(E, t), sa_sample_rate=sample_rates[-1])
+    sa = O.build_suffix_array(t)
+    assert np.array_equal(host(idx.sa).astype(np.uint32), sa)
+    fm = O.FM(O.bwt_transform(t, sa))
+    base = np.frombuffer(text, dtype=np.uint8)
+    pats, off = O.gen_patterns(seed, P, base, 1, min(64, len(base)))
+    # add empty, unseen-symbol, sentinel and whole-text patterns
+    extra = [b"", b"\x01", b"$", text[-1:] + b"$", text[:50], t]
+    ep = np.frombuffer(b"".join(extra), dtype=np.uint8)
+    pats = np.concatenate([pats, ep])
+    off = np.concatenate([off, off[-1] + np.cumsum([len(e) for e in extra])])
+    d_p, d_o = torch.from_numpy(pats).cuda(), torch.from_numpy(off).cuda()
+    lo, hi = idx.count_batch(d_p, d_o)
+    w_lo, w_hi = fm.find_range_batch(pats, off)
+    assert np.array_equal(host(lo), w_lo)
+    assert np.array_equal(host(hi), w_hi)
+    # locate through the full SA (EnhancedFMIndex.find order) and through LF walks
+    o1, p1 = idx.locate_batch(d_p, d_o, use_samples=False)
+    cnt = np.where(w_lo >= 0, w_hi - w_lo + 1, 0)
+    assert np.array_equal(host(o1), np.concatenate([[0], np.cumsum(cnt)]))
+    want = np.concatenate([sa[l:h + 1] for l, h in zip(w_lo, w_hi) if l >= 0] or [np.zeros(0, np.uint32)])
+    assert np.array_equal(host(p1).astype(np.uint32), want)
+    for rate in sample_rates:
+        idx.ssa = E.build_sampled_sa(idx.sa, rate)
+        o2, p2 = idx.locate_batch(d_p, d_o, use_samples=True)
+        assert np.array_equal(host(o2), host(o1))
+        assert np.array_equal(host(p2), host(p1)), f"sampled locate, rate {rate}"
+    return idx
+
+
+@pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "rand2_100k", "runs", "all_a_5000", "fib"])
+def test_count_locate_oracle(E, name):
+    _fm_check(E, TEXTS[name])
+
+
+def test_count_text_with_low_bytes(E):
+    # bytes below '$' make the sentinel non-minimal
+    rng = np.random.RandomState(8)
+    text = bytes(rng.choice(np.frombuffer(b" !#ab\n\t", dtype=np.uint8), 20_000))
+    _fm_check(E, text, P=1500)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_count_locate_golden(E, golden, name):
+    import torch
+    meta = golden.meta[name]
+    if "fm_queries" not in meta:
+        return
+    idx = E.DeviceIndex(dev(E, golden.text(name) + b"$"))
+    qs = meta["fm_queries"]
+    d_p, d_o = E.pack_patterns([bytes(q["p"]) for q in qs])
+    lo, hi = idx.count_batch(d_p, d_o)
+    assert host(lo).tolist() == [q["l"] for q in qs]
+    assert host(hi).tolist() == [q["r"] for q in qs]
+    o, p = idx.locate_batch(d_p, d_o)
+    o, p = host(o), host(p)
+    for k, q in enumerate(qs):
+        found = p[o[k]:o[k + 1]].tolist()
+        assert len(found) == q["find_len"] and sum(found) == q["find_sorted_sum"]
+        if q["find"] is not None:
+            assert found == q["find"]                      # SA order, as the reference returns
+    sym = np.array([c for c, _, _ in meta["fm_rank"]], dtype=np.uint8)
+    pos = np.array([i for _, i, _ in meta["fm_rank"]], dtype=np.int64)
+    assert host(idx.wt.rank(sym, pos)).tolist() == [v for _, _, v in meta["fm_rank"]]
+
+
+def test_symbol_positions(E):
+    for name in ("eng_300k", "rand256_50k", "all_a_5000"):
+        seq = TEXTS[name]
+        pos, start = E.symbol_positions(dev(E, seq))
+        w_pos, w_start = O.symbol_positions(seq)
+        assert np.array_equal(start, w_start)
+        assert np.array_equal(host(pos).astype(np.uint32), w_pos)
+
+
+def test_empty_and_tiny(E):
+    import torch
+    empty = torch.empty(0, dtype=torch.uint8, device="cuda")
+    assert E.suffix_array(empty).numel() == 0                    # build_suffix_array("") == []
+    assert E.bwt(empty, E.suffix_array(empty)).numel() == 0
+    one = dev(E, b"a")
+    assert host(E.suffix_array(one)).tolist() == [0]
+    wt = E.DeviceWaveletTree(one)
+    assert wt.levels == 0 and wt.sigma == 1
+    idx = E.DeviceIndex(dev(E, b"$"))
+    lo, hi = idx.count_batch(*E.pack_patterns([b"", b"$", b"a"]))
+    assert host(lo).tolist() == [0, 0, -1] and host(hi).tolist() == [0, 0, -1]
