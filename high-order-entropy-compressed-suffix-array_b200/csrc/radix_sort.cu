@@ -155,6 +155,202 @@ onesweep_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uin
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// (uint64 key, uint32 value) pass, the K1 hot kernel.  512 threads, 4096 pairs
+// per CTA, two CTAs per SM.  The tile is pulled into shared memory by the TMA
+// engine (cp.async.bulk + mbarrier: no registers held while the 48 KB are in
+// flight), ranked from shared memory, staged in digit order in a second
+// shared buffer and written out as coalesced runs.
+// ---------------------------------------------------------------------------
+constexpr int OS_THREADS = 512;
+constexpr int OS_IPT = 8;
+constexpr int OS_TILE = OS_THREADS * OS_IPT;     // 4096
+constexpr int OS_WARPS = OS_THREADS / 32;        // 16
+static_assert(OS_TILE == SORT64_TILE, "scratch sizing assumes the same tile");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct __align__(16) OsSmem {
+    uint64_t keys_in[OS_TILE];      // 32 KB  (TMA destination)
+    uint64_t keys_out[OS_TILE];     // 32 KB  (digit-ordered staging)
+    uint32_t vals_in[OS_TILE];      // 16 KB
+    uint32_t vals_out[OS_TILE];     // 16 KB
+    uint16_t whist[OS_WARPS][RADIX];// 8 KB   per-warp digit counters -> slots
+    uint32_t gbase[RADIX];
+    uint32_t wsum[OS_WARPS];
+    uint32_t tile;
+    uint64_t bar;
+};
+
+__global__ void __launch_bounds__(OS_THREADS, 2)
+onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout, const uint32_t *__restrict__ vin,
+                  uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
+                  uint32_t *lookback, uint32_t *ticket)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    OsSmem &S = *reinterpret_cast<OsSmem *>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) {
+        S.tile = atomicAdd(ticket, 1u);
+        mbar_init(&S.bar, 1);
+    }
+    for (int i = tid; i < OS_WARPS * RADIX / 2; i += OS_THREADS) reinterpret_cast<uint32_t *>(&S.whist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const uint32_t tile_base = tile * (uint32_t)OS_TILE;
+    const uint32_t nvalid = min((uint32_t)OS_TILE, n - tile_base);
+
+    // ---- TMA: one thread arms the barrier and issues two bulk copies (16-byte granules);
+    //      a ragged tail (last tile only) is finished with plain loads.
+    const uint32_t nk16 = nvalid & ~1u;          // keys copied in 16-byte units
+    const uint32_t nv16 = nvalid & ~3u;          // values copied in 16-byte units
+    if (tid == 0) {
+        mbar_expect_tx(&S.bar, nk16 * 8u + nv16 * 4u);
+        if (nk16) bulk_g2s(S.keys_in, kin + tile_base, nk16 * 8u, &S.bar);
+        if (nv16) bulk_g2s(S.vals_in, vin + tile_base, nv16 * 4u, &S.bar);
+    }
+    if (tid == 0 && nk16 < nvalid) S.keys_in[nk16] = kin[tile_base + nk16];                  // at most 1 key
+    if (tid < 4 && nv16 + tid < nvalid) S.vals_in[nv16 + tid] = vin[tile_base + nv16 + tid]; // at most 3 values
+    mbar_wait(&S.bar, 0);
+    __syncthreads();
+
+    // ---- rank inside the warp (warp-striped: lane l, item k <-> tile offset warp*256 + k*32 + l)
+    uint64_t key[OS_IPT];
+    uint32_t peers[OS_IPT];
+    uint16_t rnk[OS_IPT];
+    const uint32_t wbase = warp * 32u * OS_IPT + lane;
+#pragma unroll
+    for (int k = 0; k < OS_IPT; ++k) {
+        const uint32_t local = wbase + k * 32u;
+        const bool valid = local < nvalid;
+        key[k] = valid ? S.keys_in[local] : ~0ULL;
+        const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
+        peers[k] = __match_any_sync(0xffffffffu, d);
+    }
+#pragma unroll
+    for (int k = 0; k < OS_IPT; ++k) {
+        const bool valid = (wbase + k * 32u) < nvalid;
+        const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
+        const uint32_t leader = __ffs(peers[k]) - 1;
+        uint32_t before = 0;
+        uint16_t *cnt = &S.whist[warp][d];
+        if (lane == leader) {
+            before = *cnt;
+            *cnt = (uint16_t)(before + __popc(peers[k]));
+        }
+        before = __shfl_sync(0xffffffffu, before, leader);
+        rnk[k] = (uint16_t)(before + __popc(peers[k] & lanemask_lt()));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive prefix over warps, tile count, publish the aggregate
+    uint32_t bt = 0;
+    if (tid < RADIX) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < OS_WARPS; ++w) {
+            const uint32_t c = S.whist[w][tid];
+            S.whist[w][tid] = (uint16_t)run;
+            run += c;
+        }
+        bt = run;
+        st_volatile_u32(&lookback[(size_t)tile * RADIX + tid], (tile == 0 ? LB_INC : LB_AGG) | bt);
+    }
+    uint32_t wtotal;
+    const uint32_t ex = warp_excl_sum(bt, wtotal);
+    if (lane == 0) S.wsum[warp] = wtotal;
+    __syncthreads();
+    uint32_t wprefix = 0;
+    for (uint32_t w = 0; w < warp && w < RADIX / 32; ++w) wprefix += S.wsum[w];
+    const uint32_t bexcl = ex + wprefix;          // first slot of digit `tid` inside the sorted tile
+    if (tid < RADIX) {
+#pragma unroll
+        for (int w = 0; w < OS_WARPS; ++w) S.whist[w][tid] = (uint16_t)(S.whist[w][tid] + bexcl);
+    }
+    __syncthreads();
+
+    // ---- stage (key, value) in digit order
+#pragma unroll
+    for (int k = 0; k < OS_IPT; ++k) {
+        const uint32_t local = wbase + k * 32u;
+        const bool valid = local < nvalid;
+        const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
+        const uint32_t slot = (uint32_t)S.whist[warp][d] + rnk[k];
+        S.keys_out[slot] = key[k];
+        S.vals_out[slot] = S.vals_in[local];
+    }
+
+    // ---- decoupled look-back, four predecessors per round trip
+    if (tid < RADIX) {
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int64_t t = (int64_t)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[j] = (t - j >= 0) ? ld_volatile_u32(&lookback[(size_t)(t - j) * RADIX + tid]) : LB_INC;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (done) break;
+                    const uint32_t flag = v[j] >> 30;
+                    if (flag == 0) break;             // not published yet: re-poll from here
+                    excl += v[j] & LB_VAL;
+                    --t;
+                    if (flag == 2) done = true;
+                }
+            }
+            st_volatile_u32(&lookback[(size_t)tile * RADIX + tid], LB_INC | (excl + bt));
+        }
+        S.gbase[tid] = digit_base[tid] + excl - bexcl;
+    }
+    __syncthreads();
+
+    // ---- coalesced write-out: consecutive threads take consecutive sorted slots
+#pragma unroll
+    for (int k = 0; k < OS_IPT; ++k) {
+        const uint32_t i = k * OS_THREADS + tid;
+        if (i < nvalid) {
+            const uint64_t kk = S.keys_out[i];
+            const uint32_t g = S.gbase[(uint32_t)(kk >> shift) & 0xFFu] + i;
+            kout[g] = kk;
+            vout[g] = S.vals_out[i];
+        }
+    }
+}
+
 template <typename KeyT, int VAL_MODE, int THREADS, int IPT>
 static constexpr size_t onesweep_smem()
 {
@@ -228,11 +424,10 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
                                  int passes, const SortScratch &s, cudaStream_t st)
 {
     if (n == 0 || passes <= 0) return cudaSuccess;
-    constexpr size_t smem = onesweep_smem<uint64_t, 1, SORT64_THREADS, SORT64_IPT>();
-    auto kern = onesweep_kernel<uint64_t, 1, SORT64_THREADS, SORT64_IPT>;
+    constexpr size_t smem = sizeof(OsSmem) + 128;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(onesweep64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -240,7 +435,7 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
     count_launch();
     cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    const uint32_t tiles = (n + SORT64_TILE - 1) / SORT64_TILE;
+    const uint32_t tiles = (n + OS_TILE - 1) / OS_TILE;
     uint64_t *kin = k0, *kout = k1;
     uint32_t *vin = v0, *vout = v1;
     for (int p = 0; p < passes; ++p) {
@@ -248,8 +443,8 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
         if (e != cudaSuccess) return e;
         {
             prof::Scope ps(st, prof::ONESWEEP_U64, (uint64_t)n * 24);
-            kern<<<tiles, SORT64_THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, nullptr, s.base + p * RADIX,
-                                                      s.lookback, s.ticket + p);
+            onesweep64_kernel<<<tiles, OS_THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, s.base + p * RADIX,
+                                                              s.lookback, s.ticket + p);
             count_launch();
         }
         e = cudaGetLastError();
@@ -311,6 +506,9 @@ extern "C" int hkcsa_sort_pairs_u64(uint64_t *d_keys, uint32_t *d_vals, uint64_t
     HK_REQUIRE(key_bits >= 0 && key_bits <= 64, HKCSA_EINVAL, "key_bits must be in [0,64]");
     if (n == 0 || key_bits == 0) return HKCSA_OK;
     HK_REQUIRE(d_keys && d_vals && d_keys_alt && d_vals_alt && d_scratch, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(((reinterpret_cast<uintptr_t>(d_keys) | reinterpret_cast<uintptr_t>(d_vals) |
+                 reinterpret_cast<uintptr_t>(d_keys_alt) | reinterpret_cast<uintptr_t>(d_vals_alt)) & 15) == 0,
+               HKCSA_EINVAL, "sort buffers must be 16-byte aligned (TMA bulk copies)");
     Carver c(d_scratch);
     SortScratch s = carve_sort_scratch(c, n);
     HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "sort scratch too small");
