@@ -126,15 +126,15 @@ __device__ __forceinline__ uint32_t block_select(const RankBlock &b, uint32_t r)
 // superblock counts and the select samples.
 __global__ void __launch_bounds__(256)
 wt_dir_fix_kernel(RankBlock *__restrict__ blocks, uint64_t nblocks, const uint64_t *__restrict__ carry,
-                  uint64_t *__restrict__ super, uint32_t *__restrict__ select_samples, uint64_t len)
+                  uint64_t *__restrict__ super, uint32_t *__restrict__ select_samples, uint32_t blocks_per_tile)
 {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nblocks) return;
     const RankBlock b = load_block(blocks + g);
     const uint32_t rel = (uint32_t)(b.w[0] & 0xFFFFFFFFu);
-    const uint64_t abs_before = carry[g / WTP_BLOCKS_PER_CTA] + rel;
+    const uint64_t abs_before = carry[g / blocks_per_tile] + rel;
     const uint64_t sb = g / HKCSA_SUPER_BLOCKS;
-    const uint64_t sb_abs = carry[sb * (HKCSA_SUPER_BLOCKS / WTP_BLOCKS_PER_CTA)];
+    const uint64_t sb_abs = carry[sb * (HKCSA_SUPER_BLOCKS / blocks_per_tile)];
     reinterpret_cast<uint32_t *>(blocks + g)[0] = (uint32_t)(abs_before - sb_abs);
     if (g % HKCSA_SUPER_BLOCKS == 0) super[sb] = sb_abs;
     const uint32_t cnt = block_rank(b, HKCSA_BLOCK_BITS);
@@ -147,7 +147,251 @@ wt_dir_fix_kernel(RankBlock *__restrict__ blocks, uint64_t nblocks, const uint64
             select_samples[t] = (uint32_t)(g * HKCSA_BLOCK_BITS + bit);
         }
     }
-    (void)len;
+}
+
+// ---------------------------------------------------------------- all levels in one sweep
+// The sequence is cut into tiles of WTL_TILE symbols.  (1) wt_tile_hist: symbol counts per tile.
+// (2) wt_tile_scan: per symbol, exclusive prefix over tiles.  (3) wt_levels: each CTA keeps its
+// tile in shared memory and walks down the tree: at level l the tile is ordered by level-l node
+// (stable), so the elements of one node are a contiguous run whose destination in the level's
+// bit-vector is also contiguous: node start + (elements of that node in earlier tiles).  The run's
+// bits are funnel-shifted to the destination word alignment and stored (whole words) or OR-ed
+// (edge words shared with neighbouring tiles).  The next level's order is a stable split of every
+// run by its bit, computed from a tile-wide prefix sum of the bits.  The sequence is read from HBM
+// once for all levels and only bits are written.
+constexpr int WTL_THREADS = 256;
+constexpr int WTL_TILE = 8192;
+constexpr int WTL_EPT = WTL_TILE / WTL_THREADS;   // 32 symbols per thread = one bit word
+static_assert(WTL_EPT == 32, "one 32-bit word of bits per thread");
+
+__global__ void __launch_bounds__(WTL_THREADS)
+wt_tile_hist_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__restrict__ tab, uint32_t sigma,
+                    uint32_t tiles, uint32_t *__restrict__ gcnt /* [sigma][tiles+1] */)
+{
+    __shared__ uint32_t s_h[256];
+    __shared__ uint8_t s_code[256];
+    const uint32_t tid = threadIdx.x;
+    s_h[tid] = 0;
+    s_code[tid] = tab->code8_of_sym[tid];
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * WTL_TILE;
+    const uint32_t nv = (uint32_t)min((uint64_t)WTL_TILE, n - base);
+    for (uint32_t i = tid; i < nv; i += WTL_THREADS) atomicAdd(&s_h[s_code[sym[base + i]]], 1u);
+    __syncthreads();
+    if (tid < sigma) gcnt[(size_t)tid * (tiles + 1) + blockIdx.x] = s_h[tid];
+}
+
+// one CTA per symbol: in-place exclusive scan of its tiles+1 entries (the last becomes the total)
+__global__ void __launch_bounds__(1024)
+wt_tile_scan_kernel(uint32_t *__restrict__ gcnt, uint32_t tiles)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    uint32_t *row = gcnt + (size_t)blockIdx.x * (tiles + 1);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b = 0; b <= tiles; b += 1024) {
+        const uint32_t t = b + tid;
+        const uint32_t v = (t < tiles) ? row[t] : 0u;
+        uint32_t wtot;
+        const uint32_t ex = warp_excl_sum(v, wtot);
+        if (lane == 31) s_w[warp] = wtot;
+        __syncthreads();
+        uint32_t pre = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) pre += s_w[w];
+        if (t <= tiles) row[t] = pre + ex;
+        __syncthreads();
+        if (tid == 1023) s_carry = pre + ex + v;
+        __syncthreads();
+    }
+}
+
+struct LevelWords {
+    uint32_t *w[HKCSA_MAX_LEVELS];   // rank blocks of each level viewed as uint32[8] per block
+};
+
+__global__ void __launch_bounds__(WTL_THREADS)
+wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__restrict__ tab,
+                 const uint32_t *__restrict__ gpre, uint32_t tiles, LevelWords lv, uint32_t levels, uint32_t sigma)
+{
+    __shared__ __align__(16) uint8_t s_a[WTL_TILE];
+    __shared__ __align__(16) uint8_t s_b[WTL_TILE];
+    __shared__ uint32_t s_bits[WTL_THREADS + 1];
+    __shared__ uint32_t s_wpre[WTL_THREADS + 1];
+    __shared__ uint32_t s_tcum[257], s_gcum[257];
+    __shared__ uint32_t s_S[256], s_M[256], s_Ps[256];   // per code at the current level: run start, split, ones before run
+    __shared__ uint8_t s_mid[256], s_alive[256];
+    __shared__ uint8_t s_code[256];
+    __shared__ uint32_t s_scan[2][8];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t base = (uint64_t)tile * WTL_TILE;
+    const uint32_t nv = (uint32_t)min((uint64_t)WTL_TILE, n - base);
+
+    s_code[tid] = tab->code8_of_sym[tid];
+    // tile-local and global (earlier tiles) counts per code -> exclusive prefixes over codes
+    uint32_t cnt = 0, pre = 0;
+    if (tid < sigma) {
+        const uint32_t *row = gpre + (size_t)tid * (tiles + 1);
+        pre = row[tile];
+        cnt = row[tile + 1] - pre;
+    }
+    {
+        uint32_t t1, t2;
+        const uint32_t e1 = warp_excl_sum(cnt, t1);
+        const uint32_t e2 = warp_excl_sum(pre, t2);
+        if (lane == 31) { s_scan[0][warp] = t1; s_scan[1][warp] = t2; }
+        __syncthreads();
+        uint32_t p1 = 0, p2 = 0;
+        for (uint32_t w = 0; w < warp; ++w) { p1 += s_scan[0][w]; p2 += s_scan[1][w]; }
+        s_tcum[tid] = p1 + e1;
+        s_gcum[tid] = p2 + e2;
+        if (tid == 255) { s_tcum[256] = p1 + e1 + cnt; s_gcum[256] = p2 + e2 + pre; }
+    }
+    if (tid == 0) s_bits[WTL_THREADS] = 0;
+    // symbols -> codes, original order
+    {
+        const uint8_t *src = sym + base + (uint64_t)tid * WTL_EPT;
+        const bool vec = ((reinterpret_cast<uintptr_t>(sym) & 15) == 0) && (tid * WTL_EPT + WTL_EPT <= nv);
+        if (vec) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint4 x = q[h];
+                const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+                uint32_t o4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    o4[j] = (uint32_t)s_code[w4[j] & 0xFF] | ((uint32_t)s_code[(w4[j] >> 8) & 0xFF] << 8) |
+                            ((uint32_t)s_code[(w4[j] >> 16) & 0xFF] << 16) | ((uint32_t)s_code[w4[j] >> 24] << 24);
+                reinterpret_cast<uint4 *>(s_a + tid * WTL_EPT)[h] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            }
+        } else {
+            for (uint32_t k = 0; k < WTL_EPT; ++k) {
+                const uint32_t i = tid * WTL_EPT + k;
+                if (i < nv) s_a[i] = s_code[src[k]];
+            }
+        }
+    }
+    __syncthreads();
+
+    uint8_t *cur = s_a, *nxt = s_b;
+    for (uint32_t l = 0; l < levels; ++l) {
+        // (i) per code: alive at this level, split point, start of its node's run in the tile
+        {
+            const uint32_t c = tid;
+            const bool alive = c < sigma && tab->depth[c] > l;
+            uint32_t lo = 0, hi = 0, mid = 0;
+            if (alive) {
+                lo = tab->node_lo[l][c];
+                hi = (uint32_t)tab->node_hi1[l][c] + 1;
+                mid = lo + (hi - lo) / 2;
+            }
+            s_alive[c] = alive;
+            s_mid[c] = (uint8_t)mid;                  // mid <= 255 whenever the node has >= 2 codes
+            s_S[c] = alive ? s_tcum[lo] : 0;
+            s_M[c] = alive ? s_tcum[mid] : 0;
+        }
+        __syncthreads();
+        // (ii) this thread's word of bits in the current order + tile-wide prefix of ones
+        uint32_t w = 0;
+#pragma unroll 8
+        for (uint32_t k = 0; k < WTL_EPT; ++k) {
+            const uint32_t i = tid * WTL_EPT + k;
+            if (i < nv) {
+                const uint32_t c = cur[i];
+                if (s_alive[c] && c >= s_mid[c]) w |= 1u << k;
+            }
+        }
+        s_bits[tid] = w;
+        {
+            uint32_t wt;
+            const uint32_t ex = warp_excl_sum(__popc(w), wt);
+            if (lane == 31) s_scan[0][warp] = wt;
+            __syncthreads();
+            uint32_t p = 0;
+            for (uint32_t q = 0; q < warp; ++q) p += s_scan[0][q];
+            s_wpre[tid] = p + ex;
+        }
+        __syncthreads();
+        // (iii) ones before the start of each code's run
+        {
+            const uint32_t sidx = s_S[tid];
+            s_Ps[tid] = s_wpre[sidx >> 5] + __popc(s_bits[sidx >> 5] & ((1u << (sidx & 31u)) - 1u));
+        }
+        // (iv) emit every node's run of bits into the level (warps take nodes round-robin)
+        {
+            const uint32_t nnodes = tab->lvl_nodes[l];
+            uint32_t *words = lv.w[l];
+            for (uint32_t k = warp; k < nnodes; k += WTL_THREADS / 32) {
+                const uint32_t lo = tab->lvl_lo[l][k], hi = (uint32_t)tab->lvl_hi1[l][k] + 1;
+                const uint32_t s0 = s_tcum[lo], r = s_tcum[hi] - s0;
+                if (r == 0) continue;
+                const uint32_t D = (tab->node_start[l][lo] & NODE_START_MASK) + (s_gcum[hi] - s_gcum[lo]);
+                const uint32_t q0 = D >> 5, q1 = (D + r - 1) >> 5;
+                for (uint32_t q = q0 + lane; q <= q1; q += 32) {
+                    const uint32_t lo_bit = max(q << 5, D), hi_bit = min((q << 5) + 32u, D + r);
+                    const uint32_t nb = hi_bit - lo_bit;
+                    const uint32_t i0 = s0 + (lo_bit - D);
+                    const uint32_t wi = i0 >> 5, sh = i0 & 31u;
+                    const uint64_t x = (uint64_t)s_bits[wi] | ((uint64_t)s_bits[wi + 1] << 32);
+                    uint32_t v = (uint32_t)(x >> sh);
+                    if (nb < 32) v &= (1u << nb) - 1u;
+                    const uint32_t out = v << (lo_bit - (q << 5));
+                    uint32_t *dst = words + (size_t)(q / 7u) * 8u + 1u + (q % 7u);
+                    if (nb == 32) *dst = out;
+                    else if (out) atomicOr(dst, out);
+                }
+            }
+        }
+        if (l + 1 == levels) break;
+        __syncthreads();   // s_Ps visible
+        // (v) stable split of every run by its bit -> order by level l+1 node
+#pragma unroll 4
+        for (uint32_t k = 0; k < WTL_EPT; ++k) {
+            const uint32_t i = tid * WTL_EPT + k;
+            if (i < nv) {
+                const uint32_t c = cur[i];
+                uint32_t dst = i;                      // codes that are leaves already keep their slot
+                if (s_alive[c]) {
+                    const uint32_t ones_before = s_wpre[tid] + __popc(w & ((1u << k) - 1u)) - s_Ps[c];
+                    const uint32_t S0 = s_S[c];
+                    dst = ((w >> k) & 1u) ? s_M[c] + ones_before : S0 + (i - S0) - ones_before;
+                }
+                nxt[dst] = (uint8_t)c;
+            }
+        }
+        __syncthreads();
+        uint8_t *t = cur; cur = nxt; nxt = t;
+    }
+}
+
+// Headers for a level whose payload bits are already in place: per rank block, ones before it
+// inside this CTA's 256-block tile; tile totals to agg.
+constexpr int WTC_BLOCKS_PER_CTA = 256;
+static_assert(HKCSA_SUPER_BLOCKS % WTC_BLOCKS_PER_CTA == 0, "superblocks must start on a CTA tile");
+
+__global__ void __launch_bounds__(WTC_BLOCKS_PER_CTA)
+wt_count_kernel(RankBlock *__restrict__ blocks, uint64_t nblocks, uint32_t *__restrict__ agg)
+{
+    __shared__ uint32_t s_w[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t g = (uint64_t)blockIdx.x * WTC_BLOCKS_PER_CTA + tid;
+    uint32_t cnt = 0;
+    if (g < nblocks) {
+        const RankBlock b = load_block(blocks + g);
+        cnt = block_rank(b, HKCSA_BLOCK_BITS);
+    }
+    uint32_t wt;
+    const uint32_t ex = warp_excl_sum(cnt, wt);
+    if (lane == 31) s_w[warp] = wt;
+    __syncthreads();
+    uint32_t p = 0;
+    for (uint32_t q = 0; q < warp; ++q) p += s_w[q];
+    if (g < nblocks) reinterpret_cast<uint32_t *>(blocks + g)[0] = p + ex;
+    if (tid == WTC_BLOCKS_PER_CTA - 1) agg[blockIdx.x] = p + ex + cnt;
 }
 
 // node_ones[l][code] = rank1(level l, start of code's node)
@@ -317,14 +561,14 @@ extern "C" int hkcsa_wt_plan_from_hist(const uint64_t h_hist[256], hkcsa_wt_plan
         off = align_up(off + select_samples_for(bits) * sizeof(uint32_t), 256);
     }
     p->blob_bytes = off;
-    // scratch: partitioned symbols, tile aggregates, carries, ones, sort scratch
+    // scratch: per-symbol tile counts, directory tile aggregates and carries, ones per level
     Carver c(nullptr);
-    c.take<uint8_t>(n + 16);
-    const uint64_t tiles = rank_blocks_for(n) / WTP_BLOCKS_PER_CTA + 2;
+    const uint64_t wtiles = (n + WTL_TILE - 1) / WTL_TILE;
+    c.take<uint32_t>((uint64_t)(sigma ? sigma : 1) * (wtiles + 1));
+    const uint64_t tiles = rank_blocks_for(n) / WTC_BLOCKS_PER_CTA + 2;
     c.take<uint32_t>(tiles);
     c.take<uint64_t>(tiles);
     c.take<uint64_t>(HKCSA_MAX_LEVELS);
-    carve_sort_scratch(c, n);
     p->scratch_bytes = c.total();
     return HKCSA_OK;
 }
@@ -348,7 +592,7 @@ int build_bitvector(const uint8_t *d_sym, uint64_t len, const uint8_t *d_lut_bit
         wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones);
         HK_LAUNCH_CHECK();
         wt_dir_fix_kernel<<<(uint32_t)((nblocks + 255) / 256), 256, 0, st>>>(d_blocks, nblocks, d_carry, d_super,
-                                                                             d_select, len);
+                                                                             d_select, WTP_BLOCKS_PER_CTA);
         HK_LAUNCH_CHECK();
     }
     return HKCSA_OK;
@@ -381,7 +625,28 @@ extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_bl
             if (p->node_id[l][c] != 0xFF) T.bucket_base[l][p->node_id[l][c]] = p->node_start[l][c];
         }
         T.bucket_base[l][255] = (uint32_t)p->level_len[l];
+        // node extents: per code and per node
+        uint32_t lo_of[256], hi_of[256];
+        for (uint32_t k = 0; k < 256; ++k) { lo_of[k] = 0xFFFFFFFFu; hi_of[k] = 0; }
+        for (uint32_t c = 0; c < p->sigma; ++c) {
+            const uint8_t id = p->node_id[l][c];
+            if (id == 0xFF) continue;
+            if (lo_of[id] == 0xFFFFFFFFu) lo_of[id] = c;
+            hi_of[id] = c;
+        }
+        for (uint32_t c = 0; c < p->sigma; ++c) {
+            const uint8_t id = p->node_id[l][c];
+            if (id == 0xFF) continue;
+            T.node_lo[l][c] = (uint8_t)lo_of[id];
+            T.node_hi1[l][c] = (uint8_t)hi_of[id];
+        }
+        T.lvl_nodes[l] = p->level_nodes[l];
+        for (uint32_t k = 0; k < p->level_nodes[l] && k < 128; ++k) {
+            T.lvl_lo[l][k] = (uint8_t)lo_of[k];
+            T.lvl_hi1[l][k] = (uint8_t)hi_of[k];
+        }
     }
+    for (int ch = 0; ch < 256; ++ch) T.code8_of_sym[ch] = (p->code_of_sym[ch] == 0xFFFF) ? 0 : (uint8_t)p->code_of_sym[ch];
     WtTables *d_tab = reinterpret_cast<WtTables *>(blob + p->off_tables);
     HK_CUDA(cudaMemcpyAsync(d_tab, &T, sizeof(T), cudaMemcpyHostToDevice, st));
     HK_CUDA(cudaStreamSynchronize(st));   // T is reused by the next call on this thread
@@ -389,28 +654,39 @@ extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_bl
     HK_REQUIRE(d_sym && d_scratch, HKCSA_EINVAL, "null pointer");
 
     Carver c(d_scratch);
-    uint8_t *d_part = c.take<uint8_t>(n + 16);
-    const uint64_t tiles_max = rank_blocks_for(n) / WTP_BLOCKS_PER_CTA + 2;
+    const uint32_t wtiles = (uint32_t)((n + WTL_TILE - 1) / WTL_TILE);
+    uint32_t *d_gcnt = c.take<uint32_t>((uint64_t)p->sigma * (wtiles + 1));
+    const uint64_t tiles_max = rank_blocks_for(n) / WTC_BLOCKS_PER_CTA + 2;
     uint32_t *d_agg = c.take<uint32_t>(tiles_max);
     uint64_t *d_carry = c.take<uint64_t>(tiles_max);
     uint64_t *d_ones = c.take<uint64_t>(HKCSA_MAX_LEVELS);
-    SortScratch ss = carve_sort_scratch(c, n);
 
+    // payload bits are OR-ed in: the level regions must start from zero
+    HK_CUDA(cudaMemsetAsync(blob + p->off_blocks[0], 0, p->blob_bytes - p->off_blocks[0], st));
+    LevelWords lw;
+    for (uint32_t l = 0; l < HKCSA_MAX_LEVELS; ++l) lw.w[l] = reinterpret_cast<uint32_t *>(blob + p->off_blocks[l]);
+    {
+        prof::Scope ps(st, prof::WT_PARTITION, n + (uint64_t)p->levels * (n / 8));
+        wt_tile_hist_kernel<<<wtiles, WTL_THREADS, 0, st>>>(d_sym, n, d_tab, p->sigma, wtiles, d_gcnt);
+        HK_LAUNCH_CHECK();
+        wt_tile_scan_kernel<<<p->sigma, 1024, 0, st>>>(d_gcnt, wtiles);
+        HK_LAUNCH_CHECK();
+        wt_levels_kernel<<<wtiles, WTL_THREADS, 0, st>>>(d_sym, n, d_tab, d_gcnt, wtiles, lw, p->levels, p->sigma);
+        HK_LAUNCH_CHECK();
+    }
     for (uint32_t l = 0; l < p->levels; ++l) {
-        const uint8_t *level_sym = d_sym;
-        if (l > 0) {
-            // stable partition of the sequence by node id at this level
-            prof::Scope ps(st, prof::WT_PARTITION, 2 * n);
-            HK_CUDA(radix_partition_bytes(d_sym, d_part, nullptr, (uint32_t)n, d_tab->lut_node[l],
-                                          d_tab->bucket_base[l], ss, st));
-            level_sym = d_part;
-        }
-        int rc = build_bitvector(level_sym, p->level_len[l], d_tab->lut_bit[l],
-                                 reinterpret_cast<RankBlock *>(blob + p->off_blocks[l]),
-                                 reinterpret_cast<uint64_t *>(blob + p->off_super[l]),
-                                 reinterpret_cast<uint32_t *>(blob + p->off_select[l]), d_agg, d_carry,
-                                 d_ones + l, st);
-        if (rc != HKCSA_OK) return rc;
+        RankBlock *blocks = reinterpret_cast<RankBlock *>(blob + p->off_blocks[l]);
+        const uint64_t nblocks = rank_blocks_for(p->level_len[l]);
+        const uint64_t tiles = (nblocks + WTC_BLOCKS_PER_CTA - 1) / WTC_BLOCKS_PER_CTA;
+        prof::Scope ps(st, prof::WT_DIR, nblocks * 72);
+        wt_count_kernel<<<(uint32_t)tiles, WTC_BLOCKS_PER_CTA, 0, st>>>(blocks, nblocks, d_agg);
+        HK_LAUNCH_CHECK();
+        wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones + l);
+        HK_LAUNCH_CHECK();
+        wt_dir_fix_kernel<<<(uint32_t)((nblocks + 255) / 256), 256, 0, st>>>(
+            blocks, nblocks, d_carry, reinterpret_cast<uint64_t *>(blob + p->off_super[l]),
+            reinterpret_cast<uint32_t *>(blob + p->off_select[l]), WTC_BLOCKS_PER_CTA);
+        HK_LAUNCH_CHECK();
     }
     WtDev wt = make_wt_dev(d_blob, p);
     wt_node_ones_kernel<<<p->levels, 256, 0, st>>>(wt, d_tab);

@@ -19,6 +19,13 @@ struct WtTables {
     uint8_t lut_node[HKCSA_MAX_LEVELS][256];    // byte -> node id at level (0xFF: not present)
     uint8_t lut_bit[HKCSA_MAX_LEVELS][256];     // byte -> bit at level
     uint32_t bucket_base[HKCSA_MAX_LEVELS][256];// node id -> start offset; [255] = level length
+    // build-time tables (wt_levels_kernel)
+    uint8_t code8_of_sym[256];                  // byte -> dense code (present symbols only)
+    uint8_t node_lo[HKCSA_MAX_LEVELS][256];     // per (level, code): first code of the code's node
+    uint8_t node_hi1[HKCSA_MAX_LEVELS][256];    // per (level, code): last code of the code's node
+    uint8_t lvl_lo[HKCSA_MAX_LEVELS][128];      // per (level, node k): first code
+    uint8_t lvl_hi1[HKCSA_MAX_LEVELS][128];     // per (level, node k): last code
+    uint32_t lvl_nodes[HKCSA_MAX_LEVELS];
 };
 
 struct WtDev {
