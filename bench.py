@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--size", type=int, default=0, help="override the text size in bytes (debug)")
     ap.add_argument("--patterns", type=int, default=10_000_000, help="count queries after the build (C4 shape)")
-    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="bytes of the workload the CPU baseline builds")
+    ap.add_argument("--cpu-sample", type=int, default=32_000_000, help="bytes of the workload the CPU baseline builds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-queries", action="store_true")
     return ap.parse_args()
@@ -58,25 +58,58 @@ def parse():
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, every 20 ms; falls back to
+    nvidia-smi polling)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.sm_max = [], set(), None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                          ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+        if out.returncode == 0 and out.stdout.strip():
+            r = [x.strip() for x in out.stdout.strip().split(",")]
+            self.sm.append(float(r[0]))
+            self.sm_max = float(r[1])
+            for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if r[2 + i].lower() == "active":
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._t.start()
@@ -87,12 +120,9 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def measured_peak_gbs():

@@ -1,6 +1,7 @@
 // radix_sort.cu -- onesweep LSD radix sort kernels (see radix_sort.cuh).
 #include "radix_sort.cuh"
 #include "prof.cuh"
+#include <stdlib.h>
 
 namespace hkcsa {
 
@@ -163,11 +164,8 @@ onesweep_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uin
 // flight), ranked from shared memory, staged in digit order in a second
 // shared buffer and written out as coalesced runs.
 // ---------------------------------------------------------------------------
-constexpr int OS_THREADS = 512;
 constexpr int OS_IPT = 8;
-constexpr int OS_TILE = OS_THREADS * OS_IPT;     // 4096
-constexpr int OS_WARPS = OS_THREADS / 32;        // 16
-static_assert(OS_TILE == SORT64_TILE, "scratch sizing assumes the same tile");
+static_assert(SORT64_TILE >= 2048, "scratch sizing assumes tiles of at least 2048 pairs");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -199,36 +197,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Shared memory of one CTA.  The TMA destination doubles as the digit-ordered staging buffer: by the
+// time the tile is staged every thread holds its keys and values in registers.
+template <int THREADS>
 struct __align__(16) OsSmem {
-    uint64_t keys_in[OS_TILE];      // 32 KB  (TMA destination)
-    uint64_t keys_out[OS_TILE];     // 32 KB  (digit-ordered staging)
-    uint32_t vals_in[OS_TILE];      // 16 KB
-    uint32_t vals_out[OS_TILE];     // 16 KB
-    uint16_t whist[OS_WARPS][RADIX];// 8 KB   per-warp digit counters -> slots
+    static constexpr int TILE = THREADS * OS_IPT;
+    static constexpr int WARPS = THREADS / 32;
+    uint64_t keys[TILE];
+    uint32_t vals[TILE];
+    uint16_t whist[WARPS][RADIX];   // per-warp digit counters -> slots
     uint32_t gbase[RADIX];
-    uint32_t wsum[OS_WARPS];
+    uint32_t wsum[32];
     uint32_t tile;
     uint64_t bar;
 };
 
-__global__ void __launch_bounds__(OS_THREADS, 2)
+template <int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout, const uint32_t *__restrict__ vin,
                   uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
                   uint32_t *lookback, uint32_t *ticket)
 {
+    using Smem = OsSmem<THREADS>;
+    constexpr int TILE = Smem::TILE;
+    constexpr int WARPS = Smem::WARPS;
+    static_assert(THREADS >= RADIX, "one thread per digit");
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    OsSmem &S = *reinterpret_cast<OsSmem *>(smem_raw);
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) {
         S.tile = atomicAdd(ticket, 1u);
         mbar_init(&S.bar, 1);
     }
-    for (int i = tid; i < OS_WARPS * RADIX / 2; i += OS_THREADS) reinterpret_cast<uint32_t *>(&S.whist[0][0])[i] = 0;
+    for (int i = tid; i < WARPS * RADIX / 2; i += THREADS) reinterpret_cast<uint32_t *>(&S.whist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = S.tile;
-    const uint32_t tile_base = tile * (uint32_t)OS_TILE;
-    const uint32_t nvalid = min((uint32_t)OS_TILE, n - tile_base);
+    const uint32_t tile_base = tile * (uint32_t)TILE;
+    const uint32_t nvalid = min((uint32_t)TILE, n - tile_base);
 
     // ---- TMA: one thread arms the barrier and issues two bulk copies (16-byte granules);
     //      a ragged tail (last tile only) is finished with plain loads.
@@ -236,16 +242,17 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     const uint32_t nv16 = nvalid & ~3u;          // values copied in 16-byte units
     if (tid == 0) {
         mbar_expect_tx(&S.bar, nk16 * 8u + nv16 * 4u);
-        if (nk16) bulk_g2s(S.keys_in, kin + tile_base, nk16 * 8u, &S.bar);
-        if (nv16) bulk_g2s(S.vals_in, vin + tile_base, nv16 * 4u, &S.bar);
+        if (nk16) bulk_g2s(S.keys, kin + tile_base, nk16 * 8u, &S.bar);
+        if (nv16) bulk_g2s(S.vals, vin + tile_base, nv16 * 4u, &S.bar);
+        if (nk16 < nvalid) S.keys[nk16] = kin[tile_base + nk16];                             // at most 1 key
     }
-    if (tid == 0 && nk16 < nvalid) S.keys_in[nk16] = kin[tile_base + nk16];                  // at most 1 key
-    if (tid < 4 && nv16 + tid < nvalid) S.vals_in[nv16 + tid] = vin[tile_base + nv16 + tid]; // at most 3 values
+    if (tid < 4 && nv16 + tid < nvalid) S.vals[nv16 + tid] = vin[tile_base + nv16 + tid];    // at most 3 values
     mbar_wait(&S.bar, 0);
     __syncthreads();
 
-    // ---- rank inside the warp (warp-striped: lane l, item k <-> tile offset warp*256 + k*32 + l)
+    // ---- rank inside the warp (warp-striped: lane l, item k <-> tile offset warp*32*IPT + k*32 + l)
     uint64_t key[OS_IPT];
+    uint32_t val[OS_IPT];
     uint32_t peers[OS_IPT];
     uint16_t rnk[OS_IPT];
     const uint32_t wbase = warp * 32u * OS_IPT + lane;
@@ -253,7 +260,8 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     for (int k = 0; k < OS_IPT; ++k) {
         const uint32_t local = wbase + k * 32u;
         const bool valid = local < nvalid;
-        key[k] = valid ? S.keys_in[local] : ~0ULL;
+        key[k] = valid ? S.keys[local] : ~0ULL;
+        val[k] = S.vals[local];
         const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
         peers[k] = __match_any_sync(0xffffffffu, d);
     }
@@ -272,14 +280,14 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
         rnk[k] = (uint16_t)(before + __popc(peers[k] & lanemask_lt()));
         __syncwarp();
     }
-    __syncthreads();
+    __syncthreads();     // every thread holds its keys/values: S.keys / S.vals may be overwritten below
 
     // ---- per digit: exclusive prefix over warps, tile count, publish the aggregate
     uint32_t bt = 0;
     if (tid < RADIX) {
         uint32_t run = 0;
 #pragma unroll
-        for (int w = 0; w < OS_WARPS; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
             const uint32_t c = S.whist[w][tid];
             S.whist[w][tid] = (uint16_t)run;
             run += c;
@@ -296,19 +304,18 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     const uint32_t bexcl = ex + wprefix;          // first slot of digit `tid` inside the sorted tile
     if (tid < RADIX) {
 #pragma unroll
-        for (int w = 0; w < OS_WARPS; ++w) S.whist[w][tid] = (uint16_t)(S.whist[w][tid] + bexcl);
+        for (int w = 0; w < WARPS; ++w) S.whist[w][tid] = (uint16_t)(S.whist[w][tid] + bexcl);
     }
     __syncthreads();
 
     // ---- stage (key, value) in digit order
 #pragma unroll
     for (int k = 0; k < OS_IPT; ++k) {
-        const uint32_t local = wbase + k * 32u;
-        const bool valid = local < nvalid;
+        const bool valid = (wbase + k * 32u) < nvalid;
         const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
         const uint32_t slot = (uint32_t)S.whist[warp][d] + rnk[k];
-        S.keys_out[slot] = key[k];
-        S.vals_out[slot] = S.vals_in[local];
+        S.keys[slot] = key[k];
+        S.vals[slot] = val[k];
     }
 
     // ---- decoupled look-back, four predecessors per round trip
@@ -341,12 +348,12 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     // ---- coalesced write-out: consecutive threads take consecutive sorted slots
 #pragma unroll
     for (int k = 0; k < OS_IPT; ++k) {
-        const uint32_t i = k * OS_THREADS + tid;
+        const uint32_t i = k * THREADS + tid;
         if (i < nvalid) {
-            const uint64_t kk = S.keys_out[i];
+            const uint64_t kk = S.keys[i];
             const uint32_t g = S.gbase[(uint32_t)(kk >> shift) & 0xFFu] + i;
             kout[g] = kk;
-            vout[g] = S.vals_out[i];
+            vout[g] = S.vals[i];
         }
     }
 }
@@ -420,31 +427,31 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
     return cudaGetLastError();
 }
 
-cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n,
-                                 int passes, const SortScratch &s, cudaStream_t st)
+// Variant selection (HKCSA_OS_VARIANT, read once): 0 = 512 threads x 8, 2 CTAs/SM (4096 pairs per tile);
+// 1 = 256 threads x 8, 4 CTAs/SM (2048 pairs per tile).
+template <int THREADS, int MIN_CTAS>
+static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n, int passes,
+                                  const SortScratch &s, cudaStream_t st)
 {
-    if (n == 0 || passes <= 0) return cudaSuccess;
-    constexpr size_t smem = sizeof(OsSmem) + 128;
+    using Smem = OsSmem<THREADS>;
+    constexpr size_t smem = sizeof(Smem) + 128;
+    auto kern = onesweep64_kernel<THREADS, MIN_CTAS>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(onesweep64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    radix_scan_kernel<<<passes, RADIX, 0, st>>>(s.hist, s.base);
-    count_launch();
-    cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
-    const uint32_t tiles = (n + OS_TILE - 1) / OS_TILE;
+    const uint32_t tiles = (n + Smem::TILE - 1) / Smem::TILE;
     uint64_t *kin = k0, *kout = k1;
     uint32_t *vin = v0, *vout = v1;
     for (int p = 0; p < passes; ++p) {
-        e = cudaMemsetAsync(s.lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), st);
+        cudaError_t e = cudaMemsetAsync(s.lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), st);
         if (e != cudaSuccess) return e;
         {
             prof::Scope ps(st, prof::ONESWEEP_U64, (uint64_t)n * 24);
-            onesweep64_kernel<<<tiles, OS_THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, s.base + p * RADIX,
-                                                              s.lookback, s.ticket + p);
+            kern<<<tiles, THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, s.base + p * RADIX, s.lookback,
+                                               s.ticket + p);
             count_launch();
         }
         e = cudaGetLastError();
@@ -453,6 +460,23 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
         uint32_t *tv = vin; vin = vout; vout = tv;
     }
     return cudaSuccess;
+}
+
+cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n,
+                                 int passes, const SortScratch &s, cudaStream_t st)
+{
+    if (n == 0 || passes <= 0) return cudaSuccess;
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("HKCSA_OS_VARIANT");
+        variant = e ? atoi(e) : 0;
+    }
+    radix_scan_kernel<<<passes, RADIX, 0, st>>>(s.hist, s.base);
+    count_launch();
+    cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (variant == 1) return run_onesweep64<256, 4>(k0, v0, k1, v1, n, passes, s, st);
+    return run_onesweep64<512, 2>(k0, v0, k1, v1, n, passes, s, st);
 }
 
 cudaError_t radix_partition_bytes(const uint8_t *d_in, uint8_t *d_out, uint32_t *d_pos_out, uint32_t n,

@@ -111,13 +111,66 @@ sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, CodeMap map, int b
 }
 
 // ---------------------------------------------------------------- later rounds: key build
-// key[j] = (group start << b2) | (rank[idx + h] + 1), low part 0 when idx + h >= n.
+// key[j] = (group start << b2) | (rank(idx + h) + 1), low part 0 when idx + h >= n.
+//
+// rank(t) comes from the rank array when it was scattered for every suffix (EAGER), or -- when only a
+// small fraction of the suffixes survived round 0 (LAZY) -- is recomputed on demand: a suffix that was
+// already unique after round 0 has rank = lower_bound of its round-0 key in the sorted round-0 keys, so
+// the 4-byte random scatter of n ranks is replaced by a binary search for the few ranks that are read.
+// Suffixes that were NOT unique after round 0 always have their current rank in the array.
+struct LazyRank {
+    const uint8_t *text;       // nullptr = eager mode
+    const uint64_t *keys0;     // round-0 keys, sorted
+    const uint32_t *bucket;    // bucket[v] = lower_bound(keys0, v << shift), v in [0, 2^bucket_bits]
+    int b, k0;
+    int shift;                 // key >> shift = bucket id
+};
+
+constexpr int LAZY_BUCKET_BITS = 20;
+
+// bucket[v] = lower_bound(keys0, v << shift) for v in [0, nbuckets]: one binary search per bucket
+// boundary (2^20 searches whose upper levels stay in L2), not a pass over the keys
+__global__ void sa_bucket_index_kernel(const uint64_t *__restrict__ keys0, uint32_t n, int shift, uint32_t nbuckets,
+                                       uint32_t *__restrict__ bucket)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > nbuckets) return;
+    uint32_t lo = 0, hi = n;
+    if (v == nbuckets) lo = n;
+    const uint64_t key = (uint64_t)v << shift;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(keys0 + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    bucket[v] = lo;
+}
+
+__device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const uint16_t *s_code, uint32_t n,
+                                                     uint32_t t, const uint32_t *__restrict__ rank)
+{
+    uint64_t key = 0;
+    for (int q = 0; q < lz.k0; ++q) {
+        const uint32_t g = t + q;
+        key = (key << lz.b) | (g < n ? (uint64_t)s_code[lz.text[g]] : 0ull);
+    }
+    const uint32_t v = (uint32_t)(key >> lz.shift);
+    uint32_t lo = __ldg(lz.bucket + v), hi = __ldg(lz.bucket + v + 1);
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(lz.keys0 + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    const bool shared_group = (lo + 1 < n) && (__ldg(lz.keys0 + lo + 1) == key);
+    return shared_group ? rank[t] : lo;
+}
+
 __global__ void __launch_bounds__(256)
 sa_keybuild_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp,
                    const uint32_t *__restrict__ rank, uint32_t n, uint32_t h, int b2, uint32_t m, int passes,
-                   uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist)
+                   uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist, LazyRank lz, CodeMap map)
 {
     __shared__ uint32_t s_hist[8 * RADIX];
+    __shared__ uint16_t s_code[256];
+    s_code[threadIdx.x] = map.code[threadIdx.x];
     hist_zero(s_hist, passes);
     __syncthreads();
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < m; base += (uint64_t)gridDim.x * blockDim.x) {
@@ -127,7 +180,8 @@ sa_keybuild_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict
         if (valid) {
             const uint32_t i = cidx[j];
             const uint64_t t = (uint64_t)i + h;
-            const uint32_t k2 = (t < n) ? (rank[t] + 1u) : 0u;
+            uint32_t k2 = 0;
+            if (t < n) k2 = (lz.text ? lazy_rank_lookup(lz, s_code, n, (uint32_t)t, rank) : rank[t]) + 1u;
             key = ((uint64_t)cgrp[j] << b2) | k2;
             keys[j] = key;
         }
@@ -237,7 +291,7 @@ seg_apply_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__
                  const uint32_t *__restrict__ pos /* nullptr = identity */, uint32_t m,
                  const uint32_t *__restrict__ carry_head, const uint32_t *__restrict__ carry_keep,
                  uint32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint32_t *__restrict__ cpos,
-                 uint32_t *__restrict__ cidx, uint32_t *__restrict__ cgrp)
+                 uint32_t *__restrict__ cidx, uint32_t *__restrict__ cgrp, bool write_sa, bool scatter_all)
 {
     __shared__ uint32_t s_h[SEG_THREADS / 32], s_k[SEG_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -275,8 +329,8 @@ seg_apply_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__
         }
         const uint32_t p = pos ? pos[j] : j;
         const uint32_t s = sidx[j];
-        sa[p] = s;
-        rank[s] = cur_grp;
+        if (write_sa) sa[p] = s;
+        if (scatter_all || !single[e]) rank[s] = cur_grp;
         if (!single[e]) {
             cpos[slot] = p;
             cidx[slot] = s;
@@ -301,6 +355,7 @@ struct SaBuffers {
     uint32_t *agg_head, *agg_keep;
     uint32_t *counter;
     uint64_t *hist64;
+    uint32_t *bucket;
     SortScratch sort;
 };
 
@@ -320,6 +375,7 @@ SaBuffers carve_sa(Carver &c, uint64_t n)
     b.agg_keep = c.take<uint32_t>(tiles);
     b.counter = c.take<uint32_t>(64);
     b.hist64 = c.take<uint64_t>(256);
+    b.bucket = c.take<uint32_t>((1u << LAZY_BUCKET_BITS) + 2);
     b.sort = carve_sort_scratch(c, n);
     return b;
 }
@@ -348,6 +404,8 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     if (n == 0) return HKCSA_OK;   // build_suffix_array("") == []
     HK_REQUIRE(n <= HKCSA_MAX_N, HKCSA_ERANGE, "n exceeds HKCSA_MAX_N");
     HK_REQUIRE(d_text && d_sa && d_scratch, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(((reinterpret_cast<uintptr_t>(d_sa) | reinterpret_cast<uintptr_t>(d_scratch)) & 15) == 0, HKCSA_EINVAL,
+               "d_sa and d_scratch must be 16-byte aligned (TMA bulk copies)");
     Carver c(d_scratch);
     SaBuffers B = carve_sa(c, n);
     HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "SA scratch too small");
@@ -376,18 +434,24 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
 
     const uint32_t N = (uint32_t)n;
     HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
+    // Round 0.  The value ping-pong is (d_sa, val[0]) arranged so the sorted suffix ids land in d_sa:
+    // the suffix array of round 0 needs no extra copy.
+    uint64_t *ka = B.key[0], *kb = B.key[1];
+    uint32_t *va = (passes0 % 2 == 0) ? d_sa : B.val[0];
+    uint32_t *vb = (passes0 % 2 == 0) ? B.val[0] : d_sa;
     {
         const uint32_t blocks = (N + PACK_TILE - 1) / PACK_TILE;
         prof::Scope ps(st, prof::SA_PACK0, (uint64_t)N * 13);
-        sa_pack0_kernel<<<blocks, PACK_THREADS, 0, st>>>(d_text, N, map, b, k0, passes0, B.key[0], B.val[0],
-                                                        B.sort.hist);
+        sa_pack0_kernel<<<blocks, PACK_THREADS, 0, st>>>(d_text, N, map, b, k0, passes0, ka, va, B.sort.hist);
         HK_LAUNCH_CHECK();
     }
-    HK_CUDA(radix_sort_pairs_u64(B.key[0], B.val[0], B.key[1], B.val[1], N, passes0, B.sort, st));
-    int cur = passes0 & 1;             // buffer holding the sorted (key, idx)
+    HK_CUDA(radix_sort_pairs_u64(ka, va, kb, vb, N, passes0, B.sort, st));
+    uint64_t *skey = (passes0 % 2 == 0) ? ka : kb;     // sorted round-0 keys
+    uint64_t *kfree = (passes0 % 2 == 0) ? kb : ka;
+    uint32_t *sidx = d_sa;                              // sorted suffix ids
     uint32_t m = N;
-    int pcur = 0;                      // pos buffer describing the current working set (round 0: identity)
-    const uint32_t *pos = nullptr;
+    const uint32_t *pos = nullptr;                      // SA slots of the working set (round 0: identity)
+    int pcur = 0;
     uint64_t h = (uint64_t)k0;
     const int b2 = (int)bits_for(n);           // rank + 1 <= n
     const int b1 = (int)bits_for(n - 1);       // group start <= n - 1
@@ -397,12 +461,20 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     stats.sort_elem_passes = (uint64_t)m * passes0;
     stats.alg_bytes = (uint64_t)n * 13 + (uint64_t)m * (24ull * passes0);
 
+    LazyRank lz;
+    lz.text = nullptr; lz.keys0 = nullptr; lz.bucket = nullptr; lz.b = b; lz.k0 = k0;
+    const int bucket_bits = std::min(LAZY_BUCKET_BITS, bits0);
+    lz.shift = bits0 - bucket_bits;
+    uint64_t *kx = nullptr, *ky = nullptr;             // key ping-pong of the later rounds
+    uint32_t *vfree = B.val[1];                        // free value buffer (receives the compacted ids)
+    uint32_t *vother = (passes0 % 2 == 0) ? B.val[0] : B.val[0];
+
     while (true) {
         // ---- refine ranks from the sorted keys
         const uint32_t tiles = (m + SEG_TILE - 1) / SEG_TILE;
         {
             prof::Scope ps(st, prof::SEG_REDUCE, (uint64_t)m * 8);
-            seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.key[cur], m, B.agg_head, B.agg_keep);
+            seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, m, B.agg_head, B.agg_keep);
             HK_LAUNCH_CHECK();
         }
         {
@@ -410,39 +482,59 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
             seg_scan_kernel<<<1, 1024, 0, st>>>(B.agg_head, B.agg_keep, tiles, B.counter);
             HK_LAUNCH_CHECK();
         }
-        uint32_t *cpos = B.pos[pcur ^ 1];
-        uint32_t *cidx = B.val[cur ^ 1];
-        {
-            prof::Scope ps(st, prof::SEG_APPLY, (uint64_t)m * 24);
-            seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.key[cur], B.val[cur], pos, m, B.agg_head, B.agg_keep,
-                                                           d_sa, B.rank, cpos, cidx, B.grp);
-            HK_LAUNCH_CHECK();
-        }
         HK_CUDA(cudaMemcpyAsync(h_m, B.counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         HK_CUDA(cudaStreamSynchronize(st));
+        const uint32_t m_next = *h_m;
+        bool scatter_all = true;
+        if (round == 0 && m_next > 0 && (uint64_t)m_next * 4 <= n) {
+            // few survivors: scatter ranks only for them, look the others up on demand
+            lz.text = d_text;
+            lz.keys0 = skey;
+            lz.bucket = B.bucket;
+            scatter_all = false;
+            const uint32_t nbuckets = 1u << bucket_bits;
+            prof::Scope ps(st, prof::OTHER, (uint64_t)nbuckets * 8);
+            sa_bucket_index_kernel<<<(nbuckets + 1 + 255) / 256, 256, 0, st>>>(skey, N, lz.shift, nbuckets, B.bucket);
+            HK_LAUNCH_CHECK();
+        }
+        uint32_t *cpos = B.pos[pcur ^ 1];
+        uint32_t *cidx = vfree;
+        {
+            prof::Scope ps(st, prof::SEG_APPLY, (uint64_t)m * 24);
+            seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, sidx, pos, m, B.agg_head, B.agg_keep, d_sa, B.rank,
+                                                           cpos, cidx, B.grp, round != 0, scatter_all);
+            HK_LAUNCH_CHECK();
+        }
         stats.alg_bytes += (uint64_t)m * (8 + 8 + 4 + 4 + 4 + 4);
         ++round;
-        const uint32_t m_next = *h_m;
         if (m_next == 0) break;
         HK_REQUIRE(h < n, HKCSA_EINVAL, "internal: groups remain after depth >= n");
         HK_REQUIRE(round < 40, HKCSA_EINVAL, "internal: too many doubling rounds");
-        // ---- next round on the compacted working set
+        // ---- buffers of the next round
+        if (round == 1) {
+            if (lz.text) { kx = kfree; ky = kfree + m_next; }   // the sorted round-0 keys stay intact
+            else { kx = kfree; ky = skey; }
+            vother = B.val[0];
+        } else {
+            vother = sidx;                                     // the sorted ids just consumed: free again
+        }
         m = m_next;
         pcur ^= 1;
         pos = B.pos[pcur];
-        const int in = cur ^ 1;        // cidx lives in val[in]; keys are written to key[in]
+        uint32_t *vx = cidx, *vy = vother;
         const int bits = b1 + b2;
         const int passes = (bits + 7) / 8;
         HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
         {
             const int blocks = (int)std::min<uint64_t>(((uint64_t)m + 255) / 256, (uint64_t)num_sms() * 16);
             prof::Scope ps(st, prof::SA_KEYBUILD, (uint64_t)m * 20);
-            sa_keybuild_kernel<<<blocks, 256, 0, st>>>(B.val[in], B.grp, B.rank, N, (uint32_t)std::min<uint64_t>(h, n), b2,
-                                                       m, passes, B.key[in], B.sort.hist);
+            sa_keybuild_kernel<<<blocks, 256, 0, st>>>(vx, B.grp, B.rank, N, (uint32_t)std::min<uint64_t>(h, n), b2,
+                                                       m, passes, kx, B.sort.hist, lz, map);
             HK_LAUNCH_CHECK();
         }
-        HK_CUDA(radix_sort_pairs_u64(B.key[in], B.val[in], B.key[in ^ 1], B.val[in ^ 1], m, passes, B.sort, st));
-        cur = (passes & 1) ? (in ^ 1) : in;
+        HK_CUDA(radix_sort_pairs_u64(kx, vx, ky, vy, m, passes, B.sort, st));
+        if (passes & 1) { skey = ky; sidx = vy; vfree = vx; }
+        else { skey = kx; sidx = vx; vfree = vy; }
         stats.round_elems[round] = m;
         stats.round_passes[round] = (uint32_t)passes;
         stats.sort_elem_passes += (uint64_t)m * passes;

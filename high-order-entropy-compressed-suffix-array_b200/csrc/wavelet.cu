@@ -220,8 +220,7 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
     __shared__ uint32_t s_bits[WTL_THREADS + 1];
     __shared__ uint32_t s_wpre[WTL_THREADS + 1];
     __shared__ uint32_t s_tcum[257], s_gcum[257];
-    __shared__ uint32_t s_S[256], s_M[256], s_Ps[256];   // per code at the current level: run start, split, ones before run
-    __shared__ uint8_t s_mid[256], s_alive[256];
+    __shared__ uint64_t s_ent[256];
     __shared__ uint8_t s_code[256];
     __shared__ uint32_t s_scan[2][8];
 
@@ -277,32 +276,43 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
     }
     __syncthreads();
 
+    // Per level and code, one packed table entry: run start S (14 bits) | split M (14) | ones before
+    // the run Ps (14) | mid code (8) | alive (1) -- one 64-bit shared load per element.
     uint8_t *cur = s_a, *nxt = s_b;
     for (uint32_t l = 0; l < levels; ++l) {
         // (i) per code: alive at this level, split point, start of its node's run in the tile
+        uint64_t my_entry = 0;
         {
             const uint32_t c = tid;
             const bool alive = c < sigma && tab->depth[c] > l;
-            uint32_t lo = 0, hi = 0, mid = 0;
             if (alive) {
-                lo = tab->node_lo[l][c];
-                hi = (uint32_t)tab->node_hi1[l][c] + 1;
-                mid = lo + (hi - lo) / 2;
+                const uint32_t lo = tab->node_lo[l][c];
+                const uint32_t hi = (uint32_t)tab->node_hi1[l][c] + 1;
+                const uint32_t mid = lo + (hi - lo) / 2;
+                my_entry = (uint64_t)s_tcum[lo] | ((uint64_t)s_tcum[mid] << 14) | ((uint64_t)mid << 42) | (1ull << 50);
             }
-            s_alive[c] = alive;
-            s_mid[c] = (uint8_t)mid;                  // mid <= 255 whenever the node has >= 2 codes
-            s_S[c] = alive ? s_tcum[lo] : 0;
-            s_M[c] = alive ? s_tcum[mid] : 0;
+            s_ent[c] = my_entry;
         }
         __syncthreads();
+        // this thread's 32 codes, kept in registers for the whole level
+        uint32_t cw[8];
+        {
+            const uint4 x0 = reinterpret_cast<const uint4 *>(cur + tid * WTL_EPT)[0];
+            const uint4 x1 = reinterpret_cast<const uint4 *>(cur + tid * WTL_EPT)[1];
+            cw[0] = x0.x; cw[1] = x0.y; cw[2] = x0.z; cw[3] = x0.w;
+            cw[4] = x1.x; cw[5] = x1.y; cw[6] = x1.z; cw[7] = x1.w;
+        }
+        const uint32_t i_base = tid * WTL_EPT;
+        const uint32_t n_mine = (i_base >= nv) ? 0u : min((uint32_t)WTL_EPT, nv - i_base);
         // (ii) this thread's word of bits in the current order + tile-wide prefix of ones
         uint32_t w = 0;
-#pragma unroll 8
+#pragma unroll
         for (uint32_t k = 0; k < WTL_EPT; ++k) {
-            const uint32_t i = tid * WTL_EPT + k;
-            if (i < nv) {
-                const uint32_t c = cur[i];
-                if (s_alive[c] && c >= s_mid[c]) w |= 1u << k;
+            if (k < n_mine) {
+                const uint32_t c = (cw[k >> 2] >> ((k & 3u) * 8u)) & 0xFFu;
+                const uint64_t e = s_ent[c];
+                const uint32_t mid = (uint32_t)(e >> 42) & 0xFFu;
+                if ((e >> 50) && c >= mid) w |= 1u << k;
             }
         }
         s_bits[tid] = w;
@@ -316,10 +326,11 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
             s_wpre[tid] = p + ex;
         }
         __syncthreads();
-        // (iii) ones before the start of each code's run
-        {
-            const uint32_t sidx = s_S[tid];
-            s_Ps[tid] = s_wpre[sidx >> 5] + __popc(s_bits[sidx >> 5] & ((1u << (sidx & 31u)) - 1u));
+        // (iii) ones before the start of each code's run, merged into its entry
+        if (my_entry) {
+            const uint32_t sidx = (uint32_t)my_entry & 0x3FFFu;
+            const uint32_t ps = s_wpre[sidx >> 5] + __popc(s_bits[sidx >> 5] & ((1u << (sidx & 31u)) - 1u));
+            s_ent[tid] = my_entry | ((uint64_t)ps << 28);
         }
         // (iv) emit every node's run of bits into the level (warps take nodes round-robin)
         {
@@ -347,18 +358,21 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
             }
         }
         if (l + 1 == levels) break;
-        __syncthreads();   // s_Ps visible
+        __syncthreads();   // entries complete
         // (v) stable split of every run by its bit -> order by level l+1 node
-#pragma unroll 4
+        const uint32_t wp = s_wpre[tid];
+#pragma unroll
         for (uint32_t k = 0; k < WTL_EPT; ++k) {
-            const uint32_t i = tid * WTL_EPT + k;
-            if (i < nv) {
-                const uint32_t c = cur[i];
+            if (k < n_mine) {
+                const uint32_t i = i_base + k;
+                const uint32_t c = (cw[k >> 2] >> ((k & 3u) * 8u)) & 0xFFu;
+                const uint64_t e = s_ent[c];
                 uint32_t dst = i;                      // codes that are leaves already keep their slot
-                if (s_alive[c]) {
-                    const uint32_t ones_before = s_wpre[tid] + __popc(w & ((1u << k) - 1u)) - s_Ps[c];
-                    const uint32_t S0 = s_S[c];
-                    dst = ((w >> k) & 1u) ? s_M[c] + ones_before : S0 + (i - S0) - ones_before;
+                if (e >> 50) {
+                    const uint32_t S0 = (uint32_t)e & 0x3FFFu, M = (uint32_t)(e >> 14) & 0x3FFFu;
+                    const uint32_t ps = (uint32_t)(e >> 28) & 0x3FFFu;
+                    const uint32_t ones_before = wp + __popc(w & ((1u << k) - 1u)) - ps;
+                    dst = ((w >> k) & 1u) ? M + ones_before : i - ones_before;
                 }
                 nxt[dst] = (uint8_t)c;
             }

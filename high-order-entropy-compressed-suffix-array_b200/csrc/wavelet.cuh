@@ -109,7 +109,8 @@ __device__ __forceinline__ void wt_rank_code2(const WtSmem &s, const WtDev &wt, 
         const uint64_t ia = (uint64_t)start + a, ib = (uint64_t)start + b;
         const uint64_t ba = ia / HKCSA_BLOCK_BITS, bb = ib / HKCSA_BLOCK_BITS;
         const RankBlock qa = load_block(v.blocks + ba);
-        const RankBlock qb = load_block(v.blocks + bb);
+        // once the range is narrow both boundaries fall into the same 224-bit block: one sector, not two
+        const RankBlock qb = (bb == ba) ? qa : load_block(v.blocks + bb);
         const uint32_t ra = (uint32_t)(v.super[ba / HKCSA_SUPER_BLOCKS] + (uint32_t)(qa.w[0] & 0xFFFFFFFFu) +
                                        block_rank(qa, (uint32_t)(ia - ba * HKCSA_BLOCK_BITS))) - ones0;
         const uint32_t rb = (uint32_t)(v.super[bb / HKCSA_SUPER_BLOCKS] + (uint32_t)(qb.w[0] & 0xFFFFFFFFu) +
