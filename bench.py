@@ -288,11 +288,21 @@ def run_ours(args):
     top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
     one = prof.get("onesweep_u64")
     roofline = None
+    traffic = None
+    try:   # DRAM bytes per pair from the committed ncu --set full capture, scaled to this run's average launch
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)["onesweep64_kernel"]
+        per_pair = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["pairs_in_profiled_launch"]
+        if one and one["launches"]:
+            traffic = per_pair * (one["alg_bytes"] / 24.0) / one["launches"]
+    except Exception:
+        traffic = None
     if one and one["ms"] > 0:
         achieved = one["alg_bytes"] / (one["ms"] / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "onesweep_kernel<u64,u32> (one 8-bit radix pass, 24 B/pair)",
+        roofline = {"bound": "hbm", "kernel": "onesweep64_kernel (one 8-bit LSD radix pass, 24 B per (u64,u32) pair)",
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
+                    "alg_bytes_per_launch": one["alg_bytes"] / one["launches"],
                     "launches": one["launches"], "avg_launch_ms": one["ms"] / one["launches"],
                     "share_of_step": one["ms"] / max(1e-9, sum(step_ms))}
 

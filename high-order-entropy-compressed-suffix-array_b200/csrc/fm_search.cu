@@ -17,9 +17,10 @@ int build_bitvector(const uint8_t *d_sym, uint64_t len, const uint8_t *d_lut_bit
 
 constexpr int COUNT_THREADS = 256;
 
-// One lane per pattern; a warp owns groups of 32 consecutive patterns, dealt
-// round-robin over all resident warps.  find_range (csa/enhanced_fm_index.py:
-// 21-32) in half-open form:
+// One lane per pattern.  A warp owns a contiguous chunk of the batch and refills a lane as soon as
+// its pattern ends (last symbol consumed or range empty), so ragged lengths (8-64) and early misses do
+// not idle the warp: every iteration each busy lane consumes ONE symbol -- both boundaries of the SA
+// range walk the wavelet tree together.  find_range (csa/enhanced_fm_index.py:21-32) in half-open form:
 //   l = 0, r = n;  per symbol from the end: l = C[c] + occ(c, l), r = C[c] + occ(c, r);
 //   l >= r -> (-1, -1).  Result (l, r-1).
 __global__ void __launch_bounds__(COUNT_THREADS)
@@ -33,23 +34,49 @@ fm_count_kernel(WtDev wt, const uint8_t *__restrict__ pat, const int64_t *__rest
     const uint32_t n = (uint32_t)wt.n;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t base = warp * 32; base < P; base += nwarps * 32) {
-        const uint64_t p = base + lane;
-        if (p >= P) continue;
-        const int64_t b = off[p], e = off[p + 1];
-        uint32_t l = 0, r = n;
-        bool miss = false;
-        for (int64_t k = e - 1; k >= b; --k) {
-            const uint32_t code = s.code_of_sym[pat[k]];
-            if (code == 0xFFFFu) { miss = true; break; }   // symbol absent: rank 0, C 0 -> empty
-            if (wt.sigma > 1) wt_rank_code2(s, wt, code, l, r);
-            const uint32_t c0 = s.C[code];
-            l += c0;
-            r += c0;
-            if (l >= r) { miss = true; break; }
+    const uint64_t chunk = (P + nwarps - 1) / nwarps;
+    uint64_t next = min(P, warp * chunk);
+    const uint64_t end = min(P, next + chunk);
+
+    int64_t p = -1;            // pattern owned by this lane, -1 = idle
+    int64_t k = 0, b = 0;      // next symbol to consume, first symbol of the pattern
+    uint32_t l = 0, r = 0;
+    while (true) {
+        // ---- refill idle lanes with the next patterns of the chunk, in lane order
+        const uint32_t idle = __ballot_sync(0xffffffffu, p < 0);
+        if (idle) {
+            const uint64_t mine = next + __popc(idle & lanemask_lt());
+            if (p < 0 && mine < end) {
+                p = (int64_t)mine;
+                b = off[mine];
+                k = off[mine + 1] - 1;
+                l = 0;
+                r = n;
+            }
+            next += __popc(idle);
+            if (idle == 0xffffffffu && __ballot_sync(0xffffffffu, p >= 0) == 0) break;
         }
-        out_lo[p] = miss ? -1 : (int64_t)l;
-        out_hi[p] = miss ? -1 : (int64_t)r - 1;
+        if (p < 0) continue;
+        // ---- one backward-search step (or finish an exhausted / empty pattern)
+        bool done = k < b, miss = false;
+        if (!done) {
+            const uint32_t code = s.code_of_sym[pat[k]];
+            if (code == 0xFFFFu) { miss = true; }          // symbol absent: rank 0, C 0 -> empty range
+            else {
+                if (wt.sigma > 1) wt_rank_code2(s, wt, code, l, r);
+                const uint32_t c0 = s.C[code];
+                l += c0;
+                r += c0;
+                miss = l >= r;
+            }
+            --k;
+            done = miss || k < b;
+        }
+        if (done) {
+            out_lo[p] = miss ? -1 : (int64_t)l;
+            out_hi[p] = miss ? -1 : (int64_t)r - 1;
+            p = -1;
+        }
     }
 }
 
