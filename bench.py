@@ -194,7 +194,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("HKCSA_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)               # set up the communicator
+        dist.broadcast(warm, 0)
+        dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)
+        torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -267,10 +272,8 @@ def run_ours(args):
     def e2e_step():
         d = torch.empty(n, dtype=torch.uint8, device=dev)
         d.copy_(h_text, non_blocking=True)
-        ix = build_step(d)
-        h_sa.copy_(ix.sa, non_blocking=True)
-        h_bwt.copy_(ix.bwt, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        ix = E.DeviceIndex(d, sa_sample_rate=SA_SAMPLE_RATE, host_sa=h_sa, host_bwt=h_bwt)
+        torch.cuda.synchronize()      # build + both device->host copies (side stream) done
         return ix
 
     e2e_step()
@@ -306,45 +309,70 @@ def run_ours(args):
                     "launches": one["launches"], "avg_launch_ms": one["ms"] / one["launches"],
                     "share_of_step": one["ms"] / max(1e-9, sum(step_ms))}
 
-    # ---- batched count / locate on the index just built (patterns sharded over ranks)
+    # ---- batched count / locate (BASELINE config 4 shape).  N > 1: rank 0's index is broadcast over
+    #      NCCL, the SAME global batch is cut into contiguous slices balanced by total symbols
+    #      (hkcsa.dist.shard_bounds), every rank searches its slice, (lo, hi) are all-gathered.
     queries = None
     if not args.no_queries and args.patterns > 0:
+        from hkcsa import dist as hdist
         P_total = args.patterns
-        P = P_total // world
         alpha = torch.from_numpy(np.frombuffer(idx.wt.alphabet, dtype=np.uint8).copy()).to(dev)
         alpha = alpha[alpha != 0x24]
-        pats, off = E.gen_patterns(44 + rank, P, text[:nbytes], alpha)
+        pats, off = E.gen_patterns(44, P_total, text[:nbytes], alpha)       # identical on every rank
+        bcast_ms = None
+        q_idx = idx
+        if world > 1:
+            barrier()
+            t0 = time.perf_counter()
+            q_idx = hdist.broadcast_index(idx if rank == 0 else None, src=0, device=dev)
+            barrier()
+            bcast_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            bounds = hdist.shard_bounds(off.cpu().numpy(), world)
+            pb, pe = bounds[rank]
+            my_pats, my_off = hdist.local_slice(pats, off, pb, pe)
+        else:
+            my_pats, my_off = pats, off
+        P = my_off.numel() - 1
         torch.cuda.synchronize()
         for _ in range(2):
-            lo, hi = idx.count_batch(pats, off)
+            lo, hi = q_idx.count_batch(my_pats, my_off)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3
         a.record()
         for _ in range(reps):
-            lo, hi = idx.count_batch(pats, off)
+            lo, hi = q_idx.count_batch(my_pats, my_off)
         b.record()
         barrier()
         c_ms = max_over_ranks(a.elapsed_time(b) / reps)
-        hits = sum_over_ranks(float((lo >= 0).sum().item()))
-        # locate a slice of the patterns through the sampled SA (LF walks)
-        PL = min(P, 1_000_000)
-        offL = off[: PL + 1]
-        idx_ssa = idx
+        gather_ms = None
+        if world > 1:                      # results to every rank, timed apart from the search
+            t0 = time.perf_counter()
+            glo, ghi = hdist.sharded_count(lambda p_, o_: (lo, hi), pats, off)
+            barrier()
+            gather_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            hits = float((glo >= 0).sum().item())
+        else:
+            hits = float((lo >= 0).sum().item())
+        # locate a slice of this rank's patterns through the sampled SA (LF walks)
+        PL = min(P, 1_000_000 // world)
+        offL = my_off[: PL + 1]
         a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        o_off, o_pos = idx_ssa.locate_batch(pats, offL, use_samples=True)
+        o_off, o_pos = q_idx.locate_batch(my_pats, offL, use_samples=True)
         torch.cuda.synchronize()
         a2.record()
-        o_off, o_pos = idx_ssa.locate_batch(pats, offL, use_samples=True)
+        o_off, o_pos = q_idx.locate_batch(my_pats, offL, use_samples=True)
         b2.record()
         barrier()
         l_ms = max_over_ranks(a2.elapsed_time(b2))
         occ_total = sum_over_ranks(float(o_pos.numel()))
-        queries = {"count_patterns_per_s": P * world / (c_ms / 1e3), "count_patterns": P * world,
-                   "count_ms": c_ms, "hit_fraction": hits / (P * world), "pattern_len": "uniform 8-64",
+        queries = {"count_patterns_per_s": P_total / (c_ms / 1e3), "count_patterns": P_total,
+                   "count_ms": c_ms, "hit_fraction": hits / P_total, "pattern_len": "uniform 8-64",
+                   "index_broadcast_ms": bcast_ms, "result_allgather_ms": gather_ms,
                    "locate_occurrences_per_s": occ_total / (l_ms / 1e3), "locate_patterns": PL * world,
                    "locate_occurrences": occ_total, "locate_ms": l_ms, "sa_sample_rate": SA_SAMPLE_RATE,
-                   "sharding": "index replicated per rank, patterns split evenly"}
+                   "scaling": "strong (fixed global batch)",
+                   "sharding": "index broadcast from rank 0, patterns split into contiguous slices balanced by symbols"}
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same workload
     cpu = None
@@ -366,7 +394,8 @@ def run_ours(args):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "MB/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": n,
                     "d2h_bytes_per_step": 5 * n,
-                    "what": "pinned host text -> H2D -> build -> D2H of SA (4n) + BWT (n), wall clock incl. sync"},
+                    "what": "pinned host text -> H2D -> build -> D2H of SA (4n) + BWT (n) on a side stream "
+                            "overlapping the rest of the build, wall clock incl. final sync"},
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,

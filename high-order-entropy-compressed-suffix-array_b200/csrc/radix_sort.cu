@@ -212,7 +212,23 @@ struct __align__(16) OsSmem {
     uint64_t bar;
 };
 
-template <int THREADS, int MIN_CTAS>
+// lanes of the warp holding the same 8-bit digit.  MODE 0: match.any (cost grows with the number of
+// distinct digits in the warp); MODE 1: eight ballots, one per digit bit (fixed cost).
+template <int MODE>
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d)
+{
+    if (MODE == 0) return __match_any_sync(0xffffffffu, d);
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool one = (d >> bit) & 1u;
+        const uint32_t b = __ballot_sync(0xffffffffu, one);
+        peers &= one ? b : ~b;
+    }
+    return peers;
+}
+
+template <int THREADS, int MIN_CTAS, int MODE>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout, const uint32_t *__restrict__ vin,
                   uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
@@ -263,7 +279,7 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
         key[k] = valid ? S.keys[local] : ~0ULL;
         val[k] = S.vals[local];
         const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
-        peers[k] = __match_any_sync(0xffffffffu, d);
+        peers[k] = digit_peers<MODE>(d);
     }
 #pragma unroll
     for (int k = 0; k < OS_IPT; ++k) {
@@ -427,15 +443,16 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
     return cudaGetLastError();
 }
 
-// Variant selection (HKCSA_OS_VARIANT, read once): 0 = 512 threads x 8, 2 CTAs/SM (4096 pairs per tile);
-// 1 = 256 threads x 8, 4 CTAs/SM (2048 pairs per tile).
-template <int THREADS, int MIN_CTAS>
+// Variant selection (HKCSA_OS_VARIANT, read once; measured on B200, profiles/r01_onesweep_variants.txt):
+// 2 (default) = 512 threads x 8, 2 CTAs/SM (4096 pairs per tile), ballot ranking; 0 = same with match.any
+// ranking (faster only when a digit takes < ~8 distinct values); 1 = 256 threads x 8, 4 CTAs/SM, match.any.
+template <int THREADS, int MIN_CTAS, int MODE>
 static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n, int passes,
                                   const SortScratch &s, cudaStream_t st)
 {
     using Smem = OsSmem<THREADS>;
     constexpr size_t smem = sizeof(Smem) + 128;
-    auto kern = onesweep64_kernel<THREADS, MIN_CTAS>;
+    auto kern = onesweep64_kernel<THREADS, MIN_CTAS, MODE>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -469,14 +486,17 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("HKCSA_OS_VARIANT");
-        variant = e ? atoi(e) : 0;
+        variant = e ? atoi(e) : 2;
     }
     radix_scan_kernel<<<passes, RADIX, 0, st>>>(s.hist, s.base);
     count_launch();
     cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    if (variant == 1) return run_onesweep64<256, 4>(k0, v0, k1, v1, n, passes, s, st);
-    return run_onesweep64<512, 2>(k0, v0, k1, v1, n, passes, s, st);
+    if (variant == 1) return run_onesweep64<256, 4, 0>(k0, v0, k1, v1, n, passes, s, st);
+    if (variant == 2) return run_onesweep64<512, 2, 1>(k0, v0, k1, v1, n, passes, s, st);
+    if (variant == 3) return run_onesweep64<256, 4, 1>(k0, v0, k1, v1, n, passes, s, st);
+    if (variant == 4) return run_onesweep64<384, 3, 1>(k0, v0, k1, v1, n, passes, s, st);
+    return run_onesweep64<512, 2, 0>(k0, v0, k1, v1, n, passes, s, st);
 }
 
 cudaError_t radix_partition_bytes(const uint8_t *d_in, uint8_t *d_out, uint32_t *d_pos_out, uint32_t n,

@@ -328,15 +328,31 @@ class DeviceIndex:
     csa/enhanced_fm_index.py:9).  Everything stays on the device."""
 
     def __init__(self, text: torch.Tensor, *, sa_sample_rate: int = 0, keep_sa: bool = True,
-                 keep_text: bool = True):
+                 keep_text: bool = True, host_sa: torch.Tensor | None = None,
+                 host_bwt: torch.Tensor | None = None):
+        """host_sa / host_bwt: optional pinned host tensors (int32[n] / uint8[n]) that receive the suffix
+        array and the BWT; the copies run on a side stream and overlap the rest of the build.  The
+        caller synchronises (torch.cuda.synchronize()) before reading them."""
         _require_cuda()
         self.device = text.device
         self.n = text.numel()
         self.stats = BuildStats(n=self.n)
         self.sa = suffix_array(text, self.stats.sa)
+        side = None
+        if host_sa is not None or host_bwt is not None:
+            side = torch.cuda.Stream(device=self.device)
+        if host_sa is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                host_sa.copy_(self.sa, non_blocking=True)
         self.bwt = bwt(text, self.sa)
+        if host_bwt is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                host_bwt.copy_(self.bwt, non_blocking=True)
         self.wt = DeviceWaveletTree(self.bwt)
         self.ssa = build_sampled_sa(self.sa, sa_sample_rate) if sa_sample_rate > 0 else None
+        self._side = side
         self.text = text if keep_text else None
         if not keep_sa:
             if self.ssa is None:
