@@ -16,6 +16,8 @@ MAX_N = (1 << 30) - 2
 BLOCK_BITS = 224
 SUPER_BLOCKS = 65536
 SELECT_SAMPLE = 4096
+DIST_BUCKETS = 65536
+DIST_MAX_N = (1 << 32) - 2
 PROF_CLASSES = 16
 
 OK, EINVAL, ECUDA, ESCRATCH, ERANGE = 0, -1, -2, -3, -4
@@ -98,6 +100,11 @@ SIGNATURES = {
     "hkcsa_gen_pattern_bytes": (_i32, [_u64, _u64, _vp, _u64, _vp, _u32, _vp, _vp, _vp]),
     "hkcsa_sa_scratch_bytes": (_sz, [_u64]),
     "hkcsa_sa_build": (_i32, [_vp, _u64, _vp, _vp, _sz, _vp, C.POINTER(SaStats)]),
+    "hkcsa_sa_key_hist": (_i32, [_vp, _u64, _u64, _u64, C.POINTER(_u64), _vp, _vp]),
+    "hkcsa_sa_subset_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_sa_build_subset": (_i32, [_vp, _u64, C.POINTER(_u64), _u32, _u32, _vp, _u64, C.POINTER(_u64), _vp, _sz, _vp,
+                                     C.POINTER(SaStats)]),
+    "hkcsa_bwt_slice": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp]),
     "hkcsa_sort_scratch_bytes": (_sz, [_u64]),
     "hkcsa_sort_pairs_u64": (_i32, [_vp, _vp, _vp, _vp, _u64, _i32, _vp, _sz, _vp]),
     "hkcsa_bwt": (_i32, [_vp, _vp, _u64, _vp, _vp]),

@@ -374,6 +374,30 @@ class DeviceIndex:
         self.ssa = ssa
         return self
 
+    # -- persistence (the reference never writes its index to disk: SURVEY.md section 5; next-row 3)
+    def save(self, path: str) -> None:
+        """Write the query structures (wavelet-tree blob + plan, sampled SA) to one .npz file.  The blob is
+        stored exactly as it lives in HBM, so loading is a single host->device copy."""
+        parts = {"n": np.array([self.n], dtype=np.int64),
+                 "wt_plan": np.frombuffer(bytes(self.wt.plan), dtype=np.uint8),
+                 "wt_blob": self.wt.blob.cpu().numpy()}
+        if self.ssa is not None:
+            parts["ssa_plan"] = np.frombuffer(bytes(self.ssa.plan), dtype=np.uint8)
+            parts["ssa_blob"] = self.ssa.blob.cpu().numpy()
+        with open(path, "wb") as f:
+            np.savez(f, **parts)
+
+    @classmethod
+    def load(cls, path: str, device=None) -> "DeviceIndex":
+        device = device or _require_cuda()
+        z = np.load(path)
+        plan = WtPlan.from_buffer_copy(z["wt_plan"].tobytes())
+        blob = torch.from_numpy(z["wt_blob"]).to(device)
+        ssa = None
+        if "ssa_plan" in z.files:
+            ssa = SampledSA(SsaPlan.from_buffer_copy(z["ssa_plan"].tobytes()), torch.from_numpy(z["ssa_blob"]).to(device))
+        return cls.from_parts(int(z["n"][0]), plan, blob, ssa)
+
     # find_range, batched (csa/enhanced_fm_index.py:21-32)
     def count_batch(self, pat: torch.Tensor, off: torch.Tensor):
         P = off.numel() - 1

@@ -93,6 +93,27 @@ size_t hkcsa_sort_scratch_bytes(uint64_t n);
 int hkcsa_sort_pairs_u64(uint64_t *d_keys, uint32_t *d_vals, uint64_t *d_keys_alt, uint32_t *d_vals_alt,
                          uint64_t n, int key_bits, void *d_scratch, size_t scratch_bytes, void *stream);
 
+/* Distributed build (BASELINE config 5: a text beyond one GPU's working set; no   */
+/* reference counterpart -- the reference is single-process).  Every GPU holds the  */
+/* whole text (NCCL all-gather) and sorts the suffixes whose round-0 key falls into  */
+/* its range [bucket_lo, bucket_hi) of the 65536 buckets given by the top 16 key     */
+/* bits; the slices concatenated in rank order are the suffix array.  Groups are     */
+/* refined by extension rounds reading the text (no ranks of remote suffixes).       */
+/* Suffix ids are uint32: n <= 2^32-2; a slice holds at most HKCSA_MAX_N suffixes.   */
+/* h_byte_hist: byte histogram of the WHOLE text (uint64[256], host).                */
+#define HKCSA_DIST_BUCKETS 65536u
+int hkcsa_sa_key_hist(const uint8_t *d_text, uint64_t n, uint64_t begin, uint64_t end,
+                      const uint64_t *h_byte_hist, uint64_t *d_hist /* [HKCSA_DIST_BUCKETS] */, void *stream);
+size_t hkcsa_sa_subset_scratch_bytes(uint64_t capacity);
+/* syncs.  d_sa_out: uint32[capacity]; *h_count receives the slice length.           */
+int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist,
+                          uint32_t bucket_lo, uint32_t bucket_hi, uint32_t *d_sa_out, uint64_t capacity,
+                          uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
+                          hkcsa_sa_stats *h_stats);
+/* bwt[j] = text[SA[j]-1] (text[n-1] when SA[j] == 0) for a slice of the suffix array */
+int hkcsa_bwt_slice(const uint8_t *d_text, uint64_t n, const uint32_t *d_sa_slice, uint64_t m,
+                    uint8_t *d_out, void *stream);
+
 /* ------------------------------------------------------------------------ */
 /* K2  BWT gather -- replaces bwt_transform, csa/bwt.py:3-13:                   */
 /*     bwt[i] = text[SA[i]-1], text[n-1] when SA[i] == 0.                       */

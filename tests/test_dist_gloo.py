@@ -67,3 +67,18 @@ def test_sharded_count_gloo(world):
     out = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), text, pats, off, out), nprocs=world, join=True)
     assert dict(out) == {r: 1 for r in range(world)}
+
+
+def test_balanced_bucket_ranges():
+    from hkcsa.dist_sa import balanced_bucket_ranges
+    rng = np.random.RandomState(3)
+    h = rng.randint(0, 1000, 65536)
+    for parts in (1, 2, 5, 8):
+        r = balanced_bucket_ranges(h, parts)
+        assert r[0][0] == 0 and r[-1][1] == 65536 and all(r[i][1] == r[i + 1][0] for i in range(parts - 1))
+        loads = [int(h[a:b].sum()) for a, b in r]
+        assert sum(loads) == int(h.sum()) and max(loads) - min(loads) <= 2 * int(h.max())
+    assert balanced_bucket_ranges(np.zeros(16, dtype=np.int64), 4)[-1][1] == 16
+    one = np.zeros(16, dtype=np.int64); one[7] = 100                       # one giant bucket cannot be split
+    r = balanced_bucket_ranges(one, 4)
+    assert sum(int(one[a:b].sum()) for a, b in r) == 100

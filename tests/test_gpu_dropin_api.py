@@ -220,3 +220,41 @@ def test_lazy_views_above_threshold(monkeypatch):
     assert isinstance(wt.tree[0][0], views.LazyList)
     assert list(wt.tree[0][0]) == O.golomb_encode(spine[0]).tolist()
     assert int(wt.rank_structures[0].rank(17)) == int(spine[0][:17].sum())
+
+
+def test_high_order_entropy_matches_reference_formula():
+    """csa/high_order_entropy.py:4-32 restated inline (plain Python, as the reference computes it); the GPU
+    version must agree to 1e-9 relative (summation order differs)."""
+    import math
+    from collections import defaultdict
+    from csa.high_order_entropy import calculate_high_order_entropy
+
+    def ref(text, k):
+        if not text or k < 0:
+            return 0
+        n = len(text)
+        if k == 0:
+            freq = defaultdict(int)
+            for c in text:
+                freq[c] += 1
+            return -sum((c / n) * math.log2(c / n) for c in freq.values())
+        if n <= k:
+            return 0
+        ctx = defaultdict(lambda: defaultdict(int))
+        for i in range(n - k):
+            ctx[text[i:i + k]][text[i + k]] += 1
+        hk = 0
+        for cc in ctx.values():
+            tot = sum(cc.values())
+            hk += (tot / n) * -sum((c / tot) * math.log2(c / tot) for c in cc.values())
+        return hk
+
+    texts = ["banana", "mississippi", "a" * 50, "abracadabra" * 30,
+             O.gen_text(O.ENG96, 3, 20_000).tobytes().decode("latin-1"),
+             O.gen_text(O.DNA4, 3, 20_000).tobytes().decode("latin-1")]
+    for t in texts:
+        for k in (0, 1, 2, 3, 5, 7):
+            want, got = ref(t, k), calculate_high_order_entropy(t, k)
+            assert got == pytest.approx(want, rel=1e-9, abs=1e-12), (t[:12], k)
+    assert calculate_high_order_entropy("", 2) == 0 and calculate_high_order_entropy("abc", -1) == 0
+    assert calculate_high_order_entropy("abc", 5) == 0

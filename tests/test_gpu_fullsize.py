@@ -1,0 +1,60 @@
+"""GPU parity at the BASELINE.json sizes (C2: 100 MB DNA, C3: 200 MB English-like).  The oracle's suffix sort
+still finishes in seconds on the box's host cores at these sizes, so SA and BWT are compared bit for bit; the
+query path is checked against the oracle's FM index on a pattern sample and through size-independent
+properties (every located position really holds the pattern; count == number of located positions)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E(cuda):
+    from hkcsa import engine
+    return engine
+
+
+@pytest.mark.parametrize("kind,seed,n", [(1, 43, 100_000_000), (0, 42, 200_000_000)], ids=["C2_dna_100MB", "C3_eng_200MB"])
+def test_build_and_query_at_baseline_size(E, kind, seed, n):
+    import torch
+    text = E.gen_text(kind, seed, n)
+    text = torch.cat([text, torch.tensor([0x24], dtype=torch.uint8, device=text.device)])
+    h_text = text.cpu().numpy()
+    assert np.array_equal(h_text[:n], O.gen_text(kind, seed, n))             # generators agree at full size
+    idx = E.DeviceIndex(text, sa_sample_rate=32)
+    # ---- SA / BWT bit-exact against the oracle (parallel suffix sort on the host cores)
+    want_sa = O.build_suffix_array(h_text)
+    got_sa = idx.sa.cpu().numpy().astype(np.uint32)
+    assert np.array_equal(got_sa, want_sa)
+    want_bwt = O.bwt_transform(h_text, want_sa)
+    assert np.array_equal(idx.bwt.cpu().numpy(), want_bwt)
+    del got_sa
+    # ---- C[] and occ at random positions
+    cnt, Ct = O.build_count(h_text)
+    assert idx.wt.count_table() == {chr(c): int(Ct[c]) for c in range(256) if cnt[c]}
+    fm = O.FM(want_bwt)
+    rng = np.random.RandomState(7)
+    pos = rng.randint(0, n + 2, 2000).astype(np.int64)
+    sym = rng.choice(np.flatnonzero(cnt), 2000).astype(np.uint8)
+    got = idx.wt.rank(sym, pos).cpu().numpy()
+    assert got.tolist() == [fm.rank(int(c), int(i)) for c, i in zip(sym, pos)]
+    ap = rng.randint(0, n + 1, 5000).astype(np.int64)
+    assert np.array_equal(idx.wt.access(ap).cpu().numpy(), want_bwt[ap])
+    # ---- count against the oracle on 20 k patterns; locate round trip
+    pats, off = O.gen_patterns(44, 20_000, h_text[:n])
+    d_p, d_o = torch.from_numpy(pats).cuda(), torch.from_numpy(off).cuda()
+    lo, hi = idx.count_batch(d_p, d_o)
+    w_lo, w_hi = fm.find_range_batch(pats, off)
+    assert np.array_equal(lo.cpu().numpy(), w_lo) and np.array_equal(hi.cpu().numpy(), w_hi)
+    o1, p1 = idx.locate_batch(d_p, d_o, use_samples=False)
+    o2, p2 = idx.locate_batch(d_p, d_o, use_samples=True)
+    assert torch.equal(o1, o2) and torch.equal(p1, p2)                       # LF walk == full SA
+    o, p = o1.cpu().numpy(), p1.cpu().numpy()
+    cntp = np.where(w_lo >= 0, w_hi - w_lo + 1, 0)
+    assert np.array_equal(np.diff(o), cntp)
+    for k in rng.choice(20_000, 300, replace=False):                         # located positions hold the pattern
+        m = off[k + 1] - off[k]
+        for q in p[o[k]:o[k + 1]][:5]:
+            assert h_text[q:q + m].tobytes() == pats[off[k]:off[k + 1]].tobytes()

@@ -335,3 +335,68 @@ def test_empty_and_tiny(E):
     idx = E.DeviceIndex(dev(E, b"$"))
     lo, hi = idx.count_batch(*E.pack_patterns([b"", b"$", b"a"]))
     assert host(lo).tolist() == [0, 0, -1] and host(hi).tolist() == [0, 0, -1]
+
+
+# ------------------------------------------------------------------ distributed build, ranks emulated on one GPU
+@pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "runs", "rand256_50k", "dna_1m_dollar", "rand2_100k"])
+@pytest.mark.parametrize("parts", [1, 2, 3, 8])
+def test_distributed_slices_concatenate_to_the_suffix_array(E, name, parts):
+    """hkcsa.dist_sa: every 'rank' sorts the suffixes of its key-bucket range with the whole text resident;
+    the slices in rank order must be the oracle's suffix array and BWT (the collectives are exercised by
+    tools/dist_sa_check.py under torchrun)."""
+    from hkcsa import dist_sa
+    text = TEXTS[name]
+    n = len(text)
+    d_text = dev(E, text)
+    bh = E.byte_hist(d_text)
+    bounds = [n * r // parts for r in range(parts + 1)]
+    kh = sum(dist_sa.key_bucket_hist(d_text, bounds[r], bounds[r + 1], bh) for r in range(parts))
+    kh = host(kh)
+    assert int(kh.sum()) == n
+    ranges = dist_sa.balanced_bucket_ranges(kh, parts)
+    want_sa = O.build_suffix_array(text)
+    want_bwt = O.bwt_transform(text, want_sa)
+    got_sa, got_bwt = [], []
+    for lo, hi in ranges:
+        cap = int(kh[lo:hi].sum())
+        sl = dist_sa.build_slice(d_text, bh, lo, hi, cap)
+        assert sl.numel() == cap
+        got_sa.append(host(sl).astype(np.uint32))
+        got_bwt.append(host(dist_sa.bwt_slice(d_text, sl)))
+    assert np.array_equal(np.concatenate(got_sa), want_sa)
+    assert np.concatenate(got_bwt).tobytes() == want_bwt.tobytes()
+
+
+def test_distributed_slice_rejects_hugely_repetitive_text(E):
+    from hkcsa import dist_sa, _lib
+    for name in ("all_a_5000", "repeat_block", "fib"):             # LCP in the thousands: beyond 40 extension rounds
+        d_text = dev(E, TEXTS[name])
+        bh = E.byte_hist(d_text)
+        with pytest.raises(_lib.HkcsaError, match="repetitive"):
+            dist_sa.build_slice(d_text, bh, 0, 65536, len(TEXTS[name]))
+
+
+@pytest.mark.parametrize("n", [50_000, 50_001, 50_002, 50_003, 131_073])
+def test_sa_lazy_round_buffers_any_survivor_parity(E, n):
+    """The later-round key buffers are carved at an offset that depends on the number of survivors of round 0
+    (odd or even): the TMA bulk copies need 16-byte alignment whatever that number is."""
+    for kind in (O.ENG96, O.DNA4):
+        text = O.gen_text(kind, 11 + n % 7, n).tobytes()
+        sa = E.suffix_array(dev(E, text))
+        assert np.array_equal(host(sa).astype(np.uint32), O.build_suffix_array(text))
+
+
+def test_index_save_load_round_trip(E, tmp_path):
+    text = TEXTS["eng_300k"] + b"$"
+    idx = E.DeviceIndex(dev(E, text), sa_sample_rate=16)
+    path = str(tmp_path / "index.npz")
+    idx.save(path)
+    back = E.DeviceIndex.load(path)
+    pats, off = O.gen_patterns(5, 2000, np.frombuffer(TEXTS["eng_300k"], dtype=np.uint8))
+    import torch
+    d_p, d_o = torch.from_numpy(pats).cuda(), torch.from_numpy(off).cuda()
+    a, b = idx.count_batch(d_p, d_o), back.count_batch(d_p, d_o)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    o1, p1 = idx.locate_batch(d_p, d_o, use_samples=True)
+    o2, p2 = back.locate_batch(d_p, d_o)                     # replica has no full SA: LF walks
+    assert torch.equal(o1, o2) and torch.equal(p1, p2)
