@@ -15,6 +15,9 @@ int build_bitvector(const uint8_t *d_sym, uint64_t len, const uint8_t *d_lut_bit
                     uint64_t *d_super, uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones,
                     cudaStream_t st);
 
+int build_markvector(const uint32_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
+                     uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st);
+
 constexpr int COUNT_THREADS = 256;
 
 // One lane per pattern.  A warp owns a contiguous chunk of the batch and refills a lane as soon as
@@ -234,15 +237,13 @@ extern "C" int hkcsa_ssa_build(const uint32_t *d_sa, const hkcsa_ssa_plan *p, vo
     uint8_t *blob = static_cast<uint8_t *>(d_blob);
     prof::Scope ps(st, prof::SSA_BUILD, n * 10);
     const uint32_t grid = (uint32_t)((n + 255) / 256);
-    identity_lut_kernel<<<1, 256, 0, st>>>(d_lut);
-    ssa_mark_kernel<<<grid, 256, 0, st>>>(d_sa, n, p->rate, d_flag);
-    HK_LAUNCH_CHECK();
+    (void)d_flag; (void)d_lut;
     BitVec marks;
     marks.blocks = reinterpret_cast<const RankBlock *>(blob + p->off_blocks);
     marks.super = reinterpret_cast<const uint64_t *>(blob + p->off_super);
     marks.len = n;
-    int rc = build_bitvector(d_flag, n, d_lut, reinterpret_cast<RankBlock *>(blob + p->off_blocks),
-                             reinterpret_cast<uint64_t *>(blob + p->off_super), d_sel, d_agg, d_carry, d_ones, st);
+    int rc = build_markvector(d_sa, n, p->rate, reinterpret_cast<RankBlock *>(blob + p->off_blocks),
+                              reinterpret_cast<uint64_t *>(blob + p->off_super), d_sel, d_agg, d_carry, d_ones, st);
     if (rc != HKCSA_OK) return rc;
     ssa_fill_kernel<<<grid, 256, 0, st>>>(d_sa, n, p->rate, marks, reinterpret_cast<uint32_t *>(blob + p->off_samples));
     HK_LAUNCH_CHECK();

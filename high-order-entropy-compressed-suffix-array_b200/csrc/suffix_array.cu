@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "prof.cuh"
 #include "radix_sort.cuh"
+#include <math.h>
 
 namespace hkcsa {
 
@@ -23,6 +24,76 @@ constexpr int SEG_TILE = SEG_THREADS * SEG_IPT;
 struct CodeMap {
     uint16_t code[256];  // byte -> dense code + 1 (0 for bytes that do not occur)
 };
+
+// Order-preserving prefix code ("alphabetic code") over {past-the-end} + the symbols of the text: frequent
+// symbols get short codes, and comparing two code streams bit by bit equals comparing the symbol strings,
+// the end of the text being smallest.  The round-0 key of a suffix is the first `bits` bits of its code
+// stream, so a key covers as many symbols as a fixed-width packing would in fewer bits -- fewer radix passes
+// (DNA + '$': 21 symbols in 48 bits instead of 63).  Equal keys share at least bits / max_len symbols.
+struct AlphaCode {
+    uint32_t code[257];   // right-aligned; [256] = past the end
+    uint8_t len[257];
+};
+
+static void alpha_assign(const double *cum, const int *item, int lo, int hi, uint32_t code, int len, AlphaCode &ac,
+                         int &max_len)
+{
+    if (hi - lo == 1) {
+        ac.code[item[lo]] = code;
+        ac.len[item[lo]] = (uint8_t)std::max(len, 1);
+        max_len = std::max(max_len, std::max(len, 1));
+        return;
+    }
+    // split where the two halves weigh most alike
+    int best = lo + 1;
+    double best_d = 1e300;
+    for (int sp = lo + 1; sp < hi; ++sp) {
+        const double d = fabs((cum[sp] - cum[lo]) - (cum[hi] - cum[sp]));
+        if (d < best_d) { best_d = d; best = sp; }
+    }
+    alpha_assign(cum, item, lo, best, code << 1, len + 1, ac, max_len);
+    alpha_assign(cum, item, best, hi, (code << 1) | 1u, len + 1, ac, max_len);
+}
+
+// returns false when the code would be degenerate (then the caller keeps fixed-width codes)
+static bool build_alpha_code(const uint64_t *h_hist, AlphaCode &ac, double &avg_len, int &max_len)
+{
+    int item[257];
+    double w[257], cum[258];
+    int m = 0;
+    double total = 0;
+    for (int ch = 0; ch < 256; ++ch) total += (double)h_hist[ch];
+    item[m] = 256; w[m] = 0; ++m;                       // past-the-end sorts first
+    for (int ch = 0; ch < 256; ++ch)
+        if (h_hist[ch]) { item[m] = ch; w[m] = (double)h_hist[ch]; ++m; }
+    const double smooth = total / (8.0 * m) + 1.0;      // bounds the depth of rare symbols
+    cum[0] = 0;
+    for (int i = 0; i < m; ++i) cum[i + 1] = cum[i] + w[i] + smooth;
+    for (int i = 0; i < 257; ++i) { ac.code[i] = 0; ac.len[i] = 1; }
+    max_len = 0;
+    if (m == 1) { ac.code[256] = 0; ac.len[256] = 1; max_len = 1; avg_len = 1; return true; }
+    alpha_assign(cum, item, 0, m, 0u, 0, ac, max_len);
+    if (max_len > 24) return false;
+    avg_len = 0;
+    for (int i = 1; i < m; ++i) avg_len += w[i] * ac.len[item[i]];
+    avg_len = total > 0 ? avg_len / total : 1.0;
+    return true;
+}
+
+// first `bits` bits of the code stream of the suffix whose symbols are produced by next_sym(t), t = 0, 1, ...
+template <typename NextSym>
+__device__ __forceinline__ uint64_t alpha_pack(const uint32_t *s_code, const uint8_t *s_len, int bits, NextSym next_sym)
+{
+    uint64_t acc = 0;
+    int used = 0;
+    for (int t = 0; used < bits; ++t) {
+        const uint32_t c = next_sym(t);
+        const int L = s_len[c];
+        acc |= ((uint64_t)s_code[c] << (64 - L)) >> used;   // bits beyond 64 fall off: the last code is truncated
+        used += L;
+    }
+    return acc >> (64 - bits);
+}
 
 // ---------------------------------------------------------------- byte histogram
 __global__ void byte_hist_kernel(const uint8_t *__restrict__ text, uint64_t n, unsigned long long *__restrict__ ghist)
@@ -76,29 +147,62 @@ constexpr int PACK_THREADS = 256;
 constexpr int PACK_IPT = 8;
 constexpr int PACK_TILE = PACK_THREADS * PACK_IPT;
 
+// Entries are (code << 8) | length.  The per-position codes of a tile are combined by doubling into the
+// code of 2, 4, 8 consecutive symbols (as long as that still fits 56 bits), so building a key takes a few
+// shifted ORs instead of one per symbol.
+__device__ __forceinline__ uint64_t chunk_join(uint64_t a, uint64_t b)
+{
+    const uint32_t lb = (uint32_t)(b & 0xFFu);
+    return ((((a >> 8) << lb) | (b >> 8)) << 8) | ((a & 0xFFu) + lb);
+}
+
 __global__ void __launch_bounds__(PACK_THREADS)
-sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, CodeMap map, int b, int k0, int passes,
+sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, int bits, int passes, int levels,
                 uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, uint32_t *__restrict__ ghist)
 {
-    __shared__ uint16_t s_code[256];
-    __shared__ uint16_t s_sym[PACK_TILE + 64];
+    constexpr int W = PACK_TILE + 64;
+    __shared__ uint64_t s_c[2][W];
     __shared__ uint32_t s_hist[8 * RADIX];
+    __shared__ uint32_t s_code[257];
+    __shared__ uint8_t s_len[257];
     const uint32_t tid = threadIdx.x;
-    s_code[tid] = map.code[tid];
+    for (uint32_t i = tid; i < 257; i += PACK_THREADS) { s_code[i] = ac.code[i]; s_len[i] = ac.len[i]; }
     hist_zero(s_hist, passes);
     __syncthreads();
     const uint32_t base = blockIdx.x * PACK_TILE;
-    for (uint32_t j = tid; j < PACK_TILE + 64; j += PACK_THREADS) {
+    for (uint32_t j = tid; j < W; j += PACK_THREADS) {
         const uint32_t g = base + j;
-        s_sym[j] = (g < n) ? s_code[text[g]] : (uint16_t)0;
+        const uint32_t c = (g < n) ? (uint32_t)text[g] : 256u;
+        s_c[0][j] = ((uint64_t)s_code[c] << 8) | s_len[c];
     }
     __syncthreads();
+    const uint64_t pad = ((uint64_t)s_code[256] << 8) | s_len[256];
+    int cur = 0;
+    for (int l = 0; l < levels; ++l) {                    // s_c[cur][j] covers 2^l symbols from position j
+        const uint32_t step = 1u << l;
+        for (uint32_t j = tid; j < W; j += PACK_THREADS) {
+            // beyond the window only padding can follow inside the text's end; inside the text the window is
+            // wide enough for every key of the tile (64 symbols), so a clamped neighbour is never consumed
+            const uint64_t nb = (j + step < W) ? s_c[cur][j + step] : pad;
+            s_c[cur ^ 1][j] = chunk_join(s_c[cur][j], nb);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    const uint32_t S = 1u << levels;
 #pragma unroll
     for (int e = 0; e < PACK_IPT; ++e) {
         const uint32_t j = e * PACK_THREADS + tid;
         const uint32_t g = base + j;
-        uint64_t key = 0;
-        for (int t = 0; t < k0; ++t) key = (key << b) | s_sym[j + t];
+        uint64_t acc = 0;
+        int used = 0;
+        for (uint32_t t = 0; used < bits; t += S) {
+            const uint64_t en = s_c[cur][j + t];
+            const int L = (int)(en & 0xFFu);
+            acc |= ((en >> 8) << (64 - L)) >> used;
+            used += L;
+        }
+        const uint64_t key = acc >> (64 - bits);
         const bool valid = g < n;
         if (valid) {
             keys[g] = key;
@@ -122,7 +226,7 @@ struct LazyRank {
     const uint8_t *text;       // nullptr = eager mode
     const uint64_t *keys0;     // round-0 keys, sorted
     const uint32_t *bucket;    // bucket[v] = lower_bound(keys0, v << shift), v in [0, 2^bucket_bits]
-    int b, k0;
+    int bits;                  // width of a round-0 key
     int shift;                 // key >> shift = bucket id
 };
 
@@ -145,14 +249,13 @@ __global__ void sa_bucket_index_kernel(const uint64_t *__restrict__ keys0, uint3
     bucket[v] = lo;
 }
 
-__device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const uint16_t *s_code, uint32_t n,
-                                                     uint32_t t, const uint32_t *__restrict__ rank)
+__device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const uint32_t *s_code, const uint8_t *s_len,
+                                                     uint32_t n, uint32_t t, const uint32_t *__restrict__ rank)
 {
-    uint64_t key = 0;
-    for (int q = 0; q < lz.k0; ++q) {
-        const uint32_t g = t + q;
-        key = (key << lz.b) | (g < n ? (uint64_t)s_code[lz.text[g]] : 0ull);
-    }
+    const uint64_t key = alpha_pack(s_code, s_len, lz.bits, [&](int q) {
+        const uint64_t g = (uint64_t)t + q;
+        return g < n ? (uint32_t)lz.text[g] : 256u;
+    });
     const uint32_t v = (uint32_t)(key >> lz.shift);
     uint32_t lo = __ldg(lz.bucket + v), hi = __ldg(lz.bucket + v + 1);
     while (lo < hi) {
@@ -166,11 +269,12 @@ __device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const u
 __global__ void __launch_bounds__(256)
 sa_keybuild_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp,
                    const uint32_t *__restrict__ rank, uint32_t n, uint32_t h, int b2, uint32_t m, int passes,
-                   uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist, LazyRank lz, CodeMap map)
+                   uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist, LazyRank lz, AlphaCode ac)
 {
     __shared__ uint32_t s_hist[8 * RADIX];
-    __shared__ uint16_t s_code[256];
-    s_code[threadIdx.x] = map.code[threadIdx.x];
+    __shared__ uint32_t s_code[257];
+    __shared__ uint8_t s_len[257];
+    for (uint32_t i = threadIdx.x; i < 257; i += blockDim.x) { s_code[i] = ac.code[i]; s_len[i] = ac.len[i]; }
     hist_zero(s_hist, passes);
     __syncthreads();
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < m; base += (uint64_t)gridDim.x * blockDim.x) {
@@ -181,7 +285,7 @@ sa_keybuild_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict
             const uint32_t i = cidx[j];
             const uint64_t t = (uint64_t)i + h;
             uint32_t k2 = 0;
-            if (t < n) k2 = (lz.text ? lazy_rank_lookup(lz, s_code, n, (uint32_t)t, rank) : rank[t]) + 1u;
+            if (t < n) k2 = (lz.text ? lazy_rank_lookup(lz, s_code, s_len, n, (uint32_t)t, rank) : rank[t]) + 1u;
             key = ((uint64_t)cgrp[j] << b2) | k2;
             keys[j] = key;
         }
@@ -419,17 +523,29 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     HK_CUDA(byte_hist(d_text, n, B.hist64, st));
     HK_CUDA(cudaMemcpyAsync(h_hist, B.hist64, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     HK_CUDA(cudaStreamSynchronize(st));
-    CodeMap map;
-    memset(&map, 0, sizeof(map));
     uint32_t sigma = 0;
     for (int ch = 0; ch < 256; ++ch)
-        if (h_hist[ch]) map.code[ch] = (uint16_t)(++sigma);
-    const int b = (int)bits_for(sigma);      // codes 0..sigma (9 bits when all 256 bytes occur)
-    const int k0 = 64 / b;
-    const int bits0 = b * k0;
-    const int passes0 = (bits0 + 7) / 8;
+        if (h_hist[ch]) ++sigma;
+    const int b = std::max(1, (int)bits_for(sigma));   // fixed-width code size, for reference
+    // round-0 keys: the first bits0 bits of the alphabetic code stream; as many symbols on average as a
+    // fixed-width packing of 64 / b symbols would hold, in fewer bits when the symbol distribution allows
+    static thread_local AlphaCode ac;
+    double avg_len = b;
+    int max_len = b;
+    if (!build_alpha_code(h_hist, ac, avg_len, max_len)) {
+        uint32_t code = 0;                               // degenerate distribution: fixed-width codes
+        ac.code[256] = 0; ac.len[256] = (uint8_t)b;
+        for (int ch = 0; ch < 256; ++ch)
+            if (h_hist[ch]) { ac.code[ch] = ++code; ac.len[ch] = (uint8_t)b; }
+        avg_len = max_len = b;
+    }
+    const int k_target = 64 / b;
+    int bits0 = 8 * (int)ceil(k_target * avg_len / 8.0 - 1e-9);
+    bits0 = std::max(16, std::min(64, bits0));
+    const int k0 = std::max(1, bits0 / max_len);         // symbols every key is guaranteed to cover
+    const int passes0 = bits0 / 8;
     stats.sigma = sigma;
-    stats.bits_per_symbol = (uint32_t)b;
+    stats.bits_per_symbol = (uint32_t)max_len;
     stats.k0 = (uint32_t)k0;
 
     const uint32_t N = (uint32_t)n;
@@ -442,7 +558,8 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     {
         const uint32_t blocks = (N + PACK_TILE - 1) / PACK_TILE;
         prof::Scope ps(st, prof::SA_PACK0, (uint64_t)N * 13);
-        sa_pack0_kernel<<<blocks, PACK_THREADS, 0, st>>>(d_text, N, map, b, k0, passes0, ka, va, B.sort.hist);
+        const int levels = (8 * max_len <= 56) ? 3 : (4 * max_len <= 56) ? 2 : (2 * max_len <= 56) ? 1 : 0;
+        sa_pack0_kernel<<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, bits0, passes0, levels, ka, va, B.sort.hist);
         HK_LAUNCH_CHECK();
     }
     HK_CUDA(radix_sort_pairs_u64(ka, va, kb, vb, N, passes0, B.sort, st));
@@ -462,7 +579,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     stats.alg_bytes = (uint64_t)n * 13 + (uint64_t)m * (24ull * passes0);
 
     LazyRank lz;
-    lz.text = nullptr; lz.keys0 = nullptr; lz.bucket = nullptr; lz.b = b; lz.k0 = k0;
+    lz.text = nullptr; lz.keys0 = nullptr; lz.bucket = nullptr; lz.bits = bits0;
     const int bucket_bits = std::min(LAZY_BUCKET_BITS, bits0);
     lz.shift = bits0 - bucket_bits;
     uint64_t *kx = nullptr, *ky = nullptr;             // key ping-pong of the later rounds
@@ -529,7 +646,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
             const int blocks = (int)std::min<uint64_t>(((uint64_t)m + 255) / 256, (uint64_t)num_sms() * 16);
             prof::Scope ps(st, prof::SA_KEYBUILD, (uint64_t)m * 20);
             sa_keybuild_kernel<<<blocks, 256, 0, st>>>(vx, B.grp, B.rank, N, (uint32_t)std::min<uint64_t>(h, n), b2,
-                                                       m, passes, kx, B.sort.hist, lz, map);
+                                                       m, passes, kx, B.sort.hist, lz, ac);
             HK_LAUNCH_CHECK();
         }
         HK_CUDA(radix_sort_pairs_u64(kx, vx, ky, vy, m, passes, B.sort, st));

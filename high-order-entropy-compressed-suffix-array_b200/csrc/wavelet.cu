@@ -613,6 +613,66 @@ int build_bitvector(const uint8_t *d_sym, uint64_t len, const uint8_t *d_lut_bit
 }
 }  // namespace hkcsa
 
+// Mark bit-vector of the sampled suffix array, bit j = (SA[j] % rate == 0), packed straight from the suffix
+// array with warp ballots (no byte flags in between) + its directory.
+namespace hkcsa {
+__global__ void __launch_bounds__(WTP_THREADS)
+ssa_mark_pack_kernel(const uint32_t *__restrict__ sa, uint64_t n, uint32_t rate, RankBlock *__restrict__ blocks,
+                     uint64_t nblocks, uint32_t *__restrict__ agg)
+{
+    __shared__ uint32_t s_words[WTP_BLOCKS_PER_CTA * 7];
+    __shared__ uint32_t s_wsum[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t row_base = (uint64_t)blockIdx.x * WTP_SYMS;
+    for (uint32_t it = 0; it < WTP_SYMS / WTP_THREADS; ++it) {
+        const uint64_t row = row_base + it * WTP_THREADS + tid;
+        const bool flag = row < n && (sa[row] % rate == 0);
+        const uint32_t w = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) s_words[it * (WTP_THREADS / 32) + warp] = w;
+    }
+    __syncthreads();
+    const uint64_t gb = (uint64_t)blockIdx.x * WTP_BLOCKS_PER_CTA + tid;
+    uint32_t w[7] = {0, 0, 0, 0, 0, 0, 0};
+    uint32_t cnt = 0;
+    if (tid < WTP_BLOCKS_PER_CTA) {
+#pragma unroll
+        for (int t = 0; t < 7; ++t) { w[t] = s_words[tid * 7 + t]; cnt += __popc(w[t]); }
+    }
+    uint32_t wtot;
+    const uint32_t ex = warp_excl_sum(cnt, wtot);
+    if ((tid & 31u) == 31u && tid < WTP_BLOCKS_PER_CTA) s_wsum[tid >> 5] = wtot;
+    __syncthreads();
+    if (tid < WTP_BLOCKS_PER_CTA) {
+        const uint32_t rel = ex + ((tid >= 32) ? s_wsum[0] : 0u);
+        if (gb < nblocks) {
+            uint4 lo4, hi4;
+            lo4.x = rel; lo4.y = w[0]; lo4.z = w[1]; lo4.w = w[2];
+            hi4.x = w[3]; hi4.y = w[4]; hi4.z = w[5]; hi4.w = w[6];
+            uint4 *dst = reinterpret_cast<uint4 *>(blocks + gb);
+            dst[0] = lo4;
+            dst[1] = hi4;
+        }
+        if (tid == WTP_BLOCKS_PER_CTA - 1) agg[blockIdx.x] = rel + cnt;
+    }
+}
+
+int build_markvector(const uint32_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
+                     uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st)
+{
+    static_assert(WTP_SYMS % WTP_THREADS == 0 && WTP_THREADS % 32 == 0, "tile shape");
+    const uint64_t nblocks = rank_blocks_for(n);
+    const uint64_t tiles = (nblocks + WTP_BLOCKS_PER_CTA - 1) / WTP_BLOCKS_PER_CTA;
+    ssa_mark_pack_kernel<<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg);
+    HK_LAUNCH_CHECK();
+    wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones);
+    HK_LAUNCH_CHECK();
+    wt_dir_fix_kernel<<<(uint32_t)((nblocks + 255) / 256), 256, 0, st>>>(d_blocks, nblocks, d_carry, d_super, d_select,
+                                                                         WTP_BLOCKS_PER_CTA);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+}  // namespace hkcsa
+
 extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_blob, void *d_scratch,
                               size_t scratch_bytes, void *stream)
 {
