@@ -40,6 +40,17 @@ def _empty(n: int, dtype, device) -> torch.Tensor:
     return torch.empty(max(int(n), 0), dtype=dtype, device=device)
 
 
+_STREAMS: dict = {}
+
+
+def _aux_stream(device, which: str) -> "torch.cuda.Stream":
+    """Long-lived side streams (one per device and purpose): the copy-out stream and the sampled-SA stream."""
+    key = (torch.device(device).index, which)
+    if key not in _STREAMS:
+        _STREAMS[key] = torch.cuda.Stream(device=device)
+    return _STREAMS[key]
+
+
 def _scratch(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -340,18 +351,31 @@ class DeviceIndex:
         self.sa = suffix_array(text, self.stats.sa)
         side = None
         if host_sa is not None or host_bwt is not None:
-            side = torch.cuda.Stream(device=self.device)
+            side = _aux_stream(self.device, "copy")
         if host_sa is not None:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 host_sa.copy_(self.sa, non_blocking=True)
+        # the sampled SA depends on the suffix array only: build it on a second stream while the BWT and the
+        # wavelet tree are built on this one
+        main = torch.cuda.current_stream()
+        ssa_stream = None
+        self.ssa = None
+        if sa_sample_rate > 0:
+            ssa_stream = _aux_stream(self.device, "ssa")
+            ssa_stream.wait_stream(main)
+            with torch.cuda.stream(ssa_stream):
+                self.ssa = build_sampled_sa(self.sa, sa_sample_rate)
+            self.sa.record_stream(ssa_stream)
         self.bwt = bwt(text, self.sa)
         if host_bwt is not None:
-            side.wait_stream(torch.cuda.current_stream())
+            side.wait_stream(main)
             with torch.cuda.stream(side):
                 host_bwt.copy_(self.bwt, non_blocking=True)
         self.wt = DeviceWaveletTree(self.bwt)
-        self.ssa = build_sampled_sa(self.sa, sa_sample_rate) if sa_sample_rate > 0 else None
+        if ssa_stream is not None:
+            main.wait_stream(ssa_stream)
+            self.ssa.blob.record_stream(main)
         self._side = side
         self.text = text if keep_text else None
         if not keep_sa:
