@@ -165,6 +165,9 @@ onesweep_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uin
 // shared buffer and written out as coalesced runs.
 // ---------------------------------------------------------------------------
 constexpr int OS_IPT = 8;
+#ifndef OS_LB_BATCH
+#define OS_LB_BATCH 8
+#endif
 static_assert(SORT64_TILE >= 2048, "scratch sizing assumes tiles of at least 2048 pairs");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -334,19 +337,20 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
         S.vals[slot] = val[k];
     }
 
-    // ---- decoupled look-back, four predecessors per round trip
+    // ---- decoupled look-back, OS_LB_BATCH predecessors per round trip (8: measured best of 2 / 4 / 8; issuing
+    //      the first batch before the staging stores was slower -- register pressure)
     if (tid < RADIX) {
         uint32_t excl = 0;
         if (tile > 0) {
             int64_t t = (int64_t)tile - 1;
             bool done = false;
             while (!done) {
-                uint32_t v[4];
+                uint32_t v[OS_LB_BATCH];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < OS_LB_BATCH; ++j)
                     v[j] = (t - j >= 0) ? ld_volatile_u32(&lookback[(size_t)(t - j) * RADIX + tid]) : LB_INC;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < OS_LB_BATCH; ++j) {
                     if (done) break;
                     const uint32_t flag = v[j] >> 30;
                     if (flag == 0) break;             // not published yet: re-poll from here
