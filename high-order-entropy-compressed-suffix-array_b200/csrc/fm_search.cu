@@ -217,6 +217,17 @@ extern "C" int hkcsa_ssa_plan_make(uint64_t n, uint32_t rate, hkcsa_ssa_plan *p)
     return HKCSA_OK;
 }
 
+extern "C" int hkcsa_ssa_plan_make_slice(uint64_t m, uint32_t rate, uint64_t n_marks, hkcsa_ssa_plan *p)
+{
+    int rc = hkcsa_ssa_plan_make(m, rate, p);
+    if (rc != HKCSA_OK) return rc;
+    HK_REQUIRE(n_marks <= m, HKCSA_EINVAL, "more marks than rows");
+    p->n_samples = n_marks;
+    p->off_samples = p->off_super + align_up(super_for(m) * sizeof(uint64_t), 256);
+    p->blob_bytes = p->off_samples + align_up((n_marks + 1) * sizeof(uint32_t), 256);
+    return HKCSA_OK;
+}
+
 extern "C" int hkcsa_ssa_build(const uint32_t *d_sa, const hkcsa_ssa_plan *p, void *d_blob, void *d_scratch,
                                size_t scratch_bytes, void *stream)
 {

@@ -16,6 +16,7 @@ MAX_N = (1 << 30) - 2
 BLOCK_BITS = 224
 SUPER_BLOCKS = 65536
 SELECT_SAMPLE = 4096
+MAX_SLICES = 8
 DIST_BUCKETS = 65536
 DIST_MAX_N = (1 << 32) - 2
 PROF_CLASSES = 16
@@ -127,6 +128,12 @@ SIGNATURES = {
     "hkcsa_count_batch": (_i32, [_vp, C.POINTER(WtPlan), _vp, _vp, _u64, _vp, _vp, _vp]),
     "hkcsa_ssa_plan_make": (_i32, [_u64, _u32, C.POINTER(SsaPlan)]),
     "hkcsa_ssa_build": (_i32, [_vp, C.POINTER(SsaPlan), _vp, _vp, _sz, _vp]),
+    "hkcsa_ssa_plan_make_slice": (_i32, [_u64, _u32, _u64, C.POINTER(SsaPlan)]),
+    "hkcsa_multi_desc_bytes": (_sz, []),
+    "hkcsa_multi_desc_build": (_i32, [_u32, C.POINTER(_vp), C.POINTER(C.POINTER(WtPlan)), C.POINTER(_u64),
+                                      C.POINTER(_vp), C.POINTER(C.POINTER(SsaPlan)), _vp, _vp]),
+    "hkcsa_multi_count_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "hkcsa_multi_locate_rows": (_i32, [_vp, _vp, _u64, _vp, _vp]),
     "hkcsa_expand_ranges": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
     "hkcsa_gather_u32": (_i32, [_vp, _vp, _u64, _vp, _vp]),
     "hkcsa_locate_rows": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(SsaPlan), _vp, _u64, _vp, _vp]),

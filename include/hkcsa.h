@@ -264,6 +264,24 @@ int hkcsa_locate_rows(const void *d_wt_blob, const hkcsa_wt_plan *h_plan, const 
                       const hkcsa_ssa_plan *h_ssa, const uint32_t *d_rows, uint64_t m,
                       uint32_t *d_out_pos, void *stream);
 
+/* Sampled SA of a SLICE of the suffix array (distributed build): the number of marked rows of a slice is  */
+/* not ceil(m / rate), the caller passes it (count of SA[j] % rate == 0 in the slice).                        */
+int hkcsa_ssa_plan_make_slice(uint64_t m, uint32_t rate, uint64_t n_marks, hkcsa_ssa_plan *h_plan);
+
+/* Backward search over a BWT built in slices (BASELINE config 5): slice s covers global rows                 */
+/* [h_starts[s], h_starts[s+1]) with its own wavelet-tree blob / plan (hkcsa_wt_build over its BWT slice) and, */
+/* optionally, its own sampled SA.  The descriptor lives in device memory (hkcsa_multi_desc_bytes()).          */
+/* Same recurrences and miss conventions as hkcsa_count_batch; rows and positions are global (n <= 2^32-2).    */
+#define HKCSA_MAX_SLICES 8
+size_t hkcsa_multi_desc_bytes(void);
+int hkcsa_multi_desc_build(uint32_t S, const void *const *d_wt_blobs, const hkcsa_wt_plan *const *h_plans,
+                           const uint64_t *h_starts, const void *const *d_ssa_blobs,
+                           const hkcsa_ssa_plan *const *h_ssa_plans, void *d_desc, void *stream);
+int hkcsa_multi_count_batch(const void *d_desc, const uint8_t *d_pat, const int64_t *d_off, uint64_t P,
+                            int64_t *d_lo, int64_t *d_hi, void *stream);
+int hkcsa_multi_locate_rows(const void *d_desc, const uint32_t *d_rows, uint64_t m, uint32_t *d_out_pos,
+                            void *stream);
+
 /* FMIndex.precompute_rank, csa/csa.py:13-19: positions of every symbol in the  */
 /* BWT, ascending, grouped by byte value (a stable counting sort).  d_start:    */
 /* uint64[257].  d_scratch: hkcsa_symbol_positions_scratch_bytes(n).                      */

@@ -400,3 +400,31 @@ def test_index_save_load_round_trip(E, tmp_path):
     o1, p1 = idx.locate_batch(d_p, d_o, use_samples=True)
     o2, p2 = back.locate_batch(d_p, d_o)                     # replica has no full SA: LF walks
     assert torch.equal(o1, o2) and torch.equal(p1, p2)
+
+
+@pytest.mark.parametrize("name,parts", [("eng_300k", 3), ("dna_300k", 8), ("rand2_100k", 2), ("dna_1m_dollar", 5), ("runs", 4)])
+def test_multi_slice_index_matches_single_index(E, name, parts):
+    """hkcsa.dist_sa.MultiSliceIndex (the index a distributed build leaves behind) must answer exactly like the
+    single-GPU index: count ranges, and positions from LF walks that hop across slices."""
+    import torch
+    from hkcsa import dist_sa
+    text = TEXTS[name] + (b"" if name.endswith("dollar") else b"$")
+    d_text = dev(E, text)
+    idx = E.DeviceIndex(d_text, sa_sample_rate=8)
+    n = len(text)
+    cuts = [n * r // parts for r in range(parts + 1)]
+    slices = [{"bwt": idx.bwt[cuts[r]:cuts[r + 1]].clone(), "sa": idx.sa[cuts[r]:cuts[r + 1]].clone()}
+              for r in range(parts)]
+    ms = dist_sa.MultiSliceIndex(n, slices, sa_sample_rate=8)
+    base = np.frombuffer(text[:-1], dtype=np.uint8)
+    pats, off = O.gen_patterns(9, 3000, base, 1, 40)
+    extra = [b"", b"\x01", b"$", text[-2:], text[:30]]
+    pats = np.concatenate([pats, np.frombuffer(b"".join(extra), dtype=np.uint8)])
+    off = np.concatenate([off, off[-1] + np.cumsum([len(e) for e in extra])])
+    d_p, d_o = torch.from_numpy(pats).cuda(), torch.from_numpy(off).cuda()
+    lo, hi = idx.count_batch(d_p, d_o)
+    mlo, mhi = ms.count_batch(d_p, d_o)
+    assert torch.equal(lo, mlo) and torch.equal(hi, mhi)
+    o1, p1 = idx.locate_batch(d_p, d_o, use_samples=False)
+    o2, p2 = ms.locate_batch(d_p, d_o)
+    assert torch.equal(o1, o2) and torch.equal(p1, p2)

@@ -13,6 +13,7 @@ ap.add_argument("--size", type=int, default=50_000_000)
 ap.add_argument("--kind", type=int, default=0)
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--patterns", type=int, default=1_000_000)
 args = ap.parse_args()
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -47,8 +48,40 @@ if args.verify:
         bw = torch.cat([gb[r][: int(counts[r])] for r in range(world)])
         ref = E.suffix_array(sl.text)
         ok = bool(torch.equal(sa, ref)) and bool(torch.equal(bw, E.bwt(sl.text, ref)))
+# ---- the index the distributed build leaves behind: per-slice wavelet trees + sampled SAs, replicated on every
+#      rank, then the pattern batch is sharded (config 4 style) over the ranks
+from hkcsa import dist as hdist
+torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+ms = dist_sa.replicate_sliced_index(sl, sa_sample_rate=32)
+torch.cuda.synchronize(); dist.barrier()
+t_index = time.perf_counter() - t0
+P = args.patterns
+alpha = torch.unique(sl.text[: min(n, 1 << 22)])
+pats, off = E.gen_patterns(44, P, sl.text, alpha)
+bounds = hdist.shard_bounds(off.cpu().numpy(), world)
+my_p, my_o = hdist.local_slice(pats, off, *bounds[rank])
+lo, hi = ms.count_batch(my_p, my_o)
+torch.cuda.synchronize(); dist.barrier()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record(); lo, hi = ms.count_batch(my_p, my_o); b.record(); torch.cuda.synchronize()
+cms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev); dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+q_ok = None
+if args.verify:
+    glo, ghi = hdist.sharded_count(lambda p_, o_: (lo, hi), pats, off)
+    o2, p2 = ms.locate_batch(my_p[: int(my_o[min(2000, my_o.numel() - 1)])], my_o[: min(2000, my_o.numel() - 1) + 1])
+    if rank == 0:
+        txt = torch.cat([sl.text, torch.tensor([], dtype=torch.uint8, device=dev)])
+        one = E.DeviceIndex(txt, sa_sample_rate=0)
+        wlo, whi = one.count_batch(pats, off)
+        q_ok = bool(torch.equal(glo, wlo)) and bool(torch.equal(ghi, whi))
+        o1, p1 = one.locate_batch(my_p[: int(my_o[min(2000, my_o.numel() - 1)])], my_o[: min(2000, my_o.numel() - 1) + 1],
+                                  use_samples=False)
+        q_ok = q_ok and bool(torch.equal(o1, o2)) and bool(torch.equal(p1, p2))
 if rank == 0:
     print(json.dumps({"check": "distributed_suffix_array", "world": world, "text_bytes": n, "kind": args.kind,
                       "seconds": best, "MB_per_s": n / 1e6 / best, "slice_sizes": counts.cpu().tolist(),
-                      "rounds": int(sl.stats.rounds), "verified_against_single_gpu": ok}), flush=True)
+                      "rounds": int(sl.stats.rounds), "verified_against_single_gpu": ok,
+                      "sliced_index_build_and_replicate_s": t_index, "count_patterns": P,
+                      "count_patterns_per_s": P / (float(cms.item()) / 1e3),
+                      "queries_verified_against_single_gpu": q_ok}), flush=True)
 dist.destroy_process_group()
