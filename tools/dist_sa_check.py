@@ -14,6 +14,7 @@ ap.add_argument("--kind", type=int, default=0)
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--patterns", type=int, default=1_000_000)
+ap.add_argument("--props", action="store_true", help="size-independent checks (no single-GPU reference: n may exceed 2^30)")
 args = ap.parse_args()
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -22,6 +23,7 @@ os.environ["NCCL_DEBUG"] = "WARN"
 dist.init_process_group("nccl", device_id=dev)
 n = args.size
 full = E.gen_text(args.kind, 42 + args.kind, n)                 # same bytes on every rank; keep only my block
+full[n - 1] = 0x24                                              # unique sentinel (the generators never emit '$'): LF walks need it
 lo, hi = n * rank // world, n * (rank + 1) // world
 block = full[lo:hi].clone()
 del full
@@ -77,11 +79,38 @@ if args.verify:
         o1, p1 = one.locate_batch(my_p[: int(my_o[min(2000, my_o.numel() - 1)])], my_o[: min(2000, my_o.numel() - 1) + 1],
                                   use_samples=False)
         q_ok = q_ok and bool(torch.equal(o1, o2)) and bool(torch.equal(p1, p2))
+props_ok = None
+if args.props:
+    # every rank: slice is sorted (adjacent suffixes compared on a sample), located positions hold the pattern
+    import random
+    h_text = sl.text.cpu().numpy()
+    ids = sl.sa_int64().cpu().numpy()
+    rnd = random.Random(rank)
+    good = True
+    for _ in range(20000):
+        j = rnd.randrange(max(1, len(ids) - 1))
+        if j + 1 < len(ids):
+            a_, b_ = int(ids[j]), int(ids[j + 1])
+            good &= h_text[a_:a_ + 256].tobytes() <= h_text[b_:b_ + 256].tobytes()   # 256-byte prefixes, in order
+    k = min(2000, my_o.numel() - 1)
+    oo, pp = ms.locate_batch(my_p[: int(my_o[k])], my_o[: k + 1])
+    oo, pp = oo.cpu().numpy(), (pp.to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+    hp, ho = my_p.cpu().numpy(), my_o.cpu().numpy()
+    clo = lo.cpu().numpy()
+    for q in range(k):
+        m_ = int(ho[q + 1] - ho[q])
+        occ = pp[oo[q]:oo[q + 1]]
+        good &= (len(occ) > 0) == (clo[q] >= 0)
+        for x in occ[:4]:
+            good &= h_text[int(x):int(x) + m_].tobytes() == hp[ho[q]:ho[q + 1]].tobytes()
+    flag = torch.tensor([1 if good else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    props_ok = bool(flag.item())
 if rank == 0:
     print(json.dumps({"check": "distributed_suffix_array", "world": world, "text_bytes": n, "kind": args.kind,
                       "seconds": best, "MB_per_s": n / 1e6 / best, "slice_sizes": counts.cpu().tolist(),
                       "rounds": int(sl.stats.rounds), "verified_against_single_gpu": ok,
                       "sliced_index_build_and_replicate_s": t_index, "count_patterns": P,
                       "count_patterns_per_s": P / (float(cms.item()) / 1e3),
-                      "queries_verified_against_single_gpu": q_ok}), flush=True)
+                      "queries_verified_against_single_gpu": q_ok, "property_checks": props_ok}), flush=True)
 dist.destroy_process_group()
