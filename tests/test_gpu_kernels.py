@@ -428,3 +428,31 @@ def test_multi_slice_index_matches_single_index(E, name, parts):
     o1, p1 = idx.locate_batch(d_p, d_o, use_samples=False)
     o2, p2 = ms.locate_batch(d_p, d_o)
     assert torch.equal(o1, o2) and torch.equal(p1, p2)
+
+
+def test_property_random_small_texts(E):
+    """hypothesis: small texts over tiny alphabets (many repeats, every tail shape) -- SA, BWT, count and locate
+    through the C-ABI equal the oracle."""
+    import torch
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.binary(min_size=0, max_size=300).map(lambda b: bytes(97 + (x % 3) for x in b)),
+           st.binary(min_size=0, max_size=6).map(lambda b: bytes(97 + (x % 3) for x in b)))
+    def check(text, pat):
+        d = dev(E, text)
+        sa = E.suffix_array(d)
+        want = O.build_suffix_array(text)
+        assert np.array_equal(host(sa).astype(np.uint32), want)
+        assert host(E.bwt(d, sa)).tobytes() == O.bwt_transform(text, want).tobytes()
+        t = text + b"$"
+        idx = E.DeviceIndex(dev(E, t), sa_sample_rate=3)
+        sa2 = O.build_suffix_array(t)
+        fm = O.FM(O.bwt_transform(t, sa2))
+        lo, hi = idx.count_batch(*E.pack_patterns([pat]))
+        l, r = fm.find_range(pat)
+        assert (int(lo.item()), int(hi.item())) == (l, r)
+        o, p = idx.locate_batch(*E.pack_patterns([pat]), use_samples=True)
+        assert host(p).tolist() == ([] if l < 0 else sa2[l:r + 1].tolist())
+
+    check()
