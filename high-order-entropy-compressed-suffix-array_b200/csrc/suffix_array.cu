@@ -308,13 +308,29 @@ sa_keybuild_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict
 __device__ __forceinline__ void seg_flags(const uint64_t *__restrict__ skey, uint32_t m, uint32_t j0,
                                           bool head[SEG_IPT], bool single[SEG_IPT])
 {
-    // thread owns j0 .. j0+SEG_IPT-1 (blocked); needs skey[j0-1] and skey[j0+SEG_IPT]
+    // thread owns j0 .. j0+SEG_IPT-1 (blocked): four 16-byte loads; the keys just outside (j0-1 and
+    // j0+SEG_IPT) come from the neighbouring lanes, only the warp's two edge lanes load them.
+    // Must be called by all 32 lanes of the warp.
     uint64_t k[SEG_IPT + 2];
+    if (j0 + SEG_IPT <= m) {
+        const ulonglong2 *v = reinterpret_cast<const ulonglong2 *>(skey + j0);   // j0 is a multiple of 8: 64-byte aligned
 #pragma unroll
-    for (int e = 0; e < SEG_IPT + 2; ++e) {
-        const int64_t j = (int64_t)j0 + e - 1;
-        k[e] = (j >= 0 && j < (int64_t)m) ? skey[j] : 0ULL;
+        for (int e = 0; e < SEG_IPT / 2; ++e) {
+            const ulonglong2 q = v[e];
+            k[1 + 2 * e] = q.x;
+            k[2 + 2 * e] = q.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < SEG_IPT; ++e) k[1 + e] = (j0 + e < m) ? skey[j0 + e] : 0ULL;
     }
+    const uint32_t lane = lane_id();
+    uint64_t prev = __shfl_up_sync(0xffffffffu, k[SEG_IPT], 1);
+    uint64_t next = __shfl_down_sync(0xffffffffu, k[1], 1);
+    if (lane == 0) prev = (j0 > 0 && j0 - 1 < m) ? skey[j0 - 1] : 0ULL;
+    if (lane == 31) next = (j0 + SEG_IPT < m) ? skey[j0 + SEG_IPT] : 0ULL;
+    k[0] = prev;
+    k[SEG_IPT + 1] = next;
 #pragma unroll
     for (int e = 0; e < SEG_IPT; ++e) {
         const uint32_t j = j0 + e;
