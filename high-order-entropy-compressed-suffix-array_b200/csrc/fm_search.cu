@@ -28,7 +28,7 @@ constexpr int COUNT_THREADS = 256;
 //   l >= r -> (-1, -1).  Result (l, r-1).
 __global__ void __launch_bounds__(COUNT_THREADS)
 fm_count_kernel(WtDev wt, const uint8_t *__restrict__ pat, const int64_t *__restrict__ off, uint64_t P,
-                int64_t *__restrict__ out_lo, int64_t *__restrict__ out_hi)
+                int64_t *__restrict__ out_lo, int64_t *__restrict__ out_hi, const uint2 *__restrict__ kmer, uint32_t kk)
 {
     __shared__ WtSmem s;
     wt_smem_load(s, wt);
@@ -55,13 +55,31 @@ fm_count_kernel(WtDev wt, const uint8_t *__restrict__ pat, const int64_t *__rest
                 k = off[mine + 1] - 1;
                 l = 0;
                 r = n;
+                // jump table: the SA range of the pattern's last kk symbols was precomputed (by this same
+                // search) for every kk-mer over the alphabet; skip those steps
+                if (kmer != nullptr && k - b + 1 >= (int64_t)kk) {
+                    uint32_t id = 0;
+                    bool known = true;
+                    for (uint32_t t = 0; t < kk; ++t) {
+                        const uint32_t code = s.code_of_sym[pat[k - kk + 1 + t]];
+                        known = known && code != 0xFFFFu;
+                        id = id * wt.sigma + (known ? code : 0u);
+                    }
+                    if (known) {
+                        const uint2 e2 = __ldg(kmer + id);
+                        l = e2.x;
+                        r = e2.y;          // l >= r: the kk-mer does not occur
+                        k -= kk;
+                        if (l >= r) { l = 1; r = 0; k = b - 1; }   // finishes below as a miss
+                    }
+                }
             }
             next += __popc(idle);
             if (idle == 0xffffffffu && __ballot_sync(0xffffffffu, p >= 0) == 0) break;
         }
         if (p < 0) continue;
         // ---- one backward-search step (or finish an exhausted / empty pattern)
-        bool done = k < b, miss = false;
+        bool done = k < b, miss = l >= r;
         if (!done) {
             const uint32_t code = s.code_of_sym[pat[k]];
             if (code == 0xFFFFu) { miss = true; }          // symbol absent: rank 0, C 0 -> empty range
@@ -149,6 +167,29 @@ locate_rows_kernel(WtDev wt, BitVec marks, const uint32_t *__restrict__ samples,
     }
 }
 
+// every kk-mer over the index alphabet, in lexicographic (code) order, as patterns of length kk
+__global__ void kmer_patterns_kernel(WtDev wt, uint32_t kk, uint64_t count, uint8_t *__restrict__ pat,
+                                     int64_t *__restrict__ off)
+{
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id > count) return;
+    off[id] = (int64_t)(id * kk);
+    if (id == count) return;
+    uint64_t v = id;
+    for (int t = (int)kk - 1; t >= 0; --t) {
+        pat[id * kk + t] = wt.tab->sym_of_code[v % wt.sigma];
+        v /= wt.sigma;
+    }
+}
+__global__ void kmer_table_fill_kernel(const int64_t *__restrict__ lo, const int64_t *__restrict__ hi, uint64_t count,
+                                       uint2 *__restrict__ table)
+{
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= count) return;
+    const int64_t l = lo[id], h = hi[id];
+    table[id] = (l < 0) ? make_uint2(0u, 0u) : make_uint2((uint32_t)l, (uint32_t)(h + 1));
+}
+
 __global__ void identity_lut_kernel(uint8_t *lut)
 {
     lut[threadIdx.x] = (uint8_t)(threadIdx.x & 1u);
@@ -176,6 +217,64 @@ using namespace hkcsa;
 extern "C" int hkcsa_count_batch(const void *d_blob, const hkcsa_wt_plan *h_plan, const uint8_t *d_pat,
                                  const int64_t *d_off, uint64_t P, int64_t *d_lo, int64_t *d_hi, void *stream)
 {
+    return hkcsa_count_batch_kmer(d_blob, h_plan, nullptr, 0, d_pat, d_off, P, d_lo, d_hi, stream);
+}
+
+// number of symbols a jump table covers for an alphabet of sigma symbols: the largest k with sigma^k <= 2^21
+extern "C" uint32_t hkcsa_kmer_k(uint32_t sigma)
+{
+    if (sigma < 2) return 0;
+    uint32_t k = 0;
+    uint64_t v = 1;
+    while (k < 16 && v * sigma <= (1ull << 21)) { v *= sigma; ++k; }
+    return k;
+}
+extern "C" uint64_t hkcsa_kmer_entries(uint32_t sigma, uint32_t k)
+{
+    uint64_t v = 1;
+    for (uint32_t t = 0; t < k; ++t) v *= sigma;
+    return v;
+}
+extern "C" size_t hkcsa_kmer_scratch_bytes(uint32_t sigma, uint32_t k)
+{
+    const uint64_t cnt = hkcsa_kmer_entries(sigma, k);
+    Carver c(nullptr);
+    c.take<uint8_t>(cnt * k + 16);
+    c.take<int64_t>(cnt + 1);
+    c.take<int64_t>(cnt);
+    c.take<int64_t>(cnt);
+    return c.total();
+}
+// d_table: uint2[sigma^k] = half-open SA range (l, r) of every k-mer (l >= r: does not occur), computed by the
+// count kernel itself, so searches that start from the table are bit-identical to full searches.
+extern "C" int hkcsa_kmer_table_build(const void *d_blob, const hkcsa_wt_plan *h_plan, uint32_t k, void *d_table,
+                                      void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    HK_REQUIRE(h_plan && d_blob && d_table && d_scratch, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(k >= 1 && k <= 16 && h_plan->sigma >= 2, HKCSA_EINVAL, "bad k or alphabet");
+    const uint64_t cnt = hkcsa_kmer_entries(h_plan->sigma, k);
+    HK_REQUIRE(cnt <= (1ull << 22), HKCSA_EINVAL, "table too large");
+    Carver c(d_scratch);
+    uint8_t *d_pat = c.take<uint8_t>(cnt * k + 16);
+    int64_t *d_off = c.take<int64_t>(cnt + 1);
+    int64_t *d_lo = c.take<int64_t>(cnt);
+    int64_t *d_hi = c.take<int64_t>(cnt);
+    HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "k-mer scratch too small");
+    cudaStream_t st = as_stream(stream);
+    WtDev wt = make_wt_dev(d_blob, h_plan);
+    kmer_patterns_kernel<<<(uint32_t)((cnt + 256) / 256), 256, 0, st>>>(wt, k, cnt, d_pat, d_off);
+    HK_LAUNCH_CHECK();
+    int rc = hkcsa_count_batch_kmer(d_blob, h_plan, nullptr, 0, d_pat, d_off, cnt, d_lo, d_hi, stream);
+    if (rc != HKCSA_OK) return rc;
+    kmer_table_fill_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(d_lo, d_hi, cnt, static_cast<uint2 *>(d_table));
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_count_batch_kmer(const void *d_blob, const hkcsa_wt_plan *h_plan, const void *d_kmer_table,
+                                      uint32_t k, const uint8_t *d_pat, const int64_t *d_off, uint64_t P,
+                                      int64_t *d_lo, int64_t *d_hi, void *stream)
+{
     HK_REQUIRE(h_plan && d_blob, HKCSA_EINVAL, "null pointer");
     if (P == 0) return HKCSA_OK;
     HK_REQUIRE(d_off && d_lo && d_hi, HKCSA_EINVAL, "null pointer");
@@ -184,7 +283,8 @@ extern "C" int hkcsa_count_batch(const void *d_blob, const hkcsa_wt_plan *h_plan
     WtDev wt = make_wt_dev(d_blob, h_plan);
     const int blocks = (int)std::min<uint64_t>((P + COUNT_THREADS - 1) / COUNT_THREADS, (uint64_t)num_sms() * 8);
     prof::Scope ps(st, prof::COUNT, 0);
-    fm_count_kernel<<<blocks, COUNT_THREADS, 0, st>>>(wt, d_pat, d_off, P, d_lo, d_hi);
+    fm_count_kernel<<<blocks, COUNT_THREADS, 0, st>>>(wt, d_pat, d_off, P, d_lo, d_hi,
+                                                      static_cast<const uint2 *>(d_kmer_table), d_kmer_table ? k : 0u);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

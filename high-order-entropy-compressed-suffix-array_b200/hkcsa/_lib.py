@@ -126,6 +126,11 @@ SIGNATURES = {
     "hkcsa_golomb_encode": (_i32, [_vp, C.POINTER(WtPlan), _u32, _u64, _u32, _vp, _u64, C.POINTER(_u64), _vp,
                                    _sz, _vp]),
     "hkcsa_count_batch": (_i32, [_vp, C.POINTER(WtPlan), _vp, _vp, _u64, _vp, _vp, _vp]),
+    "hkcsa_kmer_k": (_u32, [_u32]),
+    "hkcsa_kmer_entries": (_u64, [_u32, _u32]),
+    "hkcsa_kmer_scratch_bytes": (_sz, [_u32, _u32]),
+    "hkcsa_kmer_table_build": (_i32, [_vp, C.POINTER(WtPlan), _u32, _vp, _vp, _sz, _vp]),
+    "hkcsa_count_batch_kmer": (_i32, [_vp, C.POINTER(WtPlan), _vp, _u32, _vp, _vp, _u64, _vp, _vp, _vp]),
     "hkcsa_ssa_plan_make": (_i32, [_u64, _u32, C.POINTER(SsaPlan)]),
     "hkcsa_ssa_build": (_i32, [_vp, C.POINTER(SsaPlan), _vp, _vp, _sz, _vp]),
     "hkcsa_ssa_plan_make_slice": (_i32, [_u64, _u32, _u64, C.POINTER(SsaPlan)]),

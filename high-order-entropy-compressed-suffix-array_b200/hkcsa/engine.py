@@ -422,15 +422,40 @@ class DeviceIndex:
             ssa = SampledSA(SsaPlan.from_buffer_copy(z["ssa_plan"].tobytes()), torch.from_numpy(z["ssa_blob"]).to(device))
         return cls.from_parts(int(z["n"][0]), plan, blob, ssa)
 
+    # k-mer jump table (query accelerator, built on first use for large batches)
+    KMER_MIN_BATCH = 1 << 18
+
+    def build_kmer_table(self):
+        """SA ranges of every k-mer over the alphabet (k = largest with sigma^k <= 2^21), computed by the count
+        kernel itself; count_batch then starts each pattern from the entry of its last k symbols."""
+        L = _lib.load()
+        k = int(L.hkcsa_kmer_k(self.wt.sigma))
+        if k == 0:
+            self._kmer = (None, 0)
+            return self._kmer
+        entries = int(L.hkcsa_kmer_entries(self.wt.sigma, k))
+        table = torch.empty(entries * 2, dtype=torch.int32, device=self.device)
+        nbytes = L.hkcsa_kmer_scratch_bytes(self.wt.sigma, k)
+        scratch = _scratch(nbytes, self.device)
+        check(L.hkcsa_kmer_table_build(_ptr(self.wt.blob), C.byref(self.wt.plan), k, _ptr(table), _ptr(scratch), nbytes,
+                                       _stream()))
+        self._kmer = (table, k)
+        return self._kmer
+
     # find_range, batched (csa/enhanced_fm_index.py:21-32)
-    def count_batch(self, pat: torch.Tensor, off: torch.Tensor):
+    def count_batch(self, pat: torch.Tensor, off: torch.Tensor, use_kmer_table: bool | None = None):
         P = off.numel() - 1
         lo = _empty(P, torch.int64, self.device)
         hi = _empty(P, torch.int64, self.device)
         if self.n == 0:
             raise ValueError("empty index")
-        check(_lib.load().hkcsa_count_batch(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(pat), _ptr(off), P,
-                                            _ptr(lo), _ptr(hi), _stream()))
+        if use_kmer_table is None:
+            use_kmer_table = getattr(self, "_kmer", None) is not None or P >= self.KMER_MIN_BATCH
+        table, k = (None, 0)
+        if use_kmer_table:
+            table, k = getattr(self, "_kmer", None) or self.build_kmer_table()
+        check(_lib.load().hkcsa_count_batch_kmer(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(table), k, _ptr(pat),
+                                                 _ptr(off), P, _ptr(lo), _ptr(hi), _stream()))
         return lo, hi
 
     # find, batched (csa/enhanced_fm_index.py:15-19): CSR (offsets, positions in SA order)

@@ -234,6 +234,19 @@ size_t hkcsa_golomb_scratch_bytes(uint64_t nbits);
 int hkcsa_count_batch(const void *d_blob, const hkcsa_wt_plan *h_plan, const uint8_t *d_pat,
                       const int64_t *d_off, uint64_t P, int64_t *d_lo, int64_t *d_hi, void *stream);
 
+/* k-mer jump table: the SA range of every k-mer over the index alphabet (k = hkcsa_kmer_k(sigma): the   */
+/* largest k with sigma^k <= 2^21), computed by the count kernel itself.  hkcsa_count_batch_kmer starts   */
+/* every pattern of length >= k from the table entry of its last k symbols and continues backwards: the   */
+/* results are identical to hkcsa_count_batch, k rank steps cheaper.  d_table: 8 bytes per entry.         */
+uint32_t hkcsa_kmer_k(uint32_t sigma);
+uint64_t hkcsa_kmer_entries(uint32_t sigma, uint32_t k);
+size_t hkcsa_kmer_scratch_bytes(uint32_t sigma, uint32_t k);
+int hkcsa_kmer_table_build(const void *d_blob, const hkcsa_wt_plan *h_plan, uint32_t k, void *d_table,
+                           void *d_scratch, size_t scratch_bytes, void *stream);
+int hkcsa_count_batch_kmer(const void *d_blob, const hkcsa_wt_plan *h_plan, const void *d_kmer_table, uint32_t k,
+                           const uint8_t *d_pat, const int64_t *d_off, uint64_t P, int64_t *d_lo, int64_t *d_hi,
+                           void *stream);
+
 /* Sampled suffix array for locate: marks rows with SA[j] % rate == 0 (a rank   */
 /* bit-vector in the block format above) and stores SA[j] / rate for them.      */
 typedef struct hkcsa_ssa_plan {

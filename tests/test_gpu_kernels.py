@@ -456,3 +456,23 @@ def test_property_random_small_texts(E):
         assert host(p).tolist() == ([] if l < 0 else sa2[l:r + 1].tolist())
 
     check()
+
+
+@pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "rand2_100k", "runs", "rand256_50k", "all_a_5000"])
+def test_kmer_jump_table_gives_identical_ranges(E, name):
+    import torch
+    text = TEXTS[name] + b"$"
+    idx = E.DeviceIndex(dev(E, text))
+    base = np.frombuffer(TEXTS[name], dtype=np.uint8)
+    pats, off = O.gen_patterns(21, 4000, base, 1, 40)
+    extra = [b"", b"\x01", b"$", text[-3:], text[:25], b"\x01" + text[:12], text[:12] + b"\x01"]
+    pats = np.concatenate([pats, np.frombuffer(b"".join(extra), dtype=np.uint8)])
+    off = np.concatenate([off, off[-1] + np.cumsum([len(e) for e in extra])])
+    d_p, d_o = torch.from_numpy(pats).cuda(), torch.from_numpy(off).cuda()
+    a = idx.count_batch(d_p, d_o, use_kmer_table=False)
+    b = idx.count_batch(d_p, d_o, use_kmer_table=True)
+    assert idx._kmer is not None
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    fm = O.FM(O.bwt_transform(text, O.build_suffix_array(text)))
+    w_lo, w_hi = fm.find_range_batch(pats, off)
+    assert np.array_equal(host(b[0]), w_lo) and np.array_equal(host(b[1]), w_hi)
