@@ -43,7 +43,7 @@ static int g_created = 0;
 static int g_used = 0;
 static const char *g_names[NUM_CLASSES] = {
     "byte_hist", "sa_pack0", "sa_keybuild", "radix_scan", "onesweep_u64", "seg_reduce", "seg_scan",
-    "seg_apply", "bwt_gather", "wt_partition", "wt_pack", "wt_dir", "count", "locate", "ssa_build", "other"};
+    "seg_apply", "bwt_gather", "wt_levels", "wt_pack", "wt_dir", "count", "locate", "ssa_build", "other"};
 
 bool enabled() { return g_on; }
 

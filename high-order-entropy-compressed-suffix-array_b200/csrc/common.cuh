@@ -113,20 +113,6 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v)
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Streaming (evict-first) accesses for data touched once per pass.
-__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p)
-{
-    uint64_t v;
-    asm volatile("ld.global.cs.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
 // Exclusive warp scan (sum) of one uint32 per lane.
 __device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t &total)
 {

@@ -11,10 +11,6 @@
 
 namespace hkcsa {
 
-int build_bitvector(const uint8_t *d_sym, uint64_t len, const uint8_t *d_lut_bit, RankBlock *d_blocks,
-                    uint64_t *d_super, uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones,
-                    cudaStream_t st);
-
 int build_markvector(const uint32_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
                      uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st);
 
@@ -122,12 +118,6 @@ __global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32
     if (q < m) out[q] = src[rows[q]];
 }
 
-// flag[j] = (SA[j] % rate == 0)
-__global__ void ssa_mark_kernel(const uint32_t *__restrict__ sa, uint64_t n, uint32_t rate, uint8_t *__restrict__ flag)
-{
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) flag[j] = (sa[j] % rate == 0) ? 1 : 0;
-}
 // samples[rank1(marks, j)] = SA[j] / rate for marked rows
 __global__ void ssa_fill_kernel(const uint32_t *__restrict__ sa, uint64_t n, uint32_t rate, BitVec marks,
                                 uint32_t *__restrict__ samples)
@@ -188,11 +178,6 @@ __global__ void kmer_table_fill_kernel(const int64_t *__restrict__ lo, const int
     if (id >= count) return;
     const int64_t l = lo[id], h = hi[id];
     table[id] = (l < 0) ? make_uint2(0u, 0u) : make_uint2((uint32_t)l, (uint32_t)(h + 1));
-}
-
-__global__ void identity_lut_kernel(uint8_t *lut)
-{
-    lut[threadIdx.x] = (uint8_t)(threadIdx.x & 1u);
 }
 
 __global__ void symbol_lut_kernel(uint8_t *lut, uint32_t *base, const uint64_t *__restrict__ hist, uint64_t *start)
@@ -306,13 +291,11 @@ extern "C" int hkcsa_ssa_plan_make(uint64_t n, uint32_t rate, hkcsa_ssa_plan *p)
     off = align_up(off + (p->n_samples + 1) * sizeof(uint32_t), 256);
     p->blob_bytes = off;
     Carver c(nullptr);
-    c.take<uint8_t>(n + 16);
     const uint64_t tiles = rank_blocks_for(n) / 64 + 2;
     c.take<uint32_t>(tiles);
     c.take<uint64_t>(tiles);
     c.take<uint64_t>(8);
     c.take<uint32_t>(select_samples_for(n));
-    c.take<uint8_t>(256);
     p->scratch_bytes = c.total();
     return HKCSA_OK;
 }
@@ -338,17 +321,14 @@ extern "C" int hkcsa_ssa_build(const uint32_t *d_sa, const hkcsa_ssa_plan *p, vo
     const uint64_t n = p->n;
     if (n == 0) return HKCSA_OK;
     Carver c(d_scratch);
-    uint8_t *d_flag = c.take<uint8_t>(n + 16);
     const uint64_t tiles = rank_blocks_for(n) / 64 + 2;
     uint32_t *d_agg = c.take<uint32_t>(tiles);
     uint64_t *d_carry = c.take<uint64_t>(tiles);
     uint64_t *d_ones = c.take<uint64_t>(8);
     uint32_t *d_sel = c.take<uint32_t>(select_samples_for(n));
-    uint8_t *d_lut = c.take<uint8_t>(256);
     uint8_t *blob = static_cast<uint8_t *>(d_blob);
     prof::Scope ps(st, prof::SSA_BUILD, n * 10);
     const uint32_t grid = (uint32_t)((n + 255) / 256);
-    (void)d_flag; (void)d_lut;
     BitVec marks;
     marks.blocks = reinterpret_cast<const RankBlock *>(blob + p->off_blocks);
     marks.super = reinterpret_cast<const uint64_t *>(blob + p->off_super);

@@ -11,7 +11,7 @@ namespace prof {
 
 enum Class {
     BYTE_HIST = 0, SA_PACK0, SA_KEYBUILD, RADIX_SCAN, ONESWEEP_U64, SEG_REDUCE, SEG_SCAN, SEG_APPLY,
-    BWT_GATHER, WT_PARTITION, WT_PACK, WT_DIR, COUNT, LOCATE, SSA_BUILD, OTHER, NUM_CLASSES
+    BWT_GATHER, WT_LEVELS, WT_PACK, WT_DIR, COUNT, LOCATE, SSA_BUILD, OTHER, NUM_CLASSES
 };
 constexpr int MAX_RECORDS = 16384;
 

@@ -21,8 +21,6 @@ constexpr uint32_t LB_AGG = 1u << 30;   // tile aggregate available
 constexpr uint32_t LB_INC = 2u << 30;   // inclusive prefix available
 constexpr uint32_t LB_VAL = (1u << 30) - 1u;
 
-constexpr int SORT64_THREADS = 256;
-constexpr int SORT64_IPT = 16;
 constexpr int SORT64_TILE = 2048;   // smallest (uint64, uint32) tile of any onesweep64 variant: sizes the look-back table
 
 constexpr int SORT8_THREADS = 256;

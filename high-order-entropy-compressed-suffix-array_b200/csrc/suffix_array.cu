@@ -600,7 +600,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     lz.shift = bits0 - bucket_bits;
     uint64_t *kx = nullptr, *ky = nullptr;             // key ping-pong of the later rounds
     uint32_t *vfree = B.val[1];                        // free value buffer (receives the compacted ids)
-    uint32_t *vother = (passes0 % 2 == 0) ? B.val[0] : B.val[0];
+    uint32_t *vother = B.val[0];                       // the round-0 sort's other value buffer: free from here on
 
     while (true) {
         // ---- refine ranks from the sorted keys

@@ -689,16 +689,10 @@ extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_bl
     memcpy(T.sym_of_code, p->sym_of_code, sizeof(T.sym_of_code));
     memcpy(T.depth, p->depth, sizeof(T.depth));
     for (uint32_t c = 0; c <= p->sigma && c < 260; ++c) T.C[c] = (uint32_t)p->C[c];
-    memset(T.lut_node, 0xFF, sizeof(T.lut_node));
     for (uint32_t l = 0; l < p->levels; ++l) {
         for (uint32_t c = 0; c < p->sigma; ++c) {
             T.node_start[l][c] = p->node_start[l][c] | (p->node_bit[l][c] ? NODE_BIT_FLAG : 0u);
-            const uint8_t ch = p->sym_of_code[c];
-            T.lut_node[l][ch] = p->node_id[l][c];
-            T.lut_bit[l][ch] = p->node_bit[l][c];
-            if (p->node_id[l][c] != 0xFF) T.bucket_base[l][p->node_id[l][c]] = p->node_start[l][c];
         }
-        T.bucket_base[l][255] = (uint32_t)p->level_len[l];
         // node extents: per code and per node
         uint32_t lo_of[256], hi_of[256];
         for (uint32_t k = 0; k < 256; ++k) { lo_of[k] = 0xFFFFFFFFu; hi_of[k] = 0; }
@@ -740,7 +734,7 @@ extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_bl
     LevelWords lw;
     for (uint32_t l = 0; l < HKCSA_MAX_LEVELS; ++l) lw.w[l] = reinterpret_cast<uint32_t *>(blob + p->off_blocks[l]);
     {
-        prof::Scope ps(st, prof::WT_PARTITION, n + (uint64_t)p->levels * (n / 8));
+        prof::Scope ps(st, prof::WT_LEVELS, n + (uint64_t)p->levels * (n / 8));
         wt_tile_hist_kernel<<<wtiles, WTL_THREADS, 0, st>>>(d_sym, n, d_tab, p->sigma, wtiles, d_gcnt);
         HK_LAUNCH_CHECK();
         wt_tile_scan_kernel<<<p->sigma, 1024, 0, st>>>(d_gcnt, wtiles);

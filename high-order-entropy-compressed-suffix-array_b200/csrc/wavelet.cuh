@@ -16,9 +16,6 @@ struct WtTables {
     uint32_t C[260];                            // C[code] (+ total at [sigma])
     uint32_t node_start[HKCSA_MAX_LEVELS][256]; // per (level, code): start of the code's node | bit << 31
     uint32_t node_ones[HKCSA_MAX_LEVELS][256];  // rank1(level, node start)
-    uint8_t lut_node[HKCSA_MAX_LEVELS][256];    // byte -> node id at level (0xFF: not present)
-    uint8_t lut_bit[HKCSA_MAX_LEVELS][256];     // byte -> bit at level
-    uint32_t bucket_base[HKCSA_MAX_LEVELS][256];// node id -> start offset; [255] = level length
     // build-time tables (wt_levels_kernel)
     uint8_t code8_of_sym[256];                  // byte -> dense code (present symbols only)
     uint8_t node_lo[HKCSA_MAX_LEVELS][256];     // per (level, code): first code of the code's node

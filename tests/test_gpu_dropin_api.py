@@ -258,3 +258,19 @@ def test_high_order_entropy_matches_reference_formula():
             assert got == pytest.approx(want, rel=1e-9, abs=1e-12), (t[:12], k)
     assert calculate_high_order_entropy("", 2) == 0 and calculate_high_order_entropy("abc", -1) == 0
     assert calculate_high_order_entropy("abc", 5) == 0
+
+
+def test_main_demo_matches_reference_output(capsys):
+    """python main.py of the reference prints the whole suffix array for 'example' (its backward search is
+    degenerate) and three Golomb lists of lengths 26 / 10 / 11."""
+    import importlib.util
+    import os
+    from conftest import PKG
+    spec = importlib.util.spec_from_file_location("hk_main", os.path.join(PKG, "main.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
+    out = capsys.readouterr().out
+    assert "Pattern 'example' found at indices: [7, 10, 4, 18, 13, 8, 17, 11, 20, 1, 5, 2, 16, 14, 9, 15, 6, 3, 22, 19, 0, 12, 21]" in out
+    lists = eval(out.split("Wavelet Tree Compression: ")[1])
+    assert [len(x) for x in lists] == [26, 10, 11]
