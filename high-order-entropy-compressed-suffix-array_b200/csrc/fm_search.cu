@@ -13,6 +13,8 @@ namespace hkcsa {
 
 int build_markvector(const uint32_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
                      uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st);
+int build_markvector64(const uint64_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
+                       uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st);
 
 constexpr int COUNT_THREADS = 256;
 
@@ -111,6 +113,20 @@ __global__ void expand_ranges_kernel(const int64_t *__restrict__ lo, const int64
     }
 }
 
+// 64-bit rows for indexes beyond 2^32 rows
+__global__ void expand_ranges64_kernel(const int64_t *__restrict__ lo, const int64_t *__restrict__ hi,
+                                       const int64_t *__restrict__ out_off, uint64_t P, uint64_t *__restrict__ rows)
+{
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = lane_id();
+    for (uint64_t p = warp; p < P; p += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
+        const int64_t l = lo[p], h = hi[p];
+        if (l < 0) continue;
+        const int64_t o = out_off[p];
+        for (int64_t k = lane; k <= h - l; k += 32) rows[o + k] = (uint64_t)(l + k);
+    }
+}
+
 __global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ rows, uint64_t m,
                                   uint32_t *__restrict__ out)
 {
@@ -119,13 +135,14 @@ __global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32
 }
 
 // samples[rank1(marks, j)] = SA[j] / rate for marked rows
-__global__ void ssa_fill_kernel(const uint32_t *__restrict__ sa, uint64_t n, uint32_t rate, BitVec marks,
+template <typename IdT>
+__global__ void ssa_fill_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, BitVec marks,
                                 uint32_t *__restrict__ samples)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    const uint32_t v = sa[j];
-    if (v % rate == 0) samples[bv_rank(marks, j)] = v / rate;
+    const IdT v = sa[j];
+    if (v % rate == 0) samples[bv_rank(marks, j)] = (uint32_t)(v / rate);
 }
 
 // position of row j: walk LF until a marked row, pos = sample * rate + steps.
@@ -311,8 +328,9 @@ extern "C" int hkcsa_ssa_plan_make_slice(uint64_t m, uint32_t rate, uint64_t n_m
     return HKCSA_OK;
 }
 
-extern "C" int hkcsa_ssa_build(const uint32_t *d_sa, const hkcsa_ssa_plan *p, void *d_blob, void *d_scratch,
-                               size_t scratch_bytes, void *stream)
+template <typename IdT>
+static int ssa_build_t(const IdT *d_sa, const hkcsa_ssa_plan *p, void *d_blob, void *d_scratch, size_t scratch_bytes,
+                       void *stream)
 {
     HK_REQUIRE(p && d_blob && d_scratch && (d_sa || p->n == 0), HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(p->scratch_bytes <= scratch_bytes, HKCSA_ESCRATCH, "sampled-SA scratch too small");
@@ -333,12 +351,28 @@ extern "C" int hkcsa_ssa_build(const uint32_t *d_sa, const hkcsa_ssa_plan *p, vo
     marks.blocks = reinterpret_cast<const RankBlock *>(blob + p->off_blocks);
     marks.super = reinterpret_cast<const uint64_t *>(blob + p->off_super);
     marks.len = n;
-    int rc = build_markvector(d_sa, n, p->rate, reinterpret_cast<RankBlock *>(blob + p->off_blocks),
-                              reinterpret_cast<uint64_t *>(blob + p->off_super), d_sel, d_agg, d_carry, d_ones, st);
+    RankBlock *blocks = reinterpret_cast<RankBlock *>(blob + p->off_blocks);
+    uint64_t *super = reinterpret_cast<uint64_t *>(blob + p->off_super);
+    int rc;
+    if constexpr (sizeof(IdT) == 8) rc = build_markvector64(d_sa, n, p->rate, blocks, super, d_sel, d_agg, d_carry, d_ones, st);
+    else rc = build_markvector(d_sa, n, p->rate, blocks, super, d_sel, d_agg, d_carry, d_ones, st);
     if (rc != HKCSA_OK) return rc;
-    ssa_fill_kernel<<<grid, 256, 0, st>>>(d_sa, n, p->rate, marks, reinterpret_cast<uint32_t *>(blob + p->off_samples));
+    ssa_fill_kernel<IdT><<<grid, 256, 0, st>>>(d_sa, n, p->rate, marks, reinterpret_cast<uint32_t *>(blob + p->off_samples));
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
+}
+
+extern "C" int hkcsa_ssa_build(const uint32_t *d_sa, const hkcsa_ssa_plan *p, void *d_blob, void *d_scratch,
+                               size_t scratch_bytes, void *stream)
+{
+    return ssa_build_t<uint32_t>(d_sa, p, d_blob, d_scratch, scratch_bytes, stream);
+}
+
+// suffix ids as uint64 (slices of a text beyond 4 GB); samples stay uint32 (id / rate must fit)
+extern "C" int hkcsa_ssa_build64(const uint64_t *d_sa, const hkcsa_ssa_plan *p, void *d_blob, void *d_scratch,
+                                 size_t scratch_bytes, void *stream)
+{
+    return ssa_build_t<uint64_t>(d_sa, p, d_blob, d_scratch, scratch_bytes, stream);
 }
 
 extern "C" int hkcsa_expand_ranges(const int64_t *d_lo, const int64_t *d_hi, const int64_t *d_out_off, uint64_t P,
@@ -348,6 +382,17 @@ extern "C" int hkcsa_expand_ranges(const int64_t *d_lo, const int64_t *d_hi, con
     HK_REQUIRE(d_lo && d_hi && d_out_off, HKCSA_EINVAL, "null pointer");
     const int blocks = (int)std::min<uint64_t>((P * 32 + 255) / 256, (uint64_t)num_sms() * 16);
     expand_ranges_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_lo, d_hi, d_out_off, P, d_rows);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_expand_ranges64(const int64_t *d_lo, const int64_t *d_hi, const int64_t *d_out_off, uint64_t P,
+                                     uint64_t *d_rows, void *stream)
+{
+    if (P == 0) return HKCSA_OK;
+    HK_REQUIRE(d_lo && d_hi && d_out_off, HKCSA_EINVAL, "null pointer");
+    const int blocks = (int)std::min<uint64_t>((P * 32 + 255) / 256, (uint64_t)num_sms() * 16);
+    expand_ranges64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_lo, d_hi, d_out_off, P, d_rows);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

@@ -15,8 +15,8 @@ struct MultiDesc {
     BitVec marks[HKCSA_MAX_SLICES];
     const uint32_t *samples[HKCSA_MAX_SLICES];
     uint64_t start[HKCSA_MAX_SLICES + 1];
-    uint32_t cum[HKCSA_MAX_SLICES + 1][256];   // occurrences of byte c in slices < s  ([S] = total)
-    uint32_t C[256];                           // symbols of the whole text smaller than byte c
+    uint64_t cum[HKCSA_MAX_SLICES + 1][256];   // occurrences of byte c in slices < s  ([S] = total)
+    uint64_t C[256];                           // symbols of the whole text smaller than byte c
     uint32_t S;
     uint32_t rate;                             // 0 = no sampled SA
     uint64_t n;
@@ -44,7 +44,7 @@ __device__ __forceinline__ uint32_t ms_rank_local(const WtDev &w, uint32_t code,
 }
 
 // occurrences of `byte` in global rows [0, i)
-__device__ __forceinline__ uint32_t ms_rank(const MultiDesc *d, uint32_t byte, uint64_t i)
+__device__ __forceinline__ uint64_t ms_rank(const MultiDesc *d, uint32_t byte, uint64_t i)
 {
     const uint32_t s = ms_slice_of(d, i);
     const WtDev &w = d->slice[s];
@@ -69,8 +69,8 @@ ms_count_kernel(const MultiDesc *__restrict__ d, const uint8_t *__restrict__ pat
     for (int64_t k = e - 1; k >= b; --k) {
         const uint32_t c = pat[k];
         if (d->cum[d->S][c] == 0) { miss = true; break; }       // symbol absent from the text
-        l = (uint64_t)d->C[c] + ms_rank(d, c, l);
-        r = (uint64_t)d->C[c] + ms_rank(d, c, r);
+        l = d->C[c] + ms_rank(d, c, l);
+        r = d->C[c] + ms_rank(d, c, r);
         if (l >= r) { miss = true; break; }
     }
     out_lo[p] = miss ? -1 : (int64_t)l;
@@ -101,8 +101,8 @@ __device__ __forceinline__ uint32_t ms_access_rank(const WtDev &w, uint32_t i, u
 
 // text position of global row j: LF walk across slices until a marked row
 __global__ void __launch_bounds__(256)
-ms_locate_kernel(const MultiDesc *__restrict__ d, const uint32_t *__restrict__ rows, uint64_t m,
-                 uint32_t *__restrict__ out)
+ms_locate_kernel(const MultiDesc *__restrict__ d, const uint64_t *__restrict__ rows, uint64_t m,
+                 uint64_t *__restrict__ out)
 {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= m) return;
@@ -117,14 +117,14 @@ ms_locate_kernel(const MultiDesc *__restrict__ d, const uint32_t *__restrict__ r
         const RankBlock b = load_block(mk.blocks + g);
         if (block_bit(b, o)) {
             const uint64_t r = mk.super[g / HKCSA_SUPER_BLOCKS] + (uint32_t)(b.w[0] & 0xFFFFFFFFu) + block_rank(b, o);
-            out[q] = d->samples[s][r] * d->rate + steps;
+            out[q] = (uint64_t)d->samples[s][r] * d->rate + steps;
             return;
         }
         const WtDev &w = d->slice[s];
         uint32_t occ;
         const uint32_t code = ms_access_rank(w, lj, occ);
         const uint32_t byte = w.tab->sym_of_code[code];
-        j = (uint64_t)d->C[byte] + d->cum[s][byte] + occ;
+        j = d->C[byte] + d->cum[s][byte] + occ;
         ++steps;
     }
 }
@@ -147,7 +147,7 @@ extern "C" int hkcsa_multi_desc_build(uint32_t S, const void *const *d_wt_blobs,
     memset(&D, 0, sizeof(D));
     D.S = S;
     D.n = h_starts[S];
-    HK_REQUIRE(D.n <= 0xFFFFFFFEull, HKCSA_ERANGE, "n exceeds 2^32-2");
+    HK_REQUIRE(D.n <= (1ull << 40), HKCSA_ERANGE, "n exceeds 2^40");
     uint64_t tot[256];
     memset(tot, 0, sizeof(tot));
     for (uint32_t s = 0; s < S; ++s) {
@@ -155,7 +155,7 @@ extern "C" int hkcsa_multi_desc_build(uint32_t S, const void *const *d_wt_blobs,
         HK_REQUIRE(h_plans[s]->n == h_starts[s + 1] - h_starts[s], HKCSA_EINVAL, "slice length != plan length");
         D.slice[s] = make_wt_dev(d_wt_blobs[s], h_plans[s]);
         D.start[s] = h_starts[s];
-        for (int c = 0; c < 256; ++c) D.cum[s][c] = (uint32_t)tot[c];
+        for (int c = 0; c < 256; ++c) D.cum[s][c] = tot[c];
         for (uint32_t k = 0; k < h_plans[s]->sigma; ++k) tot[h_plans[s]->sym_of_code[k]] += h_plans[s]->cnt[k];
         if (d_ssa_blobs && h_ssa_plans && d_ssa_blobs[s] && h_ssa_plans[s]) {
             const uint8_t *sb = static_cast<const uint8_t *>(d_ssa_blobs[s]);
@@ -169,8 +169,8 @@ extern "C" int hkcsa_multi_desc_build(uint32_t S, const void *const *d_wt_blobs,
     D.start[S] = h_starts[S];
     uint64_t run = 0;
     for (int c = 0; c < 256; ++c) {
-        D.cum[S][c] = (uint32_t)tot[c];
-        D.C[c] = (uint32_t)run;
+        D.cum[S][c] = tot[c];
+        D.C[c] = run;
         run += tot[c];
     }
     HK_REQUIRE(run == D.n, HKCSA_EINVAL, "slice symbol counts do not add up to n");
@@ -193,7 +193,7 @@ extern "C" int hkcsa_multi_count_batch(const void *d_desc, const uint8_t *d_pat,
     return HKCSA_OK;
 }
 
-extern "C" int hkcsa_multi_locate_rows(const void *d_desc, const uint32_t *d_rows, uint64_t m, uint32_t *d_out_pos,
+extern "C" int hkcsa_multi_locate_rows(const void *d_desc, const uint64_t *d_rows, uint64_t m, uint64_t *d_out_pos,
                                        void *stream)
 {
     if (m == 0) return HKCSA_OK;

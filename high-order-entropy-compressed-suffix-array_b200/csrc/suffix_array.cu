@@ -739,8 +739,8 @@ dsa_key_hist_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin
 __global__ void __launch_bounds__(PACK_THREADS)
 dsa_select_kernel(const uint8_t *__restrict__ text, uint64_t n, CodeMap map, int b, int k0, int shift,
                   uint32_t bucket_lo, uint32_t bucket_hi, int passes, uint64_t *__restrict__ keys,
-                  uint32_t *__restrict__ idx, uint32_t capacity, uint32_t *__restrict__ counter,
-                  uint32_t *__restrict__ ghist)
+                  uint32_t *__restrict__ idx, uint64_t *__restrict__ ids64 /* wide ids: idx holds ordinals */,
+                  uint32_t capacity, uint32_t *__restrict__ counter, uint32_t *__restrict__ ghist)
 {
     __shared__ uint16_t s_code[256];
     __shared__ uint16_t s_sym[PACK_TILE + 64];
@@ -771,7 +771,8 @@ dsa_select_kernel(const uint8_t *__restrict__ text, uint64_t n, CodeMap map, int
         const bool store = keep && slot < capacity;
         if (store) {
             keys[slot] = key;
-            idx[slot] = (uint32_t)g;
+            if (ids64) { ids64[slot] = g; idx[slot] = slot; }
+            else idx[slot] = (uint32_t)g;
         }
         hist_add_key(s_hist, key, passes, store);
     }
@@ -783,7 +784,8 @@ dsa_select_kernel(const uint8_t *__restrict__ text, uint64_t n, CodeMap map, int
 __global__ void __launch_bounds__(256)
 dsa_keybuild_ext_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp,
                         const uint8_t *__restrict__ text, uint64_t n, uint64_t depth, int b, int ke, int eb,
-                        uint32_t m, int passes, CodeMap map, uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist)
+                        uint32_t m, int passes, CodeMap map, uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist,
+                        const uint64_t *__restrict__ ids64)
 {
     __shared__ uint32_t s_hist[8 * RADIX];
     __shared__ uint16_t s_code[256];
@@ -795,7 +797,7 @@ dsa_keybuild_ext_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__res
         const bool valid = j < m;
         uint64_t key = 0;
         if (valid) {
-            const uint64_t g = (uint64_t)cidx[j] + depth;
+            const uint64_t g = (ids64 ? ids64[cidx[j]] : (uint64_t)cidx[j]) + depth;
             key = ((uint64_t)cgrp[j] << eb) | pack_from_text(text, n, g, s_code, b, ke);
             keys[j] = key;
         }
@@ -805,13 +807,21 @@ dsa_keybuild_ext_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__res
     hist_flush(s_hist, ghist, passes);
 }
 
-__global__ void bwt_slice_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint32_t *__restrict__ sa,
+template <typename IdT>
+__global__ void bwt_slice_kernel(const uint8_t *__restrict__ text, uint64_t n, const IdT *__restrict__ sa,
                                  uint64_t m, uint8_t *__restrict__ out)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
-    const uint32_t v = sa[j];
-    out[j] = text[v ? (uint64_t)v - 1 : n - 1];
+    const uint64_t v = sa[j];
+    out[j] = text[v ? v - 1 : n - 1];
+}
+
+__global__ void gather_ids64_kernel(const uint64_t *__restrict__ ids64, const uint32_t *__restrict__ ord, uint64_t m,
+                                    uint64_t *__restrict__ out)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) out[j] = ids64[ord[j]];
 }
 
 static int dsa_code_map(const uint64_t *h_byte_hist, CodeMap &map, int &b, int &k0, int &bits0, uint32_t &sigma)
@@ -835,7 +845,7 @@ extern "C" int hkcsa_sa_key_hist(const uint8_t *d_text, uint64_t n, uint64_t beg
                                  const uint64_t *h_byte_hist, uint64_t *d_hist, void *stream)
 {
     HK_REQUIRE(d_text && h_byte_hist && d_hist, HKCSA_EINVAL, "null pointer");
-    HK_REQUIRE(n <= HKCSA_DIST_MAX_N && begin <= end && end <= n, HKCSA_ERANGE, "range");
+    HK_REQUIRE(n <= (1ull << 40) && begin <= end && end <= n, HKCSA_ERANGE, "range");
     cudaStream_t st = as_stream(stream);
     CodeMap map; int b, k0, bits0; uint32_t sigma;
     dsa_code_map(h_byte_hist, map, b, k0, bits0, sigma);
@@ -885,10 +895,12 @@ extern "C" size_t hkcsa_sa_subset_scratch_bytes(uint64_t m)
     return c.total();
 }
 
-extern "C" int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist,
-                                     uint32_t bucket_lo, uint32_t bucket_hi, uint32_t *d_sa_out, uint64_t capacity,
-                                     uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
-                                     hkcsa_sa_stats *h_stats)
+// d_ids64 == nullptr: d_sa_out receives the suffix ids (n <= 2^32-2).  Otherwise (wide ids, n up to 2^40) the
+// sort moves 32-bit ordinals into d_sa_out and the 64-bit ids stay in d_ids64[ordinal].
+static int sa_build_subset_impl(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist, uint32_t bucket_lo,
+                                uint32_t bucket_hi, uint32_t *d_sa_out, uint64_t *d_ids64, uint64_t capacity,
+                                uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
+                                hkcsa_sa_stats *h_stats)
 {
     hkcsa_sa_stats stats;
     memset(&stats, 0, sizeof(stats));
@@ -896,7 +908,8 @@ extern "C" int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const ui
     HK_REQUIRE(h_count != nullptr, HKCSA_EINVAL, "null pointer");
     *h_count = 0;
     if (n == 0 || capacity == 0 || bucket_lo >= bucket_hi) return HKCSA_OK;
-    HK_REQUIRE(n <= HKCSA_DIST_MAX_N, HKCSA_ERANGE, "n exceeds 2^32-2");
+    HK_REQUIRE(d_ids64 != nullptr || n <= HKCSA_DIST_MAX_N, HKCSA_ERANGE, "n exceeds 2^32-2: use the 64-bit entry point");
+    HK_REQUIRE(n <= (1ull << 40), HKCSA_ERANGE, "n exceeds 2^40");
     HK_REQUIRE(capacity <= HKCSA_MAX_N, HKCSA_ERANGE, "slice exceeds HKCSA_MAX_N");
     HK_REQUIRE(d_text && h_byte_hist && d_sa_out && d_scratch, HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(((reinterpret_cast<uintptr_t>(d_sa_out) | reinterpret_cast<uintptr_t>(d_scratch)) & 15) == 0,
@@ -924,7 +937,7 @@ extern "C" int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const ui
         const uint64_t blocks = (n + PACK_TILE - 1) / PACK_TILE;
         prof::Scope ps(st, prof::SA_PACK0, n);
         dsa_select_kernel<<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, n, map, b, k0, bits0 - DSA_BUCKET_BITS,
-                                                                     bucket_lo, bucket_hi, passes0, ka, va,
+                                                                     bucket_lo, bucket_hi, passes0, ka, va, d_ids64,
                                                                      (uint32_t)capacity, B.counter, B.sort.hist);
         HK_LAUNCH_CHECK();
     }
@@ -978,7 +991,7 @@ extern "C" int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const ui
         {
             const int blocks = (int)std::min<uint64_t>(((uint64_t)m + 255) / 256, (uint64_t)num_sms() * 16);
             dsa_keybuild_ext_kernel<<<blocks, 256, 0, st>>>(vx, B.grp, d_text, n, depth, b, ke, eb, m, passes, map, kx,
-                                                            B.sort.hist);
+                                                            B.sort.hist, d_ids64);
             HK_LAUNCH_CHECK();
         }
         HK_CUDA(radix_sort_pairs_u64(kx, vx, ky, vy, m, passes, B.sort, st));
@@ -995,13 +1008,68 @@ extern "C" int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const ui
     return HKCSA_OK;
 }
 
+extern "C" int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist,
+                                     uint32_t bucket_lo, uint32_t bucket_hi, uint32_t *d_sa_out, uint64_t capacity,
+                                     uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
+                                     hkcsa_sa_stats *h_stats)
+{
+    return sa_build_subset_impl(d_text, n, h_byte_hist, bucket_lo, bucket_hi, d_sa_out, nullptr, capacity, h_count,
+                                d_scratch, scratch_bytes, stream, h_stats);
+}
+
+// 64-bit suffix ids (texts beyond 4 GB): same sort on 32-bit ordinals, ids gathered at the end.
+extern "C" size_t hkcsa_sa_subset64_scratch_bytes(uint64_t m)
+{
+    Carver c(nullptr);
+    carve_subset(c, m ? m : 1);
+    c.take<uint64_t>(m ? m : 1);
+    c.take<uint32_t>(m ? m : 1);
+    return c.total();
+}
+
+extern "C" int hkcsa_sa_build_subset64(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist,
+                                       uint32_t bucket_lo, uint32_t bucket_hi, uint64_t *d_sa_out64, uint64_t capacity,
+                                       uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
+                                       hkcsa_sa_stats *h_stats)
+{
+    HK_REQUIRE(h_count != nullptr, HKCSA_EINVAL, "null pointer");
+    *h_count = 0;
+    if (n == 0 || capacity == 0 || bucket_lo >= bucket_hi) return HKCSA_OK;
+    HK_REQUIRE(d_sa_out64 && d_scratch, HKCSA_EINVAL, "null pointer");
+    Carver c(d_scratch);
+    carve_subset(c, capacity);
+    const size_t inner = c.total();
+    uint64_t *d_ids64 = c.take<uint64_t>(capacity);
+    uint32_t *d_ord = c.take<uint32_t>(capacity);
+    HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "subset scratch too small");
+    int rc = sa_build_subset_impl(d_text, n, h_byte_hist, bucket_lo, bucket_hi, d_ord, d_ids64, capacity, h_count,
+                                  d_scratch, inner, stream, h_stats);
+    if (rc != HKCSA_OK) return rc;
+    const uint64_t m = *h_count;
+    if (m) {
+        gather_ids64_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, as_stream(stream)>>>(d_ids64, d_ord, m, d_sa_out64);
+        HK_LAUNCH_CHECK();
+    }
+    return HKCSA_OK;
+}
+
 extern "C" int hkcsa_bwt_slice(const uint8_t *d_text, uint64_t n, const uint32_t *d_sa_slice, uint64_t m,
                                uint8_t *d_out, void *stream)
 {
     if (m == 0) return HKCSA_OK;
     HK_REQUIRE(d_text && d_sa_slice && d_out, HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(n <= HKCSA_DIST_MAX_N, HKCSA_ERANGE, "n exceeds 2^32-2");
-    bwt_slice_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, as_stream(stream)>>>(d_text, n, d_sa_slice, m, d_out);
+    bwt_slice_kernel<uint32_t><<<(uint32_t)((m + 255) / 256), 256, 0, as_stream(stream)>>>(d_text, n, d_sa_slice, m, d_out);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_bwt_slice64(const uint8_t *d_text, uint64_t n, const uint64_t *d_sa_slice, uint64_t m,
+                                 uint8_t *d_out, void *stream)
+{
+    if (m == 0) return HKCSA_OK;
+    HK_REQUIRE(d_text && d_sa_slice && d_out, HKCSA_EINVAL, "null pointer");
+    bwt_slice_kernel<uint64_t><<<(uint32_t)((m + 255) / 256), 256, 0, as_stream(stream)>>>(d_text, n, d_sa_slice, m, d_out);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

@@ -616,8 +616,9 @@ int build_bitvector(const uint8_t *d_sym, uint64_t len, const uint8_t *d_lut_bit
 // Mark bit-vector of the sampled suffix array, bit j = (SA[j] % rate == 0), packed straight from the suffix
 // array with warp ballots (no byte flags in between) + its directory.
 namespace hkcsa {
+template <typename IdT>
 __global__ void __launch_bounds__(WTP_THREADS)
-ssa_mark_pack_kernel(const uint32_t *__restrict__ sa, uint64_t n, uint32_t rate, RankBlock *__restrict__ blocks,
+ssa_mark_pack_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, RankBlock *__restrict__ blocks,
                      uint64_t nblocks, uint32_t *__restrict__ agg)
 {
     __shared__ uint32_t s_words[WTP_BLOCKS_PER_CTA * 7];
@@ -656,13 +657,14 @@ ssa_mark_pack_kernel(const uint32_t *__restrict__ sa, uint64_t n, uint32_t rate,
     }
 }
 
-int build_markvector(const uint32_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
-                     uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st)
+template <typename IdT>
+static int build_markvector_t(const IdT *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
+                              uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st)
 {
     static_assert(WTP_SYMS % WTP_THREADS == 0 && WTP_THREADS % 32 == 0, "tile shape");
     const uint64_t nblocks = rank_blocks_for(n);
     const uint64_t tiles = (nblocks + WTP_BLOCKS_PER_CTA - 1) / WTP_BLOCKS_PER_CTA;
-    ssa_mark_pack_kernel<<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg);
+    ssa_mark_pack_kernel<IdT><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg);
     HK_LAUNCH_CHECK();
     wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones);
     HK_LAUNCH_CHECK();
@@ -670,6 +672,16 @@ int build_markvector(const uint32_t *d_sa, uint64_t n, uint32_t rate, RankBlock 
                                                                          WTP_BLOCKS_PER_CTA);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
+}
+int build_markvector(const uint32_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
+                     uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st)
+{
+    return build_markvector_t<uint32_t>(d_sa, n, rate, d_blocks, d_super, d_select, d_agg, d_carry, d_ones, st);
+}
+int build_markvector64(const uint64_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
+                       uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st)
+{
+    return build_markvector_t<uint64_t>(d_sa, n, rate, d_blocks, d_super, d_select, d_agg, d_carry, d_ones, st);
 }
 }  // namespace hkcsa
 

@@ -106,6 +106,12 @@ SIGNATURES = {
     "hkcsa_sa_build_subset": (_i32, [_vp, _u64, C.POINTER(_u64), _u32, _u32, _vp, _u64, C.POINTER(_u64), _vp, _sz, _vp,
                                      C.POINTER(SaStats)]),
     "hkcsa_bwt_slice": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp]),
+    "hkcsa_sa_subset64_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_sa_build_subset64": (_i32, [_vp, _u64, C.POINTER(_u64), _u32, _u32, _vp, _u64, C.POINTER(_u64), _vp, _sz, _vp,
+                                       C.POINTER(SaStats)]),
+    "hkcsa_bwt_slice64": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp]),
+    "hkcsa_ssa_build64": (_i32, [_vp, C.POINTER(SsaPlan), _vp, _vp, _sz, _vp]),
+    "hkcsa_expand_ranges64": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
     "hkcsa_sort_scratch_bytes": (_sz, [_u64]),
     "hkcsa_sort_pairs_u64": (_i32, [_vp, _vp, _vp, _vp, _u64, _i32, _vp, _sz, _vp]),
     "hkcsa_bwt": (_i32, [_vp, _vp, _u64, _vp, _vp]),

@@ -50,9 +50,23 @@ def key_bucket_hist(text: torch.Tensor, begin: int, end: int, byte_hist_np: np.n
 
 
 def build_slice(text: torch.Tensor, byte_hist_np: np.ndarray, bucket_lo: int, bucket_hi: int, capacity: int,
-                stats: SaStats | None = None) -> torch.Tensor:
-    """Sorted suffix ids (uint32 bit patterns in an int32 tensor) of the suffixes in the bucket range."""
+                stats: SaStats | None = None, wide: bool | None = None) -> torch.Tensor:
+    """Sorted suffix ids of the suffixes in the bucket range: uint32 bit patterns in an int32 tensor, or -- for
+    texts beyond 2^32-2 symbols, or when `wide` is forced -- an int64 tensor."""
     L = _lib.load()
+    if wide is None:
+        wide = text.numel() > _lib.DIST_MAX_N
+    if wide:
+        out = _empty(max(capacity, 1), torch.int64, text.device)
+        nbytes = L.hkcsa_sa_subset64_scratch_bytes(capacity)
+        scratch = _scratch(nbytes, text.device)
+        count = C.c_uint64(0)
+        bh = np.ascontiguousarray(byte_hist_np, dtype=np.uint64)
+        st = stats if stats is not None else SaStats()
+        check(L.hkcsa_sa_build_subset64(_ptr(text), text.numel(), bh.ctypes.data_as(C.POINTER(C.c_uint64)), bucket_lo,
+                                        bucket_hi, _ptr(out), capacity, C.byref(count), _ptr(scratch), nbytes,
+                                        _stream(), C.byref(st)))
+        return out[: count.value]
     out = _empty(max(capacity, 1), torch.int32, text.device)
     nbytes = L.hkcsa_sa_subset_scratch_bytes(capacity)
     scratch = _scratch(nbytes, text.device)
@@ -67,7 +81,8 @@ def build_slice(text: torch.Tensor, byte_hist_np: np.ndarray, bucket_lo: int, bu
 
 def bwt_slice(text: torch.Tensor, sa_slice: torch.Tensor) -> torch.Tensor:
     out = _empty(sa_slice.numel(), torch.uint8, text.device)
-    check(_lib.load().hkcsa_bwt_slice(_ptr(text), text.numel(), _ptr(sa_slice), sa_slice.numel(), _ptr(out), _stream()))
+    fn = _lib.load().hkcsa_bwt_slice64 if sa_slice.dtype == torch.int64 else _lib.load().hkcsa_bwt_slice
+    check(fn(_ptr(text), text.numel(), _ptr(sa_slice), sa_slice.numel(), _ptr(out), _stream()))
     return out
 
 
@@ -84,10 +99,10 @@ class SuffixArraySlice:
     stats: SaStats
 
     def sa_int64(self) -> torch.Tensor:
-        return self.sa.to(torch.int64) & 0xFFFFFFFF
+        return self.sa if self.sa.dtype == torch.int64 else self.sa.to(torch.int64) & 0xFFFFFFFF
 
 
-def distributed_suffix_array(local_block: torch.Tensor, group=None) -> SuffixArraySlice:
+def distributed_suffix_array(local_block: torch.Tensor, group=None, wide: bool | None = None) -> SuffixArraySlice:
     """local_block: this rank's contiguous part of the text (uint8, on this rank's GPU), blocks in rank order."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -99,8 +114,8 @@ def distributed_suffix_array(local_block: torch.Tensor, group=None) -> SuffixArr
     dist.all_reduce(sizes, group=group)
     sizes = sizes.cpu().tolist()
     n = int(sum(sizes))
-    if n > _lib.DIST_MAX_N:
-        raise _lib.HkcsaError(_lib.ERANGE, f"text of {n} symbols exceeds the 32-bit suffix-id limit")
+    if n > (1 << 40):
+        raise _lib.HkcsaError(_lib.ERANGE, f"text of {n} symbols exceeds 2^40")
     text = torch.empty(n, dtype=torch.uint8, device=dev)
     starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     text[starts[rank]:starts[rank + 1]] = local_block
@@ -119,7 +134,7 @@ def distributed_suffix_array(local_block: torch.Tensor, group=None) -> SuffixArr
     # 3. this rank's slice
     lo, hi = ranges[rank]
     st = SaStats()
-    sa = build_slice(text, bh_np, lo, hi, counts[rank], st)
+    sa = build_slice(text, bh_np, lo, hi, counts[rank], st, wide=wide)
     assert sa.numel() == counts[rank]
     # 4. BWT of the slice
     return SuffixArraySlice(rank, world, n, int(sum(counts[:rank])), sa, bwt_slice(text, sa), text, (lo, hi), st)
@@ -192,7 +207,7 @@ class MultiSliceIndex:
         return lo, hi
 
     def locate_batch(self, pat: torch.Tensor, off: torch.Tensor):
-        """CSR (offsets int64[P+1], positions uint32-as-int32 in SA order) through LF walks across slices."""
+        """CSR (offsets int64[P+1], positions int64 in SA order) through LF walks across slices."""
         if not self.ssas:
             raise ValueError("index was built without a sampled suffix array")
         L = _lib.load()
@@ -202,9 +217,9 @@ class MultiSliceIndex:
         out_off = torch.zeros(P + 1, dtype=torch.int64, device=self.device)
         out_off[1:] = torch.cumsum(cnt, 0)
         total = int(out_off[-1].item()) if P else 0
-        rows = _empty(total, torch.int32, self.device)
-        check(L.hkcsa_expand_ranges(_ptr(lo), _ptr(hi), _ptr(out_off), P, _ptr(rows), _stream()))
-        out = _empty(total, torch.int32, self.device)
+        rows = _empty(total, torch.int64, self.device)
+        check(L.hkcsa_expand_ranges64(_ptr(lo), _ptr(hi), _ptr(out_off), P, _ptr(rows), _stream()))
+        out = _empty(total, torch.int64, self.device)
         check(L.hkcsa_multi_locate_rows(_ptr(self.desc), _ptr(rows), total, _ptr(out), _stream()))
         return out_off, out
 
@@ -214,13 +229,15 @@ def _sampled_sa_slice(sa_slice: torch.Tensor, rate: int):
     from .engine import SampledSA
     L = _lib.load()
     m = sa_slice.numel()
-    ids = sa_slice.to(torch.int64) & 0xFFFFFFFF
+    wide = sa_slice.dtype == torch.int64
+    ids = sa_slice if wide else (sa_slice.to(torch.int64) & 0xFFFFFFFF)
     n_marks = int((ids % rate == 0).sum().item())            # plumbing: sizes the sample array
     plan = _lib.SsaPlan()
     check(L.hkcsa_ssa_plan_make_slice(m, rate, n_marks, C.byref(plan)))
     blob = torch.zeros(int(plan.blob_bytes), dtype=torch.uint8, device=sa_slice.device)
     scratch = _scratch(plan.scratch_bytes, sa_slice.device)
-    check(L.hkcsa_ssa_build(_ptr(sa_slice), C.byref(plan), _ptr(blob), _ptr(scratch), int(plan.scratch_bytes), _stream()))
+    fn = L.hkcsa_ssa_build64 if wide else L.hkcsa_ssa_build
+    check(fn(_ptr(sa_slice), C.byref(plan), _ptr(blob), _ptr(scratch), int(plan.scratch_bytes), _stream()))
     return SampledSA(plan, blob)
 
 

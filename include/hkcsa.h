@@ -113,6 +113,15 @@ int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const uint64_t *h_b
 /* bwt[j] = text[SA[j]-1] (text[n-1] when SA[j] == 0) for a slice of the suffix array */
 int hkcsa_bwt_slice(const uint8_t *d_text, uint64_t n, const uint32_t *d_sa_slice, uint64_t m,
                     uint8_t *d_out, void *stream);
+/* The same with 64-bit suffix ids, for texts beyond 4 GB (n <= 2^40; BASELINE config 5 is 8 GB): the sort    */
+/* moves 32-bit ordinals, the ids are gathered at the end.  d_sa_out64: uint64[capacity].                     */
+size_t hkcsa_sa_subset64_scratch_bytes(uint64_t capacity);
+int hkcsa_sa_build_subset64(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist,
+                            uint32_t bucket_lo, uint32_t bucket_hi, uint64_t *d_sa_out64, uint64_t capacity,
+                            uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
+                            hkcsa_sa_stats *h_stats);
+int hkcsa_bwt_slice64(const uint8_t *d_text, uint64_t n, const uint64_t *d_sa_slice, uint64_t m,
+                      uint8_t *d_out, void *stream);
 
 /* ------------------------------------------------------------------------ */
 /* K2  BWT gather -- replaces bwt_transform, csa/bwt.py:3-13:                   */
@@ -280,11 +289,16 @@ int hkcsa_locate_rows(const void *d_wt_blob, const hkcsa_wt_plan *h_plan, const 
 /* Sampled SA of a SLICE of the suffix array (distributed build): the number of marked rows of a slice is  */
 /* not ceil(m / rate), the caller passes it (count of SA[j] % rate == 0 in the slice).                        */
 int hkcsa_ssa_plan_make_slice(uint64_t m, uint32_t rate, uint64_t n_marks, hkcsa_ssa_plan *h_plan);
+/* hkcsa_ssa_build for uint64 suffix ids (samples stay uint32: id / rate must fit)                            */
+int hkcsa_ssa_build64(const uint64_t *d_sa, const hkcsa_ssa_plan *h_plan, void *d_blob, void *d_scratch,
+                      size_t scratch_bytes, void *stream);
+int hkcsa_expand_ranges64(const int64_t *d_lo, const int64_t *d_hi, const int64_t *d_out_off, uint64_t P,
+                          uint64_t *d_rows, void *stream);
 
 /* Backward search over a BWT built in slices (BASELINE config 5): slice s covers global rows                 */
 /* [h_starts[s], h_starts[s+1]) with its own wavelet-tree blob / plan (hkcsa_wt_build over its BWT slice) and, */
 /* optionally, its own sampled SA.  The descriptor lives in device memory (hkcsa_multi_desc_bytes()).          */
-/* Same recurrences and miss conventions as hkcsa_count_batch; rows and positions are global (n <= 2^32-2).    */
+/* Same recurrences and miss conventions as hkcsa_count_batch; rows and positions are global (n <= 2^40).      */
 #define HKCSA_MAX_SLICES 8
 size_t hkcsa_multi_desc_bytes(void);
 int hkcsa_multi_desc_build(uint32_t S, const void *const *d_wt_blobs, const hkcsa_wt_plan *const *h_plans,
@@ -292,7 +306,8 @@ int hkcsa_multi_desc_build(uint32_t S, const void *const *d_wt_blobs, const hkcs
                            const hkcsa_ssa_plan *const *h_ssa_plans, void *d_desc, void *stream);
 int hkcsa_multi_count_batch(const void *d_desc, const uint8_t *d_pat, const int64_t *d_off, uint64_t P,
                             int64_t *d_lo, int64_t *d_hi, void *stream);
-int hkcsa_multi_locate_rows(const void *d_desc, const uint32_t *d_rows, uint64_t m, uint32_t *d_out_pos,
+/* rows and positions are 64-bit (the sliced index may exceed 2^32 rows): use hkcsa_expand_ranges64 */
+int hkcsa_multi_locate_rows(const void *d_desc, const uint64_t *d_rows, uint64_t m, uint64_t *d_out_pos,
                             void *stream);
 
 /* FMIndex.precompute_rank, csa/csa.py:13-19: positions of every symbol in the  */

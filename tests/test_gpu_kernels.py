@@ -344,6 +344,7 @@ def test_distributed_slices_concatenate_to_the_suffix_array(E, name, parts):
     """hkcsa.dist_sa: every 'rank' sorts the suffixes of its key-bucket range with the whole text resident;
     the slices in rank order must be the oracle's suffix array and BWT (the collectives are exercised by
     tools/dist_sa_check.py under torchrun)."""
+    import torch
     from hkcsa import dist_sa
     text = TEXTS[name]
     n = len(text)
@@ -356,15 +357,16 @@ def test_distributed_slices_concatenate_to_the_suffix_array(E, name, parts):
     ranges = dist_sa.balanced_bucket_ranges(kh, parts)
     want_sa = O.build_suffix_array(text)
     want_bwt = O.bwt_transform(text, want_sa)
-    got_sa, got_bwt = [], []
-    for lo, hi in ranges:
-        cap = int(kh[lo:hi].sum())
-        sl = dist_sa.build_slice(d_text, bh, lo, hi, cap)
-        assert sl.numel() == cap
-        got_sa.append(host(sl).astype(np.uint32))
-        got_bwt.append(host(dist_sa.bwt_slice(d_text, sl)))
-    assert np.array_equal(np.concatenate(got_sa), want_sa)
-    assert np.concatenate(got_bwt).tobytes() == want_bwt.tobytes()
+    for wide in (False, True):                     # 32-bit ids, and the 64-bit path texts beyond 4 GB take
+        got_sa, got_bwt = [], []
+        for lo, hi in ranges:
+            cap = int(kh[lo:hi].sum())
+            sl = dist_sa.build_slice(d_text, bh, lo, hi, cap, wide=wide)
+            assert sl.numel() == cap and sl.dtype == (torch.int64 if wide else torch.int32)
+            got_sa.append(host(sl).astype(np.uint32))
+            got_bwt.append(host(dist_sa.bwt_slice(d_text, sl)))
+        assert np.array_equal(np.concatenate(got_sa), want_sa)
+        assert np.concatenate(got_bwt).tobytes() == want_bwt.tobytes()
 
 
 def test_distributed_slice_rejects_hugely_repetitive_text(E):
@@ -413,7 +415,9 @@ def test_multi_slice_index_matches_single_index(E, name, parts):
     idx = E.DeviceIndex(d_text, sa_sample_rate=8)
     n = len(text)
     cuts = [n * r // parts for r in range(parts + 1)]
-    slices = [{"bwt": idx.bwt[cuts[r]:cuts[r + 1]].clone(), "sa": idx.sa[cuts[r]:cuts[r + 1]].clone()}
+    wide = parts % 2 == 1                         # odd part counts exercise the 64-bit suffix-id path
+    slices = [{"bwt": idx.bwt[cuts[r]:cuts[r + 1]].clone(),
+               "sa": idx.sa[cuts[r]:cuts[r + 1]].to(torch.int64) if wide else idx.sa[cuts[r]:cuts[r + 1]].clone()}
               for r in range(parts)]
     ms = dist_sa.MultiSliceIndex(n, slices, sa_sample_rate=8)
     base = np.frombuffer(text[:-1], dtype=np.uint8)
@@ -427,7 +431,7 @@ def test_multi_slice_index_matches_single_index(E, name, parts):
     assert torch.equal(lo, mlo) and torch.equal(hi, mhi)
     o1, p1 = idx.locate_batch(d_p, d_o, use_samples=False)
     o2, p2 = ms.locate_batch(d_p, d_o)
-    assert torch.equal(o1, o2) and torch.equal(p1, p2)
+    assert torch.equal(o1, o2) and torch.equal(p1.to(torch.int64), p2)
 
 
 def test_property_random_small_texts(E):

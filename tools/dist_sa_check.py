@@ -14,6 +14,7 @@ ap.add_argument("--kind", type=int, default=0)
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--patterns", type=int, default=1_000_000)
+ap.add_argument("--wide", action="store_true", help="force 64-bit suffix ids (automatic beyond 2^32-2 symbols)")
 ap.add_argument("--props", action="store_true", help="size-independent checks (no single-GPU reference: n may exceed 2^30)")
 args = ap.parse_args()
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
@@ -31,7 +32,7 @@ torch.cuda.synchronize(); dist.barrier()
 best = None
 for _ in range(args.reps):
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-    sl = dist_sa.distributed_suffix_array(block)
+    sl = dist_sa.distributed_suffix_array(block, wide=True if args.wide else None)
     torch.cuda.synchronize(); dist.barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -41,7 +42,7 @@ dist.all_reduce(counts)
 ok = None
 if args.verify:
     cmax = int(counts.max().item())
-    pad = torch.zeros(cmax, dtype=torch.int32, device=dev); pad[: sl.sa.numel()] = sl.sa
+    pad = torch.zeros(cmax, dtype=torch.int32, device=dev); pad[: sl.sa.numel()] = sl.sa.to(torch.int32)
     bpad = torch.zeros(cmax, dtype=torch.uint8, device=dev); bpad[: sl.bwt.numel()] = sl.bwt
     gs = [torch.empty_like(pad) for _ in range(world)]; gb = [torch.empty_like(bpad) for _ in range(world)]
     dist.all_gather(gs, pad); dist.all_gather(gb, bpad)
@@ -78,7 +79,7 @@ if args.verify:
         q_ok = bool(torch.equal(glo, wlo)) and bool(torch.equal(ghi, whi))
         o1, p1 = one.locate_batch(my_p[: int(my_o[min(2000, my_o.numel() - 1)])], my_o[: min(2000, my_o.numel() - 1) + 1],
                                   use_samples=False)
-        q_ok = q_ok and bool(torch.equal(o1, o2)) and bool(torch.equal(p1, p2))
+        q_ok = q_ok and bool(torch.equal(o1, o2)) and bool(torch.equal(p1.to(torch.int64) & 0xFFFFFFFF, p2))
 props_ok = None
 if args.props:
     # ranks 0 and world/2 (host RAM: the text is copied back): the slice is sorted (adjacent suffixes compared on
@@ -96,7 +97,7 @@ if args.props:
             good &= h_text[a_:a_ + 256].tobytes() <= h_text[b_:b_ + 256].tobytes()   # 256-byte prefixes, in order
     k = min(2000, my_o.numel() - 1) if checker else 0
     oo, pp = ms.locate_batch(my_p[: int(my_o[k])], my_o[: k + 1])
-    oo, pp = oo.cpu().numpy(), (pp.to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+    oo, pp = oo.cpu().numpy(), pp.cpu().numpy()
     hp, ho = my_p.cpu().numpy(), my_o.cpu().numpy()
     clo = lo.cpu().numpy()
     for q in range(k):
