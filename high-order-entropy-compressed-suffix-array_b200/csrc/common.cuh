@@ -113,6 +113,38 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v)
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// L2 eviction policies (createpolicy, sm_80+): streams that are touched once are marked evict-first so they do
+// not push a randomly gathered table (the text under the BWT gather) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last(float fraction = 1.0f)
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(p) : "f"(fraction));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ld_u8_hint(const uint8_t *p, uint64_t pol)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_u32x4_hint(const uint32_t *p, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_u32_hint(uint32_t *p, uint32_t v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 // Exclusive warp scan (sum) of one uint32 per lane.
 __device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t &total)
 {

@@ -231,7 +231,7 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d)
     return peers;
 }
 
-template <int THREADS, int MIN_CTAS, int MODE>
+template <int THREADS, int MIN_CTAS, int MODE, bool IDENT>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout, const uint32_t *__restrict__ vin,
                   uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
@@ -259,13 +259,15 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     //      a ragged tail (last tile only) is finished with plain loads.
     const uint32_t nk16 = nvalid & ~1u;          // keys copied in 16-byte units
     const uint32_t nv16 = nvalid & ~3u;          // values copied in 16-byte units
+    //      IDENT: the values are the identity (first pass over freshly packed keys) -- nothing to load.
+    constexpr bool ident = IDENT;
     if (tid == 0) {
-        mbar_expect_tx(&S.bar, nk16 * 8u + nv16 * 4u);
+        mbar_expect_tx(&S.bar, nk16 * 8u + (ident ? 0u : nv16 * 4u));
         if (nk16) bulk_g2s(S.keys, kin + tile_base, nk16 * 8u, &S.bar);
-        if (nv16) bulk_g2s(S.vals, vin + tile_base, nv16 * 4u, &S.bar);
+        if (nv16 && !ident) bulk_g2s(S.vals, vin + tile_base, nv16 * 4u, &S.bar);
         if (nk16 < nvalid) S.keys[nk16] = kin[tile_base + nk16];                             // at most 1 key
     }
-    if (tid < 4 && nv16 + tid < nvalid) S.vals[nv16 + tid] = vin[tile_base + nv16 + tid];    // at most 3 values
+    if (!ident && tid < 4 && nv16 + tid < nvalid) S.vals[nv16 + tid] = vin[tile_base + nv16 + tid];    // at most 3 values
     mbar_wait(&S.bar, 0);
     __syncthreads();
 
@@ -280,7 +282,7 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
         const uint32_t local = wbase + k * 32u;
         const bool valid = local < nvalid;
         key[k] = valid ? S.keys[local] : ~0ULL;
-        val[k] = S.vals[local];
+        val[k] = ident ? tile_base + local : S.vals[local];
         const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
         peers[k] = digit_peers<MODE>(d);
     }
@@ -637,14 +639,17 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
 // ranking (faster only when a digit takes < ~8 distinct values); 1 = 256 threads x 8, 4 CTAs/SM, match.any.
 template <int THREADS, int MIN_CTAS, int MODE>
 static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n, int passes,
-                                  const SortScratch &s, cudaStream_t st)
+                                  const SortScratch &s, cudaStream_t st, bool identity_vals)
 {
     using Smem = OsSmem<THREADS>;
     constexpr size_t smem = sizeof(Smem) + 128;
-    auto kern = onesweep64_kernel<THREADS, MIN_CTAS, MODE>;
+    auto kern = onesweep64_kernel<THREADS, MIN_CTAS, MODE, false>;
+    auto kern_ident = onesweep64_kernel<THREADS, MIN_CTAS, MODE, true>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern_ident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -655,9 +660,12 @@ static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint
         cudaError_t e = cudaMemsetAsync(s.lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), st);
         if (e != cudaSuccess) return e;
         {
-            prof::Scope ps(st, prof::ONESWEEP_U64, (uint64_t)n * 24);
-            kern<<<tiles, THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, s.base + p * RADIX, s.lookback,
-                                               s.ticket + p);
+            prof::Scope ps(st, prof::ONESWEEP_U64, (uint64_t)n * ((p == 0 && identity_vals) ? 20 : 24));
+            if (p == 0 && identity_vals)
+                kern_ident<<<tiles, THREADS, smem, st>>>(kin, kout, nullptr, vout, n, 0, s.base, s.lookback, s.ticket);
+            else
+                kern<<<tiles, THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, s.base + p * RADIX, s.lookback,
+                                                   s.ticket + p);
             count_launch();
         }
         e = cudaGetLastError();
@@ -703,7 +711,7 @@ static cudaError_t run_onesweep64_persistent(uint64_t *k0, uint32_t *v0, uint64_
 }
 
 cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n,
-                                 int passes, const SortScratch &s, cudaStream_t st)
+                                 int passes, const SortScratch &s, cudaStream_t st, bool identity_vals)
 {
     if (n == 0 || passes <= 0) return cudaSuccess;
     static int variant = -1;
@@ -715,12 +723,12 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
     count_launch();
     cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    if (variant == 5) return run_onesweep64_persistent(k0, v0, k1, v1, n, passes, s, st);
-    if (variant == 1) return run_onesweep64<256, 4, 0>(k0, v0, k1, v1, n, passes, s, st);
-    if (variant == 2) return run_onesweep64<512, 2, 1>(k0, v0, k1, v1, n, passes, s, st);
-    if (variant == 3) return run_onesweep64<256, 4, 1>(k0, v0, k1, v1, n, passes, s, st);
-    if (variant == 4) return run_onesweep64<384, 3, 1>(k0, v0, k1, v1, n, passes, s, st);
-    return run_onesweep64<512, 2, 0>(k0, v0, k1, v1, n, passes, s, st);
+    if (variant == 5 && !identity_vals) return run_onesweep64_persistent(k0, v0, k1, v1, n, passes, s, st);
+    if (variant == 1) return run_onesweep64<256, 4, 0>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    if (variant == 3) return run_onesweep64<256, 4, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    if (variant == 4) return run_onesweep64<384, 3, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    if (variant == 0) return run_onesweep64<512, 2, 0>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    return run_onesweep64<512, 2, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
 }
 
 cudaError_t radix_partition_bytes(const uint8_t *d_in, uint8_t *d_out, uint32_t *d_pos_out, uint32_t n,

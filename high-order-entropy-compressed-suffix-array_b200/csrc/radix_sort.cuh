@@ -48,6 +48,20 @@ __device__ __forceinline__ void hist_add_key(uint32_t *s_hist, uint64_t key, int
         }
     }
 }
+// Same contract, for keys in no particular order (round 0): one uniformity test on the whole key (runs of one
+// symbol) instead of one per digit; otherwise plain shared-memory atomics.
+__device__ __forceinline__ void hist_add_key_unsorted(uint32_t *s_hist, uint64_t key, int passes, bool valid)
+{
+    const uint64_t key0 = __shfl_sync(0xffffffffu, key, 0);
+    const bool uniform = __all_sync(0xffffffffu, !valid || key == key0);
+    if (uniform) {
+        const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+        if (lane_id() == 0 && nvalid)
+            for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * RADIX + ((uint32_t)(key0 >> (8 * p)) & 0xFFu)], nvalid);
+    } else if (valid) {
+        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * RADIX + ((uint32_t)(key >> (8 * p)) & 0xFFu)], 1u);
+    }
+}
 __device__ __forceinline__ void hist_zero(uint32_t *s_hist, int passes)
 {
     for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) s_hist[i] = 0;
@@ -77,8 +91,9 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
 // Sorts on the low 8*passes bits.  s.hist must hold the digit histograms of the
 // input.  Input in (k0,v0); (k1,v1) is the ping-pong buffer.  The result is in
 // (k0,v0) when passes is even, (k1,v1) when odd.
+// identity_vals: the input values are 0, 1, 2, ... and v0 is not read (it is still the ping-pong buffer).
 cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n,
-                                 int passes, const SortScratch &s, cudaStream_t st);
+                                 int passes, const SortScratch &s, cudaStream_t st, bool identity_vals = false);
 // Stable bucket partition of bytes: element x goes to bucket lut[x]; bucket b
 // starts at d_bucket_base[b] in d_out.  No histogram pass (the caller knows the
 // bucket sizes).  If d_pos_out != nullptr the source positions are carried as values.

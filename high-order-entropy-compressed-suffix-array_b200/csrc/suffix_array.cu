@@ -142,73 +142,125 @@ cudaError_t byte_hist(const uint8_t *d_text, uint64_t n, uint64_t *d_hist, cudaS
 }
 
 // ---------------------------------------------------------------- round 0: pack
-// key[i] = code(T[i]) code(T[i+1]) ... code(T[i+k0-1]) MSB first, b bits each.
+// key[i] = the first `bits` bits of code(T[i]) code(T[i+1]) ... (the last code word truncated).
+//
+// The CTA writes the code words of its 2048 positions + 64 look-ahead positions into ONE bit stream in shared
+// memory (each thread owns 8 consecutive symbols: it sums their code lengths, a block scan gives its bit
+// offset, and it ORs its bits in 32-bit pieces); the key of a position is then the 64-bit window of the stream
+// at that position's bit offset -- three shared loads and two funnel shifts, whatever the number of symbols
+// the key covers.  Keys are produced warp-striped so the stores are fully coalesced.  The suffix ids are not
+// written at all: the first radix pass takes "value = index" (radix_sort_pairs_u64, identity_vals).
 constexpr int PACK_THREADS = 256;
 constexpr int PACK_IPT = 8;
 constexpr int PACK_TILE = PACK_THREADS * PACK_IPT;
+constexpr int PACK_LOOK = 64;                                   // >= 64 bits of look-ahead (code words >= 1 bit)
+constexpr int PACK_VT = PACK_THREADS + PACK_LOOK / PACK_IPT;    // "virtual threads" incl. the look-ahead groups
+constexpr int PACK_MAX_LEN = 24;                                // build_alpha_code never exceeds it
+constexpr int PACK_STREAM_WORDS = (PACK_TILE + PACK_LOOK) * PACK_MAX_LEN / 32 + 4;
 
-// Entries are (code << 8) | length.  The per-position codes of a tile are combined by doubling into the
-// code of 2, 4, 8 consecutive symbols (as long as that still fits 56 bits), so building a key takes a few
-// shifted ORs instead of one per symbol.
-__device__ __forceinline__ uint64_t chunk_join(uint64_t a, uint64_t b)
+// loads 8 consecutive symbols starting at g0 as (code << 8 | len) entries; returns the sum of the lengths
+__device__ __forceinline__ uint32_t pack_load8(const uint8_t *__restrict__ text, uint32_t n, uint64_t g0, bool aligned8,
+                                               const uint32_t *s_tab, uint32_t cl[PACK_IPT])
 {
-    const uint32_t lb = (uint32_t)(b & 0xFFu);
-    return ((((a >> 8) << lb) | (b >> 8)) << 8) | ((a & 0xFFu) + lb);
+    uint32_t total = 0;
+    if (aligned8 && g0 + PACK_IPT <= n) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(text + g0));
+#pragma unroll
+        for (int e = 0; e < PACK_IPT; ++e) {
+            const uint32_t c = ((e < 4 ? v.x : v.y) >> (8 * (e & 3))) & 0xFFu;
+            cl[e] = s_tab[c];
+            total += cl[e] & 0xFFu;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < PACK_IPT; ++e) {
+            const uint64_t g = g0 + e;
+            cl[e] = s_tab[g < n ? (uint32_t)text[g] : 256u];
+            total += cl[e] & 0xFFu;
+        }
+    }
+    return total;
+}
+
+// ORs the 8 code words into the stream from bit offset `off` (bit 0 = MSB of word 0) and records the bit
+// offset of every symbol
+__device__ __forceinline__ void pack_emit8(uint32_t *s_stream, uint16_t *s_off8, uint32_t off, const uint32_t cl[PACK_IPT])
+{
+    uint32_t wi = off >> 5;
+    uint32_t nacc = off & 31u;
+    uint64_t acc = 0;
+    uint32_t o = off;
+    uint32_t offs[PACK_IPT];
+#pragma unroll
+    for (int e = 0; e < PACK_IPT; ++e) {
+        const uint32_t L = cl[e] & 0xFFu;
+        offs[e] = o;
+        o += L;
+        acc |= (uint64_t)(cl[e] >> 8) << (64u - nacc - L);     // nacc + L <= 31 + 24
+        nacc += L;
+        if (nacc >= 32u) {
+            atomicOr(&s_stream[wi++], (uint32_t)(acc >> 32));
+            acc <<= 32;
+            nacc -= 32u;
+        }
+    }
+    if (nacc) atomicOr(&s_stream[wi], (uint32_t)(acc >> 32));
+    uint4 q;
+    q.x = offs[0] | (offs[1] << 16);
+    q.y = offs[2] | (offs[3] << 16);
+    q.z = offs[4] | (offs[5] << 16);
+    q.w = offs[6] | (offs[7] << 16);
+    *reinterpret_cast<uint4 *>(s_off8) = q;
 }
 
 __global__ void __launch_bounds__(PACK_THREADS)
-sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, int bits, int passes, int levels,
-                uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, uint32_t *__restrict__ ghist)
+sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, int bits, int passes,
+                uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist)
 {
-    constexpr int W = PACK_TILE + 64;
-    __shared__ uint64_t s_c[2][W];
+    __shared__ __align__(16) uint16_t s_off[PACK_TILE];
+    __shared__ uint32_t s_stream[PACK_STREAM_WORDS];
     __shared__ uint32_t s_hist[8 * RADIX];
-    __shared__ uint32_t s_code[257];
-    __shared__ uint8_t s_len[257];
-    const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < 257; i += PACK_THREADS) { s_code[i] = ac.code[i]; s_len[i] = ac.len[i]; }
+    __shared__ uint32_t s_tab[257];
+    __shared__ uint32_t s_tot[PACK_VT + 24];                    // 288 = 32 lanes x 9
+    __shared__ __align__(16) uint16_t s_off_look[PACK_IPT];     // offsets of a look-ahead group: written, never read
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (uint32_t i = tid; i < 257; i += PACK_THREADS) s_tab[i] = (ac.code[i] << 8) | ac.len[i];
+    for (uint32_t i = tid; i < PACK_STREAM_WORDS; i += PACK_THREADS) s_stream[i] = 0;
+    if (tid < 24) s_tot[PACK_VT + tid] = 0;
     hist_zero(s_hist, passes);
     __syncthreads();
-    const uint32_t base = blockIdx.x * PACK_TILE;
-    for (uint32_t j = tid; j < W; j += PACK_THREADS) {
-        const uint32_t g = base + j;
-        const uint32_t c = (g < n) ? (uint32_t)text[g] : 256u;
-        s_c[0][j] = ((uint64_t)s_code[c] << 8) | s_len[c];
+    const uint64_t base = (uint64_t)blockIdx.x * PACK_TILE;
+    const bool aligned8 = (reinterpret_cast<uintptr_t>(text) & 7) == 0;
+    uint32_t cl[PACK_IPT], cl2[PACK_IPT];
+    s_tot[tid] = pack_load8(text, n, base + (uint64_t)tid * PACK_IPT, aligned8, s_tab, cl);
+    if (tid < PACK_LOOK / PACK_IPT)
+        s_tot[PACK_THREADS + tid] = pack_load8(text, n, base + PACK_TILE + (uint64_t)tid * PACK_IPT, aligned8, s_tab, cl2);
+    __syncthreads();
+    if (warp == 0) {                                            // exclusive scan of the 264 group lengths
+        uint32_t v[9], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { v[q] = s_tot[lane * 9 + q]; sum += v[q]; }
+        uint32_t total;
+        uint32_t run = warp_excl_sum(sum, total);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { s_tot[lane * 9 + q] = run; run += v[q]; }
     }
     __syncthreads();
-    const uint64_t pad = ((uint64_t)s_code[256] << 8) | s_len[256];
-    int cur = 0;
-    for (int l = 0; l < levels; ++l) {                    // s_c[cur][j] covers 2^l symbols from position j
-        const uint32_t step = 1u << l;
-        for (uint32_t j = tid; j < W; j += PACK_THREADS) {
-            // beyond the window only padding can follow inside the text's end; inside the text the window is
-            // wide enough for every key of the tile (64 symbols), so a clamped neighbour is never consumed
-            const uint64_t nb = (j + step < W) ? s_c[cur][j + step] : pad;
-            s_c[cur ^ 1][j] = chunk_join(s_c[cur][j], nb);
-        }
-        __syncthreads();
-        cur ^= 1;
-    }
-    const uint32_t S = 1u << levels;
+    pack_emit8(s_stream, s_off + tid * PACK_IPT, s_tot[tid], cl);
+    if (tid < PACK_LOOK / PACK_IPT) pack_emit8(s_stream, s_off_look, s_tot[PACK_THREADS + tid], cl2);
+    __syncthreads();
 #pragma unroll
     for (int e = 0; e < PACK_IPT; ++e) {
-        const uint32_t j = e * PACK_THREADS + tid;
-        const uint32_t g = base + j;
-        uint64_t acc = 0;
-        int used = 0;
-        for (uint32_t t = 0; used < bits; t += S) {
-            const uint64_t en = s_c[cur][j + t];
-            const int L = (int)(en & 0xFFu);
-            acc |= ((en >> 8) << (64 - L)) >> used;
-            used += L;
-        }
-        const uint64_t key = acc >> (64 - bits);
+        const uint32_t j = warp * (32u * PACK_IPT) + e * 32u + lane;
+        const uint64_t g = base + j;
+        const uint32_t o = s_off[j];
+        const uint32_t wi = o >> 5, sh = o & 31u;
+        const uint32_t w0 = s_stream[wi], w1 = s_stream[wi + 1], w2 = s_stream[wi + 2];
+        const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+        const uint64_t key = (((uint64_t)hi << 32) | lo) >> (64 - bits);
         const bool valid = g < n;
-        if (valid) {
-            keys[g] = key;
-            idx[g] = g;
-        }
-        hist_add_key(s_hist, key, passes, valid);
+        if (valid) keys[g] = key;
+        hist_add_key_unsorted(s_hist, key, passes, valid);
     }
     __syncthreads();
     hist_flush(s_hist, ghist, passes);
@@ -344,7 +396,7 @@ __device__ __forceinline__ void seg_flags(const uint64_t *__restrict__ skey, uin
 
 __global__ void __launch_bounds__(SEG_THREADS)
 seg_reduce_kernel(const uint64_t *__restrict__ skey, uint32_t m, uint32_t *__restrict__ agg_head,
-                  uint32_t *__restrict__ agg_keep)
+                  uint32_t *__restrict__ agg_keep, uint16_t *__restrict__ flags)
 {
     __shared__ uint32_t s_h[SEG_THREADS / 32], s_k[SEG_THREADS / 32];
     const uint32_t tid = threadIdx.x;
@@ -352,11 +404,16 @@ seg_reduce_kernel(const uint64_t *__restrict__ skey, uint32_t m, uint32_t *__res
     bool head[SEG_IPT], single[SEG_IPT];
     seg_flags(skey, m, j0, head, single);
     uint32_t lasthead = 0, keep = 0;   // lasthead = (index of last head) + 1, 0 = none
+    uint32_t f = 0;
 #pragma unroll
     for (int e = 0; e < SEG_IPT; ++e) {
         if (head[e]) lasthead = j0 + e + 1;
         if (j0 + e < m && !single[e]) ++keep;
+        f |= (head[e] ? 1u : 0u) << e;
+        f |= (single[e] ? 1u : 0u) << (SEG_IPT + e);
     }
+    // 2 bits per element for the apply pass: it then reads 0.25 B instead of the 8-byte key again
+    flags[blockIdx.x * SEG_THREADS + tid] = (uint16_t)f;
     lasthead = __reduce_max_sync(0xffffffffu, lasthead);
     keep = __reduce_add_sync(0xffffffffu, keep);
     if ((tid & 31u) == 0) { s_h[tid >> 5] = lasthead; s_k[tid >> 5] = keep; }
@@ -407,7 +464,7 @@ seg_scan_kernel(uint32_t *__restrict__ agg_head, uint32_t *__restrict__ agg_keep
 }
 
 __global__ void __launch_bounds__(SEG_THREADS)
-seg_apply_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sidx,
+seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict__ sidx,
                  const uint32_t *__restrict__ pos /* nullptr = identity */, uint32_t m,
                  const uint32_t *__restrict__ carry_head, const uint32_t *__restrict__ carry_keep,
                  uint32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint32_t *__restrict__ cpos,
@@ -417,10 +474,12 @@ seg_apply_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t j0 = blockIdx.x * SEG_TILE + tid * SEG_IPT;
     bool head[SEG_IPT], single[SEG_IPT];
-    seg_flags(skey, m, j0, head, single);
+    const uint32_t f = flags[blockIdx.x * SEG_THREADS + tid];      // written by seg_reduce_kernel
     uint32_t lasthead = 0, keep = 0;
 #pragma unroll
     for (int e = 0; e < SEG_IPT; ++e) {
+        head[e] = (f >> e) & 1u;
+        single[e] = (f >> (SEG_IPT + e)) & 1u;
         if (head[e]) lasthead = j0 + e + 1;
         if (j0 + e < m && !single[e]) ++keep;
     }
@@ -448,7 +507,9 @@ seg_apply_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__
             grp_valid = true;
         }
         const uint32_t p = pos ? pos[j] : j;
-        const uint32_t s = sidx[j];
+        // round 0 with lazy ranks needs the suffix id of survivors only: most of the id stream is never read
+        const bool need_id = write_sa || scatter_all || !single[e];
+        const uint32_t s = need_id ? sidx[j] : 0u;
         if (write_sa) sa[p] = s;
         if (rank && (scatter_all || !single[e])) rank[s] = cur_grp;
         if (!single[e]) {
@@ -473,6 +534,7 @@ struct SaBuffers {
     uint32_t *grp;
     uint32_t *rank;
     uint32_t *agg_head, *agg_keep;
+    uint16_t *flags;
     uint32_t *counter;
     uint64_t *hist64;
     uint32_t *bucket;
@@ -493,6 +555,7 @@ SaBuffers carve_sa(Carver &c, uint64_t n)
     b.rank = c.take<uint32_t>(n);
     b.agg_head = c.take<uint32_t>(tiles);
     b.agg_keep = c.take<uint32_t>(tiles);
+    b.flags = c.take<uint16_t>(tiles * SEG_THREADS);
     b.counter = c.take<uint32_t>(64);
     b.hist64 = c.take<uint64_t>(256);
     b.bucket = c.take<uint32_t>((1u << LAZY_BUCKET_BITS) + 2);
@@ -573,12 +636,11 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     uint32_t *vb = (passes0 % 2 == 0) ? B.val[0] : d_sa;
     {
         const uint32_t blocks = (N + PACK_TILE - 1) / PACK_TILE;
-        prof::Scope ps(st, prof::SA_PACK0, (uint64_t)N * 13);
-        const int levels = (8 * max_len <= 56) ? 3 : (4 * max_len <= 56) ? 2 : (2 * max_len <= 56) ? 1 : 0;
-        sa_pack0_kernel<<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, bits0, passes0, levels, ka, va, B.sort.hist);
+        prof::Scope ps(st, prof::SA_PACK0, (uint64_t)N * 9);
+        sa_pack0_kernel<<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, bits0, passes0, ka, B.sort.hist);
         HK_LAUNCH_CHECK();
     }
-    HK_CUDA(radix_sort_pairs_u64(ka, va, kb, vb, N, passes0, B.sort, st));
+    HK_CUDA(radix_sort_pairs_u64(ka, va, kb, vb, N, passes0, B.sort, st, /*identity_vals=*/true));
     uint64_t *skey = (passes0 % 2 == 0) ? ka : kb;     // sorted round-0 keys
     uint64_t *kfree = (passes0 % 2 == 0) ? kb : ka;
     uint32_t *sidx = d_sa;                              // sorted suffix ids
@@ -592,7 +654,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     stats.round_elems[0] = m;
     stats.round_passes[0] = (uint32_t)passes0;
     stats.sort_elem_passes = (uint64_t)m * passes0;
-    stats.alg_bytes = (uint64_t)n * 13 + (uint64_t)m * (24ull * passes0);
+    stats.alg_bytes = (uint64_t)n * 9 + (uint64_t)m * (24ull * passes0) - (uint64_t)m * 4;   // pass 0 reads no ids
 
     LazyRank lz;
     lz.text = nullptr; lz.keys0 = nullptr; lz.bucket = nullptr; lz.bits = bits0;
@@ -606,8 +668,8 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         // ---- refine ranks from the sorted keys
         const uint32_t tiles = (m + SEG_TILE - 1) / SEG_TILE;
         {
-            prof::Scope ps(st, prof::SEG_REDUCE, (uint64_t)m * 8);
-            seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, m, B.agg_head, B.agg_keep);
+            prof::Scope ps(st, prof::SEG_REDUCE, (uint64_t)m * 8 + m / 4);
+            seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, m, B.agg_head, B.agg_keep, B.flags);
             HK_LAUNCH_CHECK();
         }
         {
@@ -633,12 +695,14 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         uint32_t *cpos = B.pos[pcur ^ 1];
         uint32_t *cidx = vfree;
         {
-            prof::Scope ps(st, prof::SEG_APPLY, (uint64_t)m * 24);
-            seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, sidx, pos, m, B.agg_head, B.agg_keep, d_sa, B.rank,
+            // flags + (round 0, lazy ranks: survivors only; otherwise ids, slots, rank scatter)
+            prof::Scope ps(st, prof::SEG_APPLY, m / 4 + (uint64_t)m_next * 20 +
+                                                 ((round != 0 || scatter_all) ? (uint64_t)m * 12 : 0));
+            seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.flags, sidx, pos, m, B.agg_head, B.agg_keep, d_sa, B.rank,
                                                            cpos, cidx, B.grp, round != 0, scatter_all);
             HK_LAUNCH_CHECK();
         }
-        stats.alg_bytes += (uint64_t)m * (8 + 8 + 4 + 4 + 4 + 4);
+        stats.alg_bytes += (uint64_t)m * 8 + m / 2 + (uint64_t)m_next * 20 + ((round != 0 || scatter_all) ? (uint64_t)m * 12 : 0);
         ++round;
         if (m_next == 0) break;
         HK_REQUIRE(h < n, HKCSA_EINVAL, "internal: groups remain after depth >= n");
@@ -866,6 +930,7 @@ struct SubsetBuffers {
     uint32_t *pos[2];
     uint32_t *grp;
     uint32_t *agg_head, *agg_keep;
+    uint16_t *flags;
     uint32_t *counter;
     SortScratch sort;
 };
@@ -882,6 +947,7 @@ SubsetBuffers carve_subset(Carver &c, uint64_t m)
     b.grp = c.take<uint32_t>(m);
     b.agg_head = c.take<uint32_t>(tiles);
     b.agg_keep = c.take<uint32_t>(tiles);
+    b.flags = c.take<uint16_t>(tiles * SEG_THREADS);
     b.counter = c.take<uint32_t>(64);
     b.sort = carve_sort_scratch(c, m);
     return b;
@@ -964,13 +1030,13 @@ static int sa_build_subset_impl(const uint8_t *d_text, uint64_t n, const uint64_
     stats.sort_elem_passes = (uint64_t)m * passes0;
     while (true) {
         const uint32_t tiles = (m + SEG_TILE - 1) / SEG_TILE;
-        seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, m, B.agg_head, B.agg_keep);
+        seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, m, B.agg_head, B.agg_keep, B.flags);
         HK_LAUNCH_CHECK();
         seg_scan_kernel<<<1, 1024, 0, st>>>(B.agg_head, B.agg_keep, tiles, B.counter);
         HK_LAUNCH_CHECK();
         uint32_t *cpos = B.pos[pcur ^ 1];
         uint32_t *cidx = vfree;
-        seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, sidx, pos, m, B.agg_head, B.agg_keep, d_sa_out, nullptr,
+        seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.flags, sidx, pos, m, B.agg_head, B.agg_keep, d_sa_out, nullptr,
                                                        cpos, cidx, B.grp, round != 0, false);
         HK_LAUNCH_CHECK();
         HK_CUDA(cudaMemcpyAsync(h_m, B.counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
