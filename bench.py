@@ -330,7 +330,7 @@ def run_ours(args):
         if world > 1:
             barrier()
             t0 = time.perf_counter()
-            q_idx = hdist.broadcast_index(idx if rank == 0 else None, src=0, device=dev)
+            q_idx = hdist.broadcast_index(idx if rank == 0 else None, src=0, device=dev, with_bwt=True)
             barrier()
             bcast_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
             bounds = hdist.shard_bounds(off.cpu().numpy(), world)
@@ -342,14 +342,14 @@ def run_ours(args):
         torch.cuda.synchronize()
         reps = 3
 
-        def time_count(use_table):
+        def time_count(use_table, use_occ=False):
             for _ in range(2):
-                q_idx.count_batch(my_pats, my_off, use_kmer_table=use_table)
+                q_idx.count_batch(my_pats, my_off, use_kmer_table=use_table, use_occ_table=use_occ)
             barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for _ in range(reps):
-                r_ = q_idx.count_batch(my_pats, my_off, use_kmer_table=use_table)
+                r_ = q_idx.count_batch(my_pats, my_off, use_kmer_table=use_table, use_occ_table=use_occ)
             b.record()
             barrier()
             return max_over_ranks(a.elapsed_time(b) / reps), r_
@@ -361,6 +361,18 @@ def run_ours(args):
         kmer_ms = (time.perf_counter() - t0) * 1e3
         c_ms, (lo, hi) = time_count(True)                   # last k symbols from the k-mer jump table
         assert torch.equal(lo, lo0) and torch.equal(hi, hi0)
+        occ_info = None
+        if q_idx.bwt is not None:          # same queries ranked on the sampled Occ table (identical ranges)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            plan_o, _ = q_idx.build_occ_table(5)
+            torch.cuda.synchronize()
+            occ_build_ms = (time.perf_counter() - t0) * 1e3
+            o_ms, (lo_o, hi_o) = time_count(True, True)
+            assert torch.equal(lo, lo_o) and torch.equal(hi, hi_o)
+            occ_info = {"count_patterns_per_s": P_total / (o_ms / 1e3), "count_ms": o_ms, "build_ms": occ_build_ms,
+                        "bytes": int(plan_o.blob_bytes), "rows_per_entry": 32}
+            q_idx._occ = None
         gather_ms = None
         if world > 1:                      # results to every rank, timed apart from the search
             t0 = time.perf_counter()
@@ -385,6 +397,7 @@ def run_ours(args):
         queries = {"count_patterns_per_s": P_total / (c_ms / 1e3), "count_patterns": P_total,
                    "count_ms": c_ms, "hit_fraction": hits / P_total, "pattern_len": "uniform 8-64",
                    "count_patterns_per_s_no_jump_table": P_total / (c_ms_plain / 1e3),
+                   "occ_table": occ_info,
                    "kmer_jump_table": {"k": int(q_idx._kmer[1]), "build_ms": kmer_ms,
                                        "bytes": int(q_idx._kmer[0].numel() * 4) if q_idx._kmer[0] is not None else 0},
                    "index_broadcast_ms": bcast_ms, "result_allgather_ms": gather_ms,
@@ -406,7 +419,7 @@ def run_ours(args):
         t3[n3] = 0x24
         idx3 = E.DeviceIndex(t3, sa_sample_rate=SA_SAMPLE_RATE) if rank == 0 or world == 1 else None
         if world > 1:
-            idx3 = hdist.broadcast_index(idx3, src=0, device=dev)
+            idx3 = hdist.broadcast_index(idx3, src=0, device=dev, with_bwt=True)
         alpha3 = torch.from_numpy(np.frombuffer(idx3.wt.alphabet, dtype=np.uint8).copy()).to(dev)
         alpha3 = alpha3[alpha3 != 0x24]
         pats3, off3 = E.gen_patterns(44, args.patterns, t3[:n3], alpha3)
@@ -428,6 +441,48 @@ def run_ours(args):
               "count_patterns_per_s": args.patterns / (c4_ms / 1e3), "count_ms": c4_ms,
               "hit_fraction": sum_over_ranks(float((lo3 >= 0).sum().item())) / args.patterns,
               "wavelet_levels": idx3.wt.levels, "kmer_k": int(idx3._kmer[1])}
+        # locate of the first 1 M patterns of this rank through the sampled SA (LF walks)
+        PL3 = min(off3.numel() - 1, 1_000_000 // world)
+
+        def time_locate3():
+            idx3.locate_batch(pats3, off3[: PL3 + 1], use_samples=True)
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            _, pos_ = idx3.locate_batch(pats3, off3[: PL3 + 1], use_samples=True)
+            b_.record()
+            barrier()
+            return max_over_ranks(a_.elapsed_time(b_)), sum_over_ranks(float(pos_.numel()))
+
+        l3_ms, l3_occ = time_locate3()
+        c4["locate_occurrences_per_s"] = l3_occ / (l3_ms / 1e3)
+        c4["locate_ms"] = l3_ms
+        c4["locate_occurrences"] = l3_occ
+        # the same queries ranked on the sampled Occ table (optional second rank structure, identical ranges)
+        if idx3.bwt is not None:
+            for shift in (5, 6):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                plan_o, blob_o = idx3.build_occ_table(shift)
+                torch.cuda.synchronize()
+                occ_ms = (time.perf_counter() - t0) * 1e3
+                for _ in range(2):
+                    idx3.count_batch(pats3, off3, use_kmer_table=True, use_occ_table=True)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(3):
+                    lo4, hi4 = idx3.count_batch(pats3, off3, use_kmer_table=True, use_occ_table=True)
+                b.record()
+                barrier()
+                o_ms = max_over_ranks(a.elapsed_time(b) / 3)
+                assert torch.equal(lo4, lo3) and torch.equal(hi4, hi3)
+                l_ms, l_occ = time_locate3()
+                c4[f"occ_table_rows_{1 << shift}"] = {"count_patterns_per_s": args.patterns / (o_ms / 1e3), "count_ms": o_ms,
+                                                       "build_ms": occ_ms, "bytes": int(plan_o.blob_bytes),
+                                                       "locate_occurrences_per_s": l_occ / (l_ms / 1e3), "locate_ms": l_ms}
+                del blob_o
+                idx3._occ = None
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same workload
     cpu = None

@@ -81,6 +81,7 @@ extern "C" size_t hkcsa_struct_size(int which)
         case 1: return sizeof(hkcsa_wt_plan);
         case 2: return sizeof(hkcsa_ssa_plan);
         case 3: return sizeof(hkcsa_prof_entry);
+        case 4: return sizeof(hkcsa_occ_plan);
         default: return 0;
     }
 }

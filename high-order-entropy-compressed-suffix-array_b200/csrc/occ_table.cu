@@ -1,0 +1,365 @@
+// occ_table.cu -- sampled Occ table: a second rank structure for the query path.
+//
+// The reference's FM index answers rank(c, i) from a DENSE table occ[c][i] for every symbol and every row
+// (build_occ, utils/utils.py:26-32; read by EnhancedFMIndex.rank, csa/enhanced_fm_index.py:34-40) --
+// n * sigma integers, impossible beyond a few MB.  This file keeps that table at every B-th row only
+// (B = 32 or 64) and stores, next to each kept row, the B BWT symbols the remainder is counted from:
+//
+//   row r (stride bytes):  [ B BWT bytes of rows r*B .. r*B+B-1 ][ sigma x u32: occ[code][r*B] ]
+//   occ(c, i) = row[i / B].count[code(c)] + #{ j < i % B : row[i / B].bwt[j] == c }
+//
+// One rank = one counter sector + one (B = 32) or two adjacent (B = 64) symbol sectors, independent of the
+// alphabet, against one sector PER LEVEL of the wavelet tree (7 levels for the 97-symbol text).  The wavelet
+// tree stays the compact index (0.14 B/char/level); this table trades memory (B + 4 sigma bytes per B rows)
+// for random-access traffic and is optional.  Ranges are identical by construction (same recurrences).
+#include "common.cuh"
+#include "prof.cuh"
+#include "wavelet.cuh"
+
+namespace hkcsa {
+
+constexpr int OCC_THREADS = 256;
+constexpr int OCC_SUB = 32;           // blocks per sub-chunk of a tile (4 per warp)
+
+struct OccDev {
+    const uint8_t *rows;
+    uint64_t stride;
+    uint32_t sigma;
+    uint32_t n;
+};
+
+// ---------------------------------------------------------------- build
+// One CTA per WTL_TILE rows.  gpre[code][tile] (wt_tile_hist + wt_tile_scan) = occurrences before the tile.
+template <int SHIFT>
+__global__ void __launch_bounds__(OCC_THREADS)
+occ_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTables *__restrict__ tab,
+                const uint32_t *__restrict__ gpre, uint32_t tiles, uint32_t sigma, uint64_t stride,
+                uint8_t *__restrict__ rows, uint64_t nrows)
+{
+    constexpr uint32_t B = 1u << SHIFT;
+    extern __shared__ uint16_t s_cnt[];                 // [OCC_SUB][sigma]
+    __shared__ uint32_t s_base[256];
+    __shared__ uint8_t s_code[256];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    s_code[tid] = tab->code8_of_sym[tid];
+    s_base[tid] = (tid < sigma) ? gpre[(size_t)tid * (tiles + 1) + blockIdx.x] : 0u;
+    const uint64_t tile_row0 = (uint64_t)blockIdx.x * (WTL_TILE / B);
+    for (uint32_t sub = 0; sub < WTL_TILE / B / OCC_SUB; ++sub) {
+        const uint64_t row0 = tile_row0 + (uint64_t)sub * OCC_SUB;
+        if (row0 >= nrows) break;
+        for (uint32_t i = tid; i < OCC_SUB * sigma; i += OCC_THREADS) s_cnt[i] = 0;
+        __syncthreads();
+        // ---- per block: copy the symbols, count them per code (match.any: one leader lane adds the group)
+        for (uint32_t q = 0; q < OCC_SUB / (OCC_THREADS / 32); ++q) {
+            const uint32_t blk = warp * (OCC_SUB / (OCC_THREADS / 32)) + q;
+            const uint64_t row = row0 + blk;
+            if (row >= nrows) break;
+            uint8_t *dst = rows + row * stride;
+#pragma unroll
+            for (uint32_t r = 0; r < B / 32; ++r) {
+                const uint64_t pos = row * B + r * 32u + lane;
+                const bool valid = pos < n;
+                const uint32_t ch = valid ? (uint32_t)bwt[pos] : 0u;
+                dst[r * 32u + lane] = (uint8_t)ch;
+                const uint32_t code = valid ? (uint32_t)s_code[ch] : 256u + lane;
+                const uint32_t peers = __match_any_sync(0xffffffffu, code);
+                if (valid && lane == (uint32_t)(__ffs(peers) - 1)) s_cnt[blk * sigma + code] += (uint16_t)__popc(peers);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // ---- per code: running count over the blocks of the sub-chunk -> the rows' counters
+        if (tid < sigma) {
+            uint32_t run = s_base[tid];
+            for (uint32_t blk = 0; blk < OCC_SUB; ++blk) {
+                const uint64_t row = row0 + blk;
+                if (row >= nrows) break;
+                reinterpret_cast<uint32_t *>(rows + row * stride + B)[tid] = run;
+                run += s_cnt[blk * sigma + tid];
+            }
+            s_base[tid] = run;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- rank
+// occurrences of byte `ch4` (replicated in all four bytes) among the first ta / tb bytes of a block
+template <int SHIFT>
+__device__ __forceinline__ void occ_count2(const uint8_t *blk, uint32_t ch4, uint32_t ta, uint32_t tb, bool both,
+                                           uint32_t &ca, uint32_t &cb)
+{
+    constexpr int VECS = (1 << SHIFT) / 16;
+    const uint4 *q = reinterpret_cast<const uint4 *>(blk);
+    const uint32_t tmax = both ? max(ta, tb) : ta;
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int v = 0; v < VECS; ++v) {
+        if (tmax > 16u * v) {
+            const uint4 x = __ldg(q + v);
+            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t m = __vcmpeq4(w[j], ch4);          // 0xFF per equal byte
+                const int first = 16 * v + 4 * j;
+                const int na = min(4, max(0, (int)ta - first)), nb = min(4, max(0, (int)tb - first));
+                a += __popc(m & (na >= 4 ? 0xFFFFFFFFu : ((1u << (8 * na)) - 1u)));
+                b += __popc(m & (nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u)));
+            }
+        }
+    }
+    ca = a >> 3;
+    cb = b >> 3;
+}
+
+// both boundaries of a backward-search step: a <- occ(code, a), b <- occ(code, b)
+template <int SHIFT>
+__device__ __forceinline__ void occ_rank2(const OccDev &o, uint32_t code, uint32_t ch, uint32_t &a, uint32_t &b)
+{
+    constexpr uint32_t B = 1u << SHIFT;
+    const uint32_t ch4 = ch * 0x01010101u;
+    const uint32_t ra = a >> SHIFT, rb = b >> SHIFT;
+    const uint8_t *pa = o.rows + (uint64_t)ra * o.stride;
+    const uint32_t base_a = __ldg(reinterpret_cast<const uint32_t *>(pa + B) + code);
+    uint32_t ca, cb;
+    if (ra == rb) {            // narrow range: one row serves both boundaries
+        occ_count2<SHIFT>(pa, ch4, a & (B - 1), b & (B - 1), true, ca, cb);
+        a = base_a + ca;
+        b = base_a + cb;
+    } else {
+        const uint8_t *pb = o.rows + (uint64_t)rb * o.stride;
+        const uint32_t base_b = __ldg(reinterpret_cast<const uint32_t *>(pb + B) + code);
+        uint32_t dummy;
+        occ_count2<SHIFT>(pa, ch4, a & (B - 1), 0, false, ca, dummy);
+        occ_count2<SHIFT>(pb, ch4, b & (B - 1), 0, false, cb, dummy);
+        a = base_a + ca;
+        b = base_b + cb;
+    }
+}
+
+// Same search as fm_count_kernel (fm_search.cu): one lane per pattern, lanes refilled as patterns end;
+// find_range (csa/enhanced_fm_index.py:21-32) in half-open form.  Only the rank primitive differs.
+template <int SHIFT>
+__global__ void __launch_bounds__(OCC_THREADS)
+fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t *__restrict__ pat,
+                    const int64_t *__restrict__ off, uint64_t P, int64_t *__restrict__ out_lo,
+                    int64_t *__restrict__ out_hi, const uint2 *__restrict__ kmer, uint32_t kk)
+{
+    __shared__ uint32_t s_C[260];
+    __shared__ uint16_t s_code[256];
+    for (uint32_t i = threadIdx.x; i < 260u; i += blockDim.x) s_C[i] = tab->C[i];
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) s_code[i] = tab->code_of_sym[i];
+    __syncthreads();
+    const uint32_t n = occ.n;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t chunk = (P + nwarps - 1) / nwarps;
+    uint64_t next = min(P, warp * chunk);
+    const uint64_t end = min(P, next + chunk);
+
+    int64_t p = -1;
+    int64_t k = 0, b = 0;
+    uint32_t l = 0, r = 0;
+    while (true) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, p < 0);
+        if (idle) {
+            const uint64_t mine = next + __popc(idle & lanemask_lt());
+            if (p < 0 && mine < end) {
+                p = (int64_t)mine;
+                b = off[mine];
+                k = off[mine + 1] - 1;
+                l = 0;
+                r = n;
+                if (kmer != nullptr && k - b + 1 >= (int64_t)kk) {
+                    uint32_t id = 0;
+                    bool known = true;
+                    for (uint32_t t = 0; t < kk; ++t) {
+                        const uint32_t code = s_code[pat[k - kk + 1 + t]];
+                        known = known && code != 0xFFFFu;
+                        id = id * occ.sigma + (known ? code : 0u);
+                    }
+                    if (known) {
+                        const uint2 e2 = __ldg(kmer + id);
+                        l = e2.x;
+                        r = e2.y;
+                        k -= kk;
+                        if (l >= r) { l = 1; r = 0; k = b - 1; }
+                    }
+                }
+            }
+            next += __popc(idle);
+            if (idle == 0xffffffffu && __ballot_sync(0xffffffffu, p >= 0) == 0) break;
+        }
+        if (p < 0) continue;
+        bool done = k < b, miss = l >= r;
+        if (!done) {
+            const uint32_t ch = pat[k];
+            const uint32_t code = s_code[ch];
+            if (code == 0xFFFFu) { miss = true; }
+            else {
+                occ_rank2<SHIFT>(occ, code, ch, l, r);
+                const uint32_t c0 = s_C[code];
+                l += c0;
+                r += c0;
+                miss = l >= r;
+            }
+            --k;
+            done = miss || k < b;
+        }
+        if (done) {
+            out_lo[p] = miss ? -1 : (int64_t)l;
+            out_hi[p] = miss ? -1 : (int64_t)r - 1;
+            p = -1;
+        }
+    }
+}
+
+// position of row j: LF walk until a marked row (locate_rows_kernel of fm_search.cu with the LF step read from
+// the Occ table: the symbol bwt[j] and its count before j come from the same row -- two sectors per step)
+template <int SHIFT>
+__global__ void __launch_bounds__(256)
+locate_rows_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, BitVec marks, const uint32_t *__restrict__ samples,
+                       uint32_t rate, const uint32_t *__restrict__ rows, uint64_t m, uint32_t *__restrict__ out)
+{
+    constexpr uint32_t B = 1u << SHIFT;
+    __shared__ uint32_t s_C[260];
+    __shared__ uint16_t s_code[256];
+    for (uint32_t i = threadIdx.x; i < 260u; i += blockDim.x) s_C[i] = tab->C[i];
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) s_code[i] = tab->code_of_sym[i];
+    __syncthreads();
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    uint32_t j = rows[q];
+    uint32_t steps = 0;
+    while (true) {
+        const uint64_t g = j / HKCSA_BLOCK_BITS;
+        const uint32_t o = j - (uint32_t)g * HKCSA_BLOCK_BITS;
+        const RankBlock b = load_block(marks.blocks + g);
+        if (block_bit(b, o)) {
+            const uint64_t r = marks.super[g / HKCSA_SUPER_BLOCKS] + (uint32_t)(b.w[0] & 0xFFFFFFFFu) + block_rank(b, o);
+            out[q] = samples[r] * rate + steps;
+            return;
+        }
+        const uint8_t *row = occ.rows + (uint64_t)(j >> SHIFT) * occ.stride;
+        const uint32_t t = j & (B - 1);
+        const uint32_t ch = __ldg(row + t);
+        const uint32_t code = s_code[ch];
+        const uint32_t base = __ldg(reinterpret_cast<const uint32_t *>(row + B) + code);
+        uint32_t c, dummy;
+        occ_count2<SHIFT>(row, ch * 0x01010101u, t, 0, false, c, dummy);
+        j = s_C[code] + base + c;
+        ++steps;
+    }
+}
+
+}  // namespace hkcsa
+
+using namespace hkcsa;
+
+extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, hkcsa_occ_plan *p)
+{
+    HK_REQUIRE(p != nullptr, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(shift == 5 || shift == 6, HKCSA_EINVAL, "shift must be 5 (32 rows per entry) or 6 (64)");
+    HK_REQUIRE(sigma >= 1 && sigma <= 256, HKCSA_EINVAL, "bad alphabet size");
+    HK_REQUIRE(n >= 1 && n <= HKCSA_MAX_N, HKCSA_ERANGE, "n out of range");
+    memset(p, 0, sizeof(*p));
+    p->n = n;
+    p->sigma = sigma;
+    p->shift = shift;
+    p->rows = (n >> shift) + 1;
+    p->stride = align_up(((size_t)1 << shift) + 4 * (size_t)sigma, 32);
+    p->blob_bytes = align_up(p->rows * p->stride, 256);
+    const uint64_t tiles = (n + WTL_TILE - 1) / WTL_TILE;
+    Carver c(nullptr);
+    c.take<uint32_t>((uint64_t)sigma * (tiles + 2));
+    p->scratch_bytes = c.total();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt, const uint8_t *d_bwt,
+                               const hkcsa_occ_plan *p, void *d_blob, void *d_scratch, size_t scratch_bytes,
+                               void *stream)
+{
+    HK_REQUIRE(d_wt_blob && h_wt && d_bwt && p && d_blob && d_scratch, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(p->n == h_wt->n && p->sigma == h_wt->sigma, HKCSA_EINVAL, "occ plan does not match the index");
+    HK_REQUIRE(scratch_bytes >= p->scratch_bytes, HKCSA_ESCRATCH, "occ scratch too small");
+    HK_REQUIRE((reinterpret_cast<uintptr_t>(d_blob) & 31) == 0, HKCSA_EINVAL, "d_blob must be 32-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const uint64_t n = p->n;
+    const uint32_t tiles = (uint32_t)((n + WTL_TILE - 1) / WTL_TILE);
+    const WtTables *d_tab = reinterpret_cast<const WtTables *>(static_cast<const uint8_t *>(d_wt_blob) + h_wt->off_tables);
+    Carver c(d_scratch);
+    uint32_t *d_gcnt = c.take<uint32_t>((uint64_t)p->sigma * (tiles + 2));
+    prof::Scope ps(st, prof::OTHER, n + p->rows * p->stride);
+    wt_tile_hist_kernel<<<tiles, WTL_THREADS, 0, st>>>(d_bwt, n, d_tab, p->sigma, tiles, d_gcnt);
+    HK_LAUNCH_CHECK();
+    wt_tile_scan_kernel<<<p->sigma, 1024, 0, st>>>(d_gcnt, tiles);
+    HK_LAUNCH_CHECK();
+    // the row of position n exists even when n is a multiple of the tile: one more CTA then reads the totals
+    const uint32_t grid = (uint32_t)(n / WTL_TILE) + 1;
+    const size_t smem = (size_t)OCC_SUB * p->sigma * sizeof(uint16_t);
+    uint8_t *rows = static_cast<uint8_t *>(d_blob);
+    if (p->shift == 5)
+        occ_fill_kernel<5><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows);
+    else
+        occ_fill_kernel<6><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt, const void *d_occ_blob,
+                                     const hkcsa_occ_plan *p, const void *d_kmer_table, uint32_t k,
+                                     const uint8_t *d_pat, const int64_t *d_off, uint64_t P, int64_t *d_lo,
+                                     int64_t *d_hi, void *stream)
+{
+    HK_REQUIRE(d_wt_blob && h_wt && d_occ_blob && p, HKCSA_EINVAL, "null pointer");
+    if (P == 0) return HKCSA_OK;
+    HK_REQUIRE(d_off && d_lo && d_hi, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(p->n == h_wt->n && p->sigma == h_wt->sigma && p->n >= 1, HKCSA_EINVAL, "occ plan does not match the index");
+    cudaStream_t st = as_stream(stream);
+    const WtTables *d_tab = reinterpret_cast<const WtTables *>(static_cast<const uint8_t *>(d_wt_blob) + h_wt->off_tables);
+    OccDev occ;
+    occ.rows = static_cast<const uint8_t *>(d_occ_blob);
+    occ.stride = p->stride;
+    occ.sigma = p->sigma;
+    occ.n = (uint32_t)p->n;
+    const int blocks = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 8);
+    const uint2 *kmer = static_cast<const uint2 *>(d_kmer_table);
+    prof::Scope ps(st, prof::COUNT, 0);
+    if (p->shift == 5)
+        fm_count_occ_kernel<5><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
+    else
+        fm_count_occ_kernel<6><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt, const void *d_occ_blob,
+                                     const hkcsa_occ_plan *p, const void *d_ssa_blob, const hkcsa_ssa_plan *h_ssa,
+                                     const uint32_t *d_rows, uint64_t m, uint32_t *d_out_pos, void *stream)
+{
+    if (m == 0) return HKCSA_OK;
+    HK_REQUIRE(d_wt_blob && h_wt && d_occ_blob && p && d_ssa_blob && h_ssa && d_rows && d_out_pos, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(p->n == h_wt->n && p->sigma == h_wt->sigma && h_ssa->n == p->n, HKCSA_EINVAL, "plans do not match");
+    cudaStream_t st = as_stream(stream);
+    const WtTables *d_tab = reinterpret_cast<const WtTables *>(static_cast<const uint8_t *>(d_wt_blob) + h_wt->off_tables);
+    OccDev occ;
+    occ.rows = static_cast<const uint8_t *>(d_occ_blob);
+    occ.stride = p->stride;
+    occ.sigma = p->sigma;
+    occ.n = (uint32_t)p->n;
+    const uint8_t *sb = static_cast<const uint8_t *>(d_ssa_blob);
+    BitVec marks;
+    marks.blocks = reinterpret_cast<const RankBlock *>(sb + h_ssa->off_blocks);
+    marks.super = reinterpret_cast<const uint64_t *>(sb + h_ssa->off_super);
+    marks.len = h_ssa->n;
+    const uint32_t *samples = reinterpret_cast<const uint32_t *>(sb + h_ssa->off_samples);
+    const uint32_t grid = (uint32_t)((m + 255) / 256);
+    prof::Scope ps(st, prof::LOCATE, 0);
+    if (p->shift == 5)
+        locate_rows_occ_kernel<5><<<grid, 256, 0, st>>>(occ, d_tab, marks, samples, h_ssa->rate, d_rows, m, d_out_pos);
+    else
+        locate_rows_occ_kernel<6><<<grid, 256, 0, st>>>(occ, d_tab, marks, samples, h_ssa->rate, d_rows, m, d_out_pos);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}

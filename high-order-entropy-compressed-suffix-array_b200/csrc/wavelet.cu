@@ -159,8 +159,6 @@ wt_dir_fix_kernel(RankBlock *__restrict__ blocks, uint64_t nblocks, const uint64
 // (edge words shared with neighbouring tiles).  The next level's order is a stable split of every
 // run by its bit, computed from a tile-wide prefix sum of the bits.  The sequence is read from HBM
 // once for all levels and only bits are written.
-constexpr int WTL_THREADS = 256;
-constexpr int WTL_TILE = 8192;
 constexpr int WTL_EPT = WTL_TILE / WTL_THREADS;   // 32 symbols per thread = one bit word
 static_assert(WTL_EPT == 32, "one 32-bit word of bits per thread");
 

@@ -53,6 +53,14 @@ static inline WtDev make_wt_dev(const void *d_blob, const hkcsa_wt_plan *p)
     return d;
 }
 
+// Tile histogram + per-symbol exclusive prefix over tiles (wavelet.cu); also used by the sampled Occ table.
+constexpr int WTL_THREADS = 256;
+constexpr int WTL_TILE = 8192;
+__global__ void __launch_bounds__(WTL_THREADS)
+wt_tile_hist_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__restrict__ tab, uint32_t sigma,
+                    uint32_t tiles, uint32_t *__restrict__ gcnt /* [sigma][tiles+1] */);
+__global__ void __launch_bounds__(1024) wt_tile_scan_kernel(uint32_t *__restrict__ gcnt, uint32_t tiles);
+
 // Shared-memory copy of what a symbol-rank walk needs ("C[] held in shared memory").
 struct WtSmem {
     uint32_t node_start[HKCSA_MAX_LEVELS][256];

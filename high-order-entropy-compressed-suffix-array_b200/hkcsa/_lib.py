@@ -81,6 +81,18 @@ class SsaPlan(C.Structure):
     ]
 
 
+class OccPlan(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint64),
+        ("sigma", C.c_uint32),
+        ("shift", C.c_uint32),
+        ("rows", C.c_uint64),
+        ("stride", C.c_uint64),
+        ("blob_bytes", C.c_uint64),
+        ("scratch_bytes", C.c_uint64),
+    ]
+
+
 class ProfEntry(C.Structure):
     _fields_ = [
         ("name", C.c_char * 32),
@@ -132,6 +144,12 @@ SIGNATURES = {
     "hkcsa_golomb_encode": (_i32, [_vp, C.POINTER(WtPlan), _u32, _u64, _u32, _vp, _u64, C.POINTER(_u64), _vp,
                                    _sz, _vp]),
     "hkcsa_count_batch": (_i32, [_vp, C.POINTER(WtPlan), _vp, _vp, _u64, _vp, _vp, _vp]),
+    "hkcsa_occ_plan_make": (_i32, [_u64, _u32, _u32, C.POINTER(OccPlan)]),
+    "hkcsa_occ_build": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(OccPlan), _vp, _vp, _sz, _vp]),
+    "hkcsa_count_batch_occ": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(OccPlan), _vp, _u32, _vp, _vp, _u64,
+                                     _vp, _vp, _vp]),
+    "hkcsa_locate_rows_occ": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(OccPlan), _vp, C.POINTER(SsaPlan), _vp,
+                                     _u64, _vp, _vp]),
     "hkcsa_kmer_k": (_u32, [_u32]),
     "hkcsa_kmer_entries": (_u64, [_u32, _u32]),
     "hkcsa_kmer_scratch_bytes": (_sz, [_u32, _u32]),
@@ -175,7 +193,7 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if L.hkcsa_abi_version() != 1:
         raise ImportError("libhkcsa.so ABI version mismatch")
-    for idx, st in enumerate((SaStats, WtPlan, SsaPlan, ProfEntry)):
+    for idx, st in enumerate((SaStats, WtPlan, SsaPlan, ProfEntry, OccPlan)):
         if L.hkcsa_struct_size(idx) != C.sizeof(st):
             raise ImportError(f"struct layout mismatch for {st.__name__}: "
                               f"C {L.hkcsa_struct_size(idx)} vs ctypes {C.sizeof(st)}")

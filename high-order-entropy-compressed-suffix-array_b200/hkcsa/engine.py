@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import HkcsaError, SaStats, SsaPlan, WtPlan, check
+from ._lib import HkcsaError, OccPlan, SaStats, SsaPlan, WtPlan, check
 
 ENG96, DNA4 = 0, 1
 
@@ -442,8 +442,29 @@ class DeviceIndex:
         self._kmer = (table, k)
         return self._kmer
 
+    def build_occ_table(self, shift: int = 5, bwt: torch.Tensor | None = None):
+        """Sampled Occ table (csrc/occ_table.cu): the reference's dense occ (utils/utils.py:26-32) kept at every
+        2^shift-th row next to the BWT bytes of that stretch.  Optional: costs 2^shift + 4 sigma bytes per 2^shift
+        rows, makes a rank one or two sector reads instead of one per wavelet level.  Needs the BWT (kept by the
+        builder; replicas pass it in)."""
+        L = _lib.load()
+        bwt = self.bwt if bwt is None else bwt
+        if bwt is None:
+            raise ValueError("the sampled Occ table is built from the BWT, which this index no longer holds")
+        plan = OccPlan()
+        check(L.hkcsa_occ_plan_make(self.n, self.wt.sigma, shift, C.byref(plan)))
+        blob = _empty(int(plan.blob_bytes), torch.uint8, self.device)
+        scratch = _scratch(int(plan.scratch_bytes), self.device)
+        check(L.hkcsa_occ_build(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(bwt), C.byref(plan), _ptr(blob),
+                                _ptr(scratch), int(plan.scratch_bytes), _stream()))
+        self._occ = (plan, blob)
+        return self._occ
+
     # find_range, batched (csa/enhanced_fm_index.py:21-32)
-    def count_batch(self, pat: torch.Tensor, off: torch.Tensor, use_kmer_table: bool | None = None):
+    def count_batch(self, pat: torch.Tensor, off: torch.Tensor, use_kmer_table: bool | None = None,
+                    use_occ_table: bool | None = None):
+        """use_occ_table: None = use the sampled Occ table when one was built (build_occ_table); False = always
+        rank on the wavelet tree.  Both give identical ranges."""
         P = off.numel() - 1
         lo = _empty(P, torch.int64, self.device)
         hi = _empty(P, torch.int64, self.device)
@@ -454,6 +475,16 @@ class DeviceIndex:
         table, k = (None, 0)
         if use_kmer_table:
             table, k = getattr(self, "_kmer", None) or self.build_kmer_table()
+        occ = getattr(self, "_occ", None)
+        if use_occ_table is None:
+            use_occ_table = occ is not None
+        if use_occ_table:
+            if occ is None:
+                raise ValueError("no sampled Occ table: call build_occ_table() first")
+            check(_lib.load().hkcsa_count_batch_occ(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(occ[1]),
+                                                    C.byref(occ[0]), _ptr(table), k, _ptr(pat), _ptr(off), P,
+                                                    _ptr(lo), _ptr(hi), _stream()))
+            return lo, hi
         check(_lib.load().hkcsa_count_batch_kmer(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(table), k, _ptr(pat),
                                                  _ptr(off), P, _ptr(lo), _ptr(hi), _stream()))
         return lo, hi
@@ -479,6 +510,12 @@ class DeviceIndex:
         if use_samples:
             if self.ssa is None:
                 raise ValueError("index was built without a sampled suffix array")
+            occ = getattr(self, "_occ", None)
+            if occ is not None:      # LF steps from the sampled Occ table: two sectors instead of one per level
+                check(L.hkcsa_locate_rows_occ(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(occ[1]), C.byref(occ[0]),
+                                              _ptr(self.ssa.blob), C.byref(self.ssa.plan), _ptr(rows), rows.numel(),
+                                              _ptr(out), _stream()))
+                return out
             check(L.hkcsa_locate_rows(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(self.ssa.blob),
                                       C.byref(self.ssa.plan), _ptr(rows), rows.numel(), _ptr(out), _stream()))
         else:

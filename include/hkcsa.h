@@ -47,7 +47,7 @@ extern "C" {
 int         hkcsa_abi_version(void);
 const char *hkcsa_last_error(void);
 /* sizeof of the public structs (0 hkcsa_sa_stats, 1 hkcsa_wt_plan, 2 hkcsa_ssa_plan, */
-/* 3 hkcsa_prof_entry) so a binding can verify its mirror of the layout.              */
+/* 3 hkcsa_prof_entry, 4 hkcsa_occ_plan) so a binding can verify its mirror.          */
 size_t      hkcsa_struct_size(int which);
 
 /* ------------------------------------------------------------------------ */
@@ -335,6 +335,33 @@ unsigned long long hkcsa_launch_count(void);
 int hkcsa_prof_enable(int on);
 int hkcsa_prof_reset(void);
 int hkcsa_prof_read(hkcsa_prof_entry *h_out, int max_entries, int *h_n);
+
+/* ------------------------------------------------------------------------ */
+/* Sampled Occ table (optional second rank structure): the reference's dense occ[c][i] (build_occ,          */
+/* utils/utils.py:26-32; read by EnhancedFMIndex.rank, csa/enhanced_fm_index.py:34-40) kept at every       */
+/* 2^shift-th row, each kept row stored next to the 2^shift BWT bytes the remainder is counted from:       */
+/*   row r = [2^shift BWT bytes][sigma x uint32 occ[code][r << shift]], `stride` bytes apart, rows = (n >> shift) + 1. */
+/* One rank touches one counter sector + the symbol sector(s), whatever the alphabet (the wavelet tree: one */
+/* sector per level).  hkcsa_count_batch_occ returns exactly what hkcsa_count_batch returns.                */
+typedef struct hkcsa_occ_plan {
+    uint64_t n;
+    uint32_t sigma;
+    uint32_t shift;          /* 5 or 6 */
+    uint64_t rows;
+    uint64_t stride;         /* bytes per row, multiple of 32 */
+    uint64_t blob_bytes;
+    uint64_t scratch_bytes;  /* for hkcsa_occ_build */
+} hkcsa_occ_plan;
+int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, hkcsa_occ_plan *h_plan);
+int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const uint8_t *d_bwt,
+                    const hkcsa_occ_plan *h_plan, void *d_blob, void *d_scratch, size_t scratch_bytes, void *stream);
+int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const void *d_occ_blob,
+                          const hkcsa_occ_plan *h_plan, const void *d_kmer_table, uint32_t k, const uint8_t *d_pat,
+                          const int64_t *d_off, uint64_t P, int64_t *d_lo, int64_t *d_hi, void *stream);
+/* hkcsa_locate_rows with the LF step (symbol + its count) read from the Occ table; same positions. */
+int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const void *d_occ_blob,
+                          const hkcsa_occ_plan *h_plan, const void *d_ssa_blob, const hkcsa_ssa_plan *h_ssa,
+                          const uint32_t *d_rows, uint64_t m, uint32_t *d_out_pos, void *stream);
 
 #ifdef __cplusplus
 }
