@@ -194,16 +194,26 @@ __device__ __forceinline__ uint32_t block_bit(const RankBlock &b, uint32_t o)
     const uint32_t t = o + 32u;
     return (uint32_t)(b.w[t >> 6] >> (t & 63u)) & 1u;
 }
+// one 256-bit read-only load (sm_100: LDG.E.256) of a 32-byte-aligned sector
+__device__ __forceinline__ void ld_nc_256(const void *p, uint64_t &w0, uint64_t &w1, uint64_t &w2, uint64_t &w3)
+{
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(p));
+}
+// same, not allocated in L1: isolated random sectors that are used once must not evict the streams L1 serves
+__device__ __forceinline__ void ld_nc_256_na(const void *p, uint64_t &w0, uint64_t &w1, uint64_t &w2, uint64_t &w3)
+{
+    asm("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(p));
+}
+__device__ __forceinline__ uint32_t ld_nc_u32_na(const uint32_t *p)
+{
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ RankBlock load_block(const RankBlock *p)
 {
-    // two 16-byte loads of the same sector
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    uint4 a = __ldg(q), c = __ldg(q + 1);
-    RankBlock b;
-    b.w[0] = ((uint64_t)a.y << 32) | a.x;
-    b.w[1] = ((uint64_t)a.w << 32) | a.z;
-    b.w[2] = ((uint64_t)c.y << 32) | c.x;
-    b.w[3] = ((uint64_t)c.w << 32) | c.z;
+    RankBlock b;          // the whole block = one sector = one load instruction
+    ld_nc_256(p, b.w[0], b.w[1], b.w[2], b.w[3]);
     return b;
 }
 

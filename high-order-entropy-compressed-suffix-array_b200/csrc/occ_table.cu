@@ -26,7 +26,19 @@ struct OccDev {
     uint64_t stride;
     uint32_t sigma;
     uint32_t n;
+    uint32_t grouped;     // layout 1: every row is ceil(sigma / 8) chunks of 64 bytes = [32 BWT bytes][8 counters]
 };
+
+// where the symbols / the counter of `code` live inside a row (B = bytes per row in layout 0)
+__device__ __forceinline__ const uint8_t *occ_sym_ptr(const OccDev &o, uint32_t row, uint32_t code)
+{
+    return o.rows + (uint64_t)row * o.stride + (o.grouped ? (code >> 3) * 64u : 0u);
+}
+__device__ __forceinline__ const uint32_t *occ_cnt_ptr(const OccDev &o, const uint8_t *sym, uint32_t code, uint32_t B)
+{
+    return o.grouped ? reinterpret_cast<const uint32_t *>(sym + 32) + (code & 7u)
+                     : reinterpret_cast<const uint32_t *>(sym + B) + code;
+}
 
 // ---------------------------------------------------------------- build
 // One CTA per WTL_TILE rows.  gpre[code][tile] (wt_tile_hist + wt_tile_scan) = occurrences before the tile.
@@ -34,9 +46,10 @@ template <int SHIFT>
 __global__ void __launch_bounds__(OCC_THREADS)
 occ_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTables *__restrict__ tab,
                 const uint32_t *__restrict__ gpre, uint32_t tiles, uint32_t sigma, uint64_t stride,
-                uint8_t *__restrict__ rows, uint64_t nrows)
+                uint8_t *__restrict__ rows, uint64_t nrows, uint32_t grouped)
 {
     constexpr uint32_t B = 1u << SHIFT;
+    const uint32_t groups = grouped ? (sigma + 7u) / 8u : 1u;
     extern __shared__ uint16_t s_cnt[];                 // [OCC_SUB][sigma]
     __shared__ uint32_t s_base[256];
     __shared__ uint8_t s_code[256];
@@ -60,7 +73,7 @@ occ_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTables *__r
                 const uint64_t pos = row * B + r * 32u + lane;
                 const bool valid = pos < n;
                 const uint32_t ch = valid ? (uint32_t)bwt[pos] : 0u;
-                dst[r * 32u + lane] = (uint8_t)ch;
+                for (uint32_t g = 0; g < groups; ++g) dst[g * 64u + r * 32u + lane] = (uint8_t)ch;
                 const uint32_t code = valid ? (uint32_t)s_code[ch] : 256u + lane;
                 const uint32_t peers = __match_any_sync(0xffffffffu, code);
                 if (valid && lane == (uint32_t)(__ffs(peers) - 1)) s_cnt[blk * sigma + code] += (uint16_t)__popc(peers);
@@ -74,7 +87,8 @@ occ_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTables *__r
             for (uint32_t blk = 0; blk < OCC_SUB; ++blk) {
                 const uint64_t row = row0 + blk;
                 if (row >= nrows) break;
-                reinterpret_cast<uint32_t *>(rows + row * stride + B)[tid] = run;
+                if (grouped) reinterpret_cast<uint32_t *>(rows + row * stride + (tid >> 3) * 64u + 32u)[tid & 7u] = run;
+                else reinterpret_cast<uint32_t *>(rows + row * stride + B)[tid] = run;
                 run += s_cnt[blk * sigma + tid];
             }
             s_base[tid] = run;
@@ -84,63 +98,60 @@ occ_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTables *__r
 }
 
 // ---------------------------------------------------------------- rank
-// occurrences of byte `ch4` (replicated in all four bytes) among the first ta / tb bytes of a block
+// bit j of the result = (byte j of the block == ch), for the 2^SHIFT bytes held in x[]
 template <int SHIFT>
-__device__ __forceinline__ void occ_count2(const uint8_t *blk, uint32_t ch4, uint32_t ta, uint32_t tb, bool both,
-                                           uint32_t &ca, uint32_t &cb)
+__device__ __forceinline__ uint64_t occ_match_bits(const uint64_t (&x)[(1 << SHIFT) / 8], uint32_t ch4)
 {
-    constexpr int VECS = (1 << SHIFT) / 16;
-    const uint4 *q = reinterpret_cast<const uint4 *>(blk);
-    const uint32_t tmax = both ? max(ta, tb) : ta;
-    uint32_t a = 0, b = 0;
+    uint64_t bits = 0;
 #pragma unroll
-    for (int v = 0; v < VECS; ++v) {
-        if (tmax > 16u * v) {
-            const uint4 x = __ldg(q + v);
-            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t m = __vcmpeq4(w[j], ch4);          // 0xFF per equal byte
-                const int first = 16 * v + 4 * j;
-                const int na = min(4, max(0, (int)ta - first)), nb = min(4, max(0, (int)tb - first));
-                a += __popc(m & (na >= 4 ? 0xFFFFFFFFu : ((1u << (8 * na)) - 1u)));
-                b += __popc(m & (nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u)));
-            }
-        }
+    for (int v = 0; v < (1 << SHIFT) / 8; ++v) {
+        const uint32_t lo = __vcmpeq4((uint32_t)x[v], ch4) & 0x01010101u;           // 1 per equal byte
+        const uint32_t hi = __vcmpeq4((uint32_t)(x[v] >> 32), ch4) & 0x01010101u;
+        const uint32_t byte = ((lo * 0x01020408u) >> 24) | (((hi * 0x01020408u) >> 24) << 4);   // byte i -> bit i
+        bits |= (uint64_t)byte << (8 * v);
     }
-    ca = a >> 3;
-    cb = b >> 3;
+    return bits;
+}
+// the row's symbols: one 256-bit load per 32 bytes (LDG.E.256), not allocated in L1 (isolated random sectors
+// must not evict the pattern bytes L1 serves)
+template <int SHIFT>
+__device__ __forceinline__ void occ_load_row(const uint8_t *sym, uint64_t (&x)[(1 << SHIFT) / 8])
+{
+#pragma unroll
+    for (int v = 0; v < (1 << SHIFT) / 32; ++v) ld_nc_256_na(sym + 32 * v, x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
+}
+// occurrences of `ch` among the first t bytes (t < 2^SHIFT) of the row whose symbols start at `sym`
+template <int SHIFT>
+__device__ __forceinline__ uint32_t occ_count(const uint8_t *sym, uint32_t ch4, uint32_t t)
+{
+    uint64_t x[(1 << SHIFT) / 8];
+    occ_load_row<SHIFT>(sym, x);
+    return __popcll(occ_match_bits<SHIFT>(x, ch4) & ((1ull << t) - 1ull));
 }
 
-// both boundaries of a backward-search step: a <- occ(code, a), b <- occ(code, b)
+// both boundaries of a backward-search step: a <- occ(code, a), b <- occ(code, b).  The four loads (two
+// counters, two symbol blocks) are issued together whether or not the boundaries share a row: no divergent
+// paths inside the warp, one memory round trip per step (a shared row is served by the same sectors).
 template <int SHIFT>
 __device__ __forceinline__ void occ_rank2(const OccDev &o, uint32_t code, uint32_t ch, uint32_t &a, uint32_t &b)
 {
     constexpr uint32_t B = 1u << SHIFT;
     const uint32_t ch4 = ch * 0x01010101u;
-    const uint32_t ra = a >> SHIFT, rb = b >> SHIFT;
-    const uint8_t *pa = o.rows + (uint64_t)ra * o.stride;
-    const uint32_t base_a = __ldg(reinterpret_cast<const uint32_t *>(pa + B) + code);
-    uint32_t ca, cb;
-    if (ra == rb) {            // narrow range: one row serves both boundaries
-        occ_count2<SHIFT>(pa, ch4, a & (B - 1), b & (B - 1), true, ca, cb);
-        a = base_a + ca;
-        b = base_a + cb;
-    } else {
-        const uint8_t *pb = o.rows + (uint64_t)rb * o.stride;
-        const uint32_t base_b = __ldg(reinterpret_cast<const uint32_t *>(pb + B) + code);
-        uint32_t dummy;
-        occ_count2<SHIFT>(pa, ch4, a & (B - 1), 0, false, ca, dummy);
-        occ_count2<SHIFT>(pb, ch4, b & (B - 1), 0, false, cb, dummy);
-        a = base_a + ca;
-        b = base_b + cb;
-    }
+    const uint8_t *pa = occ_sym_ptr(o, a >> SHIFT, code);
+    const uint8_t *pb = occ_sym_ptr(o, b >> SHIFT, code);
+    const uint32_t base_a = ld_nc_u32_na(occ_cnt_ptr(o, pa, code, B));
+    const uint32_t base_b = ld_nc_u32_na(occ_cnt_ptr(o, pb, code, B));
+    uint64_t xa[B / 8], xb[B / 8];
+    occ_load_row<SHIFT>(pa, xa);
+    occ_load_row<SHIFT>(pb, xb);
+    a = base_a + __popcll(occ_match_bits<SHIFT>(xa, ch4) & ((1ull << (a & (B - 1))) - 1ull));
+    b = base_b + __popcll(occ_match_bits<SHIFT>(xb, ch4) & ((1ull << (b & (B - 1))) - 1ull));
 }
 
 // Same search as fm_count_kernel (fm_search.cu): one lane per pattern, lanes refilled as patterns end;
 // find_range (csa/enhanced_fm_index.py:21-32) in half-open form.  Only the rank primitive differs.
 template <int SHIFT>
-__global__ void __launch_bounds__(OCC_THREADS)
+__global__ void __launch_bounds__(OCC_THREADS, 4)
 fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t *__restrict__ pat,
                     const int64_t *__restrict__ off, uint64_t P, int64_t *__restrict__ out_lo,
                     int64_t *__restrict__ out_hi, const uint2 *__restrict__ kmer, uint32_t kk)
@@ -160,6 +171,7 @@ fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t 
     int64_t p = -1;
     int64_t k = 0, b = 0;
     uint32_t l = 0, r = 0;
+    uint32_t ch_next = 0;      // pat[k], loaded one step ahead so the step's rank loads do not wait for it
     while (true) {
         const uint32_t idle = __ballot_sync(0xffffffffu, p < 0);
         if (idle) {
@@ -186,6 +198,7 @@ fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t 
                         if (l >= r) { l = 1; r = 0; k = b - 1; }
                     }
                 }
+                if (k >= b) ch_next = pat[k];
             }
             next += __popc(idle);
             if (idle == 0xffffffffu && __ballot_sync(0xffffffffu, p >= 0) == 0) break;
@@ -193,7 +206,8 @@ fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t 
         if (p < 0) continue;
         bool done = k < b, miss = l >= r;
         if (!done) {
-            const uint32_t ch = pat[k];
+            const uint32_t ch = ch_next;
+            if (k > b) ch_next = pat[k - 1];
             const uint32_t code = s_code[ch];
             if (code == 0xFFFFu) { miss = true; }
             else {
@@ -240,14 +254,12 @@ locate_rows_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, BitVec mark
             out[q] = samples[r] * rate + steps;
             return;
         }
-        const uint8_t *row = occ.rows + (uint64_t)(j >> SHIFT) * occ.stride;
         const uint32_t t = j & (B - 1);
-        const uint32_t ch = __ldg(row + t);
+        const uint32_t ch = __ldg(occ.rows + (uint64_t)(j >> SHIFT) * occ.stride + t);   // chunk 0 always holds the symbols
         const uint32_t code = s_code[ch];
-        const uint32_t base = __ldg(reinterpret_cast<const uint32_t *>(row + B) + code);
-        uint32_t c, dummy;
-        occ_count2<SHIFT>(row, ch * 0x01010101u, t, 0, false, c, dummy);
-        j = s_C[code] + base + c;
+        const uint8_t *row = occ_sym_ptr(occ, j >> SHIFT, code);
+        const uint32_t base = __ldg(occ_cnt_ptr(occ, row, code, B));
+        j = s_C[code] + base + occ_count<SHIFT>(row, ch * 0x01010101u, t);
         ++steps;
     }
 }
@@ -256,10 +268,11 @@ locate_rows_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, BitVec mark
 
 using namespace hkcsa;
 
-extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, hkcsa_occ_plan *p)
+extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, uint32_t layout, hkcsa_occ_plan *p)
 {
     HK_REQUIRE(p != nullptr, HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(shift == 5 || shift == 6, HKCSA_EINVAL, "shift must be 5 (32 rows per entry) or 6 (64)");
+    HK_REQUIRE(layout == 0 || (layout == 1 && shift == 5), HKCSA_EINVAL, "layout 1 (64-byte chunks) needs shift 5");
     HK_REQUIRE(sigma >= 1 && sigma <= 256, HKCSA_EINVAL, "bad alphabet size");
     HK_REQUIRE(n >= 1 && n <= HKCSA_MAX_N, HKCSA_ERANGE, "n out of range");
     memset(p, 0, sizeof(*p));
@@ -267,7 +280,8 @@ extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, h
     p->sigma = sigma;
     p->shift = shift;
     p->rows = (n >> shift) + 1;
-    p->stride = align_up(((size_t)1 << shift) + 4 * (size_t)sigma, 32);
+    p->layout = layout;
+    p->stride = layout ? 64 * (((size_t)sigma + 7) / 8) : align_up(((size_t)1 << shift) + 4 * (size_t)sigma, 32);
     p->blob_bytes = align_up(p->rows * p->stride, 256);
     const uint64_t tiles = (n + WTL_TILE - 1) / WTL_TILE;
     Carver c(nullptr);
@@ -283,7 +297,7 @@ extern "C" int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt,
     HK_REQUIRE(d_wt_blob && h_wt && d_bwt && p && d_blob && d_scratch, HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(p->n == h_wt->n && p->sigma == h_wt->sigma, HKCSA_EINVAL, "occ plan does not match the index");
     HK_REQUIRE(scratch_bytes >= p->scratch_bytes, HKCSA_ESCRATCH, "occ scratch too small");
-    HK_REQUIRE((reinterpret_cast<uintptr_t>(d_blob) & 31) == 0, HKCSA_EINVAL, "d_blob must be 32-byte aligned");
+    HK_REQUIRE((reinterpret_cast<uintptr_t>(d_blob) & 63) == 0, HKCSA_EINVAL, "d_blob must be 64-byte aligned");
     cudaStream_t st = as_stream(stream);
     const uint64_t n = p->n;
     const uint32_t tiles = (uint32_t)((n + WTL_TILE - 1) / WTL_TILE);
@@ -300,9 +314,9 @@ extern "C" int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt,
     const size_t smem = (size_t)OCC_SUB * p->sigma * sizeof(uint16_t);
     uint8_t *rows = static_cast<uint8_t *>(d_blob);
     if (p->shift == 5)
-        occ_fill_kernel<5><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows);
+        occ_fill_kernel<5><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows, p->layout);
     else
-        occ_fill_kernel<6><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows);
+        occ_fill_kernel<6><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows, p->layout);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }
@@ -323,6 +337,7 @@ extern "C" int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan 
     occ.stride = p->stride;
     occ.sigma = p->sigma;
     occ.n = (uint32_t)p->n;
+    occ.grouped = p->layout;
     const int blocks = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 8);
     const uint2 *kmer = static_cast<const uint2 *>(d_kmer_table);
     prof::Scope ps(st, prof::COUNT, 0);
@@ -348,6 +363,7 @@ extern "C" int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan 
     occ.stride = p->stride;
     occ.sigma = p->sigma;
     occ.n = (uint32_t)p->n;
+    occ.grouped = p->layout;
     const uint8_t *sb = static_cast<const uint8_t *>(d_ssa_blob);
     BitVec marks;
     marks.blocks = reinterpret_cast<const RankBlock *>(sb + h_ssa->off_blocks);
