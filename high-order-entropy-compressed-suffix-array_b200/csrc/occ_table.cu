@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "prof.cuh"
 #include "wavelet.cuh"
+#include <stdlib.h>
 
 namespace hkcsa {
 
@@ -26,18 +27,16 @@ struct OccDev {
     uint64_t stride;
     uint32_t sigma;
     uint32_t n;
-    uint32_t grouped;     // layout 1: every row is ceil(sigma / 8) chunks of 64 bytes = [32 BWT bytes][8 counters]
 };
 
-// where the symbols / the counter of `code` live inside a row (B = bytes per row in layout 0)
-__device__ __forceinline__ const uint8_t *occ_sym_ptr(const OccDev &o, uint32_t row, uint32_t code)
+// where the symbols / the counter of `code` live inside a row (B = symbols per row)
+__device__ __forceinline__ const uint8_t *occ_sym_ptr(const OccDev &o, uint32_t row)
 {
-    return o.rows + (uint64_t)row * o.stride + (o.grouped ? (code >> 3) * 64u : 0u);
+    return o.rows + (uint64_t)row * o.stride;
 }
-__device__ __forceinline__ const uint32_t *occ_cnt_ptr(const OccDev &o, const uint8_t *sym, uint32_t code, uint32_t B)
+__device__ __forceinline__ const uint32_t *occ_cnt_ptr(const uint8_t *sym, uint32_t code, uint32_t B)
 {
-    return o.grouped ? reinterpret_cast<const uint32_t *>(sym + 32) + (code & 7u)
-                     : reinterpret_cast<const uint32_t *>(sym + B) + code;
+    return reinterpret_cast<const uint32_t *>(sym + B) + code;
 }
 
 // ---------------------------------------------------------------- build
@@ -46,10 +45,9 @@ template <int SHIFT>
 __global__ void __launch_bounds__(OCC_THREADS)
 occ_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTables *__restrict__ tab,
                 const uint32_t *__restrict__ gpre, uint32_t tiles, uint32_t sigma, uint64_t stride,
-                uint8_t *__restrict__ rows, uint64_t nrows, uint32_t grouped)
+                uint8_t *__restrict__ rows, uint64_t nrows)
 {
     constexpr uint32_t B = 1u << SHIFT;
-    const uint32_t groups = grouped ? (sigma + 7u) / 8u : 1u;
     extern __shared__ uint16_t s_cnt[];                 // [OCC_SUB][sigma]
     __shared__ uint32_t s_base[256];
     __shared__ uint8_t s_code[256];
@@ -73,7 +71,7 @@ occ_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTables *__r
                 const uint64_t pos = row * B + r * 32u + lane;
                 const bool valid = pos < n;
                 const uint32_t ch = valid ? (uint32_t)bwt[pos] : 0u;
-                for (uint32_t g = 0; g < groups; ++g) dst[g * 64u + r * 32u + lane] = (uint8_t)ch;
+                dst[r * 32u + lane] = (uint8_t)ch;
                 const uint32_t code = valid ? (uint32_t)s_code[ch] : 256u + lane;
                 const uint32_t peers = __match_any_sync(0xffffffffu, code);
                 if (valid && lane == (uint32_t)(__ffs(peers) - 1)) s_cnt[blk * sigma + code] += (uint16_t)__popc(peers);
@@ -87,8 +85,7 @@ occ_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTables *__r
             for (uint32_t blk = 0; blk < OCC_SUB; ++blk) {
                 const uint64_t row = row0 + blk;
                 if (row >= nrows) break;
-                if (grouped) reinterpret_cast<uint32_t *>(rows + row * stride + (tid >> 3) * 64u + 32u)[tid & 7u] = run;
-                else reinterpret_cast<uint32_t *>(rows + row * stride + B)[tid] = run;
+                reinterpret_cast<uint32_t *>(rows + row * stride + B)[tid] = run;
                 run += s_cnt[blk * sigma + tid];
             }
             s_base[tid] = run;
@@ -112,13 +109,13 @@ __device__ __forceinline__ uint64_t occ_match_bits(const uint64_t (&x)[(1 << SHI
     }
     return bits;
 }
-// the row's symbols: one 256-bit load per 32 bytes (LDG.E.256), not allocated in L1 (isolated random sectors
-// must not evict the pattern bytes L1 serves)
+// the row's symbols: one 256-bit load per 32 bytes (LDG.E.256).  (L1::no_allocate was measured: same L2 and DRAM
+// traffic, 60 % slower on the 2.8 GB table -- fewer requests in flight on that path.)
 template <int SHIFT>
 __device__ __forceinline__ void occ_load_row(const uint8_t *sym, uint64_t (&x)[(1 << SHIFT) / 8])
 {
 #pragma unroll
-    for (int v = 0; v < (1 << SHIFT) / 32; ++v) ld_nc_256_na(sym + 32 * v, x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
+    for (int v = 0; v < (1 << SHIFT) / 32; ++v) ld_nc_256(sym + 32 * v, x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
 }
 // occurrences of `ch` among the first t bytes (t < 2^SHIFT) of the row whose symbols start at `sym`
 template <int SHIFT>
@@ -137,10 +134,10 @@ __device__ __forceinline__ void occ_rank2(const OccDev &o, uint32_t code, uint32
 {
     constexpr uint32_t B = 1u << SHIFT;
     const uint32_t ch4 = ch * 0x01010101u;
-    const uint8_t *pa = occ_sym_ptr(o, a >> SHIFT, code);
-    const uint8_t *pb = occ_sym_ptr(o, b >> SHIFT, code);
-    const uint32_t base_a = ld_nc_u32_na(occ_cnt_ptr(o, pa, code, B));
-    const uint32_t base_b = ld_nc_u32_na(occ_cnt_ptr(o, pb, code, B));
+    const uint8_t *pa = occ_sym_ptr(o, a >> SHIFT);
+    const uint8_t *pb = occ_sym_ptr(o, b >> SHIFT);
+    const uint32_t base_a = __ldg(occ_cnt_ptr(pa, code, B));
+    const uint32_t base_b = __ldg(occ_cnt_ptr(pb, code, B));
     uint64_t xa[B / 8], xb[B / 8];
     occ_load_row<SHIFT>(pa, xa);
     occ_load_row<SHIFT>(pb, xb);
@@ -150,8 +147,8 @@ __device__ __forceinline__ void occ_rank2(const OccDev &o, uint32_t code, uint32
 
 // Same search as fm_count_kernel (fm_search.cu): one lane per pattern, lanes refilled as patterns end;
 // find_range (csa/enhanced_fm_index.py:21-32) in half-open form.  Only the rank primitive differs.
-template <int SHIFT>
-__global__ void __launch_bounds__(OCC_THREADS, 4)
+template <int SHIFT, int MIN_CTAS>
+__global__ void __launch_bounds__(OCC_THREADS, MIN_CTAS)
 fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t *__restrict__ pat,
                     const int64_t *__restrict__ off, uint64_t P, int64_t *__restrict__ out_lo,
                     int64_t *__restrict__ out_hi, const uint2 *__restrict__ kmer, uint32_t kk)
@@ -255,10 +252,10 @@ locate_rows_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, BitVec mark
             return;
         }
         const uint32_t t = j & (B - 1);
-        const uint32_t ch = __ldg(occ.rows + (uint64_t)(j >> SHIFT) * occ.stride + t);   // chunk 0 always holds the symbols
+        const uint8_t *row = occ_sym_ptr(occ, j >> SHIFT);
+        const uint32_t ch = __ldg(row + t);
         const uint32_t code = s_code[ch];
-        const uint8_t *row = occ_sym_ptr(occ, j >> SHIFT, code);
-        const uint32_t base = __ldg(occ_cnt_ptr(occ, row, code, B));
+        const uint32_t base = __ldg(occ_cnt_ptr(row, code, B));
         j = s_C[code] + base + occ_count<SHIFT>(row, ch * 0x01010101u, t);
         ++steps;
     }
@@ -268,11 +265,10 @@ locate_rows_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, BitVec mark
 
 using namespace hkcsa;
 
-extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, uint32_t layout, hkcsa_occ_plan *p)
+extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, hkcsa_occ_plan *p)
 {
     HK_REQUIRE(p != nullptr, HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(shift == 5 || shift == 6, HKCSA_EINVAL, "shift must be 5 (32 rows per entry) or 6 (64)");
-    HK_REQUIRE(layout == 0 || (layout == 1 && shift == 5), HKCSA_EINVAL, "layout 1 (64-byte chunks) needs shift 5");
     HK_REQUIRE(sigma >= 1 && sigma <= 256, HKCSA_EINVAL, "bad alphabet size");
     HK_REQUIRE(n >= 1 && n <= HKCSA_MAX_N, HKCSA_ERANGE, "n out of range");
     memset(p, 0, sizeof(*p));
@@ -280,8 +276,7 @@ extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, u
     p->sigma = sigma;
     p->shift = shift;
     p->rows = (n >> shift) + 1;
-    p->layout = layout;
-    p->stride = layout ? 64 * (((size_t)sigma + 7) / 8) : align_up(((size_t)1 << shift) + 4 * (size_t)sigma, 32);
+    p->stride = align_up(((size_t)1 << shift) + 4 * (size_t)sigma, 32);
     p->blob_bytes = align_up(p->rows * p->stride, 256);
     const uint64_t tiles = (n + WTL_TILE - 1) / WTL_TILE;
     Carver c(nullptr);
@@ -314,9 +309,9 @@ extern "C" int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt,
     const size_t smem = (size_t)OCC_SUB * p->sigma * sizeof(uint16_t);
     uint8_t *rows = static_cast<uint8_t *>(d_blob);
     if (p->shift == 5)
-        occ_fill_kernel<5><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows, p->layout);
+        occ_fill_kernel<5><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows);
     else
-        occ_fill_kernel<6><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows, p->layout);
+        occ_fill_kernel<6><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }
@@ -337,14 +332,14 @@ extern "C" int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan 
     occ.stride = p->stride;
     occ.sigma = p->sigma;
     occ.n = (uint32_t)p->n;
-    occ.grouped = p->layout;
-    const int blocks = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 8);
     const uint2 *kmer = static_cast<const uint2 *>(d_kmer_table);
     prof::Scope ps(st, prof::COUNT, 0);
+    // 4 CTAs/SM (53 registers): measured best of 4 / 5 / 6 / 8 on the 2.8 GB table (more lanes in flight were slower)
+    const int blocks = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 8);
     if (p->shift == 5)
-        fm_count_occ_kernel<5><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
+        fm_count_occ_kernel<5, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
     else
-        fm_count_occ_kernel<6><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
+        fm_count_occ_kernel<6, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }
@@ -363,7 +358,6 @@ extern "C" int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan 
     occ.stride = p->stride;
     occ.sigma = p->sigma;
     occ.n = (uint32_t)p->n;
-    occ.grouped = p->layout;
     const uint8_t *sb = static_cast<const uint8_t *>(d_ssa_blob);
     BitVec marks;
     marks.blocks = reinterpret_cast<const RankBlock *>(sb + h_ssa->off_blocks);

@@ -347,14 +347,12 @@ typedef struct hkcsa_occ_plan {
     uint64_t n;
     uint32_t sigma;
     uint32_t shift;          /* 5 or 6 */
-    uint32_t layout;         /* 0: rows as above; 1 (shift 5): a row is ceil(sigma/8) chunks of 64 bytes =      */
-    uint32_t reserved;       /*    [32 BWT bytes][8 counters], so a rank reads ONE 64-byte-aligned chunk        */
     uint64_t rows;
     uint64_t stride;         /* bytes per row, multiple of 32 */
     uint64_t blob_bytes;
     uint64_t scratch_bytes;  /* for hkcsa_occ_build */
 } hkcsa_occ_plan;
-int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, uint32_t layout, hkcsa_occ_plan *h_plan);
+int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, hkcsa_occ_plan *h_plan);
 int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const uint8_t *d_bwt,
                     const hkcsa_occ_plan *h_plan, void *d_blob, void *d_scratch, size_t scratch_bytes, void *stream);
 int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const void *d_occ_blob,

@@ -482,9 +482,9 @@ def test_kmer_jump_table_gives_identical_ranges(E, name):
     assert np.array_equal(host(b[0]), w_lo) and np.array_equal(host(b[1]), w_hi)
 
 
-@pytest.mark.parametrize("shift,layout", [(5, 0), (6, 0), (5, 1)])
+@pytest.mark.parametrize("shift", [5, 6])
 @pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "rand2_100k", "runs", "rand256_50k", "all_a_5000", "fib"])
-def test_occ_table_count_matches_wavelet_count_and_oracle(E, name, shift, layout):
+def test_occ_table_count_matches_wavelet_count_and_oracle(E, name, shift):
     """hkcsa_count_batch_occ (sampled Occ table, the reference's build_occ kept at every 2^shift-th row) against the
     wavelet-tree count and the oracle's find_range; with and without the k-mer jump table."""
     import torch
@@ -499,7 +499,7 @@ def test_occ_table_count_matches_wavelet_count_and_oracle(E, name, shift, layout
     a = idx.count_batch(d_p, d_o, use_kmer_table=False)
     idx.ssa = E.build_sampled_sa(idx.sa, 16)
     o_ref, p_ref = idx.locate_batch(d_p, d_o, use_samples=True)     # LF walks on the wavelet tree
-    plan, blob = idx.build_occ_table(shift, layout=layout)
+    plan, blob = idx.build_occ_table(shift)
     assert plan.rows == (len(text) >> shift) + 1 and plan.stride % 32 == 0
     o_occ, p_occ = idx.locate_batch(d_p, d_o, use_samples=True)     # LF walks on the Occ table
     assert torch.equal(o_ref, o_occ) and torch.equal(p_ref, p_occ)
@@ -516,12 +516,7 @@ def test_occ_table_count_matches_wavelet_count_and_oracle(E, name, shift, layout
     bwt = np.asarray(fm.bwt, dtype=np.uint8)
     flat = rows[:, :B].reshape(-1)[:len(text)]
     assert np.array_equal(flat, bwt)
-    if layout == 0:
-        counters = rows[:, B:B + 4 * plan.sigma].copy().view(np.uint32)
-    else:       # 64-byte chunks: [32 symbols][8 counters]; every chunk repeats the symbols
-        chunks = rows.reshape(plan.rows, -1, 64)
-        assert all(np.array_equal(chunks[:, g, :32], chunks[:, 0, :32]) for g in range(chunks.shape[1]))
-        counters = chunks[:, :, 32:].copy().view(np.uint32).reshape(plan.rows, -1)[:, :plan.sigma]
+    counters = rows[:, B:B + 4 * plan.sigma].copy().view(np.uint32)
     syms = sorted(set(text))
     for r in (0, 1, plan.rows // 2, plan.rows - 1):
         pos = min(r << shift, len(text))
