@@ -624,6 +624,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     const int k0 = std::max(1, bits0 / max_len);         // symbols every key is guaranteed to cover
     const int passes0 = bits0 / 8;
     stats.sigma = sigma;
+    memcpy(stats.byte_hist, h_hist, sizeof(stats.byte_hist));
     stats.bits_per_symbol = (uint32_t)max_len;
     stats.k0 = (uint32_t)k0;
 

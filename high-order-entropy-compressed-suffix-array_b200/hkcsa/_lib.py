@@ -40,6 +40,7 @@ class SaStats(C.Structure):
         ("alg_bytes", C.c_uint64),
         ("round_elems", C.c_uint64 * 40),
         ("round_passes", C.c_uint32 * 40),
+        ("byte_hist", C.c_uint64 * 256),
     ]
 
 

@@ -167,7 +167,7 @@ class DeviceWaveletTree:
         self.hist = hist
         self.plan = WtPlan()
         check(L.hkcsa_wt_plan_from_hist(hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(self.plan)))
-        self.blob = torch.zeros(int(self.plan.blob_bytes), dtype=torch.uint8, device=self.device)
+        self.blob = torch.empty(int(self.plan.blob_bytes), dtype=torch.uint8, device=self.device)   # zeroed by the build
         scratch = _scratch(self.plan.scratch_bytes, self.device)
         check(L.hkcsa_wt_build(_ptr(sym), C.byref(self.plan), _ptr(self.blob), _ptr(scratch),
                                int(self.plan.scratch_bytes), _stream()))
@@ -372,7 +372,9 @@ class DeviceIndex:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 host_bwt.copy_(self.bwt, non_blocking=True)
-        self.wt = DeviceWaveletTree(self.bwt)
+        # the BWT is a permutation of the text: the byte histogram of the suffix-array build serves the tree
+        hist = np.ctypeslib.as_array(self.stats.sa.byte_hist).copy() if self.n else None
+        self.wt = DeviceWaveletTree(self.bwt, hist=hist)
         if ssa_stream is not None:
             main.wait_stream(ssa_stream)
             self.ssa.blob.record_stream(main)

@@ -79,6 +79,8 @@ typedef struct hkcsa_sa_stats {
     uint64_t alg_bytes;         /* algorithmic HBM bytes moved   */
     uint64_t round_elems[40];   /* working-set size per round                   */
     uint32_t round_passes[40];  /* radix passes per round                       */
+    uint64_t byte_hist[256];    /* occurrences per byte value (the BWT has the  */
+                                /* same histogram: hkcsa_wt_plan_from_hist)     */
 } hkcsa_sa_stats;
 
 size_t hkcsa_sa_scratch_bytes(uint64_t n);
