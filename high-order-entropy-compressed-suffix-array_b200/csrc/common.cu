@@ -33,6 +33,7 @@ void *pinned_page()
 // ---------------------------------------------------------------- profiler
 namespace prof {
 static bool g_on = false;
+static uint32_t g_mask = 0xFFFFFFFFu;     // classes that are timed while g_on
 struct Rec {
     cudaEvent_t a, b;
     int cls;
@@ -49,7 +50,7 @@ bool enabled() { return g_on; }
 
 Scope::Scope(cudaStream_t st, int cls, uint64_t bytes) : st_(st), slot_(-1)
 {
-    if (!g_on || g_used >= MAX_RECORDS) return;
+    if (!g_on || !((g_mask >> cls) & 1u) || g_used >= MAX_RECORDS) return;
     if (g_used >= g_created) {
         if (cudaEventCreate(&g_rec[g_created].a) != cudaSuccess) return;
         if (cudaEventCreate(&g_rec[g_created].b) != cudaSuccess) return;
@@ -89,7 +90,20 @@ extern "C" size_t hkcsa_struct_size(int which)
 extern "C" int hkcsa_prof_enable(int on)
 {
     prof::g_on = (on != 0);
+    prof::g_mask = 0xFFFFFFFFu;
     return HKCSA_OK;
+}
+extern "C" int hkcsa_prof_enable_classes(uint32_t class_mask)
+{
+    prof::g_on = (class_mask != 0);
+    prof::g_mask = class_mask;
+    return HKCSA_OK;
+}
+extern "C" int hkcsa_prof_class_index(const char *name)
+{
+    for (int c = 0; c < prof::NUM_CLASSES; ++c)
+        if (name && strcmp(name, prof::g_names[c]) == 0) return c;
+    return -1;
 }
 extern "C" int hkcsa_prof_reset(void)
 {

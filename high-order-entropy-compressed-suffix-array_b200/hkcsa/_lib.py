@@ -171,6 +171,8 @@ SIGNATURES = {
     "hkcsa_symbol_positions": (_i32, [_vp, _u64, _vp, _vp, _vp, _sz, _vp]),
     "hkcsa_launch_count": (C.c_ulonglong, []),
     "hkcsa_prof_enable": (_i32, [_i32]),
+    "hkcsa_prof_enable_classes": (_i32, [_u32]),
+    "hkcsa_prof_class_index": (_i32, [C.c_char_p]),
     "hkcsa_prof_reset": (_i32, []),
     "hkcsa_prof_read": (_i32, [C.POINTER(ProfEntry), _i32, C.POINTER(_i32)]),
 }

@@ -361,13 +361,18 @@ class DeviceIndex:
         main = torch.cuda.current_stream()
         ssa_stream = None
         self.ssa = None
+        sa_done = None
+        if sa_sample_rate > 0:
+            sa_done = torch.cuda.Event()
+            sa_done.record(main)
+        # the BWT gather goes out first: the host-side set-up of the side stream must not delay the main stream
+        self.bwt = bwt(text, self.sa)
         if sa_sample_rate > 0:
             ssa_stream = _aux_stream(self.device, "ssa")
-            ssa_stream.wait_stream(main)
+            ssa_stream.wait_event(sa_done)
             with torch.cuda.stream(ssa_stream):
                 self.ssa = build_sampled_sa(self.sa, sa_sample_rate)
             self.sa.record_stream(ssa_stream)
-        self.bwt = bwt(text, self.sa)
         if host_bwt is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
@@ -526,10 +531,20 @@ class DeviceIndex:
 
 
 # ------------------------------------------------------------------ measurement hook
-def prof_enable(on: bool) -> None:
+def prof_enable(on: bool, classes=None) -> None:
+    """classes: names of the kernel classes to time (None = all)."""
     L = _lib.load()
     check(L.hkcsa_prof_reset())
-    check(L.hkcsa_prof_enable(1 if on else 0))
+    if on and classes:
+        mask = 0
+        for name in classes:
+            idx = L.hkcsa_prof_class_index(name.encode())
+            if idx < 0:
+                raise ValueError(f"unknown kernel class {name!r}")
+            mask |= 1 << idx
+        check(L.hkcsa_prof_enable_classes(mask))
+    else:
+        check(L.hkcsa_prof_enable(1 if on else 0))
 
 
 def prof_read() -> dict:

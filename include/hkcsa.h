@@ -335,6 +335,10 @@ typedef struct hkcsa_prof_entry {
 /* kernels launched by the library so far in this process */
 unsigned long long hkcsa_launch_count(void);
 int hkcsa_prof_enable(int on);
+/* time only the classes whose bit is set (bit = hkcsa_prof_class_index(name)): a timed region that needs one */
+/* kernel's durations does not pay two event records around every other launch                                */
+int hkcsa_prof_enable_classes(uint32_t class_mask);
+int hkcsa_prof_class_index(const char *name);
 int hkcsa_prof_reset(void);
 int hkcsa_prof_read(hkcsa_prof_entry *h_out, int max_entries, int *h_n);
 
