@@ -12,6 +12,14 @@
 // alphabet, against one sector PER LEVEL of the wavelet tree (7 levels for the 97-symbol text).  The wavelet
 // tree stays the compact index (0.14 B/char/level); this table trades memory (B + 4 sigma bytes per B rows)
 // for random-access traffic and is optional.  Ranges are identical by construction (same recurrences).
+//
+// Layout 1 ("bitmaps") goes one step further: per symbol and per stretch of 32 rows ONE 8-byte entry
+//   entry[code][r] = { occ[code][32 r] (u32), bitmap of the rows 32 r .. 32 r + 31 whose BWT symbol is `code` (u32) }
+//   occ(c, i) = entry.count + popc(entry.bitmap & ((1 << (i % 32)) - 1))
+// so a rank is ONE memory request (the row layout needs the counter sector and the symbol sector; on B200 the
+// search is bound by the rate of random requests, not by their size: tools/probes/sector_probe.cu).  Costs
+// 8 sigma bytes per 32 rows (24 B per symbol for the 97-symbol text); the blob ends with a copy of the BWT for
+// the LF steps of locate.
 #include "common.cuh"
 #include "prof.cuh"
 #include "wavelet.cuh"
@@ -24,7 +32,8 @@ constexpr int OCC_SUB = 32;           // blocks per sub-chunk of a tile (4 per w
 
 struct OccDev {
     const uint8_t *rows;
-    uint64_t stride;
+    uint64_t stride;      // layout 0: bytes per row; layout 1: entries per code
+    const uint8_t *bwt;   // layout 1: the BWT copy at the end of the blob
     uint32_t sigma;
     uint32_t n;
 };
@@ -145,6 +154,62 @@ __device__ __forceinline__ void occ_rank2(const OccDev &o, uint32_t code, uint32
     b = base_b + __popcll(occ_match_bits<SHIFT>(xb, ch4) & ((1ull << (b & (B - 1))) - 1ull));
 }
 
+// ---------------------------------------------------------------- layout 1: per-symbol bitmaps
+__global__ void __launch_bounds__(OCC_THREADS)
+occ_bitmap_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTables *__restrict__ tab,
+                       const uint32_t *__restrict__ gpre, uint32_t tiles, uint32_t sigma, uint64_t per_code,
+                       uint2 *__restrict__ entries, uint64_t nrows)
+{
+    extern __shared__ uint32_t s_mask[];                // [OCC_SUB][sigma]
+    __shared__ uint32_t s_base[256];
+    __shared__ uint8_t s_code[256];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    s_code[tid] = tab->code8_of_sym[tid];
+    s_base[tid] = (tid < sigma) ? gpre[(size_t)tid * (tiles + 1) + blockIdx.x] : 0u;
+    const uint64_t tile_row0 = (uint64_t)blockIdx.x * (WTL_TILE / 32);
+    for (uint32_t sub = 0; sub < WTL_TILE / 32 / OCC_SUB; ++sub) {
+        const uint64_t row0 = tile_row0 + (uint64_t)sub * OCC_SUB;
+        if (row0 >= nrows) break;
+        for (uint32_t i = tid; i < OCC_SUB * sigma; i += OCC_THREADS) s_mask[i] = 0;
+        __syncthreads();
+        for (uint32_t q = 0; q < OCC_SUB / (OCC_THREADS / 32); ++q) {
+            const uint32_t blk = warp * (OCC_SUB / (OCC_THREADS / 32)) + q;
+            const uint64_t row = row0 + blk;
+            if (row >= nrows) break;
+            const uint64_t pos = row * 32u + lane;
+            const bool valid = pos < n;
+            const uint32_t code = valid ? (uint32_t)s_code[bwt[pos]] : 256u + lane;
+            const uint32_t peers = __match_any_sync(0xffffffffu, code);      // the lanes = the rows holding `code`
+            if (valid && lane == (uint32_t)(__ffs(peers) - 1)) s_mask[blk * sigma + code] = peers;
+        }
+        __syncthreads();
+        if (tid < sigma) {
+            uint32_t run = s_base[tid];
+            uint2 *dst = entries + (uint64_t)tid * per_code;
+            for (uint32_t blk = 0; blk < OCC_SUB; ++blk) {
+                const uint64_t row = row0 + blk;
+                if (row >= nrows) break;
+                const uint32_t m = s_mask[blk * sigma + tid];
+                dst[row] = make_uint2(run, m);
+                run += __popc(m);
+            }
+            s_base[tid] = run;
+        }
+        __syncthreads();
+    }
+}
+
+// SHIFT = 0 selects the bitmap layout in the search kernels
+template <>
+__device__ __forceinline__ void occ_rank2<0>(const OccDev &o, uint32_t code, uint32_t ch, uint32_t &a, uint32_t &b)
+{
+    const uint2 *e = reinterpret_cast<const uint2 *>(o.rows) + (uint64_t)code * o.stride;
+    const uint2 ea = __ldg(e + (a >> 5));
+    const uint2 eb = __ldg(e + (b >> 5));           // the same entry once the range is narrow (merged in L1)
+    a = ea.x + __popc(ea.y & ((1u << (a & 31u)) - 1u));
+    b = eb.x + __popc(eb.y & ((1u << (b & 31u)) - 1u));
+}
+
 // Same search as fm_count_kernel (fm_search.cu): one lane per pattern, lanes refilled as patterns end;
 // find_range (csa/enhanced_fm_index.py:21-32) in half-open form.  Only the rank primitive differs.
 template <int SHIFT, int MIN_CTAS>
@@ -252,11 +317,18 @@ locate_rows_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, BitVec mark
             return;
         }
         const uint32_t t = j & (B - 1);
-        const uint8_t *row = occ_sym_ptr(occ, j >> SHIFT);
-        const uint32_t ch = __ldg(row + t);
-        const uint32_t code = s_code[ch];
-        const uint32_t base = __ldg(occ_cnt_ptr(row, code, B));
-        j = s_C[code] + base + occ_count<SHIFT>(row, ch * 0x01010101u, t);
+        if (SHIFT == 0) {
+            const uint32_t ch = __ldg(occ.bwt + j);
+            const uint32_t code = s_code[ch];
+            const uint2 e = __ldg(reinterpret_cast<const uint2 *>(occ.rows) + (uint64_t)code * occ.stride + (j >> 5));
+            j = s_C[code] + e.x + __popc(e.y & ((1u << (j & 31u)) - 1u));
+        } else {
+            const uint8_t *row = occ_sym_ptr(occ, j >> SHIFT);
+            const uint32_t ch = __ldg(row + t);
+            const uint32_t code = s_code[ch];
+            const uint32_t base = __ldg(occ_cnt_ptr(row, code, B));
+            j = s_C[code] + base + occ_count<(SHIFT ? SHIFT : 5)>(row, ch * 0x01010101u, t);
+        }
         ++steps;
     }
 }
@@ -265,10 +337,11 @@ locate_rows_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, BitVec mark
 
 using namespace hkcsa;
 
-extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, hkcsa_occ_plan *p)
+extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, uint32_t layout, hkcsa_occ_plan *p)
 {
     HK_REQUIRE(p != nullptr, HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(shift == 5 || shift == 6, HKCSA_EINVAL, "shift must be 5 (32 rows per entry) or 6 (64)");
+    HK_REQUIRE(layout == 0 || (layout == 1 && shift == 5), HKCSA_EINVAL, "layout 1 (per-symbol bitmaps) has 32 rows per entry");
     HK_REQUIRE(sigma >= 1 && sigma <= 256, HKCSA_EINVAL, "bad alphabet size");
     HK_REQUIRE(n >= 1 && n <= HKCSA_MAX_N, HKCSA_ERANGE, "n out of range");
     memset(p, 0, sizeof(*p));
@@ -276,8 +349,15 @@ extern "C" int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, h
     p->sigma = sigma;
     p->shift = shift;
     p->rows = (n >> shift) + 1;
-    p->stride = align_up(((size_t)1 << shift) + 4 * (size_t)sigma, 32);
-    p->blob_bytes = align_up(p->rows * p->stride, 256);
+    p->layout = layout;
+    if (layout == 1) {
+        p->stride = align_up(p->rows, 4);                                  // entries per code (32-byte multiples)
+        p->off_bwt = align_up((uint64_t)sigma * p->stride * 8, 256);
+        p->blob_bytes = align_up(p->off_bwt + n, 256);
+    } else {
+        p->stride = align_up(((size_t)1 << shift) + 4 * (size_t)sigma, 32);
+        p->blob_bytes = align_up(p->rows * p->stride, 256);
+    }
     const uint64_t tiles = (n + WTL_TILE - 1) / WTL_TILE;
     Carver c(nullptr);
     c.take<uint32_t>((uint64_t)sigma * (tiles + 2));
@@ -306,8 +386,16 @@ extern "C" int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt,
     HK_LAUNCH_CHECK();
     // the row of position n exists even when n is a multiple of the tile: one more CTA then reads the totals
     const uint32_t grid = (uint32_t)(n / WTL_TILE) + 1;
-    const size_t smem = (size_t)OCC_SUB * p->sigma * sizeof(uint16_t);
     uint8_t *rows = static_cast<uint8_t *>(d_blob);
+    if (p->layout == 1) {
+        const size_t smem1 = (size_t)OCC_SUB * p->sigma * sizeof(uint32_t);
+        occ_bitmap_fill_kernel<<<grid, OCC_THREADS, smem1, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride,
+                                                                 reinterpret_cast<uint2 *>(rows), p->rows);
+        HK_LAUNCH_CHECK();
+        HK_CUDA(cudaMemcpyAsync(rows + p->off_bwt, d_bwt, n, cudaMemcpyDeviceToDevice, st));
+        return HKCSA_OK;
+    }
+    const size_t smem = (size_t)OCC_SUB * p->sigma * sizeof(uint16_t);
     if (p->shift == 5)
         occ_fill_kernel<5><<<grid, OCC_THREADS, smem, st>>>(d_bwt, n, d_tab, d_gcnt, tiles, p->sigma, p->stride, rows, p->rows);
     else
@@ -330,13 +418,22 @@ extern "C" int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan 
     OccDev occ;
     occ.rows = static_cast<const uint8_t *>(d_occ_blob);
     occ.stride = p->stride;
+    occ.bwt = occ.rows + p->off_bwt;
     occ.sigma = p->sigma;
     occ.n = (uint32_t)p->n;
     const uint2 *kmer = static_cast<const uint2 *>(d_kmer_table);
     prof::Scope ps(st, prof::COUNT, 0);
     // 4 CTAs/SM (53 registers): measured best of 4 / 5 / 6 / 8 on the 2.8 GB table (more lanes in flight were slower)
     const int blocks = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 8);
-    if (p->shift == 5)
+    if (p->layout == 1) {
+        // lanes in flight: DRAM-resident tables run best at 4 CTAs/SM, tables near the L2 size at 6 (measured:
+        // 1.42 vs 1.34 G patterns/s on the 4.8 GB table of the 200 MB text, 3.4 vs 4.0 on the 225 MB DNA table)
+        const int ctas = (p->blob_bytes > (1ull << 30)) ? 4 : 6;
+        const int blocks1 = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 2 * ctas);
+        if (ctas == 6) fm_count_occ_kernel<0, 6><<<blocks1, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
+        else fm_count_occ_kernel<0, 4><<<blocks1, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
+    }
+    else if (p->shift == 5)
         fm_count_occ_kernel<5, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
     else
         fm_count_occ_kernel<6, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
@@ -356,6 +453,7 @@ extern "C" int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan 
     OccDev occ;
     occ.rows = static_cast<const uint8_t *>(d_occ_blob);
     occ.stride = p->stride;
+    occ.bwt = occ.rows + p->off_bwt;
     occ.sigma = p->sigma;
     occ.n = (uint32_t)p->n;
     const uint8_t *sb = static_cast<const uint8_t *>(d_ssa_blob);
@@ -366,7 +464,9 @@ extern "C" int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan 
     const uint32_t *samples = reinterpret_cast<const uint32_t *>(sb + h_ssa->off_samples);
     const uint32_t grid = (uint32_t)((m + 255) / 256);
     prof::Scope ps(st, prof::LOCATE, 0);
-    if (p->shift == 5)
+    if (p->layout == 1)
+        locate_rows_occ_kernel<0><<<grid, 256, 0, st>>>(occ, d_tab, marks, samples, h_ssa->rate, d_rows, m, d_out_pos);
+    else if (p->shift == 5)
         locate_rows_occ_kernel<5><<<grid, 256, 0, st>>>(occ, d_tab, marks, samples, h_ssa->rate, d_rows, m, d_out_pos);
     else
         locate_rows_occ_kernel<6><<<grid, 256, 0, st>>>(occ, d_tab, marks, samples, h_ssa->rate, d_rows, m, d_out_pos);

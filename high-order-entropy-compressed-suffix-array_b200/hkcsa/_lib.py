@@ -87,6 +87,9 @@ class OccPlan(C.Structure):
         ("n", C.c_uint64),
         ("sigma", C.c_uint32),
         ("shift", C.c_uint32),
+        ("layout", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("off_bwt", C.c_uint64),
         ("rows", C.c_uint64),
         ("stride", C.c_uint64),
         ("blob_bytes", C.c_uint64),
@@ -145,7 +148,7 @@ SIGNATURES = {
     "hkcsa_golomb_encode": (_i32, [_vp, C.POINTER(WtPlan), _u32, _u64, _u32, _vp, _u64, C.POINTER(_u64), _vp,
                                    _sz, _vp]),
     "hkcsa_count_batch": (_i32, [_vp, C.POINTER(WtPlan), _vp, _vp, _u64, _vp, _vp, _vp]),
-    "hkcsa_occ_plan_make": (_i32, [_u64, _u32, _u32, C.POINTER(OccPlan)]),
+    "hkcsa_occ_plan_make": (_i32, [_u64, _u32, _u32, _u32, C.POINTER(OccPlan)]),
     "hkcsa_occ_build": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(OccPlan), _vp, _vp, _sz, _vp]),
     "hkcsa_count_batch_occ": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(OccPlan), _vp, _u32, _vp, _vp, _u64,
                                      _vp, _vp, _vp]),

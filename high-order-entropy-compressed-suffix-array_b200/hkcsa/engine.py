@@ -449,17 +449,18 @@ class DeviceIndex:
         self._kmer = (table, k)
         return self._kmer
 
-    def build_occ_table(self, shift: int = 5, bwt: torch.Tensor | None = None):
+    def build_occ_table(self, shift: int = 5, bwt: torch.Tensor | None = None, layout: int = 0):
         """Sampled Occ table (csrc/occ_table.cu): the reference's dense occ (utils/utils.py:26-32) kept at every
         2^shift-th row next to the BWT bytes of that stretch.  Optional: costs 2^shift + 4 sigma bytes per 2^shift
-        rows, makes a rank one or two sector reads instead of one per wavelet level.  Needs the BWT (kept by the
-        builder; replicas pass it in)."""
+        rows, makes a rank one or two sector reads instead of one per wavelet level.  layout=1: per-symbol
+        bitmaps, one 8-byte entry per symbol and 32 rows (8 sigma bytes per 32 rows): a rank is a single memory
+        request.  Needs the BWT (kept by the builder; replicas pass it in)."""
         L = _lib.load()
         bwt = self.bwt if bwt is None else bwt
         if bwt is None:
             raise ValueError("the sampled Occ table is built from the BWT, which this index no longer holds")
         plan = OccPlan()
-        check(L.hkcsa_occ_plan_make(self.n, self.wt.sigma, shift, C.byref(plan)))
+        check(L.hkcsa_occ_plan_make(self.n, self.wt.sigma, shift, layout, C.byref(plan)))
         blob = _empty(int(plan.blob_bytes), torch.uint8, self.device)
         scratch = _scratch(int(plan.scratch_bytes), self.device)
         check(L.hkcsa_occ_build(_ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(bwt), C.byref(plan), _ptr(blob),

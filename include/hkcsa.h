@@ -353,12 +353,16 @@ typedef struct hkcsa_occ_plan {
     uint64_t n;
     uint32_t sigma;
     uint32_t shift;          /* 5 or 6 */
+    uint32_t layout;         /* 0: rows as above.  1 (shift 5): per symbol and per 32 rows ONE 8-byte entry         */
+    uint32_t reserved;       /*    { occ[code][32 r], bitmap of the rows 32 r .. 32 r + 31 holding `code` }: a rank  */
+                             /*    is one memory request; entry[code * stride + r]; the blob ends with a BWT copy   */
+    uint64_t off_bwt;        /* layout 1: byte offset of the BWT copy (LF steps of locate)                          */
     uint64_t rows;
-    uint64_t stride;         /* bytes per row, multiple of 32 */
+    uint64_t stride;         /* layout 0: bytes per row, multiple of 32; layout 1: entries per code */
     uint64_t blob_bytes;
     uint64_t scratch_bytes;  /* for hkcsa_occ_build */
 } hkcsa_occ_plan;
-int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, hkcsa_occ_plan *h_plan);
+int hkcsa_occ_plan_make(uint64_t n, uint32_t sigma, uint32_t shift, uint32_t layout, hkcsa_occ_plan *h_plan);
 int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const uint8_t *d_bwt,
                     const hkcsa_occ_plan *h_plan, void *d_blob, void *d_scratch, size_t scratch_bytes, void *stream);
 int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const void *d_occ_blob,

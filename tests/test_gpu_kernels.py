@@ -482,9 +482,9 @@ def test_kmer_jump_table_gives_identical_ranges(E, name):
     assert np.array_equal(host(b[0]), w_lo) and np.array_equal(host(b[1]), w_hi)
 
 
-@pytest.mark.parametrize("shift", [5, 6])
+@pytest.mark.parametrize("shift,layout", [(5, 0), (6, 0), (5, 1)])
 @pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "rand2_100k", "runs", "rand256_50k", "all_a_5000", "fib"])
-def test_occ_table_count_matches_wavelet_count_and_oracle(E, name, shift):
+def test_occ_table_count_matches_wavelet_count_and_oracle(E, name, shift, layout):
     """hkcsa_count_batch_occ (sampled Occ table, the reference's build_occ kept at every 2^shift-th row) against the
     wavelet-tree count and the oracle's find_range; with and without the k-mer jump table."""
     import torch
@@ -499,8 +499,8 @@ def test_occ_table_count_matches_wavelet_count_and_oracle(E, name, shift):
     a = idx.count_batch(d_p, d_o, use_kmer_table=False)
     idx.ssa = E.build_sampled_sa(idx.sa, 16)
     o_ref, p_ref = idx.locate_batch(d_p, d_o, use_samples=True)     # LF walks on the wavelet tree
-    plan, blob = idx.build_occ_table(shift)
-    assert plan.rows == (len(text) >> shift) + 1 and plan.stride % 32 == 0
+    plan, blob = idx.build_occ_table(shift, layout=layout)
+    assert plan.rows == (len(text) >> shift) + 1
     o_occ, p_occ = idx.locate_batch(d_p, d_o, use_samples=True)     # LF walks on the Occ table
     assert torch.equal(o_ref, o_occ) and torch.equal(p_ref, p_occ)
     b = idx.count_batch(d_p, d_o, use_kmer_table=False, use_occ_table=True)
@@ -511,16 +511,27 @@ def test_occ_table_count_matches_wavelet_count_and_oracle(E, name, shift):
     w_lo, w_hi = fm.find_range_batch(pats, off)
     assert np.array_equal(host(b[0]), w_lo) and np.array_equal(host(b[1]), w_hi)
     # the kept rows are the reference's occ[c][r << shift] and the stored symbols are the BWT
-    rows = host(blob)[:plan.rows * plan.stride].reshape(plan.rows, plan.stride)
-    B = 1 << shift
     bwt = np.asarray(fm.bwt, dtype=np.uint8)
-    flat = rows[:, :B].reshape(-1)[:len(text)]
-    assert np.array_equal(flat, bwt)
-    counters = rows[:, B:B + 4 * plan.sigma].copy().view(np.uint32)
     syms = sorted(set(text))
-    for r in (0, 1, plan.rows // 2, plan.rows - 1):
-        pos = min(r << shift, len(text))
-        assert counters[r].tolist() == [int(np.count_nonzero(bwt[:pos] == s)) for s in syms]
+    check_rows = (0, 1, plan.rows // 2, plan.rows - 1)
+    if layout == 0:
+        assert plan.stride % 32 == 0
+        rows = host(blob)[:plan.rows * plan.stride].reshape(plan.rows, plan.stride)
+        B = 1 << shift
+        assert np.array_equal(rows[:, :B].reshape(-1)[:len(text)], bwt)
+        counters = rows[:, B:B + 4 * plan.sigma].copy().view(np.uint32)
+        for r in check_rows:
+            pos = min(r << shift, len(text))
+            assert counters[r].tolist() == [int(np.count_nonzero(bwt[:pos] == s)) for s in syms]
+    else:       # per symbol: entry[code][r] = (occ[code][32 r], bitmap of the 32 rows holding the symbol); BWT copy at the end
+        h = host(blob)
+        ent = h[:plan.sigma * plan.stride * 8].copy().view(np.uint32).reshape(plan.sigma, plan.stride, 2)
+        assert np.array_equal(h[plan.off_bwt:plan.off_bwt + len(text)], bwt)
+        for r in check_rows:
+            pos = min(r << 5, len(text))
+            assert ent[:, r, 0].tolist() == [int(np.count_nonzero(bwt[:pos] == s)) for s in syms]
+            seg = bwt[pos:pos + 32]
+            assert ent[:, r, 1].tolist() == [sum(1 << j for j in range(len(seg)) if seg[j] == s) for s in syms]
 
 
 @pytest.mark.parametrize("n", [8192, 16384, 8191, 8193, 64, 1])
@@ -529,7 +540,7 @@ def test_occ_table_at_tile_boundaries(E, n):
     rng = np.random.RandomState(n)
     text = bytes(rng.choice(np.frombuffer(b"abc", dtype=np.uint8), n - 1)) + b"$" if n > 1 else b"$"
     idx = E.DeviceIndex(dev(E, text))
-    idx.build_occ_table(5)
+    idx.build_occ_table(5, layout=n % 2)
     pats = [text[i:i + 6] for i in range(0, max(1, len(text) - 6), max(1, len(text) // 50))] + [b"", b"$", b"zz"]
     d_p, d_o = E.pack_patterns(pats)
     a = idx.count_batch(d_p, d_o, use_occ_table=False)

@@ -23,7 +23,7 @@ for g in (0,):
     idx._occ = None
     wt_ms = t(lambda: idx.count_batch(pats, off, use_kmer_table=True, use_occ_table=False))
     loc_ms = t(lambda: idx.locate_batch(pats, off[: P // 8 + 1], use_samples=True))
-    idx.build_occ_table(5)
+    idx.build_occ_table(5, layout=int(os.environ.get("LAYOUT", 0)))
     occ_ms = t(lambda: idx.count_batch(pats, off, use_kmer_table=True, use_occ_table=True))
     loc2_ms = t(lambda: idx.locate_batch(pats, off[: P // 8 + 1], use_samples=True))
     idx._occ = None
