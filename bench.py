@@ -379,13 +379,13 @@ def run_ours(args):
         if q_idx.bwt is not None:          # same queries ranked on the sampled Occ table (identical ranges)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            plan_o, _ = q_idx.build_occ_table(5)
+            plan_o, _ = q_idx.build_occ_table(5, layout=1)
             torch.cuda.synchronize()
             occ_build_ms = (time.perf_counter() - t0) * 1e3
             o_ms, (lo_o, hi_o) = time_count(True, True)
             assert torch.equal(lo, lo_o) and torch.equal(hi, hi_o)
             occ_info = {"count_patterns_per_s": P_total / (o_ms / 1e3), "count_ms": o_ms, "build_ms": occ_build_ms,
-                        "bytes": int(plan_o.blob_bytes), "rows_per_entry": 32}
+                        "bytes": int(plan_o.blob_bytes), "layout": "per-symbol bitmaps, one 8-byte entry per 32 rows"}
             q_idx._occ = None
         gather_ms = None
         if world > 1:                      # results to every rank, timed apart from the search
@@ -411,7 +411,7 @@ def run_ours(args):
         best_ms = min(c_ms, occ_info["count_ms"]) if occ_info else c_ms
         queries = {"count_patterns_per_s": P_total / (best_ms / 1e3), "count_patterns": P_total,
                    "count_ms": best_ms,
-                   "rank_structure": ("sampled Occ table, 32 rows per entry" if occ_info and occ_info["count_ms"] < c_ms
+                   "rank_structure": ("sampled Occ table (per-symbol bitmaps)" if occ_info and occ_info["count_ms"] < c_ms
                                       else "wavelet tree") + " + k-mer jump table",
                    "count_patterns_per_s_wavelet_tree": P_total / (c_ms / 1e3),
                    "hit_fraction": hits / P_total, "pattern_len": "uniform 8-64",
