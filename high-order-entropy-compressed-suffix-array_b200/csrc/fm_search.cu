@@ -142,7 +142,11 @@ __global__ void ssa_fill_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const IdT v = sa[j];
-    if (v % rate == 0) samples[bv_rank(marks, j)] = (uint32_t)(v / rate);
+    if ((rate & (rate - 1u)) == 0) {          // power-of-two rate: no division per entry
+        if ((v & (IdT)(rate - 1u)) == 0) samples[bv_rank(marks, j)] = (uint32_t)(v >> (__ffs(rate) - 1));
+    } else if (v % rate == 0) {
+        samples[bv_rank(marks, j)] = (uint32_t)(v / rate);
+    }
 }
 
 // position of row j: walk LF until a marked row, pos = sample * rate + steps.

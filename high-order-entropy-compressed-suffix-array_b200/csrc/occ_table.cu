@@ -183,17 +183,18 @@ occ_bitmap_fill_kernel(const uint8_t *__restrict__ bwt, uint64_t n, const WtTabl
             if (valid && lane == (uint32_t)(__ffs(peers) - 1)) s_mask[blk * sigma + code] = peers;
         }
         __syncthreads();
-        if (tid < sigma) {
-            uint32_t run = s_base[tid];
-            uint2 *dst = entries + (uint64_t)tid * per_code;
-            for (uint32_t blk = 0; blk < OCC_SUB; ++blk) {
-                const uint64_t row = row0 + blk;
-                if (row >= nrows) break;
-                const uint32_t m = s_mask[blk * sigma + tid];
-                dst[row] = make_uint2(run, m);
-                run += __popc(m);
-            }
-            s_base[tid] = run;
+        // one warp per code: lane l owns row row0 + l, the running count is a warp scan of the popcounts, and the
+        // 32 entries of the code go out as one contiguous 256-byte store
+        static_assert(OCC_SUB == 32, "one lane per row of the sub-chunk");
+        for (uint32_t c = warp; c < sigma; c += OCC_THREADS / 32) {
+            const uint64_t row = row0 + lane;
+            const uint32_t m = (row < nrows) ? s_mask[lane * sigma + c] : 0u;
+            uint32_t total;
+            const uint32_t ex = warp_excl_sum(__popc(m), total);
+            const uint32_t base = s_base[c];
+            if (row < nrows) entries[(uint64_t)c * per_code + row] = make_uint2(base + ex, m);
+            __syncwarp();
+            if (lane == 0) s_base[c] = base + total;
         }
         __syncthreads();
     }

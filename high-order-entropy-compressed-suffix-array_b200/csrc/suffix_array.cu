@@ -493,6 +493,8 @@ seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict_
     __syncthreads();
     uint32_t ph = carry_head[blockIdx.x], pk = carry_keep[blockIdx.x];
     for (uint32_t w = 0; w < warp; ++w) { ph = max(ph, s_h[w]); pk += s_k[w]; }
+    // round 0 with lazy ranks: a thread whose eight elements are all singletons has nothing to write
+    if (!write_sa && !scatter_all && ((f >> SEG_IPT) & 0xFFu) == 0xFFu) return;
     uint32_t cur_head = max(ph, eh);   // (index of governing head) + 1 before this thread's first element
     uint32_t slot = pk + ek;
     uint32_t cur_grp = 0;

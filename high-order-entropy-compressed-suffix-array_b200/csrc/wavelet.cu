@@ -623,9 +623,10 @@ ssa_mark_pack_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, Rank
     __shared__ uint32_t s_wsum[2];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t row_base = (uint64_t)blockIdx.x * WTP_SYMS;
+    const bool pow2 = (rate & (rate - 1u)) == 0;      // power-of-two rate: no division per entry
     for (uint32_t it = 0; it < WTP_SYMS / WTP_THREADS; ++it) {
         const uint64_t row = row_base + it * WTP_THREADS + tid;
-        const bool flag = row < n && (sa[row] % rate == 0);
+        const bool flag = row < n && (pow2 ? ((sa[row] & (IdT)(rate - 1u)) == 0) : (sa[row] % rate == 0));
         const uint32_t w = __ballot_sync(0xffffffffu, flag);
         if (lane == 0) s_words[it * (WTP_THREADS / 32) + warp] = w;
     }

@@ -19,7 +19,7 @@ alpha = alpha[alpha != 0x24]
 pats, off = E.gen_patterns(44, P, text[:n], alpha)
 idx.build_kmer_table()
 a = idx.count_batch(pats, off, use_kmer_table=True, use_occ_table=False)
-idx.build_occ_table(int(os.environ.get("SHIFT", 5)))
+idx.build_occ_table(int(os.environ.get("SHIFT", 5)), layout=int(os.environ.get("LAYOUT", 1)))
 b = idx.count_batch(pats, off, use_kmer_table=True, use_occ_table=True)
 torch.cuda.synchronize()
 assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
