@@ -221,6 +221,22 @@ template <int MODE>
 __device__ __forceinline__ uint32_t digit_peers(uint32_t d)
 {
     if (MODE == 0) return __match_any_sync(0xffffffffu, d);
+    if (MODE == 2) {       // same ballots, spelled in PTX: test, vote, conditional complement, and -- four
+                           // instructions per bit (the C++ form compiles to six: shift, and, two compares, select, and)
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+            uint32_t x;
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                         "and.b32 t, %1, %2;\n\t"
+                         "setp.ne.u32 p, t, 0;\n\t"
+                         "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+                         "@!p not.b32 %0, %0;\n\t}"
+                         : "=r"(x) : "r"(d), "r"(1u << bit));
+            peers &= x;
+        }
+        return peers;
+    }
     uint32_t peers = 0xffffffffu;
 #pragma unroll
     for (int bit = 0; bit < 8; ++bit) {
@@ -272,33 +288,31 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     __syncthreads();
 
     // ---- rank inside the warp (warp-striped: lane l, item k <-> tile offset warp*32*IPT + k*32 + l)
+    //      Slots past the end of the array read as all-ones keys: digit 255 at every shift, ranked last.
     uint64_t key[OS_IPT];
     uint32_t val[OS_IPT];
     uint32_t peers[OS_IPT];
-    uint16_t rnk[OS_IPT];
+    uint32_t dr[OS_IPT];          // digit << 16 | rank of the item among the warp's items with that digit
     const uint32_t wbase = warp * 32u * OS_IPT + lane;
 #pragma unroll
     for (int k = 0; k < OS_IPT; ++k) {
         const uint32_t local = wbase + k * 32u;
-        const bool valid = local < nvalid;
-        key[k] = valid ? S.keys[local] : ~0ULL;
+        key[k] = (local < nvalid) ? S.keys[local] : ~0ULL;
         val[k] = ident ? tile_base + local : S.vals[local];
-        const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
+        const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
+        dr[k] = d << 16;
         peers[k] = digit_peers<MODE>(d);
     }
+    const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int k = 0; k < OS_IPT; ++k) {
-        const bool valid = (wbase + k * 32u) < nvalid;
-        const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
-        const uint32_t leader = __ffs(peers[k]) - 1;
-        uint32_t before = 0;
-        uint16_t *cnt = &S.whist[warp][d];
-        if (lane == leader) {
-            before = *cnt;
-            *cnt = (uint16_t)(before + __popc(peers[k]));
-        }
-        before = __shfl_sync(0xffffffffu, before, leader);
-        rnk[k] = (uint16_t)(before + __popc(peers[k] & lanemask_lt()));
+        // the lowest lane of a digit group adds the group to the warp's counter; everybody reads the counter back
+        // and takes its place from the end: rank = counter - #(peers at or above me)
+        uint16_t *cnt = &S.whist[warp][dr[k] >> 16];
+        const uint32_t np = __popc(peers[k]);
+        if ((peers[k] & lt) == 0u) *cnt = (uint16_t)(*cnt + np);
+        __syncwarp();
+        dr[k] |= (uint32_t)*cnt - (uint32_t)__popc(peers[k] & ~lt);
         __syncwarp();
     }
     __syncthreads();     // every thread holds its keys/values: S.keys / S.vals may be overwritten below
@@ -332,9 +346,7 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     // ---- stage (key, value) in digit order
 #pragma unroll
     for (int k = 0; k < OS_IPT; ++k) {
-        const bool valid = (wbase + k * 32u) < nvalid;
-        const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
-        const uint32_t slot = (uint32_t)S.whist[warp][d] + rnk[k];
+        const uint32_t slot = (uint32_t)S.whist[warp][dr[k] >> 16] + (dr[k] & 0xFFFFu);
         S.keys[slot] = key[k];
         S.vals[slot] = val[k];
     }
@@ -635,7 +647,8 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
 }
 
 // Variant selection (HKCSA_OS_VARIANT, read once; measured on B200, profiles/r01_onesweep_variants.txt):
-// 2 (default) = 512 threads x 8, 2 CTAs/SM (4096 pairs per tile), ballot ranking; 0 = same with match.any
+// 6 (default) = 512 threads x 8, 2 CTAs/SM (4096 pairs per tile), ballot ranking spelled in PTX (4 instructions
+// per digit bit; 2 = the same ballots in C++: 6 per bit, 0.78 vs 0.73 ms per pass); 0 = same with match.any
 // ranking (faster only when a digit takes < ~8 distinct values); 1 = 256 threads x 8, 4 CTAs/SM, match.any.
 template <int THREADS, int MIN_CTAS, int MODE>
 static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n, int passes,
@@ -717,7 +730,7 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("HKCSA_OS_VARIANT");
-        variant = e ? atoi(e) : 2;
+        variant = e ? atoi(e) : 6;
     }
     radix_scan_kernel<<<passes, RADIX, 0, st>>>(s.hist, s.base);
     count_launch();
@@ -728,7 +741,8 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
     if (variant == 3) return run_onesweep64<256, 4, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
     if (variant == 4) return run_onesweep64<384, 3, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
     if (variant == 0) return run_onesweep64<512, 2, 0>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
-    return run_onesweep64<512, 2, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    if (variant == 2) return run_onesweep64<512, 2, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    return run_onesweep64<512, 2, 2>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
 }
 
 cudaError_t radix_partition_bytes(const uint8_t *d_in, uint8_t *d_out, uint32_t *d_pos_out, uint32_t n,
