@@ -278,11 +278,22 @@ struct LazyRank {
     const uint8_t *text;       // nullptr = eager mode
     const uint64_t *keys0;     // round-0 keys, sorted
     const uint32_t *bucket;    // bucket[v] = lower_bound(keys0, v << shift), v in [0, 2^bucket_bits]
+    const uint64_t *samples;   // samples[j] = keys0[j << LAZY_SAMPLE_SHIFT]
     int bits;                  // width of a round-0 key
     int shift;                 // key >> shift = bucket id
 };
 
 constexpr int LAZY_BUCKET_BITS = 20;
+// Every 64th sorted key, kept apart: n / 8 bytes (25 MB at C3), L2-resident, so the long part of a look-up's
+// binary search (buckets of frequent prefixes hold millions of keys) runs on L2 hits and only the last six
+// steps -- inside 64 consecutive keys = four lines -- go to DRAM.
+constexpr int LAZY_SAMPLE_SHIFT = 6;
+
+__global__ void sa_key_samples_kernel(const uint64_t *__restrict__ keys0, uint32_t n, uint64_t *__restrict__ samples)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (((uint64_t)j << LAZY_SAMPLE_SHIFT) < n) samples[j] = keys0[(uint64_t)j << LAZY_SAMPLE_SHIFT];
+}
 
 // bucket[v] = lower_bound(keys0, v << shift) for v in [0, nbuckets]: one binary search per bucket
 // boundary (2^20 searches whose upper levels stay in L2), not a pass over the keys
@@ -310,6 +321,19 @@ __device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const u
     });
     const uint32_t v = (uint32_t)(key >> lz.shift);
     uint32_t lo = __ldg(lz.bucket + v), hi = __ldg(lz.bucket + v + 1);
+    if (hi - lo > (2u << LAZY_SAMPLE_SHIFT)) {
+        // first the samples whose positions lie in [lo, hi): smallest j with samples[j] >= key
+        const uint32_t jlo = (lo + (1u << LAZY_SAMPLE_SHIFT) - 1u) >> LAZY_SAMPLE_SHIFT;
+        const uint32_t jhi = (hi + (1u << LAZY_SAMPLE_SHIFT) - 1u) >> LAZY_SAMPLE_SHIFT;
+        uint32_t a = jlo, b = jhi;
+        while (a < b) {
+            const uint32_t mid = a + ((b - a) >> 1);
+            if (__ldg(lz.samples + mid) < key) a = mid + 1; else b = mid;
+        }
+        // the answer lies in (position of sample a-1, position of sample a], clipped to [lo, hi)
+        if (a > jlo) lo = max(lo, ((a - 1u) << LAZY_SAMPLE_SHIFT) + 1u);
+        if (a < jhi) hi = min(hi, a << LAZY_SAMPLE_SHIFT);
+    }
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         if (__ldg(lz.keys0 + mid) < key) lo = mid + 1; else hi = mid;
@@ -540,6 +564,7 @@ struct SaBuffers {
     uint32_t *counter;
     uint64_t *hist64;
     uint32_t *bucket;
+    uint64_t *samples;
     SortScratch sort;
 };
 
@@ -561,6 +586,7 @@ SaBuffers carve_sa(Carver &c, uint64_t n)
     b.counter = c.take<uint32_t>(64);
     b.hist64 = c.take<uint64_t>(256);
     b.bucket = c.take<uint32_t>((1u << LAZY_BUCKET_BITS) + 2);
+    b.samples = c.take<uint64_t>((n >> LAZY_SAMPLE_SHIFT) + 2);
     b.sort = carve_sort_scratch(c, n);
     return b;
 }
@@ -660,7 +686,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     stats.alg_bytes = (uint64_t)n * 9 + (uint64_t)m * (24ull * passes0) - (uint64_t)m * 4;   // pass 0 reads no ids
 
     LazyRank lz;
-    lz.text = nullptr; lz.keys0 = nullptr; lz.bucket = nullptr; lz.bits = bits0;
+    lz.text = nullptr; lz.keys0 = nullptr; lz.bucket = nullptr; lz.samples = nullptr; lz.bits = bits0;
     const int bucket_bits = std::min(LAZY_BUCKET_BITS, bits0);
     lz.shift = bits0 - bucket_bits;
     uint64_t *kx = nullptr, *ky = nullptr;             // key ping-pong of the later rounds
@@ -693,6 +719,10 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
             const uint32_t nbuckets = 1u << bucket_bits;
             prof::Scope ps(st, prof::OTHER, (uint64_t)nbuckets * 8);
             sa_bucket_index_kernel<<<(nbuckets + 1 + 255) / 256, 256, 0, st>>>(skey, N, lz.shift, nbuckets, B.bucket);
+            HK_LAUNCH_CHECK();
+            lz.samples = B.samples;
+            const uint32_t nsamp = (uint32_t)(((uint64_t)N + (1u << LAZY_SAMPLE_SHIFT) - 1) >> LAZY_SAMPLE_SHIFT);
+            sa_key_samples_kernel<<<(nsamp + 255) / 256, 256, 0, st>>>(skey, N, B.samples);
             HK_LAUNCH_CHECK();
         }
         uint32_t *cpos = B.pos[pcur ^ 1];
