@@ -647,8 +647,9 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
 }
 
 // Variant selection (HKCSA_OS_VARIANT, read once; measured on B200, profiles/r01_onesweep_variants.txt):
-// 6 (default) = 512 threads x 8, 2 CTAs/SM (4096 pairs per tile), ballot ranking spelled in PTX (4 instructions
-// per digit bit; 2 = the same ballots in C++: 6 per bit, 0.78 vs 0.73 ms per pass); 0 = same with match.any
+// 7 (default) = 384 threads x 8, 3 CTAs/SM (3072 pairs per tile, 56 registers), ballot ranking spelled in PTX
+// (3.2 instructions per digit bit); 6 = the same with 512 threads, 2 CTAs/SM (0.729 vs 0.715 ms per pass);
+// 2 = 512 threads with the ballots in C++ (6 instructions per bit: 0.78 ms per pass); 0 = same with match.any
 // ranking (faster only when a digit takes < ~8 distinct values); 1 = 256 threads x 8, 4 CTAs/SM, match.any.
 template <int THREADS, int MIN_CTAS, int MODE>
 static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n, int passes,
@@ -730,7 +731,7 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("HKCSA_OS_VARIANT");
-        variant = e ? atoi(e) : 6;
+        variant = e ? atoi(e) : 7;
     }
     radix_scan_kernel<<<passes, RADIX, 0, st>>>(s.hist, s.base);
     count_launch();
@@ -742,7 +743,9 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
     if (variant == 4) return run_onesweep64<384, 3, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
     if (variant == 0) return run_onesweep64<512, 2, 0>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
     if (variant == 2) return run_onesweep64<512, 2, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
-    return run_onesweep64<512, 2, 2>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    if (variant == 8) return run_onesweep64<256, 4, 2>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    if (variant == 6) return run_onesweep64<512, 2, 2>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    return run_onesweep64<384, 3, 2>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
 }
 
 cudaError_t radix_partition_bytes(const uint8_t *d_in, uint8_t *d_out, uint32_t *d_pos_out, uint32_t n,
