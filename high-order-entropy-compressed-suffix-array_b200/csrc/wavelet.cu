@@ -160,6 +160,9 @@ wt_dir_fix_kernel(RankBlock *__restrict__ blocks, uint64_t nblocks, const uint64
 // run by its bit, computed from a tile-wide prefix sum of the bits.  The sequence is read from HBM
 // once for all levels and only bits are written.
 constexpr int WTL_EPT = WTL_TILE / WTL_THREADS;   // 32 symbols per thread = one bit word
+// resident CTAs per SM asked of the compiler for wt_levels_kernel: 77 registers gave 3 (C3: 3.41 ms), 4 CTAs 3.04 ms,
+// 5 CTAs (47 registers, no spills) 2.63 ms, 6 CTAs 2.73 ms
+#define WTL_MIN_CTAS 5
 static_assert(WTL_EPT == 32, "one 32-bit word of bits per thread");
 
 __global__ void __launch_bounds__(WTL_THREADS)
@@ -209,7 +212,7 @@ struct LevelWords {
     uint32_t *w[HKCSA_MAX_LEVELS];   // rank blocks of each level viewed as uint32[8] per block
 };
 
-__global__ void __launch_bounds__(WTL_THREADS)
+__global__ void __launch_bounds__(WTL_THREADS, WTL_MIN_CTAS)
 wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__restrict__ tab,
                  const uint32_t *__restrict__ gpre, uint32_t tiles, LevelWords lv, uint32_t levels, uint32_t sigma)
 {
