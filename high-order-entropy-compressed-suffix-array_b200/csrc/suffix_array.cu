@@ -487,7 +487,7 @@ seg_scan_kernel(uint32_t *__restrict__ agg_head, uint32_t *__restrict__ agg_keep
     if (tid == 0) *out_m = s_carry_k;
 }
 
-__global__ void __launch_bounds__(SEG_THREADS)
+__global__ void __launch_bounds__(SEG_THREADS, 6)
 seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict__ sidx,
                  const uint32_t *__restrict__ pos /* nullptr = identity */, uint32_t m,
                  const uint32_t *__restrict__ carry_head, const uint32_t *__restrict__ carry_keep,
