@@ -213,7 +213,7 @@ __device__ __forceinline__ void pack_emit8(uint32_t *s_stream, uint16_t *s_off8,
     *reinterpret_cast<uint4 *>(s_off8) = q;
 }
 
-__global__ void __launch_bounds__(PACK_THREADS)
+__global__ void __launch_bounds__(PACK_THREADS, 6)
 sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, int bits, int passes,
                 uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist)
 {
