@@ -83,7 +83,7 @@ extern "C" int hkcsa_bwt(const uint8_t *d_text, const uint32_t *d_sa, uint64_t n
     static double range_mb = -1;
     if (range_mb < 0) {
         const char *e = getenv("HKCSA_BWT_RANGE_MB");
-        range_mb = e ? atof(e) : 64.0;
+        range_mb = e ? atof(e) : 70.0;
         if (range_mb <= 0) range_mb = 1e12;
     }
     uint64_t phases = (uint64_t)((double)n / (range_mb * 1e6)) + 1;
