@@ -431,6 +431,7 @@ class DeviceIndex:
 
     # k-mer jump table (query accelerator, built on first use for large batches)
     KMER_MIN_BATCH = 1 << 18
+    OCC_MIN_BATCH = 1 << 20      # batches from which count_batch builds the sampled Occ table on its own
 
     def build_kmer_table(self):
         """SA ranges of every k-mer over the alphabet (k = largest with sigma^k <= 2^21), computed by the count
@@ -471,8 +472,8 @@ class DeviceIndex:
     # find_range, batched (csa/enhanced_fm_index.py:21-32)
     def count_batch(self, pat: torch.Tensor, off: torch.Tensor, use_kmer_table: bool | None = None,
                     use_occ_table: bool | None = None):
-        """use_occ_table: None = use the sampled Occ table when one was built (build_occ_table); False = always
-        rank on the wavelet tree.  Both give identical ranges."""
+        """use_occ_table: None = use the sampled Occ table when one was built (build_occ_table) or build it for a
+        batch of OCC_MIN_BATCH patterns or more; False = always rank on the wavelet tree.  Identical ranges."""
         P = off.numel() - 1
         lo = _empty(P, torch.int64, self.device)
         hi = _empty(P, torch.int64, self.device)
@@ -485,6 +486,12 @@ class DeviceIndex:
             table, k = getattr(self, "_kmer", None) or self.build_kmer_table()
         occ = getattr(self, "_occ", None)
         if use_occ_table is None:
+            # large batches amortise the table (0.5-2 ms to build) many times over: build it when the BWT is at
+            # hand and the table takes at most a quarter of the free device memory
+            if occ is None and P >= self.OCC_MIN_BATCH and self.bwt is not None:
+                need = 8 * self.wt.sigma * (self.n // 32 + 4) + self.n
+                if need <= torch.cuda.mem_get_info(self.device)[0] // 4:
+                    occ = self.build_occ_table(5, layout=1)
             use_occ_table = occ is not None
         if use_occ_table:
             if occ is None:
