@@ -48,6 +48,15 @@ def test_build_and_query_at_baseline_size(E, kind, seed, n):
     lo, hi = idx.count_batch(d_p, d_o)
     w_lo, w_hi = fm.find_range_batch(pats, off)
     assert np.array_equal(lo.cpu().numpy(), w_lo) and np.array_equal(hi.cpu().numpy(), w_hi)
+    # ---- the sampled Occ table (both layouts) gives the same ranges and the same LF walks at full size
+    o_wt, p_wt = idx.locate_batch(d_p[: int(off[2000])], d_o[:2001], use_samples=True)
+    for layout in (1, 0):
+        idx.build_occ_table(5, layout=layout)
+        lo2, hi2 = idx.count_batch(d_p, d_o, use_occ_table=True)
+        assert torch.equal(lo, lo2) and torch.equal(hi, hi2)
+        o_oc, p_oc = idx.locate_batch(d_p[: int(off[2000])], d_o[:2001], use_samples=True)
+        assert torch.equal(o_wt, o_oc) and torch.equal(p_wt, p_oc)
+        idx._occ = None
     o1, p1 = idx.locate_batch(d_p, d_o, use_samples=False)
     o2, p2 = idx.locate_batch(d_p, d_o, use_samples=True)
     assert torch.equal(o1, o2) and torch.equal(p1, p2)                       # LF walk == full SA
