@@ -347,7 +347,7 @@ def run_ours(args):
             q_idx = hdist.broadcast_index(idx if rank == 0 else None, src=0, device=dev, with_bwt=True)
             barrier()
             bcast_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-            bounds = hdist.shard_bounds(off.cpu().numpy(), world)
+            bounds = hdist.shard_bounds(off, world)
             pb, pe = bounds[rank]
             my_pats, my_off = hdist.local_slice(pats, off, pb, pe)
         else:
@@ -389,8 +389,10 @@ def run_ours(args):
             q_idx._occ = None
         gather_ms = None
         if world > 1:                      # results to every rank, timed apart from the search
+            hdist.gather_ranges(lo, hi, bounds)                      # first call: NCCL channel set-up
+            barrier()
             t0 = time.perf_counter()
-            glo, ghi = hdist.sharded_count(lambda p_, o_: (lo, hi), pats, off)
+            glo, ghi = hdist.gather_ranges(lo, hi, bounds)
             barrier()
             gather_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
             hits = float((glo >= 0).sum().item())
@@ -442,8 +444,9 @@ def run_ours(args):
         alpha3 = torch.from_numpy(np.frombuffer(idx3.wt.alphabet, dtype=np.uint8).copy()).to(dev)
         alpha3 = alpha3[alpha3 != 0x24]
         pats3, off3 = E.gen_patterns(44, args.patterns, t3[:n3], alpha3)
+        pats3_full, off3_full = pats3, off3
         if world > 1:
-            pb, pe = hdist.shard_bounds(off3.cpu().numpy(), world)[rank]
+            pb, pe = hdist.shard_bounds(off3, world)[rank]
             pats3, off3 = hdist.local_slice(pats3, off3, pb, pe)
         idx3.build_kmer_table()
         for _ in range(2):
@@ -498,6 +501,37 @@ def run_ours(args):
                 o_ms = max_over_ranks(a.elapsed_time(b) / 3)
                 assert torch.equal(lo4, lo3) and torch.equal(hi4, hi3)
                 l_ms, l_occ = time_locate3()
+                if world > 1 and layout == 1:
+                    # every rank needs every answer: NCCL all-gather after the search, against the search kernel
+                    # storing its slice into all ranks' arrays itself (peer-mapped symmetric memory over NVLink)
+                    bounds3 = hdist.shard_bounds(off3_full, world)
+                    peers = hdist.PeerRanges(args.patterns, dev)
+
+                    def timed3(fn):
+                        fn()
+                        torch.cuda.synchronize()
+                        barrier()
+                        t0_ = time.perf_counter()
+                        for _ in range(3):
+                            r_ = fn()
+                        torch.cuda.synchronize()
+                        barrier()
+                        return max_over_ranks((time.perf_counter() - t0_) / 3 * 1e3), r_
+
+                    def nccl3():
+                        l_, h_ = idx3.count_batch(pats3, off3, use_kmer_table=True, use_occ_table=True)
+                        return hdist.gather_ranges(l_, h_, bounds3)
+
+                    g_ms, (glo3, ghi3) = timed3(nccl3)
+                    f_ms, (flo3, fhi3) = timed3(lambda: hdist.sharded_count_fused(idx3, pats3_full, off3_full, peers,
+                                                                                 bounds=bounds3, use_kmer_table=True))
+                    assert torch.equal(glo3, flo3) and torch.equal(ghi3, fhi3)
+                    c4["all_answers_on_all_ranks"] = {
+                        "search_plus_nccl_allgather": {"ms": g_ms, "patterns_per_s": args.patterns / (g_ms / 1e3)},
+                        "search_with_fused_peer_stores": {"ms": f_ms, "patterns_per_s": args.patterns / (f_ms / 1e3)},
+                        "note": "wall clock incl. launch and the cross-rank barrier; hkcsa_count_batch_peers writes every "
+                                "range into the result arrays of all ranks from inside the search kernel"}
+                    del peers
                 c4["occ_table_bitmaps" if layout else f"occ_table_rows_{1 << shift}"] = {"count_patterns_per_s": args.patterns / (o_ms / 1e3), "count_ms": o_ms,
                                                        "build_ms": occ_ms, "bytes": int(plan_o.blob_bytes),
                                                        "locate_occurrences_per_s": l_occ / (l_ms / 1e3), "locate_ms": l_ms}

@@ -26,7 +26,8 @@ constexpr int COUNT_THREADS = 256;
 //   l >= r -> (-1, -1).  Result (l, r-1).
 __global__ void __launch_bounds__(COUNT_THREADS)
 fm_count_kernel(WtDev wt, const uint8_t *__restrict__ pat, const int64_t *__restrict__ off, uint64_t P,
-                int64_t *__restrict__ out_lo, int64_t *__restrict__ out_hi, const uint2 *__restrict__ kmer, uint32_t kk)
+                int64_t *__restrict__ out_lo, int64_t *__restrict__ out_hi, const uint2 *__restrict__ kmer, uint32_t kk,
+                PeerOut po)
 {
     __shared__ WtSmem s;
     wt_smem_load(s, wt);
@@ -92,8 +93,7 @@ fm_count_kernel(WtDev wt, const uint8_t *__restrict__ pat, const int64_t *__rest
             done = miss || k < b;
         }
         if (done) {
-            out_lo[p] = miss ? -1 : (int64_t)l;
-            out_hi[p] = miss ? -1 : (int64_t)r - 1;
+            put_range(po, out_lo, out_hi, p, miss ? -1 : (int64_t)l, miss ? -1 : (int64_t)r - 1);
             p = -1;
         }
     }
@@ -285,12 +285,18 @@ extern "C" int hkcsa_count_batch_kmer(const void *d_blob, const hkcsa_wt_plan *h
     if (P == 0) return HKCSA_OK;
     HK_REQUIRE(d_off && d_lo && d_hi, HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(h_plan->n >= 1, HKCSA_EINVAL, "empty index");
-    cudaStream_t st = as_stream(stream);
-    WtDev wt = make_wt_dev(d_blob, h_plan);
+    PeerOut po;
+    memset(&po, 0, sizeof(po));
+    return count_wt_launch(make_wt_dev(d_blob, h_plan), static_cast<const uint2 *>(d_kmer_table), k, d_pat, d_off, P,
+                           d_lo, d_hi, po, as_stream(stream));
+}
+
+int hkcsa::count_wt_launch(const WtDev &wt, const uint2 *kmer, uint32_t k, const uint8_t *d_pat, const int64_t *d_off,
+                           uint64_t P, int64_t *d_lo, int64_t *d_hi, const PeerOut &po, cudaStream_t st)
+{
     const int blocks = (int)std::min<uint64_t>((P + COUNT_THREADS - 1) / COUNT_THREADS, (uint64_t)num_sms() * 8);
     prof::Scope ps(st, prof::COUNT, 0);
-    fm_count_kernel<<<blocks, COUNT_THREADS, 0, st>>>(wt, d_pat, d_off, P, d_lo, d_hi,
-                                                      static_cast<const uint2 *>(d_kmer_table), d_kmer_table ? k : 0u);
+    fm_count_kernel<<<blocks, COUNT_THREADS, 0, st>>>(wt, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u, po);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

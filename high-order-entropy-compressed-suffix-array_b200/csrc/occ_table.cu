@@ -217,7 +217,7 @@ template <int SHIFT, int MIN_CTAS>
 __global__ void __launch_bounds__(OCC_THREADS, MIN_CTAS)
 fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t *__restrict__ pat,
                     const int64_t *__restrict__ off, uint64_t P, int64_t *__restrict__ out_lo,
-                    int64_t *__restrict__ out_hi, const uint2 *__restrict__ kmer, uint32_t kk)
+                    int64_t *__restrict__ out_hi, const uint2 *__restrict__ kmer, uint32_t kk, PeerOut po)
 {
     __shared__ uint32_t s_C[260];
     __shared__ uint16_t s_code[256];
@@ -284,8 +284,7 @@ fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t 
             done = miss || k < b;
         }
         if (done) {
-            out_lo[p] = miss ? -1 : (int64_t)l;
-            out_hi[p] = miss ? -1 : (int64_t)r - 1;
+            put_range(po, out_lo, out_hi, p, miss ? -1 : (int64_t)l, miss ? -1 : (int64_t)r - 1);
             p = -1;
         }
     }
@@ -405,16 +404,12 @@ extern "C" int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt,
     return HKCSA_OK;
 }
 
-extern "C" int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt, const void *d_occ_blob,
-                                     const hkcsa_occ_plan *p, const void *d_kmer_table, uint32_t k,
-                                     const uint8_t *d_pat, const int64_t *d_off, uint64_t P, int64_t *d_lo,
-                                     int64_t *d_hi, void *stream)
+static int count_occ_launch(const void *d_wt_blob, const hkcsa_wt_plan *h_wt, const void *d_occ_blob,
+                            const hkcsa_occ_plan *p, const void *d_kmer_table, uint32_t k, const uint8_t *d_pat,
+                            const int64_t *d_off, uint64_t P, int64_t *d_lo, int64_t *d_hi, const PeerOut &po,
+                            cudaStream_t st)
 {
-    HK_REQUIRE(d_wt_blob && h_wt && d_occ_blob && p, HKCSA_EINVAL, "null pointer");
-    if (P == 0) return HKCSA_OK;
-    HK_REQUIRE(d_off && d_lo && d_hi, HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(p->n == h_wt->n && p->sigma == h_wt->sigma && p->n >= 1, HKCSA_EINVAL, "occ plan does not match the index");
-    cudaStream_t st = as_stream(stream);
     const WtTables *d_tab = reinterpret_cast<const WtTables *>(static_cast<const uint8_t *>(d_wt_blob) + h_wt->off_tables);
     OccDev occ;
     occ.rows = static_cast<const uint8_t *>(d_occ_blob);
@@ -423,6 +418,7 @@ extern "C" int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan 
     occ.sigma = p->sigma;
     occ.n = (uint32_t)p->n;
     const uint2 *kmer = static_cast<const uint2 *>(d_kmer_table);
+    const uint32_t kk = kmer ? k : 0u;
     prof::Scope ps(st, prof::COUNT, 0);
     // 4 CTAs/SM (53 registers): measured best of 4 / 5 / 6 / 8 on the 2.8 GB table (more lanes in flight were slower)
     const int blocks = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 8);
@@ -431,15 +427,55 @@ extern "C" int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan 
         // 1.42 vs 1.34 G patterns/s on the 4.8 GB table of the 200 MB text, 3.4 vs 4.0 on the 225 MB DNA table)
         const int ctas = (p->blob_bytes > (1ull << 30)) ? 4 : 6;
         const int blocks1 = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 2 * ctas);
-        if (ctas == 6) fm_count_occ_kernel<0, 6><<<blocks1, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
-        else fm_count_occ_kernel<0, 4><<<blocks1, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
+        if (ctas == 6) fm_count_occ_kernel<0, 6><<<blocks1, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);
+        else fm_count_occ_kernel<0, 4><<<blocks1, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);
+    } else if (p->shift == 5) {
+        fm_count_occ_kernel<5, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);
+    } else {
+        fm_count_occ_kernel<6, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);
     }
-    else if (p->shift == 5)
-        fm_count_occ_kernel<5, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
-    else
-        fm_count_occ_kernel<6, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
+}
+
+extern "C" int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt, const void *d_occ_blob,
+                                     const hkcsa_occ_plan *p, const void *d_kmer_table, uint32_t k,
+                                     const uint8_t *d_pat, const int64_t *d_off, uint64_t P, int64_t *d_lo,
+                                     int64_t *d_hi, void *stream)
+{
+    HK_REQUIRE(d_wt_blob && h_wt && d_occ_blob && p, HKCSA_EINVAL, "null pointer");
+    if (P == 0) return HKCSA_OK;
+    HK_REQUIRE(d_off && d_lo && d_hi, HKCSA_EINVAL, "null pointer");
+    PeerOut po;
+    memset(&po, 0, sizeof(po));
+    return count_occ_launch(d_wt_blob, h_wt, d_occ_blob, p, d_kmer_table, k, d_pat, d_off, P, d_lo, d_hi, po, as_stream(stream));
+}
+
+extern "C" int hkcsa_count_batch_peers(const void *d_wt_blob, const hkcsa_wt_plan *h_wt, const void *d_occ_blob,
+                                       const hkcsa_occ_plan *h_occ, const void *d_kmer_table, uint32_t k,
+                                       const uint8_t *d_pat, const int64_t *d_off, uint64_t P, uint64_t out_base,
+                                       uint32_t n_peers, const uint64_t *h_peer_lo, const uint64_t *h_peer_hi, void *stream)
+{
+    HK_REQUIRE(d_wt_blob && h_wt && h_peer_lo && h_peer_hi, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(n_peers >= 1 && n_peers <= HKCSA_MAX_PEERS, HKCSA_EINVAL, "n_peers must be in [1, HKCSA_MAX_PEERS]");
+    HK_REQUIRE((d_occ_blob == nullptr) == (h_occ == nullptr), HKCSA_EINVAL, "occ blob and plan go together");
+    if (P == 0) return HKCSA_OK;
+    HK_REQUIRE(d_off != nullptr, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(h_wt->n >= 1, HKCSA_EINVAL, "empty index");
+    PeerOut po;
+    memset(&po, 0, sizeof(po));
+    po.n = n_peers;
+    po.base = out_base;
+    for (uint32_t r = 0; r < n_peers; ++r) {
+        HK_REQUIRE(h_peer_lo[r] && h_peer_hi[r], HKCSA_EINVAL, "null peer pointer");
+        po.lo[r] = reinterpret_cast<int64_t *>(static_cast<uintptr_t>(h_peer_lo[r]));
+        po.hi[r] = reinterpret_cast<int64_t *>(static_cast<uintptr_t>(h_peer_hi[r]));
+    }
+    cudaStream_t st = as_stream(stream);
+    if (d_occ_blob)
+        return count_occ_launch(d_wt_blob, h_wt, d_occ_blob, h_occ, d_kmer_table, k, d_pat, d_off, P, nullptr, nullptr, po, st);
+    return count_wt_launch(make_wt_dev(d_wt_blob, h_wt), static_cast<const uint2 *>(d_kmer_table), k, d_pat, d_off, P,
+                           nullptr, nullptr, po, st);
 }
 
 extern "C" int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt, const void *d_occ_blob,

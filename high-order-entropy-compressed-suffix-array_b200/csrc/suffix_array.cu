@@ -14,6 +14,7 @@
 #include "prof.cuh"
 #include "radix_sort.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace hkcsa {
 
@@ -649,6 +650,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     const int k_target = 64 / b;
     int bits0 = 8 * (int)ceil(k_target * avg_len / 8.0 - 1e-9);
     bits0 = std::max(16, std::min(64, bits0));
+    if (const char *e = getenv("HKCSA_BITS0")) bits0 = std::max(16, std::min(64, 8 * (atoi(e) / 8)));   // tuning knob
     const int k0 = std::max(1, bits0 / max_len);         // symbols every key is guaranteed to cover
     const int passes0 = bits0 / 8;
     stats.sigma = sigma;

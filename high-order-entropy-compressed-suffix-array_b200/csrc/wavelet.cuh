@@ -61,6 +61,31 @@ wt_tile_hist_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables 
                     uint32_t tiles, uint32_t *__restrict__ gcnt /* [sigma][tiles+1] */);
 __global__ void __launch_bounds__(1024) wt_tile_scan_kernel(uint32_t *__restrict__ gcnt, uint32_t tiles);
 
+// Where a count kernel puts its answers.  n == 0: the caller's own lo / hi arrays.  n > 0 (multi-GPU, patterns
+// sharded): every rank's kernel writes its slice straight into the result arrays of ALL ranks through
+// peer-mapped pointers (NVLink stores from inside the search kernel) at [base + pattern]: the all-gather of
+// the results is fused into the search, there is no collective afterwards.
+struct PeerOut {
+    int64_t *lo[HKCSA_MAX_PEERS];
+    int64_t *hi[HKCSA_MAX_PEERS];
+    uint64_t base;
+    uint32_t n;
+};
+__device__ __forceinline__ void put_range(const PeerOut &po, int64_t *out_lo, int64_t *out_hi, int64_t p, int64_t l, int64_t h)
+{
+    if (po.n == 0) {
+        out_lo[p] = l;
+        out_hi[p] = h;
+    } else {
+        for (uint32_t r = 0; r < po.n; ++r) {
+            po.lo[r][po.base + p] = l;
+            po.hi[r][po.base + p] = h;
+        }
+    }
+}
+int count_wt_launch(const WtDev &wt, const uint2 *kmer, uint32_t k, const uint8_t *d_pat, const int64_t *d_off, uint64_t P,
+                    int64_t *d_lo, int64_t *d_hi, const PeerOut &po, cudaStream_t st);
+
 // Shared-memory copy of what a symbol-rank walk needs ("C[] held in shared memory").
 struct WtSmem {
     uint32_t node_start[HKCSA_MAX_LEVELS][256];

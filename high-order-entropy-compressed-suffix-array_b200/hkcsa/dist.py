@@ -15,9 +15,26 @@ import torch
 import torch.distributed as dist
 
 
-def shard_bounds(offsets: np.ndarray, world: int) -> list[tuple[int, int]]:
+def shard_bounds(offsets, world: int) -> list[tuple[int, int]]:
     """Split P patterns (CSR offsets int64[P+1]) into `world` contiguous slices with near-equal
-    total length (the work of a backward search is one step per symbol)."""
+    total length (the work of a backward search is one step per symbol).  A torch tensor (any device) is
+    searched where it lives -- only the `world` cut points come back to the host."""
+    if isinstance(offsets, torch.Tensor):
+        P = offsets.numel() - 1
+        if P <= 0:
+            return [(0, max(P, 0))] * world
+        first, last = int(offsets[0].item()), int(offsets[-1].item())
+        total = last - first
+        if total == 0:
+            cuts = [min(P, (P * r) // world) for r in range(world)] + [P]
+        else:
+            targets = torch.tensor([first + (total * r) // world for r in range(1, world)], dtype=offsets.dtype,
+                                   device=offsets.device)
+            mid = torch.searchsorted(offsets, targets, right=False).tolist() if world > 1 else []
+            cuts = [0] + [int(x) for x in mid] + [P]
+        for i in range(1, len(cuts)):
+            cuts[i] = max(cuts[i], cuts[i - 1])
+        return [(cuts[r], cuts[r + 1]) for r in range(world)]
     offsets = np.asarray(offsets, dtype=np.int64)
     P = len(offsets) - 1
     total = int(offsets[-1] - offsets[0]) if P > 0 else 0
@@ -47,22 +64,35 @@ def sharded_count(count_fn, pat: torch.Tensor, off: torch.Tensor, group=None):
     (lo, hi)` and the (lo, hi) pairs are all-gathered so every rank ends with all P answers."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    bounds = shard_bounds(off.cpu().numpy(), world)
+    bounds = shard_bounds(off, world)
     b, e = bounds[rank]
     lp, lo_ = local_slice(pat, off, b, e)
     lo, hi = count_fn(lp, lo_)
-    P = off.numel() - 1
+    return gather_ranges(lo, hi, bounds, group=group)
+
+
+def gather_ranges(lo: torch.Tensor, hi: torch.Tensor, bounds, group=None):
+    """All-gather of the per-rank (lo, hi) slices into the full batch order: one collective on a padded
+    (2, width) block per rank, then `world` slice copies."""
+    world = dist.get_world_size(group)
+    P = bounds[-1][1] if bounds else 0
     width = max(x[1] - x[0] for x in bounds) if bounds else 0
-    send = torch.full((2, width), -2, dtype=torch.int64, device=lo.device)
-    send[0, : e - b] = lo
-    send[1, : e - b] = hi
-    recv = [torch.empty_like(send) for _ in range(world)]
-    dist.all_gather(recv, send, group=group)
+    k = lo.numel()
+    send = torch.empty((2, width), dtype=torch.int64, device=lo.device)
+    send[0, :k] = lo
+    send[1, :k] = hi
+    recv = torch.empty((world, 2, width), dtype=torch.int64, device=lo.device)
+    if hasattr(dist, "all_gather_into_tensor") and lo.is_cuda:
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:       # gloo (CPU tests)
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send, group=group)
+        recv = torch.stack(parts)
     out_lo = torch.empty(P, dtype=torch.int64, device=lo.device)
     out_hi = torch.empty(P, dtype=torch.int64, device=lo.device)
     for r, (rb, re_) in enumerate(bounds):
-        out_lo[rb:re_] = recv[r][0, : re_ - rb]
-        out_hi[rb:re_] = recv[r][1, : re_ - rb]
+        out_lo[rb:re_] = recv[r, 0, : re_ - rb]
+        out_hi[rb:re_] = recv[r, 1, : re_ - rb]
     return out_lo, out_hi
 
 
@@ -112,3 +142,46 @@ def broadcast_index(index, src: int = 0, group=None, device=None, with_bwt: bool
     replica = engine.DeviceIndex.from_parts(n, plan, blob, ssa)
     replica.bwt = bwt
     return replica
+
+
+class PeerRanges:
+    """The (lo, hi) answer arrays of a GLOBAL pattern batch, allocated in torch symmetric memory (peer-mapped over
+    NVLink): every rank's count kernel writes its slice into the arrays of all ranks, so the all-gather of the
+    results is part of the search kernel (hkcsa_count_batch_peers) and no collective follows it."""
+
+    def __init__(self, P: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.P = int(P)
+        self.buf = symm.empty((2, max(self.P, 1)), dtype=torch.int64, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.world = self.hdl.world_size
+        self.rank = self.hdl.rank
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.peer_lo = (C.c_uint64 * self.world)(*ptrs)
+        self.peer_hi = (C.c_uint64 * self.world)(*[p + 8 * max(self.P, 1) for p in ptrs])
+
+    @property
+    def lo(self) -> torch.Tensor:
+        return self.buf[0, : self.P]
+
+    @property
+    def hi(self) -> torch.Tensor:
+        return self.buf[1, : self.P]
+
+    def barrier(self) -> None:
+        """Device-side barrier over the symmetric-memory signal pads, on the current stream: after it every
+        rank's writes into this rank's arrays have landed."""
+        self.hdl.barrier()
+
+
+def sharded_count_fused(index, pat: torch.Tensor, off: torch.Tensor, out: PeerRanges, bounds=None,
+                        use_kmer_table=None):
+    """Every rank holds the full batch and searches slice `rank`; the kernel stores the answers into `out` on
+    every rank.  Returns (lo, hi) of the whole batch (views of `out`)."""
+    bounds = bounds if bounds is not None else shard_bounds(off, out.world)
+    b, e = bounds[out.rank]
+    lp, lo_ = local_slice(pat, off, b, e)
+    index.count_batch_peers(lp, lo_, b, out.peer_lo, out.peer_hi, use_kmer_table=use_kmer_table)
+    out.barrier()
+    return out.lo, out.hi

@@ -504,6 +504,24 @@ class DeviceIndex:
                                                  _ptr(off), P, _ptr(lo), _ptr(hi), _stream()))
         return lo, hi
 
+    def count_batch_peers(self, pat: torch.Tensor, off: torch.Tensor, out_base: int, peer_lo, peer_hi,
+                          use_kmer_table: bool | None = None) -> None:
+        """count_batch for one rank's slice of a global batch, the gather fused into the search: the ranges are
+        written at [out_base + p] of the lo / hi arrays of every rank (peer_lo / peer_hi: ctypes uint64 arrays of
+        peer-mapped device pointers, hkcsa.dist.PeerRanges).  Ranks on the sampled Occ table when one was built."""
+        P = off.numel() - 1
+        if self.n == 0:
+            raise ValueError("empty index")
+        if use_kmer_table is None:
+            use_kmer_table = getattr(self, "_kmer", None) is not None or P >= self.KMER_MIN_BATCH
+        table, k = (None, 0)
+        if use_kmer_table:
+            table, k = getattr(self, "_kmer", None) or self.build_kmer_table()
+        occ = getattr(self, "_occ", None)
+        check(_lib.load().hkcsa_count_batch_peers(
+            _ptr(self.wt.blob), C.byref(self.wt.plan), _ptr(occ[1]) if occ else None, C.byref(occ[0]) if occ else None,
+            _ptr(table), k, _ptr(pat), _ptr(off), P, int(out_base), len(peer_lo), peer_lo, peer_hi, _stream()))
+
     # find, batched (csa/enhanced_fm_index.py:15-19): CSR (offsets, positions in SA order)
     def locate_batch(self, pat: torch.Tensor, off: torch.Tensor, *, use_samples: bool | None = None):
         L = _lib.load()

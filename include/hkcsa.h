@@ -368,6 +368,16 @@ int hkcsa_occ_build(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const
 int hkcsa_count_batch_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const void *d_occ_blob,
                           const hkcsa_occ_plan *h_plan, const void *d_kmer_table, uint32_t k, const uint8_t *d_pat,
                           const int64_t *d_off, uint64_t P, int64_t *d_lo, int64_t *d_hi, void *stream);
+/* Multi-GPU count with the gather of the results fused into the search: this rank's kernel writes the ranges of */
+/* its P patterns (a slice of the global batch starting at out_base) into the lo / hi arrays of ALL n_peers ranks  */
+/* through peer-mapped device pointers (h_peer_lo[r], h_peer_hi[r]: int64 arrays of the global batch size, e.g.    */
+/* torch symmetric memory or cudaIpc mappings; the own rank included).  No collective follows; the caller        */
+/* synchronises the ranks before reading.  d_occ_blob / h_occ_plan may both be NULL (wavelet-tree ranks).          */
+#define HKCSA_MAX_PEERS 16
+int hkcsa_count_batch_peers(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const void *d_occ_blob,
+                            const hkcsa_occ_plan *h_occ_plan, const void *d_kmer_table, uint32_t k,
+                            const uint8_t *d_pat, const int64_t *d_off, uint64_t P, uint64_t out_base,
+                            uint32_t n_peers, const uint64_t *h_peer_lo, const uint64_t *h_peer_hi, void *stream);
 /* hkcsa_locate_rows with the LF step (symbol + its count) read from the Occ table; same positions. */
 int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const void *d_occ_blob,
                           const hkcsa_occ_plan *h_plan, const void *d_ssa_blob, const hkcsa_ssa_plan *h_ssa,

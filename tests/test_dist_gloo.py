@@ -29,6 +29,10 @@ def test_shard_bounds_balance_by_symbols():
     skew = np.array([0, 1000, 1001, 1002, 1003], dtype=np.int64)
     b = shard_bounds(skew, 2)
     assert b[0][1] >= 1 and b[-1][1] == 4
+    # offsets given as a tensor are searched with torch (on the GPU box: on the device): same cuts
+    for arr in (off, np.array([0], dtype=np.int64), np.array([0, 0, 0, 0], dtype=np.int64), skew):
+        for world in (1, 2, 3, 8):
+            assert shard_bounds(torch.from_numpy(arr), world) == shard_bounds(arr, world)
 
 
 def _free_port():
