@@ -546,3 +546,29 @@ def test_occ_table_at_tile_boundaries(E, n):
     a = idx.count_batch(d_p, d_o, use_occ_table=False)
     b = idx.count_batch(d_p, d_o, use_occ_table=True)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("use_occ", [False, True])
+def test_count_batch_peers_writes_every_peer_array(E, use_occ):
+    """hkcsa_count_batch_peers (the gather fused into the search) with the "peers" being plain buffers on this GPU:
+    a slice of the batch searched with out_base lands at its place in every peer array, equal to count_batch."""
+    import ctypes as C
+    import torch
+    text = TEXTS["eng_300k"] + b"$"
+    idx = E.DeviceIndex(dev(E, text))
+    if use_occ:
+        idx.build_occ_table(5, layout=1)
+    pats, off = O.gen_patterns(29, 3000, np.frombuffer(TEXTS["eng_300k"], dtype=np.uint8), 1, 40)
+    d_p, d_o = torch.from_numpy(pats).cuda(), torch.from_numpy(off).cuda()
+    want_lo, want_hi = idx.count_batch(d_p, d_o, use_kmer_table=False)
+    P = 3000
+    bufs = [torch.full((2, P), -7, dtype=torch.int64, device="cuda") for _ in range(3)]
+    peer_lo = (C.c_uint64 * 3)(*[b.data_ptr() for b in bufs])
+    peer_hi = (C.c_uint64 * 3)(*[b.data_ptr() + 8 * P for b in bufs])
+    from hkcsa import dist as hdist
+    for b0, e0 in ((0, 1100), (1100, 1100), (1100, 3000)):            # three "ranks", one of them with an empty slice
+        lp, lo_ = hdist.local_slice(d_p, d_o, b0, e0)
+        idx.count_batch_peers(lp, lo_, b0, peer_lo, peer_hi, use_kmer_table=False)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b[0], want_lo) and torch.equal(b[1], want_hi)
