@@ -24,6 +24,7 @@ constexpr int COUNT_THREADS = 256;
 // range walk the wavelet tree together.  find_range (csa/enhanced_fm_index.py:21-32) in half-open form:
 //   l = 0, r = n;  per symbol from the end: l = C[c] + occ(c, l), r = C[c] + occ(c, r);
 //   l >= r -> (-1, -1).  Result (l, r-1).
+template <bool PEERS>
 __global__ void __launch_bounds__(COUNT_THREADS)
 fm_count_kernel(WtDev wt, const uint8_t *__restrict__ pat, const int64_t *__restrict__ off, uint64_t P,
                 int64_t *__restrict__ out_lo, int64_t *__restrict__ out_hi, const uint2 *__restrict__ kmer, uint32_t kk,
@@ -93,7 +94,7 @@ fm_count_kernel(WtDev wt, const uint8_t *__restrict__ pat, const int64_t *__rest
             done = miss || k < b;
         }
         if (done) {
-            put_range(po, out_lo, out_hi, p, miss ? -1 : (int64_t)l, miss ? -1 : (int64_t)r - 1);
+            put_range<PEERS>(po, out_lo, out_hi, p, miss ? -1 : (int64_t)l, miss ? -1 : (int64_t)r - 1);
             p = -1;
         }
     }
@@ -296,7 +297,8 @@ int hkcsa::count_wt_launch(const WtDev &wt, const uint2 *kmer, uint32_t k, const
 {
     const int blocks = (int)std::min<uint64_t>((P + COUNT_THREADS - 1) / COUNT_THREADS, (uint64_t)num_sms() * 8);
     prof::Scope ps(st, prof::COUNT, 0);
-    fm_count_kernel<<<blocks, COUNT_THREADS, 0, st>>>(wt, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u, po);
+    if (po.n) fm_count_kernel<true><<<blocks, COUNT_THREADS, 0, st>>>(wt, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u, po);
+    else fm_count_kernel<false><<<blocks, COUNT_THREADS, 0, st>>>(wt, d_pat, d_off, P, d_lo, d_hi, kmer, kmer ? k : 0u, po);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

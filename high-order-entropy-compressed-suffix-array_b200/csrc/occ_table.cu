@@ -213,7 +213,7 @@ __device__ __forceinline__ void occ_rank2<0>(const OccDev &o, uint32_t code, uin
 
 // Same search as fm_count_kernel (fm_search.cu): one lane per pattern, lanes refilled as patterns end;
 // find_range (csa/enhanced_fm_index.py:21-32) in half-open form.  Only the rank primitive differs.
-template <int SHIFT, int MIN_CTAS>
+template <int SHIFT, int MIN_CTAS, bool PEERS>
 __global__ void __launch_bounds__(OCC_THREADS, MIN_CTAS)
 fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t *__restrict__ pat,
                     const int64_t *__restrict__ off, uint64_t P, int64_t *__restrict__ out_lo,
@@ -284,7 +284,7 @@ fm_count_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, const uint8_t 
             done = miss || k < b;
         }
         if (done) {
-            put_range(po, out_lo, out_hi, p, miss ? -1 : (int64_t)l, miss ? -1 : (int64_t)r - 1);
+            put_range<PEERS>(po, out_lo, out_hi, p, miss ? -1 : (int64_t)l, miss ? -1 : (int64_t)r - 1);
             p = -1;
         }
     }
@@ -422,18 +422,24 @@ static int count_occ_launch(const void *d_wt_blob, const hkcsa_wt_plan *h_wt, co
     prof::Scope ps(st, prof::COUNT, 0);
     // 4 CTAs/SM (53 registers): measured best of 4 / 5 / 6 / 8 on the 2.8 GB table (more lanes in flight were slower)
     const int blocks = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 8);
+#define OCC_COUNT(SH, MC, GRID)                                                                                         \
+    do {                                                                                                                \
+        if (po.n) fm_count_occ_kernel<SH, MC, true><<<GRID, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);  \
+        else fm_count_occ_kernel<SH, MC, false><<<GRID, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);      \
+    } while (0)
     if (p->layout == 1) {
         // lanes in flight: DRAM-resident tables run best at 4 CTAs/SM, tables near the L2 size at 6 (measured:
         // 1.42 vs 1.34 G patterns/s on the 4.8 GB table of the 200 MB text, 3.4 vs 4.0 on the 225 MB DNA table)
         const int ctas = (p->blob_bytes > (1ull << 30)) ? 4 : 6;
         const int blocks1 = (int)std::min<uint64_t>((P + OCC_THREADS - 1) / OCC_THREADS, (uint64_t)num_sms() * 2 * ctas);
-        if (ctas == 6) fm_count_occ_kernel<0, 6><<<blocks1, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);
-        else fm_count_occ_kernel<0, 4><<<blocks1, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);
+        if (ctas == 6) OCC_COUNT(0, 6, blocks1);
+        else OCC_COUNT(0, 4, blocks1);
     } else if (p->shift == 5) {
-        fm_count_occ_kernel<5, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);
+        OCC_COUNT(5, 4, blocks);
     } else {
-        fm_count_occ_kernel<6, 4><<<blocks, OCC_THREADS, 0, st>>>(occ, d_tab, d_pat, d_off, P, d_lo, d_hi, kmer, kk, po);
+        OCC_COUNT(6, 4, blocks);
     }
+#undef OCC_COUNT
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

@@ -71,9 +71,10 @@ struct PeerOut {
     uint64_t base;
     uint32_t n;
 };
+template <bool PEERS>
 __device__ __forceinline__ void put_range(const PeerOut &po, int64_t *out_lo, int64_t *out_hi, int64_t p, int64_t l, int64_t h)
 {
-    if (po.n == 0) {
+    if (!PEERS) {
         out_lo[p] = l;
         out_hi[p] = h;
     } else {
