@@ -450,6 +450,15 @@ class DeviceIndex:
         self._kmer = (table, k)
         return self._kmer
 
+    def psi(self) -> torch.Tensor:
+        """The Psi function of the compressed suffix array (Grossi-Vitter; README.md:4 of the reference): psi[i] =
+        the row of the suffix that starts one symbol later, SA[psi[i]] = SA[i] + 1 (mod n), i.e. the inverse of LF.
+        It is the concatenation, over the symbols in order, of FMIndex.precompute_rank's ascending position lists
+        (csa/csa.py:13-19) -- one stable partition of the row numbers by BWT symbol (hkcsa_symbol_positions)."""
+        if self.bwt is None:
+            raise ValueError("psi is derived from the BWT, which this index no longer holds")
+        return symbol_positions(self.bwt)[0]
+
     def build_occ_table(self, shift: int = 5, bwt: torch.Tensor | None = None, layout: int = 0):
         """Sampled Occ table (csrc/occ_table.cu): the reference's dense occ (utils/utils.py:26-32) kept at every
         2^shift-th row next to the BWT bytes of that stretch.  Optional: costs 2^shift + 4 sigma bytes per 2^shift

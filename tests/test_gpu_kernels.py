@@ -572,3 +572,17 @@ def test_count_batch_peers_writes_every_peer_array(E, use_occ):
     torch.cuda.synchronize()
     for b in bufs:
         assert torch.equal(b[0], want_lo) and torch.equal(b[1], want_hi)
+
+
+@pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "runs", "fib"])
+def test_psi_is_the_inverse_of_lf(E, name):
+    """DeviceIndex.psi(): SA[psi[i]] = SA[i] + 1 (mod n) for every row, and psi equals the concatenation of the
+    reference's precompute_rank position lists (oracle restatement)."""
+    text = TEXTS[name] + b"$"
+    idx = E.DeviceIndex(dev(E, text))
+    psi = host(idx.psi()).astype(np.int64)
+    sa = host(idx.sa).astype(np.int64)
+    n = len(text)
+    assert np.array_equal(sa[psi], (sa + 1) % n)
+    w_pos, _ = O.symbol_positions(host(idx.bwt))
+    assert np.array_equal(psi.astype(np.uint32), w_pos)
