@@ -501,11 +501,20 @@ def run_ours(args):
                 o_ms = max_over_ranks(a.elapsed_time(b) / 3)
                 assert torch.equal(lo4, lo3) and torch.equal(hi4, hi3)
                 l_ms, l_occ = time_locate3()
+                peers = None
                 if world > 1 and layout == 1:
                     # every rank needs every answer: NCCL all-gather after the search, against the search kernel
                     # storing its slice into all ranks' arrays itself (peer-mapped symmetric memory over NVLink)
                     bounds3 = hdist.shard_bounds(off3_full, world)
-                    peers = hdist.PeerRanges(args.patterns, dev)
+                    try:
+                        peers = hdist.PeerRanges(args.patterns, dev)
+                    except Exception as exc:       # symmetric memory unavailable on this box: report, do not fail
+                        peers = None
+                        c4["all_answers_on_all_ranks"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+                    ok_all = sum_over_ranks(1.0 if peers is not None else 0.0) == world
+                    if not ok_all:
+                        peers = None
+                if peers is not None:
 
                     def timed3(fn):
                         fn()
