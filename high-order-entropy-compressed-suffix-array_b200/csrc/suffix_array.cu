@@ -280,6 +280,8 @@ struct LazyRank {
     const uint64_t *keys0;     // round-0 keys, sorted
     const uint32_t *bucket;    // bucket[v] = lower_bound(keys0, v << shift), v in [0, 2^bucket_bits]
     const uint64_t *samples;   // samples[j] = keys0[j << LAZY_SAMPLE_SHIFT]
+    int first_round;           // round 1: every rank still IS the round-0 group start = the lower bound itself,
+                               // so the rank array is neither written in round 0 nor read here
     int bits;                  // width of a round-0 key
     int shift;                 // key >> shift = bucket id
 };
@@ -339,6 +341,7 @@ __device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const u
         const uint32_t mid = lo + ((hi - lo) >> 1);
         if (__ldg(lz.keys0 + mid) < key) lo = mid + 1; else hi = mid;
     }
+    if (lz.first_round) return lo;
     const bool shared_group = (lo + 1 < n) && (__ldg(lz.keys0 + lo + 1) == key);
     return shared_group ? rank[t] : lo;
 }
@@ -688,7 +691,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     stats.alg_bytes = (uint64_t)n * 9 + (uint64_t)m * (24ull * passes0) - (uint64_t)m * 4;   // pass 0 reads no ids
 
     LazyRank lz;
-    lz.text = nullptr; lz.keys0 = nullptr; lz.bucket = nullptr; lz.samples = nullptr; lz.bits = bits0;
+    lz.text = nullptr; lz.keys0 = nullptr; lz.bucket = nullptr; lz.samples = nullptr; lz.first_round = 0; lz.bits = bits0;
     const int bucket_bits = std::min(LAZY_BUCKET_BITS, bits0);
     lz.shift = bits0 - bucket_bits;
     uint64_t *kx = nullptr, *ky = nullptr;             // key ping-pong of the later rounds
@@ -733,7 +736,10 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
             // flags + (round 0, lazy ranks: survivors only; otherwise ids, slots, rank scatter)
             prof::Scope ps(st, prof::SEG_APPLY, m / 4 + (uint64_t)m_next * 20 +
                                                  ((round != 0 || scatter_all) ? (uint64_t)m * 12 : 0));
-            seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.flags, sidx, pos, m, B.agg_head, B.agg_keep, d_sa, B.rank,
+            // round 0 with lazy ranks writes no ranks at all: round 1 takes them from the look-up (group start =
+            // lower bound), and round 1's own scatter covers every survivor before round 2 reads the array
+            uint32_t *rank_out = (round == 0 && !scatter_all) ? nullptr : B.rank;
+            seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.flags, sidx, pos, m, B.agg_head, B.agg_keep, d_sa, rank_out,
                                                            cpos, cidx, B.grp, round != 0, scatter_all);
             HK_LAUNCH_CHECK();
         }
@@ -757,6 +763,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         const int bits = b1 + b2;
         const int passes = (bits + 7) / 8;
         HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
+        lz.first_round = (round == 1) ? 1 : 0;
         {
             const int blocks = (int)std::min<uint64_t>(((uint64_t)m + 255) / 256, (uint64_t)num_sms() * 16);
             prof::Scope ps(st, prof::SA_KEYBUILD, (uint64_t)m * 20);
