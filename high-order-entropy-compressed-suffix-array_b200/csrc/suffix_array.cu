@@ -315,8 +315,10 @@ __global__ void sa_bucket_index_kernel(const uint64_t *__restrict__ keys0, uint3
     bucket[v] = lo;
 }
 
+// COHERENT: the rank array is written by the calling kernel itself (sa_finish_small_kernel): read it with volatile loads
+template <bool COHERENT = false>
 __device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const uint32_t *s_code, const uint8_t *s_len,
-                                                     uint32_t n, uint32_t t, const uint32_t *__restrict__ rank)
+                                                     uint32_t n, uint32_t t, const uint32_t *rank)
 {
     const uint64_t key = alpha_pack(s_code, s_len, lz.bits, [&](int q) {
         const uint64_t g = (uint64_t)t + q;
@@ -343,7 +345,8 @@ __device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const u
     }
     if (lz.first_round) return lo;
     const bool shared_group = (lo + 1 < n) && (__ldg(lz.keys0 + lo + 1) == key);
-    return shared_group ? rank[t] : lo;
+    if (!shared_group) return lo;
+    return COHERENT ? *reinterpret_cast<const volatile uint32_t *>(rank + t) : rank[t];
 }
 
 __global__ void __launch_bounds__(256)
@@ -551,6 +554,103 @@ seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict_
     }
 }
 
+// ---------------------------------------------------------------- the last, tiny rounds in one CTA
+// Once at most FIN_MAX suffixes are left (C2: 6 after two rounds, C3: 20) a round of the general path is ~25 launches
+// and two host round trips for nothing.  One CTA finishes the job on its own: key build (same look-ups), bitonic sort
+// of the (group, rank) keys in shared memory, head flags, SA / rank writes, compaction, doubling -- until every group
+// is a singleton.  Same recurrences as sa_keybuild_kernel + the radix sort + seg_* kernels.
+constexpr int FIN_MAX = 1024;
+
+__global__ void __launch_bounds__(FIN_MAX)
+sa_finish_small_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp,
+                       const uint32_t *__restrict__ cpos, uint32_t m, uint32_t n, uint64_t h, uint32_t *sa,
+                       uint32_t *rank, LazyRank lz, AlphaCode ac)
+{
+    __shared__ uint64_t s_key[FIN_MAX];
+    __shared__ uint32_t s_idx[FIN_MAX], s_grp[FIN_MAX], s_pos[FIN_MAX], s_aux[FIN_MAX];
+    __shared__ uint32_t s_code[257];
+    __shared__ uint8_t s_len[257];
+    __shared__ uint32_t s_w[32], s_w2[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (uint32_t i = tid; i < 257; i += FIN_MAX) { s_code[i] = ac.code[i]; s_len[i] = ac.len[i]; }
+    if (tid < m) { s_idx[tid] = cidx[tid]; s_grp[tid] = cgrp[tid]; s_pos[tid] = cpos[tid]; }
+    __syncthreads();
+    for (int iter = 0; iter < 64 && m > 0; ++iter) {
+        // ---- keys: (group start, rank of the suffix h symbols later + 1), padding sorts last
+        uint64_t key = ~0ULL;
+        uint32_t idx = 0;
+        if (tid < m) {
+            idx = s_idx[tid];
+            const uint64_t t = (uint64_t)idx + h;
+            uint32_t k2 = 0;
+            if (t < n)
+                k2 = (lz.text ? lazy_rank_lookup<true>(lz, s_code, s_len, n, (uint32_t)t, rank)
+                              : *reinterpret_cast<const volatile uint32_t *>(rank + t)) + 1u;
+            key = ((uint64_t)s_grp[tid] << 32) | k2;
+        }
+        s_key[tid] = key;
+        s_aux[tid] = idx;
+        __syncthreads();
+        // ---- bitonic sort of (key, suffix id): equal keys stay one group, their order inside does not matter
+        for (uint32_t k = 2; k <= FIN_MAX; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                const uint32_t partner = tid ^ j;
+                if (partner > tid) {
+                    const uint64_t a = s_key[tid], b = s_key[partner];
+                    const bool up = (tid & k) == 0;
+                    if ((a > b) == up) {
+                        s_key[tid] = b; s_key[partner] = a;
+                        const uint32_t x = s_aux[tid]; s_aux[tid] = s_aux[partner]; s_aux[partner] = x;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        key = s_key[tid];
+        idx = s_aux[tid];
+        const bool in = tid < m;
+        const bool head = in && (tid == 0 || key != s_key[tid - 1]);
+        const bool next_head = (tid + 1 >= m) || (s_key[tid + 1] != key);
+        const bool single = head && next_head;
+        // ---- group start = slot of the governing head (inclusive max-scan of head indices over the block)
+        uint32_t hv = head ? tid + 1 : 0u;
+        hv = warp_incl_max(hv);
+        if (lane == 31) s_w[warp] = hv;
+        // ---- compaction slots of the non-singletons (exclusive sum-scan)
+        const uint32_t keep = (in && !single) ? 1u : 0u;
+        uint32_t wtot;
+        const uint32_t ex = warp_excl_sum(keep, wtot);
+        if (lane == 31) s_w2[warp] = wtot;
+        __syncthreads();
+        uint32_t ph = 0, pk = 0, total = 0;
+        for (uint32_t w = 0; w < FIN_MAX / 32; ++w) {
+            if (w < warp) { ph = max(ph, s_w[w]); pk += s_w2[w]; }
+            total += s_w2[w];
+        }
+        const uint32_t gslot = max(ph, hv);                     // (index of the governing head) + 1
+        const uint32_t p = in ? s_pos[tid] : 0u;
+        const uint32_t newgrp = in ? s_pos[gslot - 1] : 0u;
+        __syncthreads();                                        // every thread has read s_pos / s_key
+        if (in) {
+            sa[p] = idx;
+            *reinterpret_cast<volatile uint32_t *>(rank + idx) = newgrp;
+        }
+        if (keep) {
+            const uint32_t slot = pk + ex;
+            s_idx[slot] = idx;
+            s_grp[slot] = newgrp;
+            s_aux[slot] = p;                                    // the new slot list, moved to s_pos below
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (tid < total) s_pos[tid] = s_aux[tid];
+        m = total;
+        h *= 2;
+        lz.first_round = 0;
+        __syncthreads();
+    }
+}
+
 }  // namespace hkcsa
 
 // ------------------------------------------------------------------ host driver
@@ -748,6 +848,18 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         if (m_next == 0) break;
         HK_REQUIRE(h < n, HKCSA_EINVAL, "internal: groups remain after depth >= n");
         HK_REQUIRE(round < 40, HKCSA_EINVAL, "internal: too many doubling rounds");
+        if (m_next <= (uint32_t)FIN_MAX) {
+            // the few suffixes left are finished by one CTA: no more launches per round, no more host round trips
+            lz.first_round = (round == 1) ? 1 : 0;
+            prof::Scope ps(st, prof::OTHER, (uint64_t)m_next * 32);
+            sa_finish_small_kernel<<<1, FIN_MAX, 0, st>>>(cidx, B.grp, cpos, m_next, N, std::min<uint64_t>(h, n), d_sa,
+                                                          B.rank, lz, ac);
+            HK_LAUNCH_CHECK();
+            stats.round_elems[round] = m_next;
+            stats.round_passes[round] = 0;                      // 0 passes = finished in shared memory
+            ++round;
+            break;
+        }
         // ---- buffers of the next round
         if (round == 1) {
             if (lz.text) { kx = kfree; ky = kfree + align_up(m_next, 32); }   // round-0 keys stay intact; 16-byte aligned for TMA
