@@ -251,7 +251,7 @@ template <int THREADS, int MIN_CTAS, int MODE, bool IDENT>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout, const uint32_t *__restrict__ vin,
                   uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
-                  uint32_t *lookback, uint32_t *ticket)
+                  uint32_t *lookback, uint32_t *ticket, uint32_t *__restrict__ lookback_next)
 {
     using Smem = OsSmem<THREADS>;
     constexpr int TILE = Smem::TILE;
@@ -270,6 +270,10 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     const uint32_t tile = S.tile;
     const uint32_t tile_base = tile * (uint32_t)TILE;
     const uint32_t nvalid = min((uint32_t)TILE, n - tile_base);
+
+    // the look-back rows of the NEXT pass (the other half of the table) are cleared here, tile by tile: no memset
+    // launch between the passes
+    if (tid < RADIX) lookback_next[(size_t)tile * RADIX + tid] = 0u;
 
     // ---- TMA: one thread arms the barrier and issues two bulk copies (16-byte granules);
     //      a ragged tail (last tile only) is finished with plain loads.
@@ -619,7 +623,7 @@ __global__ void radix_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *_
 size_t sort_scratch_words(uint64_t n)
 {
     const uint64_t tiles = (n + SORT64_TILE - 1) / SORT64_TILE + 1;
-    return 8 * RADIX * 2 + 64 + tiles * RADIX + 256;
+    return 8 * RADIX * 2 + 64 + 2 * tiles * RADIX + 256;
 }
 
 SortScratch carve_sort_scratch(Carver &c, uint64_t n)
@@ -629,7 +633,7 @@ SortScratch carve_sort_scratch(Carver &c, uint64_t n)
     s.hist = c.take<uint32_t>(8 * RADIX);
     s.base = c.take<uint32_t>(8 * RADIX);
     s.ticket = c.take<uint32_t>(64);
-    s.lookback_words = tiles * RADIX;
+    s.lookback_words = 2 * tiles * RADIX;      // two halves, used by alternate passes of the (u64, u32) sort
     s.lookback = c.take<uint32_t>(s.lookback_words);
     return s;
 }
@@ -670,16 +674,19 @@ static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint
     const uint32_t tiles = (n + Smem::TILE - 1) / Smem::TILE;
     uint64_t *kin = k0, *kout = k1;
     uint32_t *vin = v0, *vout = v1;
+    // the look-back table has two halves used by alternate passes; a pass clears the other half for its successor
+    const size_t half = (size_t)tiles * RADIX;
+    cudaError_t e = cudaMemsetAsync(s.lookback, 0, 2 * half * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
     for (int p = 0; p < passes; ++p) {
-        cudaError_t e = cudaMemsetAsync(s.lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), st);
-        if (e != cudaSuccess) return e;
+        uint32_t *lb = s.lookback + (size_t)(p & 1) * half, *lb_next = s.lookback + (size_t)((p + 1) & 1) * half;
         {
             prof::Scope ps(st, prof::ONESWEEP_U64, (uint64_t)n * ((p == 0 && identity_vals) ? 20 : 24));
             if (p == 0 && identity_vals)
-                kern_ident<<<tiles, THREADS, smem, st>>>(kin, kout, nullptr, vout, n, 0, s.base, s.lookback, s.ticket);
+                kern_ident<<<tiles, THREADS, smem, st>>>(kin, kout, nullptr, vout, n, 0, s.base, lb, s.ticket, lb_next);
             else
-                kern<<<tiles, THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, s.base + p * RADIX, s.lookback,
-                                                   s.ticket + p);
+                kern<<<tiles, THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, s.base + p * RADIX, lb,
+                                                   s.ticket + p, lb_next);
             count_launch();
         }
         e = cudaGetLastError();

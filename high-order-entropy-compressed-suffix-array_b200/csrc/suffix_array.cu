@@ -457,7 +457,10 @@ seg_reduce_kernel(const uint64_t *__restrict__ skey, uint32_t m, uint32_t *__res
     }
 }
 
-// single CTA: exclusive (max, sum) scan over tile aggregates, in place; total keep -> *out_m
+// single CTA: exclusive (max, sum) scan over tile aggregates, in place; total keep -> *out_m.
+// Each thread scans SCAN_IPT consecutive tiles in registers, so a pass of the block covers 8192 tiles between
+// barriers (C3 round 0 has 97 k tiles: 12 block passes instead of 96).
+constexpr int SCAN_IPT = 8;
 __global__ void __launch_bounds__(1024)
 seg_scan_kernel(uint32_t *__restrict__ agg_head, uint32_t *__restrict__ agg_keep, uint32_t tiles,
                 uint32_t *__restrict__ out_m)
@@ -467,27 +470,42 @@ seg_scan_kernel(uint32_t *__restrict__ agg_head, uint32_t *__restrict__ agg_keep
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) { s_carry_h = 0; s_carry_k = 0; }
     __syncthreads();
-    for (uint32_t base = 0; base < tiles; base += 1024) {
-        const uint32_t t = base + tid;
-        const uint32_t h = (t < tiles) ? agg_head[t] : 0u;
-        const uint32_t k = (t < tiles) ? agg_keep[t] : 0u;
-        const uint32_t ih = warp_incl_max(h);
+    for (uint32_t base = 0; base < tiles; base += 1024 * SCAN_IPT) {
+        const uint32_t t0 = base + tid * SCAN_IPT;
+        uint32_t h[SCAN_IPT], k[SCAN_IPT];
+        uint32_t th = 0, tk = 0;                       // this thread's (max, sum) over its tiles
+#pragma unroll
+        for (int e = 0; e < SCAN_IPT; ++e) {
+            const uint32_t t = t0 + e;
+            h[e] = (t < tiles) ? agg_head[t] : 0u;
+            k[e] = (t < tiles) ? agg_keep[t] : 0u;
+            th = max(th, h[e]);
+            tk += k[e];
+        }
+        const uint32_t ih = warp_incl_max(th);
         uint32_t wk_total;
-        const uint32_t ek = warp_excl_sum(k, wk_total);
+        const uint32_t ek = warp_excl_sum(tk, wk_total);
         const uint32_t eh = __shfl_up_sync(0xffffffffu, ih, 1);
         const uint32_t excl_h_in_warp = lane ? eh : 0u;
         if (lane == 31) { s_h[warp] = ih; s_k[warp] = wk_total; }
         __syncthreads();
         uint32_t ph = s_carry_h, pk = s_carry_k;
         for (uint32_t w = 0; w < warp; ++w) { ph = max(ph, s_h[w]); pk += s_k[w]; }
-        if (t < tiles) {
-            agg_head[t] = max(ph, excl_h_in_warp);
-            agg_keep[t] = pk + ek;
+        uint32_t run_h = max(ph, excl_h_in_warp), run_k = pk + ek;
+#pragma unroll
+        for (int e = 0; e < SCAN_IPT; ++e) {
+            const uint32_t t = t0 + e;
+            if (t < tiles) {
+                agg_head[t] = run_h;
+                agg_keep[t] = run_k;
+            }
+            run_h = max(run_h, h[e]);
+            run_k += k[e];
         }
         __syncthreads();
         if (tid == 1023) {
-            s_carry_h = max(ph, ih);
-            s_carry_k = pk + ek + k;
+            s_carry_h = run_h;
+            s_carry_k = run_k;
         }
         __syncthreads();
     }
