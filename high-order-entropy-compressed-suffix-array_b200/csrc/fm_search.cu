@@ -135,18 +135,34 @@ __global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32
     if (q < m) out[q] = src[rows[q]];
 }
 
-// samples[rank1(marks, j)] = SA[j] / rate for marked rows
+// samples[rank1(marks, j)] = SA[j] / rate for marked rows.  A thread takes four consecutive rows (one 16-byte load
+// for 32-bit ids): a quarter of the threads and CTAs of the one-row-per-thread form.
 template <typename IdT>
-__global__ void ssa_fill_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, BitVec marks,
-                                uint32_t *__restrict__ samples)
+__device__ __forceinline__ void ssa_fill_one(IdT v, uint64_t j, uint32_t rate, bool pow2, int sh, const BitVec &marks,
+                                             uint32_t *__restrict__ samples)
 {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const IdT v = sa[j];
-    if ((rate & (rate - 1u)) == 0) {          // power-of-two rate: no division per entry
-        if ((v & (IdT)(rate - 1u)) == 0) samples[bv_rank(marks, j)] = (uint32_t)(v >> (__ffs(rate) - 1));
+    if (pow2) {                                   // power-of-two rate: no division per entry
+        if ((v & (IdT)(rate - 1u)) == 0) samples[bv_rank(marks, j)] = (uint32_t)(v >> sh);
     } else if (v % rate == 0) {
         samples[bv_rank(marks, j)] = (uint32_t)(v / rate);
+    }
+}
+template <typename IdT>
+__global__ void __launch_bounds__(256)
+ssa_fill_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, BitVec marks, uint32_t *__restrict__ samples)
+{
+    const uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= n) return;
+    const bool pow2 = (rate & (rate - 1u)) == 0;
+    const int sh = __ffs(rate) - 1;
+    if (sizeof(IdT) == 4 && j0 + 4 <= n && (reinterpret_cast<uintptr_t>(sa) & 15) == 0) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(sa + j0);
+        ssa_fill_one<IdT>((IdT)q.x, j0, rate, pow2, sh, marks, samples);
+        ssa_fill_one<IdT>((IdT)q.y, j0 + 1, rate, pow2, sh, marks, samples);
+        ssa_fill_one<IdT>((IdT)q.z, j0 + 2, rate, pow2, sh, marks, samples);
+        ssa_fill_one<IdT>((IdT)q.w, j0 + 3, rate, pow2, sh, marks, samples);
+    } else {
+        for (uint64_t j = j0; j < n && j < j0 + 4; ++j) ssa_fill_one<IdT>(sa[j], j, rate, pow2, sh, marks, samples);
     }
 }
 
@@ -358,7 +374,7 @@ static int ssa_build_t(const IdT *d_sa, const hkcsa_ssa_plan *p, void *d_blob, v
     uint32_t *d_sel = c.take<uint32_t>(select_samples_for(n));
     uint8_t *blob = static_cast<uint8_t *>(d_blob);
     prof::Scope ps(st, prof::SSA_BUILD, n * 10);
-    const uint32_t grid = (uint32_t)((n + 255) / 256);
+    const uint32_t grid = (uint32_t)(((n + 3) / 4 + 255) / 256);      // four rows per thread
     BitVec marks;
     marks.blocks = reinterpret_cast<const RankBlock *>(blob + p->off_blocks);
     marks.super = reinterpret_cast<const uint64_t *>(blob + p->off_super);
