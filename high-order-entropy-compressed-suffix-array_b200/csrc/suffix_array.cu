@@ -524,6 +524,13 @@ seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict_
     const uint32_t j0 = blockIdx.x * SEG_TILE + tid * SEG_IPT;
     bool head[SEG_IPT], single[SEG_IPT];
     const uint32_t f = flags[blockIdx.x * SEG_THREADS + tid];      // written by seg_reduce_kernel
+    // round 0 with lazy ranks: a warp whose 256 elements are all singletons (97-99.7 % of them) has nothing to write
+    // and its part of the block scan is known without shuffles: last head = its last element, nothing kept
+    if (!write_sa && !scatter_all && __all_sync(0xffffffffu, ((f >> SEG_IPT) & 0xFFu) == 0xFFu)) {
+        if (lane == 31) { s_h[warp] = j0 + SEG_IPT; s_k[warp] = 0; }
+        __syncthreads();
+        return;
+    }
     uint32_t lasthead = 0, keep = 0;
 #pragma unroll
     for (int e = 0; e < SEG_IPT; ++e) {
