@@ -199,17 +199,6 @@ __device__ __forceinline__ void ld_nc_256(const void *p, uint64_t &w0, uint64_t 
 {
     asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(p));
 }
-// same, not allocated in L1: isolated random sectors that are used once must not evict the streams L1 serves
-__device__ __forceinline__ void ld_nc_256_na(const void *p, uint64_t &w0, uint64_t &w1, uint64_t &w2, uint64_t &w3)
-{
-    asm("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(p));
-}
-__device__ __forceinline__ uint32_t ld_nc_u32_na(const uint32_t *p)
-{
-    uint32_t v;
-    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ RankBlock load_block(const RankBlock *p)
 {
     RankBlock b;          // the whole block = one sector = one load instruction

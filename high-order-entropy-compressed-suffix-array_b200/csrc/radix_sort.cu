@@ -18,7 +18,7 @@ onesweep_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uin
     static_assert(THREADS >= RADIX, "one thread per digit is required");
     static_assert(WARPS <= 32, "warp totals live in s_misc");
 
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_whist = reinterpret_cast<uint32_t *>(smem_raw);   // [WARPS][RADIX]
     uint32_t *s_gbase = s_whist + WARPS * RADIX;                  // [RADIX]
     uint32_t *s_misc = s_gbase + RADIX;                           // [64]

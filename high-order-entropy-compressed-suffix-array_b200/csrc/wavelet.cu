@@ -370,7 +370,7 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
                 const uint64_t e = s_ent[c];
                 uint32_t dst = i;                      // codes that are leaves already keep their slot
                 if (e >> 50) {
-                    const uint32_t S0 = (uint32_t)e & 0x3FFFu, M = (uint32_t)(e >> 14) & 0x3FFFu;
+                    const uint32_t M = (uint32_t)(e >> 14) & 0x3FFFu;
                     const uint32_t ps = (uint32_t)(e >> 28) & 0x3FFFu;
                     const uint32_t ones_before = wp + __popc(w & ((1u << k) - 1u)) - ps;
                     dst = ((w >> k) & 1u) ? M + ones_before : i - ones_before;
