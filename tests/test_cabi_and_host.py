@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_mirrors_match_c_layout():
     from hkcsa import _lib
     L = _lib.load()
-    for idx, st in enumerate((_lib.SaStats, _lib.WtPlan, _lib.SsaPlan, _lib.ProfEntry)):
+    for idx, st in enumerate((_lib.SaStats, _lib.WtPlan, _lib.SsaPlan, _lib.ProfEntry, _lib.OccPlan)):
         assert L.hkcsa_struct_size(idx) == C.sizeof(st)
 
 
@@ -165,3 +165,53 @@ def test_golomb_m_matches_golden(golden):
     enc = wt.GolombRiceEncoder.__new__(wt.GolombRiceEncoder)
     for ones, total, m in golden.meta["_golomb_m"]:
         assert enc.compute_dynamic_m(ones, total) == m
+
+
+def test_occ_table_plans_are_host_only():
+    """hkcsa_occ_plan_make: layouts, sizes and argument checks (no GPU involved)."""
+    from hkcsa import _lib
+    L = _lib.load()
+    p = _lib.OccPlan()
+    n, sigma = 200_000_001, 97
+    # layout 0, 32 rows per entry: [32 BWT bytes][sigma x u32], rows padded to 32 bytes
+    assert L.hkcsa_occ_plan_make(n, sigma, 5, 0, C.byref(p)) == 0
+    assert (p.rows, p.stride, p.layout, p.shift) == ((n >> 5) + 1, 448, 0, 5)
+    assert p.blob_bytes >= p.rows * p.stride and p.blob_bytes % 256 == 0 and p.scratch_bytes > 0
+    assert L.hkcsa_occ_plan_make(n, sigma, 6, 0, C.byref(p)) == 0 and p.stride == 480 and p.rows == (n >> 6) + 1
+    # layout 1: one 8-byte entry per symbol and 32 rows, the BWT copy behind the entries
+    assert L.hkcsa_occ_plan_make(n, sigma, 5, 1, C.byref(p)) == 0
+    assert p.stride >= p.rows and p.stride % 4 == 0 and p.off_bwt >= 8 * sigma * p.stride
+    assert p.blob_bytes >= p.off_bwt + n
+    assert L.hkcsa_occ_plan_make(1, 1, 5, 1, C.byref(p)) == 0 and p.rows == 1
+    # argument checks
+    assert L.hkcsa_occ_plan_make(n, sigma, 4, 0, C.byref(p)) == _lib.EINVAL
+    assert L.hkcsa_occ_plan_make(n, sigma, 6, 1, C.byref(p)) == _lib.EINVAL
+    assert L.hkcsa_occ_plan_make(n, 0, 5, 0, C.byref(p)) == _lib.EINVAL
+    assert L.hkcsa_occ_plan_make(n, 257, 5, 0, C.byref(p)) == _lib.EINVAL
+    assert L.hkcsa_occ_plan_make(0, sigma, 5, 0, C.byref(p)) == _lib.ERANGE
+    assert L.hkcsa_occ_plan_make(_lib.MAX_N + 1, sigma, 5, 0, C.byref(p)) == _lib.ERANGE
+
+
+def test_peer_count_argument_checks_without_gpu():
+    """hkcsa_count_batch_peers refuses malformed peer lists before touching the device."""
+    from hkcsa import _lib
+    L = _lib.load()
+    wt = _plan(b"banana$")
+    lo = (C.c_uint64 * 2)(0, 0)
+    hi = (C.c_uint64 * 2)(0, 0)
+    blob = C.create_string_buffer(64)
+    args = (C.cast(blob, C.c_void_p), C.byref(wt), None, None, None, 0, None, None, 3, 0)
+    assert L.hkcsa_count_batch_peers(*args, 0, lo, hi, None) == _lib.EINVAL          # no peers
+    assert L.hkcsa_count_batch_peers(*args, 17, lo, hi, None) == _lib.EINVAL         # more than HKCSA_MAX_PEERS
+    assert L.hkcsa_count_batch_peers(*args, 2, lo, hi, None) == _lib.EINVAL          # null offsets / null peer pointers
+    occ = _lib.OccPlan()
+    bad = (C.cast(blob, C.c_void_p), C.byref(wt), None, C.byref(occ), None, 0, None, None, 3, 0)
+    assert L.hkcsa_count_batch_peers(*bad, 1, lo, hi, None) == _lib.EINVAL           # occ plan without its blob
+
+
+def test_prof_class_names():
+    from hkcsa import _lib
+    L = _lib.load()
+    assert L.hkcsa_prof_class_index(b"onesweep_u64") >= 0
+    assert L.hkcsa_prof_class_index(b"bwt_gather") >= 0
+    assert L.hkcsa_prof_class_index(b"no such kernel") == -1
