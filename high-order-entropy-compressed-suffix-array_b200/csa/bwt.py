@@ -14,7 +14,8 @@ def bwt_transform(text, suffix_array):
     """
     import torch
     from hkcsa import engine
-    d_text = engine.to_device_u8(text)
+    smap = engine.SymbolMap(text) if isinstance(text, str) else None
+    d_text = engine.to_device_u8(smap.encode(text) if smap is not None else text)
     n = d_text.numel()
     if len(suffix_array) < n:
         raise IndexError("list index out of range")
@@ -25,7 +26,7 @@ def bwt_transform(text, suffix_array):
         d_sa = torch.clamp(d_sa, min=0)          # pos = SA[i]-1 < 0 -> n-1 (csa/bwt.py:9-10)
     out = engine.bwt(d_text, d_sa)
     if isinstance(text, str):
-        return out.cpu().numpy().tobytes().decode("latin-1")
+        return smap.decode(out.cpu().numpy().tobytes())
     if isinstance(text, (bytes, bytearray, memoryview)):
         return out.cpu().numpy().tobytes()
     return out

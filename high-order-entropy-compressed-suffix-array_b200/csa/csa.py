@@ -74,43 +74,74 @@ class CompressedSuffixArray:
         self._E = engine
         self.text = text
         self.epsilon = epsilon
-        d = engine.to_device_u8(text)
-        import torch
-        d_text = torch.cat([d, torch.tensor([0x24], dtype=torch.uint8, device=d.device)])
+        self._smap = engine.SymbolMap(text, extra="$") if isinstance(text, str) else None
+        if self._smap is not None:
+            d_text = engine.to_device_u8(self._smap.encode(text), tail=self._smap.encode("$"))
+            has_sentinel = "$" in text
+        else:
+            d_text = engine.to_device_u8(text, tail=b"$")
+            has_sentinel = bool((d_text[:-1] == 0x24).any().item())
         n = d_text.numel()
         if sa_sample_rate is None:
             sa_sample_rate = max(1, math.ceil(max(1.0, math.log2(max(2, n))) ** epsilon))
         self.sa_sample_rate = int(sa_sample_rate)
-        self._idx = engine.DeviceIndex(d_text, sa_sample_rate=self.sa_sample_rate, keep_sa=False, keep_text=False)
+        # A text that already holds '$' has no unique sentinel: suffix order is then not rotation order and LF walks
+        # need not reach a sampled row.  Such an index keeps the full suffix array and locates through it (the
+        # answers EnhancedFMIndex.find gives, csa/enhanced_fm_index.py:15-19) instead of through the samples.
+        self.sentinel_unique = not has_sentinel
+        self._idx = engine.DeviceIndex(d_text, sa_sample_rate=self.sa_sample_rate, keep_sa=has_sentinel,
+                                       keep_text=False)
         self.n = n
+        self._hk_cache = {}
 
     @property
     def device_index(self):
         return self._idx
 
+    def _pack(self, patterns):
+        """Patterns -> device CSR; a str pattern with a symbol the text cannot hold becomes a pattern that misses."""
+        enc = []
+        for q in patterns:
+            if isinstance(q, str):
+                b = self._smap.encode(q) if self._smap is not None else q.encode("latin-1", "replace")
+                if b is None:
+                    b = self._miss_pattern()
+                    if b is None:
+                        raise ValueError("pattern holds a symbol outside the 256 byte symbols of the text")
+                enc.append(b)
+            else:
+                enc.append(bytes(q))
+        return self._E.pack_patterns(enc, self._idx.device)
+
+    def _miss_pattern(self):
+        plan = self._idx.wt.plan
+        for b in range(255, -1, -1):
+            if plan.code_of_sym[b] == 0xFFFF:
+                return bytes([b])
+        return None
+
     def count(self, pattern):
-        lo, hi = self._idx.count_batch(*self._E.pack_patterns([pattern], self._idx.device))
-        lo, hi = int(lo.item()), int(hi.item())
-        return 0 if lo < 0 else hi - lo + 1
+        return int(self.count_batch([pattern])[0])
 
     def locate(self, pattern):
         """Sorted text positions of every occurrence of `pattern`."""
-        off, pos = self._idx.locate_batch(*self._E.pack_patterns([pattern], self._idx.device), use_samples=True)
-        return sorted(pos.cpu().tolist())
+        return self.locate_batch([pattern])[0]
 
     def count_batch(self, patterns):
-        lo, hi = self._idx.count_batch(*self._E.pack_patterns(patterns, self._idx.device))
+        lo, hi = self._idx.count_batch(*self._pack(patterns))
         lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
         return np.where(lo >= 0, hi - lo + 1, 0)
 
     def locate_batch(self, patterns):
-        off, pos = self._idx.locate_batch(*self._E.pack_patterns(patterns, self._idx.device), use_samples=True)
+        off, pos = self._idx.locate_batch(*self._pack(patterns), use_samples=self.sentinel_unique)
         off, pos = off.cpu().numpy(), pos.cpu().numpy()
         return [sorted(pos[off[k]:off[k + 1]].tolist()) for k in range(len(off) - 1)]
 
     def index_bytes(self):
-        """Device bytes held by the index (wavelet tree blob + sampled SA blob)."""
-        return int(self._idx.wt.blob.numel() + self._idx.ssa.blob.numel())
+        """Device bytes held by the index (wavelet tree blob + sampled SA blob [+ the suffix array, kept only when
+        the text already holds the sentinel])."""
+        extra = self._idx.sa.numel() * 4 if self._idx.sa is not None else 0
+        return int(self._idx.wt.blob.numel() + self._idx.ssa.blob.numel() + extra)
 
 
 def main():

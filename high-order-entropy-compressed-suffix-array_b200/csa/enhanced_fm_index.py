@@ -16,13 +16,14 @@ class EnhancedFMIndex:
     def __init__(self, text):
         from hkcsa import engine
         self._E = engine
+        self._smap = None
         if isinstance(text, str):
             self.text = text + "$"                                   # :9
-            d_text = engine.to_device_u8(self.text)
+            self._smap = engine.SymbolMap(text, extra="$")           # identity for latin-1 text
+            d_text = engine.to_device_u8(self._smap.encode(text), tail=self._smap.encode("$"))
         else:                                                        # bytes / uint8 array / tensor (extension)
             import torch
-            d = engine.to_device_u8(text)
-            d_text = torch.cat([d, torch.tensor([0x24], dtype=torch.uint8, device=d.device)])
+            d_text = engine.to_device_u8(text, tail=b"$")
             self.text = d_text if isinstance(text, torch.Tensor) else bytes(text) + b"$"
         self._idx = engine.DeviceIndex(d_text)                       # :10-12 (SA, BWT, wavelet tree = occ)
         self._sa = None
@@ -32,6 +33,8 @@ class EnhancedFMIndex:
         self.count = self._idx.wt.count_table()                      # :13  build_count(self.text)
         if not self._str:
             self.count = {ord(k): v for k, v in self.count.items()}
+        elif not self._smap.identity:
+            self.count = {self._smap.symbol(ord(k)): v for k, v in self.count.items()}
 
     # ---- attributes of the reference, materialised on first use
     @property
@@ -44,13 +47,15 @@ class EnhancedFMIndex:
     def bwt(self):
         if self._bwt is None:
             raw = self._idx.bwt.cpu().numpy().tobytes()
-            self._bwt = raw.decode("latin-1") if self._str else raw
+            self._bwt = self._smap.decode(raw) if self._str else raw
         return self._bwt
 
     @property
     def occ(self):
         if self._occ is None:
             self._occ = _views.occ_mapping(self._idx.wt)
+            if self._str and not self._smap.identity:
+                self._occ = {self._smap.symbol(ord(k)): v for k, v in self._occ.items()}
         return self._occ
 
     @property
@@ -73,7 +78,13 @@ class EnhancedFMIndex:
 
     def rank(self, character, index):
         """occ[character][index]; 0 for a symbol that never occurs; index clamped to n (:34-40)."""
-        b = ord(character) if isinstance(character, str) else int(character)
+        if isinstance(character, str) and self._smap is not None:
+            enc = self._smap.encode(character)
+            if enc is None or len(enc) != 1:
+                return 0
+            b = enc[0]
+        else:
+            b = ord(character) if isinstance(character, str) else int(character)
         if not 0 <= b < 256:
             return 0
         return int(self._idx.wt.rank(np.array([b], dtype=np.uint8), np.array([max(0, index)], dtype=np.int64)).item())
@@ -81,9 +92,13 @@ class EnhancedFMIndex:
     # ---- batched additions
     def find_range_batch(self, queries):
         """Inclusive SA ranges for many patterns at once: (lo, hi) int64 numpy arrays; (-1, -1) = miss."""
-        pat, off = self._pack(queries)
+        pat, off, absent = self._pack(queries)
         lo, hi = self._idx.count_batch(pat, off)
-        return lo.cpu().numpy(), hi.cpu().numpy()
+        lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+        if absent:                                   # a symbol the text cannot hold: (-1, -1) like :27-28
+            lo[absent] = -1
+            hi[absent] = -1
+        return lo, hi
 
     def count_batch(self, queries):
         lo, hi = self.find_range_batch(queries)
@@ -91,13 +106,34 @@ class EnhancedFMIndex:
 
     def find_batch(self, queries):
         """find() for many patterns: list of lists of positions, each in SA order."""
-        pat, off = self._pack(queries)
+        pat, off, absent = self._pack(queries)
         o, p = self._idx.locate_batch(pat, off, use_samples=False)
         o, p = o.cpu().numpy(), p.cpu().numpy()
-        return [p[o[k]:o[k + 1]].tolist() for k in range(len(o) - 1)]
+        gone = set(absent)
+        return [[] if k in gone else p[o[k]:o[k + 1]].tolist() for k in range(len(o) - 1)]
+
+    def _miss_pattern(self):
+        """One byte the text does not hold (a search for it ends at once), b"" when all 256 occur."""
+        plan = self._idx.wt.plan
+        for b in range(255, -1, -1):
+            if plan.code_of_sym[b] == 0xFFFF:
+                return bytes([b])
+        return b""
 
     def _pack(self, queries):
-        for q in queries:
-            if isinstance(q, str) and any(ord(ch) > 255 for ch in q):
-                raise ValueError("patterns must be latin-1 (one byte per code point)")
-        return self._E.pack_patterns(queries, self._idx.device)
+        """Patterns -> device CSR.  A str pattern holding a symbol the text's symbol map cannot express (a code point
+        above 255 on latin-1 text, or one that never occurs in a re-coded text) is a miss by definition
+        (csa/enhanced_fm_index.py:27-28: unseen symbol -> rank 0 -> (-1, -1)): it is searched as the one-symbol
+        pattern of a byte the text does not hold, or overridden on the host when every byte occurs."""
+        enc, absent = [], []
+        for k, q in enumerate(queries):
+            if isinstance(q, str):
+                b = self._smap.encode(q) if self._smap is not None else q.encode("latin-1")
+                if b is None:
+                    absent.append(k)
+                    b = self._miss_pattern()
+                enc.append(b)
+            else:
+                enc.append(bytes(q))
+        pat, off = self._E.pack_patterns(enc, self._idx.device)
+        return pat, off, absent

@@ -27,6 +27,8 @@ def build_suffix_array(text):
     semantics above hkcsa.views.MATERIALIZE_MAX entries).  "" -> [].
     """
     from hkcsa import engine
+    if isinstance(text, str):
+        text = engine.SymbolMap(text).encode(text)      # code points above 255: order-preserving re-coding to bytes
     d_text = engine.to_device_u8(text)
     return _views.int_sequence(engine.suffix_array(d_text))
 

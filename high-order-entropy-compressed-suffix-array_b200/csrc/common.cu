@@ -3,11 +3,12 @@
 #include "prof.cuh"
 
 #include <stdarg.h>
+#include <mutex>
 
 namespace hkcsa {
 
 static thread_local char g_err[512] = "";
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const char *fmt, ...)
 {
@@ -17,9 +18,11 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+// one page per calling thread: two host threads (or two devices driven from two threads) building at the same time
+// must not share the histogram / survivor-count read-back slots
 void *pinned_page()
 {
-    static void *page = nullptr;
+    static thread_local void *page = nullptr;
     if (!page) {
         cudaError_t e = cudaHostAlloc(&page, 4096, cudaHostAllocDefault);
         if (e != cudaSuccess) {
@@ -48,15 +51,21 @@ static const char *g_names[NUM_CLASSES] = {
 
 bool enabled() { return g_on; }
 
+static std::mutex g_mu;     // the record array is shared by every thread that launches kernels
+
 Scope::Scope(cudaStream_t st, int cls, uint64_t bytes) : st_(st), slot_(-1)
 {
-    if (!g_on || !((g_mask >> cls) & 1u) || g_used >= MAX_RECORDS) return;
-    if (g_used >= g_created) {
-        if (cudaEventCreate(&g_rec[g_created].a) != cudaSuccess) return;
-        if (cudaEventCreate(&g_rec[g_created].b) != cudaSuccess) return;
-        ++g_created;
+    if (!g_on || !((g_mask >> cls) & 1u)) return;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (g_used >= MAX_RECORDS) return;
+        if (g_used >= g_created) {
+            if (cudaEventCreate(&g_rec[g_created].a) != cudaSuccess) return;
+            if (cudaEventCreate(&g_rec[g_created].b) != cudaSuccess) return;
+            ++g_created;
+        }
+        slot_ = g_used++;
     }
-    slot_ = g_used++;
     g_rec[slot_].cls = cls;
     g_rec[slot_].bytes = bytes;
     cudaEventRecord(g_rec[slot_].a, st_);
@@ -73,7 +82,7 @@ using namespace hkcsa;
 extern "C" int hkcsa_abi_version(void) { return HKCSA_ABI_VERSION; }
 extern "C" const char *hkcsa_last_error(void) { return g_err; }
 
-extern "C" unsigned long long hkcsa_launch_count(void) { return g_launches; }
+extern "C" unsigned long long hkcsa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" size_t hkcsa_struct_size(int which)
 {

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 
 #include "../../include/hkcsa.h"
 
@@ -24,8 +25,8 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 // every kernel launch of the library is counted (bench.py reports gpu_launches)
-extern unsigned long long g_launches;
-static inline void count_launch(unsigned long long k = 1) { g_launches += k; }
+extern std::atomic<unsigned long long> g_launches;
+static inline void count_launch(unsigned long long k = 1) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 
 #define HK_LAUNCH_CHECK()                                                                  \
     do {                                                                                   \
@@ -41,7 +42,7 @@ static inline void count_launch(unsigned long long k = 1) { g_launches += k; }
         }                                                                                  \
     } while (0)
 
-// One pinned host page per process for scalar read-backs (the library's only
+// One pinned host page per calling thread for scalar read-backs (the library's only
 // allocation).  Returns nullptr on failure (error already set).
 void *pinned_page();   // 4096 bytes
 

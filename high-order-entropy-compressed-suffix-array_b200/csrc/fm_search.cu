@@ -188,6 +188,9 @@ locate_rows_kernel(WtDev wt, BitVec marks, const uint32_t *__restrict__ samples,
             out[q] = samples[r] * rate + steps;
             return;
         }
+        // a sampled row is at most rate-1 LF steps away when the sentinel is unique; on a text that already holds
+        // the sentinel LF is a permutation whose cycles may miss every mark: stop, report HKCSA_NO_POSITION
+        if (steps >= rate) { out[q] = HKCSA_NO_POSITION; return; }
         uint32_t occ;
         const uint32_t code = wt_access_rank(s, wt, j, occ);
         j = s.C[code] + occ;

@@ -120,6 +120,7 @@ ms_locate_kernel(const MultiDesc *__restrict__ d, const uint64_t *__restrict__ r
             out[q] = (uint64_t)d->samples[s][r] * d->rate + steps;
             return;
         }
+        if (steps >= d->rate) { out[q] = ~0ull; return; }       // sentinel not unique: see locate_rows_kernel
         const WtDev &w = d->slice[s];
         uint32_t occ;
         const uint32_t code = ms_access_rank(w, lj, occ);

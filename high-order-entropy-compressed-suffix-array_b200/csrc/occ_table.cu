@@ -316,6 +316,7 @@ locate_rows_occ_kernel(OccDev occ, const WtTables *__restrict__ tab, BitVec mark
             out[q] = samples[r] * rate + steps;
             return;
         }
+        if (steps >= rate) { out[q] = HKCSA_NO_POSITION; return; }   // sentinel not unique: see locate_rows_kernel
         const uint32_t t = j & (B - 1);
         if (SHIFT == 0) {
             const uint32_t ch = __ldg(occ.bwt + j);

@@ -56,22 +56,101 @@ def _scratch(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def to_device_u8(data, device=None) -> torch.Tensor:
-    """str (latin-1: utils/data_loader.py:4) / bytes / numpy / tensor -> contiguous uint8 CUDA tensor."""
+class SymbolMap:
+    """Order-preserving map between the code points of a ``str`` and bytes.
+
+    The reference compares Python strings (csa/suffix_array.py:132), so any code point is a legal symbol.  Text in
+    the latin-1 range maps to itself (one byte per code point, utils/data_loader.py:4).  A text with code points
+    above 255 is re-coded: its distinct code points (plus those of `extra`, e.g. the '$' sentinel), sorted, become
+    bytes 0, 1, 2, ... -- suffix order, BWT, C[] and every SA range are unchanged by an order-preserving re-coding.
+    More than 256 distinct code points cannot be held in byte symbols: ValueError."""
+
+    def __init__(self, text: str, extra: str = ""):
+        self.back = None                      # identity
+        try:
+            text.encode("latin-1")
+        except UnicodeEncodeError:
+            cps = sorted(set(text) | set(extra))
+            if len(cps) > 256:
+                raise ValueError(f"text holds {len(cps)} distinct symbols; byte symbols allow at most 256") from None
+            self.back = cps
+            self._fwd = {ord(c): i for i, c in enumerate(cps)}
+
+    @property
+    def identity(self) -> bool:
+        return self.back is None
+
+    def encode(self, s: str):
+        """bytes, or None when `s` holds a symbol outside the map (such a pattern cannot occur in the text)."""
+        if self.back is None:
+            try:
+                return s.encode("latin-1")
+            except UnicodeEncodeError:
+                return None
+        if any(ord(c) not in self._fwd for c in set(s)):
+            return None
+        return s.translate(self._fwd).encode("latin-1")
+
+    def decode(self, b: bytes) -> str:
+        if self.back is None:
+            return b.decode("latin-1")
+        return b.decode("latin-1").translate({i: c for i, c in enumerate(self.back)})
+
+    def symbol(self, byte: int) -> str:
+        return chr(byte) if self.back is None else self.back[byte]
+
+
+_PINNED: dict = {}
+
+
+def _staged_h2d(arr: np.ndarray, device, tail: bytes = b"") -> torch.Tensor:
+    """Host bytes (+ an optional tail, e.g. the sentinel) -> device through a cached pinned staging buffer: one
+    memcpy into pinned memory and one asynchronous DMA, instead of a pageable copy (which the driver stages in
+    small chunks)."""
+    n = arr.size + len(tail)
+    key = torch.device(device).index
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1 << 20), dtype=torch.uint8).pin_memory()
+        _PINNED[key] = buf
+    ev = _PINNED.get((key, "ev"))
+    if ev is not None:
+        ev.synchronize()                               # an earlier copy out of the staging buffer may be in flight
+    view = buf.numpy()
+    view[: arr.size] = arr
+    if tail:
+        view[arr.size:n] = np.frombuffer(tail, dtype=np.uint8)
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    out.copy_(buf[:n], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _PINNED[(key, "ev")] = ev
+    return out
+
+
+def to_device_u8(data, device=None, tail: bytes = b"") -> torch.Tensor:
+    """str (latin-1: utils/data_loader.py:4) / bytes / numpy / tensor -> contiguous uint8 CUDA tensor (`tail`
+    appended: the callers that add the '$' sentinel do not build a second host copy for it)."""
     device = device or _require_cuda()
     if isinstance(data, torch.Tensor):
         if data.dtype != torch.uint8:
             raise TypeError("text tensors must be uint8")
-        return data.to(device).contiguous()
+        d = data.to(device).contiguous()
+        if tail:
+            d = torch.cat([d, torch.tensor(list(tail), dtype=torch.uint8, device=d.device)])
+        return d
     if isinstance(data, str):
-        data = data.encode("latin-1")
+        try:
+            data = data.encode("latin-1")
+        except UnicodeEncodeError:
+            raise ValueError("text has code points above 255: encode it through engine.SymbolMap") from None
     if isinstance(data, (bytes, bytearray, memoryview)):
         arr = np.frombuffer(data, dtype=np.uint8)
     else:
         arr = np.ascontiguousarray(data, dtype=np.uint8)
-    if arr.size == 0:
+    if arr.size + len(tail) == 0:
         return torch.empty(0, dtype=torch.uint8, device=device)
-    return torch.from_numpy(arr.copy() if not arr.flags.writeable else arr).to(device)
+    return _staged_h2d(arr, device, tail)
 
 
 # ------------------------------------------------------------------ workload
@@ -357,6 +436,7 @@ class DeviceIndex:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 host_sa.copy_(self.sa, non_blocking=True)
+            self.sa.record_stream(side)        # keep_sa=False must not hand the buffer back while the copy runs
         # the sampled SA depends on the suffix array only: build it on a second stream while the BWT and the
         # wavelet tree are built on this one
         main = torch.cuda.current_stream()
@@ -385,6 +465,7 @@ class DeviceIndex:
             side.wait_stream(crit)
             with torch.cuda.stream(side):
                 host_bwt.copy_(self.bwt, non_blocking=True)
+            self.bwt.record_stream(side)
         # the BWT is a permutation of the text: the byte histogram of the suffix-array build serves the tree
         hist = np.ctypeslib.as_array(self.stats.sa.byte_hist).copy() if self.n else None
         with torch.cuda.stream(crit):

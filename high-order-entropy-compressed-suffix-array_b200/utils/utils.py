@@ -19,11 +19,12 @@ def build_count(text):
     """C[c] = number of symbols in `text` with a smaller code point, for every symbol present,
     keys in sorted order (utils/utils.py:16-24).  One byte-histogram kernel."""
     from hkcsa import engine
-    hist = engine.byte_hist(engine.to_device_u8(text))
+    smap = engine.SymbolMap(text) if isinstance(text, str) else None
+    hist = engine.byte_hist(engine.to_device_u8(smap.encode(text) if smap is not None else text))
     count, total = {}, 0
     for b in range(256):
         if hist[b]:
-            count[chr(b)] = total
+            count[smap.symbol(b) if smap is not None else chr(b)] = total
             total += int(hist[b])
     return count
 

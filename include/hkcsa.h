@@ -17,7 +17,7 @@
  *  - Pointers prefixed d_ are DEVICE pointers, h_ are HOST pointers.  The
  *    caller allocates every device buffer, scratch included (sizes come from
  *    the *_bytes queries); the library allocates no device memory.  Its only
- *    allocation is one small pinned host page per process for scalar read-backs.
+ *    allocation is one small pinned host page per calling thread for scalar read-backs.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *    Work is enqueued on that stream.  Functions documented as "syncs" wait on
  *    the stream because they return scalars to the host; all others are async.
@@ -283,7 +283,11 @@ int hkcsa_expand_ranges(const int64_t *d_lo, const int64_t *d_hi, const int64_t 
 /* csa/enhanced_fm_index.py:19): out[q] = SA[rows[q]], SA order preserved.       */
 int hkcsa_gather_u32(const uint32_t *d_src, const uint32_t *d_rows, uint64_t m, uint32_t *d_out,
                      void *stream);
-/* locate, step 2b: positions by LF walk to the next sampled row.               */
+/* locate, step 2b: positions by LF walk to the next sampled row.  With a unique */
+/* sentinel a walk takes at most rate-1 steps; a walk that exceeds them (text    */
+/* that already contains the sentinel: LF is then not the inverse of the suffix  */
+/* order) stops and writes HKCSA_NO_POSITION instead of spinning.                */
+#define HKCSA_NO_POSITION 0xFFFFFFFFu
 int hkcsa_locate_rows(const void *d_wt_blob, const hkcsa_wt_plan *h_plan, const void *d_ssa_blob,
                       const hkcsa_ssa_plan *h_ssa, const uint32_t *d_rows, uint64_t m,
                       uint32_t *d_out_pos, void *stream);
