@@ -13,28 +13,11 @@
 #include "common.cuh"
 #include "prof.cuh"
 #include "radix_sort.cuh"
+#include "suffix_array.cuh"
 #include <math.h>
 #include <stdlib.h>
 
 namespace hkcsa {
-
-constexpr int SEG_THREADS = 256;
-constexpr int SEG_IPT = 8;
-constexpr int SEG_TILE = SEG_THREADS * SEG_IPT;
-
-struct CodeMap {
-    uint16_t code[256];  // byte -> dense code + 1 (0 for bytes that do not occur)
-};
-
-// Order-preserving prefix code ("alphabetic code") over {past-the-end} + the symbols of the text: frequent
-// symbols get short codes, and comparing two code streams bit by bit equals comparing the symbol strings,
-// the end of the text being smallest.  The round-0 key of a suffix is the first `bits` bits of its code
-// stream, so a key covers as many symbols as a fixed-width packing would in fewer bits -- fewer radix passes
-// (DNA + '$': 21 symbols in 48 bits instead of 63).  Equal keys share at least bits / max_len symbols.
-struct AlphaCode {
-    uint32_t code[257];   // right-aligned; [256] = past the end
-    uint8_t len[257];
-};
 
 static void alpha_assign(const double *cum, const int *item, int lo, int hi, uint32_t code, int len, AlphaCode &ac,
                          int &max_len)
@@ -57,7 +40,7 @@ static void alpha_assign(const double *cum, const int *item, int lo, int hi, uin
 }
 
 // returns false when the code would be degenerate (then the caller keeps fixed-width codes)
-static bool build_alpha_code(const uint64_t *h_hist, AlphaCode &ac, double &avg_len, int &max_len)
+bool build_alpha_code(const uint64_t *h_hist, AlphaCode &ac, double &avg_len, int &max_len)
 {
     int item[257];
     double w[257], cum[258];
@@ -81,19 +64,34 @@ static bool build_alpha_code(const uint64_t *h_hist, AlphaCode &ac, double &avg_
     return true;
 }
 
-// first `bits` bits of the code stream of the suffix whose symbols are produced by next_sym(t), t = 0, 1, ...
-template <typename NextSym>
-__device__ __forceinline__ uint64_t alpha_pack(const uint32_t *s_code, const uint8_t *s_len, int bits, NextSym next_sym)
+void make_round0_plan(const uint64_t *h_hist, Round0Plan &p)
 {
-    uint64_t acc = 0;
-    int used = 0;
-    for (int t = 0; used < bits; ++t) {
-        const uint32_t c = next_sym(t);
-        const int L = s_len[c];
-        acc |= ((uint64_t)s_code[c] << (64 - L)) >> used;   // bits beyond 64 fall off: the last code is truncated
-        used += L;
+    uint32_t sigma = 0;
+    for (int ch = 0; ch < 256; ++ch)
+        if (h_hist[ch]) ++sigma;
+    const int b = std::max(1, (int)bits_for(sigma));   // fixed-width code size, for reference
+    // round-0 keys: the first bits0 bits of the alphabetic code stream; as many symbols on average as a
+    // fixed-width packing of 64 / b symbols would hold, in fewer bits when the symbol distribution allows
+    AlphaCode &ac = p.ac;
+    double avg_len = b;
+    int max_len = b;
+    if (!build_alpha_code(h_hist, ac, avg_len, max_len)) {
+        uint32_t code = 0;                               // degenerate distribution: fixed-width codes
+        ac.code[256] = 0; ac.len[256] = (uint8_t)b;
+        for (int ch = 0; ch < 256; ++ch)
+            if (h_hist[ch]) { ac.code[ch] = ++code; ac.len[ch] = (uint8_t)b; }
+        avg_len = max_len = b;
     }
-    return acc >> (64 - bits);
+    const int k_target = 64 / b;
+    int bits0 = 8 * (int)ceil(k_target * avg_len / 8.0 - 1e-9);
+    bits0 = std::max(16, std::min(64, bits0));
+    if (const char *e = getenv("HKCSA_BITS0")) bits0 = std::max(16, std::min(64, 8 * (atoi(e) / 8)));   // tuning knob
+    p.sigma = sigma;
+    p.b = b;
+    p.max_len = max_len;
+    p.bits0 = bits0;
+    p.k0 = std::max(1, bits0 / max_len);         // symbols every key is guaranteed to cover
+    p.passes0 = bits0 / 8;
 }
 
 // ---------------------------------------------------------------- byte histogram
@@ -151,69 +149,6 @@ cudaError_t byte_hist(const uint8_t *d_text, uint64_t n, uint64_t *d_hist, cudaS
 // at that position's bit offset -- three shared loads and two funnel shifts, whatever the number of symbols
 // the key covers.  Keys are produced warp-striped so the stores are fully coalesced.  The suffix ids are not
 // written at all: the first radix pass takes "value = index" (radix_sort_pairs_u64, identity_vals).
-constexpr int PACK_THREADS = 256;
-constexpr int PACK_IPT = 8;
-constexpr int PACK_TILE = PACK_THREADS * PACK_IPT;
-constexpr int PACK_LOOK = 64;                                   // >= 64 bits of look-ahead (code words >= 1 bit)
-constexpr int PACK_VT = PACK_THREADS + PACK_LOOK / PACK_IPT;    // "virtual threads" incl. the look-ahead groups
-constexpr int PACK_MAX_LEN = 24;                                // build_alpha_code never exceeds it
-constexpr int PACK_STREAM_WORDS = (PACK_TILE + PACK_LOOK) * PACK_MAX_LEN / 32 + 4;
-
-// loads 8 consecutive symbols starting at g0 as (code << 8 | len) entries; returns the sum of the lengths
-__device__ __forceinline__ uint32_t pack_load8(const uint8_t *__restrict__ text, uint32_t n, uint64_t g0, bool aligned8,
-                                               const uint32_t *s_tab, uint32_t cl[PACK_IPT])
-{
-    uint32_t total = 0;
-    if (aligned8 && g0 + PACK_IPT <= n) {
-        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(text + g0));
-#pragma unroll
-        for (int e = 0; e < PACK_IPT; ++e) {
-            const uint32_t c = ((e < 4 ? v.x : v.y) >> (8 * (e & 3))) & 0xFFu;
-            cl[e] = s_tab[c];
-            total += cl[e] & 0xFFu;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < PACK_IPT; ++e) {
-            const uint64_t g = g0 + e;
-            cl[e] = s_tab[g < n ? (uint32_t)text[g] : 256u];
-            total += cl[e] & 0xFFu;
-        }
-    }
-    return total;
-}
-
-// ORs the 8 code words into the stream from bit offset `off` (bit 0 = MSB of word 0) and records the bit
-// offset of every symbol
-__device__ __forceinline__ void pack_emit8(uint32_t *s_stream, uint16_t *s_off8, uint32_t off, const uint32_t cl[PACK_IPT])
-{
-    uint32_t wi = off >> 5;
-    uint32_t nacc = off & 31u;
-    uint64_t acc = 0;
-    uint32_t o = off;
-    uint32_t offs[PACK_IPT];
-#pragma unroll
-    for (int e = 0; e < PACK_IPT; ++e) {
-        const uint32_t L = cl[e] & 0xFFu;
-        offs[e] = o;
-        o += L;
-        acc |= (uint64_t)(cl[e] >> 8) << (64u - nacc - L);     // nacc + L <= 31 + 24
-        nacc += L;
-        if (nacc >= 32u) {
-            atomicOr(&s_stream[wi++], (uint32_t)(acc >> 32));
-            acc <<= 32;
-            nacc -= 32u;
-        }
-    }
-    if (nacc) atomicOr(&s_stream[wi], (uint32_t)(acc >> 32));
-    uint4 q;
-    q.x = offs[0] | (offs[1] << 16);
-    q.y = offs[2] | (offs[3] << 16);
-    q.z = offs[4] | (offs[5] << 16);
-    q.w = offs[6] | (offs[7] << 16);
-    *reinterpret_cast<uint4 *>(s_off8) = q;
-}
-
 __global__ void __launch_bounds__(PACK_THREADS, 6)
 sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, int bits, int passes,
                 uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist)
@@ -759,28 +694,11 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     HK_CUDA(byte_hist(d_text, n, B.hist64, st));
     HK_CUDA(cudaMemcpyAsync(h_hist, B.hist64, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     HK_CUDA(cudaStreamSynchronize(st));
-    uint32_t sigma = 0;
-    for (int ch = 0; ch < 256; ++ch)
-        if (h_hist[ch]) ++sigma;
-    const int b = std::max(1, (int)bits_for(sigma));   // fixed-width code size, for reference
-    // round-0 keys: the first bits0 bits of the alphabetic code stream; as many symbols on average as a
-    // fixed-width packing of 64 / b symbols would hold, in fewer bits when the symbol distribution allows
-    static thread_local AlphaCode ac;
-    double avg_len = b;
-    int max_len = b;
-    if (!build_alpha_code(h_hist, ac, avg_len, max_len)) {
-        uint32_t code = 0;                               // degenerate distribution: fixed-width codes
-        ac.code[256] = 0; ac.len[256] = (uint8_t)b;
-        for (int ch = 0; ch < 256; ++ch)
-            if (h_hist[ch]) { ac.code[ch] = ++code; ac.len[ch] = (uint8_t)b; }
-        avg_len = max_len = b;
-    }
-    const int k_target = 64 / b;
-    int bits0 = 8 * (int)ceil(k_target * avg_len / 8.0 - 1e-9);
-    bits0 = std::max(16, std::min(64, bits0));
-    if (const char *e = getenv("HKCSA_BITS0")) bits0 = std::max(16, std::min(64, 8 * (atoi(e) / 8)));   // tuning knob
-    const int k0 = std::max(1, bits0 / max_len);         // symbols every key is guaranteed to cover
-    const int passes0 = bits0 / 8;
+    static thread_local Round0Plan r0;
+    make_round0_plan(h_hist, r0);
+    const AlphaCode &ac = r0.ac;
+    const uint32_t sigma = r0.sigma;
+    const int max_len = r0.max_len, bits0 = r0.bits0, k0 = r0.k0, passes0 = r0.passes0;
     stats.sigma = sigma;
     memcpy(stats.byte_hist, h_hist, sizeof(stats.byte_hist));
     stats.bits_per_symbol = (uint32_t)max_len;
@@ -919,402 +837,5 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     }
     stats.rounds = round;
     if (h_stats) *h_stats = stats;
-    return HKCSA_OK;
-}
-
-
-// ====================================================================================================
-// Distributed build (BASELINE config 5: a text beyond one GPU's working set).
-//
-// Every GPU holds the WHOLE text (one NCCL all-gather; 8 GB fit a B200 many times over) and sorts only the
-// suffixes whose round-0 key falls into its bucket range [bucket_lo, bucket_hi) of the 65536 buckets formed
-// by the top 16 key bits; the bucket histogram is all-reduced so every rank derives the same balanced
-// ranges.  The concatenation of the per-GPU slices, in rank order, is the suffix array.  Because the text is
-// replicated the sub-sorts need no exchange: after the packed-key radix sort, groups are refined by
-// EXTENSION rounds -- key = (group start, next ke symbols read straight from the text) -- instead of rank
-// doubling, which would need the ranks of suffixes owned by other GPUs.  Suffix ids are 32-bit: n <= 2^32-2.
-// ====================================================================================================
-namespace hkcsa {
-
-constexpr int DSA_BUCKET_BITS = 16;
-
-// key of suffix g at depth `skip`: the next `k` symbol codes (b bits each), MSB first; 0 past the end
-__device__ __forceinline__ uint64_t pack_from_text(const uint8_t *__restrict__ text, uint64_t n, uint64_t g,
-                                                   const uint16_t *s_code, int b, int k)
-{
-    uint64_t key = 0;
-    for (int q = 0; q < k; ++q) {
-        const uint64_t t = g + q;
-        key = (key << b) | (t < n ? (uint64_t)s_code[text[t]] : 0ull);
-    }
-    return key;
-}
-
-// histogram of the bucket (top DSA_BUCKET_BITS bits of the round-0 key) of suffixes [begin, end)
-__global__ void __launch_bounds__(PACK_THREADS)
-dsa_key_hist_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin, uint64_t end, CodeMap map, int b,
-                    int k0, int shift, unsigned long long *__restrict__ hist)
-{
-    __shared__ uint16_t s_code[256];
-    __shared__ uint16_t s_sym[PACK_TILE + 64];
-    const uint32_t tid = threadIdx.x;
-    s_code[tid] = map.code[tid];
-    __syncthreads();
-    const uint64_t base = begin + (uint64_t)blockIdx.x * PACK_TILE;
-    for (uint32_t j = tid; j < PACK_TILE + 64; j += PACK_THREADS) {
-        const uint64_t g = base + j;
-        s_sym[j] = (g < n) ? s_code[text[g]] : (uint16_t)0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < PACK_IPT; ++e) {
-        const uint32_t j = e * PACK_THREADS + tid;
-        const uint64_t g = base + j;
-        if (g < end) {
-            uint64_t key = 0;
-            for (int t = 0; t < k0; ++t) key = (key << b) | s_sym[j + t];
-            atomicAdd(&hist[key >> shift], 1ull);
-        }
-    }
-}
-
-// append (key, suffix id) of every suffix whose bucket lies in [bucket_lo, bucket_hi); order is irrelevant
-__global__ void __launch_bounds__(PACK_THREADS)
-dsa_select_kernel(const uint8_t *__restrict__ text, uint64_t n, CodeMap map, int b, int k0, int shift,
-                  uint32_t bucket_lo, uint32_t bucket_hi, int passes, uint64_t *__restrict__ keys,
-                  uint32_t *__restrict__ idx, uint64_t *__restrict__ ids64 /* wide ids: idx holds ordinals */,
-                  uint32_t capacity, uint32_t *__restrict__ counter, uint32_t *__restrict__ ghist)
-{
-    __shared__ uint16_t s_code[256];
-    __shared__ uint16_t s_sym[PACK_TILE + 64];
-    __shared__ uint32_t s_hist[8 * RADIX];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    s_code[tid] = map.code[tid];
-    hist_zero(s_hist, passes);
-    __syncthreads();
-    const uint64_t base = (uint64_t)blockIdx.x * PACK_TILE;
-    for (uint32_t j = tid; j < PACK_TILE + 64; j += PACK_THREADS) {
-        const uint64_t g = base + j;
-        s_sym[j] = (g < n) ? s_code[text[g]] : (uint16_t)0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < PACK_IPT; ++e) {
-        const uint32_t j = e * PACK_THREADS + tid;
-        const uint64_t g = base + j;
-        uint64_t key = 0;
-        for (int t = 0; t < k0; ++t) key = (key << b) | s_sym[j + t];
-        const uint32_t bucket = (uint32_t)(key >> shift);
-        const bool keep = g < n && bucket >= bucket_lo && bucket < bucket_hi;
-        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-        uint32_t slot0 = 0;
-        if (mask && lane == (uint32_t)(__ffs(mask) - 1)) slot0 = atomicAdd(counter, __popc(mask));
-        slot0 = __shfl_sync(0xffffffffu, slot0, mask ? __ffs(mask) - 1 : 0);
-        const uint32_t slot = slot0 + __popc(mask & lanemask_lt());
-        const bool store = keep && slot < capacity;
-        if (store) {
-            keys[slot] = key;
-            if (ids64) { ids64[slot] = g; idx[slot] = slot; }
-            else idx[slot] = (uint32_t)g;
-        }
-        hist_add_key(s_hist, key, passes, store);
-    }
-    __syncthreads();
-    hist_flush(s_hist, ghist, passes);
-}
-
-// extension round: key[j] = (group start << eb) | next `ke` symbols of suffix cidx[j] at depth `depth`
-__global__ void __launch_bounds__(256)
-dsa_keybuild_ext_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp,
-                        const uint8_t *__restrict__ text, uint64_t n, uint64_t depth, int b, int ke, int eb,
-                        uint32_t m, int passes, CodeMap map, uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist,
-                        const uint64_t *__restrict__ ids64)
-{
-    __shared__ uint32_t s_hist[8 * RADIX];
-    __shared__ uint16_t s_code[256];
-    s_code[threadIdx.x] = map.code[threadIdx.x];
-    hist_zero(s_hist, passes);
-    __syncthreads();
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < m; base += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t j = base + threadIdx.x;
-        const bool valid = j < m;
-        uint64_t key = 0;
-        if (valid) {
-            const uint64_t g = (ids64 ? ids64[cidx[j]] : (uint64_t)cidx[j]) + depth;
-            key = ((uint64_t)cgrp[j] << eb) | pack_from_text(text, n, g, s_code, b, ke);
-            keys[j] = key;
-        }
-        hist_add_key(s_hist, key, passes, valid);
-    }
-    __syncthreads();
-    hist_flush(s_hist, ghist, passes);
-}
-
-template <typename IdT>
-__global__ void bwt_slice_kernel(const uint8_t *__restrict__ text, uint64_t n, const IdT *__restrict__ sa,
-                                 uint64_t m, uint8_t *__restrict__ out)
-{
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const uint64_t v = sa[j];
-    out[j] = text[v ? v - 1 : n - 1];
-}
-
-__global__ void gather_ids64_kernel(const uint64_t *__restrict__ ids64, const uint32_t *__restrict__ ord, uint64_t m,
-                                    uint64_t *__restrict__ out)
-{
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < m) out[j] = ids64[ord[j]];
-}
-
-static int dsa_code_map(const uint64_t *h_byte_hist, CodeMap &map, int &b, int &k0, int &bits0, uint32_t &sigma)
-{
-    memset(&map, 0, sizeof(map));
-    sigma = 0;
-    for (int ch = 0; ch < 256; ++ch)
-        if (h_byte_hist[ch]) map.code[ch] = (uint16_t)(++sigma);
-    b = (int)bits_for(sigma);
-    if (b == 0) b = 1;
-    k0 = 64 / b;
-    bits0 = b * k0;
-    return HKCSA_OK;
-}
-
-}  // namespace hkcsa
-
-#define HKCSA_DIST_MAX_N ((uint64_t)0xFFFFFFFEull)
-
-extern "C" int hkcsa_sa_key_hist(const uint8_t *d_text, uint64_t n, uint64_t begin, uint64_t end,
-                                 const uint64_t *h_byte_hist, uint64_t *d_hist, void *stream)
-{
-    HK_REQUIRE(d_text && h_byte_hist && d_hist, HKCSA_EINVAL, "null pointer");
-    HK_REQUIRE(n <= (1ull << 40) && begin <= end && end <= n, HKCSA_ERANGE, "range");
-    cudaStream_t st = as_stream(stream);
-    CodeMap map; int b, k0, bits0; uint32_t sigma;
-    dsa_code_map(h_byte_hist, map, b, k0, bits0, sigma);
-    HK_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)(1u << DSA_BUCKET_BITS) * sizeof(uint64_t), st));
-    if (begin == end) return HKCSA_OK;
-    const uint64_t blocks = (end - begin + PACK_TILE - 1) / PACK_TILE;
-    dsa_key_hist_kernel<<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, n, begin, end, map, b, k0,
-                                                                   bits0 - DSA_BUCKET_BITS,
-                                                                   reinterpret_cast<unsigned long long *>(d_hist));
-    HK_LAUNCH_CHECK();
-    return HKCSA_OK;
-}
-
-namespace {
-struct SubsetBuffers {
-    uint64_t *key[2];
-    uint32_t *val[2];
-    uint32_t *pos[2];
-    uint32_t *grp;
-    uint32_t *agg_head, *agg_keep;
-    uint16_t *flags;
-    uint32_t *counter;
-    SortScratch sort;
-};
-SubsetBuffers carve_subset(Carver &c, uint64_t m)
-{
-    SubsetBuffers b;
-    const uint64_t tiles = (m + SEG_TILE - 1) / SEG_TILE + 1;
-    b.key[0] = c.take<uint64_t>(m);
-    b.key[1] = c.take<uint64_t>(m);
-    b.val[0] = c.take<uint32_t>(m);
-    b.val[1] = c.take<uint32_t>(m);
-    b.pos[0] = c.take<uint32_t>(m);
-    b.pos[1] = c.take<uint32_t>(m);
-    b.grp = c.take<uint32_t>(m);
-    b.agg_head = c.take<uint32_t>(tiles);
-    b.agg_keep = c.take<uint32_t>(tiles);
-    b.flags = c.take<uint16_t>(tiles * SEG_THREADS);
-    b.counter = c.take<uint32_t>(64);
-    b.sort = carve_sort_scratch(c, m);
-    return b;
-}
-}  // namespace
-
-extern "C" size_t hkcsa_sa_subset_scratch_bytes(uint64_t m)
-{
-    Carver c(nullptr);
-    carve_subset(c, m ? m : 1);
-    return c.total();
-}
-
-// d_ids64 == nullptr: d_sa_out receives the suffix ids (n <= 2^32-2).  Otherwise (wide ids, n up to 2^40) the
-// sort moves 32-bit ordinals into d_sa_out and the 64-bit ids stay in d_ids64[ordinal].
-static int sa_build_subset_impl(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist, uint32_t bucket_lo,
-                                uint32_t bucket_hi, uint32_t *d_sa_out, uint64_t *d_ids64, uint64_t capacity,
-                                uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
-                                hkcsa_sa_stats *h_stats)
-{
-    hkcsa_sa_stats stats;
-    memset(&stats, 0, sizeof(stats));
-    if (h_stats) *h_stats = stats;
-    HK_REQUIRE(h_count != nullptr, HKCSA_EINVAL, "null pointer");
-    *h_count = 0;
-    if (n == 0 || capacity == 0 || bucket_lo >= bucket_hi) return HKCSA_OK;
-    HK_REQUIRE(d_ids64 != nullptr || n <= HKCSA_DIST_MAX_N, HKCSA_ERANGE, "n exceeds 2^32-2: use the 64-bit entry point");
-    HK_REQUIRE(n <= (1ull << 40), HKCSA_ERANGE, "n exceeds 2^40");
-    HK_REQUIRE(capacity <= HKCSA_MAX_N, HKCSA_ERANGE, "slice exceeds HKCSA_MAX_N");
-    HK_REQUIRE(d_text && h_byte_hist && d_sa_out && d_scratch, HKCSA_EINVAL, "null pointer");
-    HK_REQUIRE(((reinterpret_cast<uintptr_t>(d_sa_out) | reinterpret_cast<uintptr_t>(d_scratch)) & 15) == 0,
-               HKCSA_EINVAL, "d_sa_out and d_scratch must be 16-byte aligned (TMA bulk copies)");
-    Carver c(d_scratch);
-    SubsetBuffers B = carve_subset(c, capacity);
-    HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "subset scratch too small");
-    cudaStream_t st = as_stream(stream);
-    uint8_t *pin = static_cast<uint8_t *>(pinned_page());
-    HK_REQUIRE(pin != nullptr, HKCSA_ECUDA, "pinned page allocation failed");
-    uint32_t *h_m = reinterpret_cast<uint32_t *>(pin + 2048);
-
-    CodeMap map; int b, k0, bits0; uint32_t sigma;
-    dsa_code_map(h_byte_hist, map, b, k0, bits0, sigma);
-    const int passes0 = (bits0 + 7) / 8;
-    stats.sigma = sigma; stats.bits_per_symbol = (uint32_t)b; stats.k0 = (uint32_t)k0;
-
-    // ---- select + pack this GPU's suffixes, values arranged so the sorted ids land in d_sa_out
-    uint64_t *ka = B.key[0], *kb = B.key[1];
-    uint32_t *va = (passes0 % 2 == 0) ? d_sa_out : B.val[0];
-    uint32_t *vb = (passes0 % 2 == 0) ? B.val[0] : d_sa_out;
-    HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
-    HK_CUDA(cudaMemsetAsync(B.counter, 0, 64 * sizeof(uint32_t), st));
-    {
-        const uint64_t blocks = (n + PACK_TILE - 1) / PACK_TILE;
-        prof::Scope ps(st, prof::SA_PACK0, n);
-        dsa_select_kernel<<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, n, map, b, k0, bits0 - DSA_BUCKET_BITS,
-                                                                     bucket_lo, bucket_hi, passes0, ka, va, d_ids64,
-                                                                     (uint32_t)capacity, B.counter, B.sort.hist);
-        HK_LAUNCH_CHECK();
-    }
-    HK_CUDA(cudaMemcpyAsync(h_m, B.counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    HK_CUDA(cudaStreamSynchronize(st));
-    const uint32_t M = *h_m;
-    HK_REQUIRE(M <= capacity, HKCSA_ESCRATCH, "more suffixes in the bucket range than the output capacity");
-    *h_count = M;
-    if (M == 0) return HKCSA_OK;
-    HK_CUDA(radix_sort_pairs_u64(ka, va, kb, vb, M, passes0, B.sort, st));
-    uint64_t *skey = (passes0 % 2 == 0) ? ka : kb;
-    uint64_t *kx = (passes0 % 2 == 0) ? kb : ka, *ky = skey;
-    uint32_t *sidx = d_sa_out;
-    uint32_t *vfree = B.val[1], *vother = B.val[0];
-    uint32_t m = M;
-    const uint32_t *pos = nullptr;
-    int pcur = 0;
-    uint64_t depth = (uint64_t)k0;
-    const int gb = (int)bits_for(M > 1 ? M - 1 : 1);        // bits of a group start
-    const int ke = std::max(1, (64 - gb) / b);              // symbols per extension round
-    const int eb = ke * b;
-    uint32_t round = 0;
-    stats.round_elems[0] = m; stats.round_passes[0] = (uint32_t)passes0;
-    stats.sort_elem_passes = (uint64_t)m * passes0;
-    while (true) {
-        const uint32_t tiles = (m + SEG_TILE - 1) / SEG_TILE;
-        seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, m, B.agg_head, B.agg_keep, B.flags);
-        HK_LAUNCH_CHECK();
-        seg_scan_kernel<<<1, 1024, 0, st>>>(B.agg_head, B.agg_keep, tiles, B.counter);
-        HK_LAUNCH_CHECK();
-        uint32_t *cpos = B.pos[pcur ^ 1];
-        uint32_t *cidx = vfree;
-        seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.flags, sidx, pos, m, B.agg_head, B.agg_keep, d_sa_out, nullptr,
-                                                       cpos, cidx, B.grp, round != 0, false);
-        HK_LAUNCH_CHECK();
-        HK_CUDA(cudaMemcpyAsync(h_m, B.counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        HK_CUDA(cudaStreamSynchronize(st));
-        ++round;
-        const uint32_t m_next = *h_m;
-        if (m_next == 0) break;
-        HK_REQUIRE(depth < n, HKCSA_EINVAL, "internal: groups remain after depth >= n");
-        HK_REQUIRE(round < 40, HKCSA_EINVAL,
-                   "text too repetitive for extension rounds (LCP beyond 40 rounds): use the single-GPU builder");
-        if (round > 1) vother = sidx;
-        m = m_next;
-        pcur ^= 1;
-        pos = B.pos[pcur];
-        uint32_t *vx = cidx, *vy = vother;
-        const int passes = (gb + eb + 7) / 8;
-        HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
-        {
-            const int blocks = (int)std::min<uint64_t>(((uint64_t)m + 255) / 256, (uint64_t)num_sms() * 16);
-            dsa_keybuild_ext_kernel<<<blocks, 256, 0, st>>>(vx, B.grp, d_text, n, depth, b, ke, eb, m, passes, map, kx,
-                                                            B.sort.hist, d_ids64);
-            HK_LAUNCH_CHECK();
-        }
-        HK_CUDA(radix_sort_pairs_u64(kx, vx, ky, vy, m, passes, B.sort, st));
-        if (passes & 1) { skey = ky; sidx = vy; vfree = vx; uint64_t *t = kx; kx = ky; ky = t; }
-        else { skey = kx; sidx = vx; vfree = vy; }
-        // after the swap above kx is always a buffer that does not hold the sorted keys
-        if (skey == kx) { uint64_t *t = kx; kx = ky; ky = t; }
-        stats.round_elems[round] = m; stats.round_passes[round] = (uint32_t)passes;
-        stats.sort_elem_passes += (uint64_t)m * passes;
-        depth += (uint64_t)ke;
-    }
-    stats.rounds = round;
-    if (h_stats) *h_stats = stats;
-    return HKCSA_OK;
-}
-
-extern "C" int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist,
-                                     uint32_t bucket_lo, uint32_t bucket_hi, uint32_t *d_sa_out, uint64_t capacity,
-                                     uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
-                                     hkcsa_sa_stats *h_stats)
-{
-    return sa_build_subset_impl(d_text, n, h_byte_hist, bucket_lo, bucket_hi, d_sa_out, nullptr, capacity, h_count,
-                                d_scratch, scratch_bytes, stream, h_stats);
-}
-
-// 64-bit suffix ids (texts beyond 4 GB): same sort on 32-bit ordinals, ids gathered at the end.
-extern "C" size_t hkcsa_sa_subset64_scratch_bytes(uint64_t m)
-{
-    Carver c(nullptr);
-    carve_subset(c, m ? m : 1);
-    c.take<uint64_t>(m ? m : 1);
-    c.take<uint32_t>(m ? m : 1);
-    return c.total();
-}
-
-extern "C" int hkcsa_sa_build_subset64(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist,
-                                       uint32_t bucket_lo, uint32_t bucket_hi, uint64_t *d_sa_out64, uint64_t capacity,
-                                       uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
-                                       hkcsa_sa_stats *h_stats)
-{
-    HK_REQUIRE(h_count != nullptr, HKCSA_EINVAL, "null pointer");
-    *h_count = 0;
-    if (n == 0 || capacity == 0 || bucket_lo >= bucket_hi) return HKCSA_OK;
-    HK_REQUIRE(d_sa_out64 && d_scratch, HKCSA_EINVAL, "null pointer");
-    Carver c(d_scratch);
-    carve_subset(c, capacity);
-    const size_t inner = c.total();
-    uint64_t *d_ids64 = c.take<uint64_t>(capacity);
-    uint32_t *d_ord = c.take<uint32_t>(capacity);
-    HK_REQUIRE(c.total() <= scratch_bytes, HKCSA_ESCRATCH, "subset scratch too small");
-    int rc = sa_build_subset_impl(d_text, n, h_byte_hist, bucket_lo, bucket_hi, d_ord, d_ids64, capacity, h_count,
-                                  d_scratch, inner, stream, h_stats);
-    if (rc != HKCSA_OK) return rc;
-    const uint64_t m = *h_count;
-    if (m) {
-        gather_ids64_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, as_stream(stream)>>>(d_ids64, d_ord, m, d_sa_out64);
-        HK_LAUNCH_CHECK();
-    }
-    return HKCSA_OK;
-}
-
-extern "C" int hkcsa_bwt_slice(const uint8_t *d_text, uint64_t n, const uint32_t *d_sa_slice, uint64_t m,
-                               uint8_t *d_out, void *stream)
-{
-    if (m == 0) return HKCSA_OK;
-    HK_REQUIRE(d_text && d_sa_slice && d_out, HKCSA_EINVAL, "null pointer");
-    HK_REQUIRE(n <= HKCSA_DIST_MAX_N, HKCSA_ERANGE, "n exceeds 2^32-2");
-    bwt_slice_kernel<uint32_t><<<(uint32_t)((m + 255) / 256), 256, 0, as_stream(stream)>>>(d_text, n, d_sa_slice, m, d_out);
-    HK_LAUNCH_CHECK();
-    return HKCSA_OK;
-}
-
-extern "C" int hkcsa_bwt_slice64(const uint8_t *d_text, uint64_t n, const uint64_t *d_sa_slice, uint64_t m,
-                                 uint8_t *d_out, void *stream)
-{
-    if (m == 0) return HKCSA_OK;
-    HK_REQUIRE(d_text && d_sa_slice && d_out, HKCSA_EINVAL, "null pointer");
-    bwt_slice_kernel<uint64_t><<<(uint32_t)((m + 255) / 256), 256, 0, as_stream(stream)>>>(d_text, n, d_sa_slice, m, d_out);
-    HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

@@ -1,0 +1,137 @@
+// suffix_array.cuh -- pieces of K1 shared by the single-GPU builder (suffix_array.cu) and the distributed
+// builder (dist_sa.cu): the order-preserving prefix code of round 0, the shared-memory bit-stream packer, and the
+// segmented rank-update kernels.
+#pragma once
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+namespace hkcsa {
+
+constexpr int SEG_THREADS = 256;
+constexpr int SEG_IPT = 8;
+constexpr int SEG_TILE = SEG_THREADS * SEG_IPT;
+
+struct CodeMap {
+    uint16_t code[256];  // byte -> dense code + 1 (0 for bytes that do not occur)
+};
+
+// Order-preserving prefix code ("alphabetic code") over {past-the-end} + the symbols of the text: frequent
+// symbols get short codes, and comparing two code streams bit by bit equals comparing the symbol strings,
+// the end of the text being smallest.  The round-0 key of a suffix is the first `bits` bits of its code
+// stream, so a key covers as many symbols as a fixed-width packing would in fewer bits -- fewer radix passes
+// (DNA + '$': 21 symbols in 48 bits instead of 63).  Equal keys share at least bits / max_len symbols.
+struct AlphaCode {
+    uint32_t code[257];   // right-aligned; [256] = past the end
+    uint8_t len[257];
+};
+
+// returns false when the code would be degenerate (then the caller keeps fixed-width codes)
+bool build_alpha_code(const uint64_t *h_hist, AlphaCode &ac, double &avg_len, int &max_len);
+
+// Round-0 parameters derived from the byte histogram of the text -- the single-GPU and the distributed builder
+// must key suffixes identically.
+struct Round0Plan {
+    AlphaCode ac;
+    uint32_t sigma;
+    int b;          // fixed-width code size
+    int max_len;    // longest code word
+    int bits0;      // key width (multiple of 8, 16..64)
+    int k0;         // symbols every key is guaranteed to cover
+    int passes0;    // radix passes of round 0
+};
+void make_round0_plan(const uint64_t *h_hist, Round0Plan &p);
+
+// first `bits` bits of the code stream of the suffix whose symbols are produced by next_sym(t), t = 0, 1, ...
+template <typename NextSym>
+__device__ __forceinline__ uint64_t alpha_pack(const uint32_t *s_code, const uint8_t *s_len, int bits, NextSym next_sym)
+{
+    uint64_t acc = 0;
+    int used = 0;
+    for (int t = 0; used < bits; ++t) {
+        const uint32_t c = next_sym(t);
+        const int L = s_len[c];
+        acc |= ((uint64_t)s_code[c] << (64 - L)) >> used;   // bits beyond 64 fall off: the last code is truncated
+        used += L;
+    }
+    return acc >> (64 - bits);
+}
+
+// ---------------------------------------------------------------- round 0: the bit-stream packer
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_IPT = 8;
+constexpr int PACK_TILE = PACK_THREADS * PACK_IPT;
+constexpr int PACK_LOOK = 64;                                   // >= 64 bits of look-ahead (code words >= 1 bit)
+constexpr int PACK_VT = PACK_THREADS + PACK_LOOK / PACK_IPT;    // "virtual threads" incl. the look-ahead groups
+constexpr int PACK_MAX_LEN = 24;                                // build_alpha_code never exceeds it
+constexpr int PACK_STREAM_WORDS = (PACK_TILE + PACK_LOOK) * PACK_MAX_LEN / 32 + 4;
+
+// loads 8 consecutive symbols starting at g0 as (code << 8 | len) entries; returns the sum of the lengths
+template <typename LenT>
+__device__ __forceinline__ uint32_t pack_load8(const uint8_t *__restrict__ text, LenT n, uint64_t g0, bool aligned8,
+                                               const uint32_t *s_tab, uint32_t cl[PACK_IPT])
+{
+    uint32_t total = 0;
+    if (aligned8 && g0 + PACK_IPT <= n) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(text + g0));
+#pragma unroll
+        for (int e = 0; e < PACK_IPT; ++e) {
+            const uint32_t c = ((e < 4 ? v.x : v.y) >> (8 * (e & 3))) & 0xFFu;
+            cl[e] = s_tab[c];
+            total += cl[e] & 0xFFu;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < PACK_IPT; ++e) {
+            const uint64_t g = g0 + e;
+            cl[e] = s_tab[g < n ? (uint32_t)text[g] : 256u];
+            total += cl[e] & 0xFFu;
+        }
+    }
+    return total;
+}
+
+// ORs the 8 code words into the stream from bit offset `off` (bit 0 = MSB of word 0) and records the bit
+// offset of every symbol
+__device__ __forceinline__ void pack_emit8(uint32_t *s_stream, uint16_t *s_off8, uint32_t off, const uint32_t cl[PACK_IPT])
+{
+    uint32_t wi = off >> 5;
+    uint32_t nacc = off & 31u;
+    uint64_t acc = 0;
+    uint32_t o = off;
+    uint32_t offs[PACK_IPT];
+#pragma unroll
+    for (int e = 0; e < PACK_IPT; ++e) {
+        const uint32_t L = cl[e] & 0xFFu;
+        offs[e] = o;
+        o += L;
+        acc |= (uint64_t)(cl[e] >> 8) << (64u - nacc - L);     // nacc + L <= 31 + 24
+        nacc += L;
+        if (nacc >= 32u) {
+            atomicOr(&s_stream[wi++], (uint32_t)(acc >> 32));
+            acc <<= 32;
+            nacc -= 32u;
+        }
+    }
+    if (nacc) atomicOr(&s_stream[wi], (uint32_t)(acc >> 32));
+    uint4 q;
+    q.x = offs[0] | (offs[1] << 16);
+    q.y = offs[2] | (offs[3] << 16);
+    q.z = offs[4] | (offs[5] << 16);
+    q.w = offs[6] | (offs[7] << 16);
+    *reinterpret_cast<uint4 *>(s_off8) = q;
+}
+
+cudaError_t byte_hist(const uint8_t *d_text, uint64_t n, uint64_t *d_hist, cudaStream_t st);
+
+// ---------------------------------------------------------------- segmented rank update (suffix_array.cu)
+__global__ void __launch_bounds__(SEG_THREADS) seg_reduce_kernel(const uint64_t *__restrict__ skey, uint32_t m, uint32_t *__restrict__ agg_head,
+                                  uint32_t *__restrict__ agg_keep, uint16_t *__restrict__ flags);
+__global__ void __launch_bounds__(1024) seg_scan_kernel(uint32_t *__restrict__ agg_head, uint32_t *__restrict__ agg_keep, uint32_t tiles,
+                                uint32_t *__restrict__ out_m);
+__global__ void __launch_bounds__(SEG_THREADS, 6) seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict__ sidx,
+                                 const uint32_t *__restrict__ pos /* nullptr = identity */, uint32_t m,
+                                 const uint32_t *__restrict__ carry_head, const uint32_t *__restrict__ carry_keep,
+                                 uint32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint32_t *__restrict__ cpos,
+                                 uint32_t *__restrict__ cidx, uint32_t *__restrict__ cgrp, bool write_sa, bool scatter_all);
+
+}  // namespace hkcsa

@@ -17,8 +17,9 @@ BLOCK_BITS = 224
 SUPER_BLOCKS = 65536
 SELECT_SAMPLE = 4096
 MAX_SLICES = 8
-DIST_BUCKETS = 65536
-DIST_MAX_N = (1 << 32) - 2
+DSA_BUCKETS = 65536
+DSA_MAX_RANKS = 8
+DSA_MAX_N32 = (1 << 32) - 2
 PROF_CLASSES = 16
 
 OK, EINVAL, ECUDA, ESCRATCH, ERANGE = 0, -1, -2, -3, -4
@@ -97,6 +98,21 @@ class OccPlan(C.Structure):
     ]
 
 
+class DsaPlan(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint64),
+        ("sigma", C.c_uint32),
+        ("bits0", C.c_uint32),
+        ("k0", C.c_uint32),
+        ("passes0", C.c_uint32),
+        ("b_fixed", C.c_uint32),
+        ("wide", C.c_uint32),
+        ("code", C.c_uint32 * 257),
+        ("len", C.c_uint8 * 257),
+        ("fixed_code", C.c_uint16 * 256),
+    ]
+
+
 class ProfEntry(C.Structure):
     _fields_ = [
         ("name", C.c_char * 32),
@@ -117,14 +133,24 @@ SIGNATURES = {
     "hkcsa_gen_pattern_bytes": (_i32, [_u64, _u64, _vp, _u64, _vp, _u32, _vp, _vp, _vp]),
     "hkcsa_sa_scratch_bytes": (_sz, [_u64]),
     "hkcsa_sa_build": (_i32, [_vp, _u64, _vp, _vp, _sz, _vp, C.POINTER(SaStats)]),
-    "hkcsa_sa_key_hist": (_i32, [_vp, _u64, _u64, _u64, C.POINTER(_u64), _vp, _vp]),
-    "hkcsa_sa_subset_scratch_bytes": (_sz, [_u64]),
-    "hkcsa_sa_build_subset": (_i32, [_vp, _u64, C.POINTER(_u64), _u32, _u32, _vp, _u64, C.POINTER(_u64), _vp, _sz, _vp,
-                                     C.POINTER(SaStats)]),
+    "hkcsa_dsa_plan_make": (_i32, [C.POINTER(_u64), _u64, _i32, C.POINTER(DsaPlan)]),
+    "hkcsa_dsa_bucket_hist": (_i32, [_vp, C.POINTER(DsaPlan), _u64, _u64, _vp, _vp]),
+    "hkcsa_dsa_pack_exchange": (_i32, [_vp, C.POINTER(DsaPlan), _u64, _u64, _u32, C.POINTER(_u32), C.POINTER(_u64),
+                                       C.POINTER(_u64), C.POINTER(_u64), _vp, _vp]),
+    "hkcsa_dsa_state_bytes": (_sz, []),
+    "hkcsa_dsa_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_dsa_begin": (_i32, [_vp, C.POINTER(DsaPlan), _vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _sz, _vp]),
+    "hkcsa_dsa_working_set": (_u64, [_vp]),
+    "hkcsa_dsa_depth": (_u64, [_vp]),
+    "hkcsa_dsa_slice": (_vp, [_vp]),
+    "hkcsa_dsa_rounds": (_i32, [_vp, C.POINTER(_u32), C.POINTER(_u64), _u32]),
+    "hkcsa_dsa_ext_round": (_i32, [_vp, _vp]),
+    "hkcsa_dsa_isa_publish": (_i32, [_vp, _u32, C.POINTER(_u64), _u64, _u64, _i32, _vp]),
+    "hkcsa_dsa_dbl_keys": (_i32, [_vp, _u32, C.POINTER(_u64), _u64, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64),
+                                  C.POINTER(_u32), _vp]),
+    "hkcsa_dsa_dbl_sort": (_i32, [_vp, _vp]),
+    "hkcsa_dsa_gather_ids64": (_i32, [_vp, _vp, _vp]),
     "hkcsa_bwt_slice": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp]),
-    "hkcsa_sa_subset64_scratch_bytes": (_sz, [_u64]),
-    "hkcsa_sa_build_subset64": (_i32, [_vp, _u64, C.POINTER(_u64), _u32, _u32, _vp, _u64, C.POINTER(_u64), _vp, _sz, _vp,
-                                       C.POINTER(SaStats)]),
     "hkcsa_bwt_slice64": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp]),
     "hkcsa_ssa_build64": (_i32, [_vp, C.POINTER(SsaPlan), _vp, _vp, _sz, _vp]),
     "hkcsa_expand_ranges64": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
@@ -201,7 +227,7 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if L.hkcsa_abi_version() != 1:
         raise ImportError("libhkcsa.so ABI version mismatch")
-    for idx, st in enumerate((SaStats, WtPlan, SsaPlan, ProfEntry, OccPlan)):
+    for idx, st in enumerate((SaStats, WtPlan, SsaPlan, ProfEntry, OccPlan, DsaPlan)):
         if L.hkcsa_struct_size(idx) != C.sizeof(st):
             raise ImportError(f"struct layout mismatch for {st.__name__}: "
                               f"C {L.hkcsa_struct_size(idx)} vs ctypes {C.sizeof(st)}")

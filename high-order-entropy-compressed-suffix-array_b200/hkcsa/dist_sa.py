@@ -1,28 +1,35 @@
 """Distributed suffix-array build for texts beyond one GPU's working set (SURVEY.md section 8e,
-BASELINE config 5).  One process per GPU.
+BASELINE config 5).  One process per GPU; csrc/dist_sa.cu holds the kernels.
 
-    1. every rank holds a contiguous block of the text; the blocks are all-gathered over NCCL so that
-       every GPU has the whole text (8 GB fit a 180 GB B200 many times over);
-    2. byte histogram and the 65536-bucket histogram of the top 16 bits of the round-0 keys are computed
-       on each rank's own block and all-reduced; every rank derives the same balanced bucket ranges;
-    3. rank r sorts the suffixes whose key falls into range r (libhkcsa: select + pack, onesweep radix
-       sort, extension rounds that read the replicated text) -- no exchange during the sort;
-    4. the slices, concatenated in rank order, are the suffix array; the BWT slice is a local gather.
+    1. every rank holds a contiguous block of the text; the blocks are all-gathered over NCCL (one collective on
+       equal blocks) so that every GPU has the whole text -- the BWT gather needs it anyway;
+    2. byte histogram -> the same round-0 prefix code on every rank; every rank histograms the top 16 key bits of
+       the suffixes of ITS block; the histograms are all-gathered and every rank derives the same balanced cut
+       points and the (source, destination) count matrix;
+    3. the all-to-all bucket exchange: the pack kernel stores each (key, suffix id) straight into the receive
+       arrays of the rank owning its bucket -- symmetric memory, peer-mapped over NVLink, no collective;
+    4. every rank radix-sorts what it received and refines: extension rounds on the replicated text, then -- for
+       repetitive texts -- rank doubling through the ranks' peer-mapped ISA blocks (any text is sorted);
+    5. the slices, concatenated in rank order, are the suffix array; the BWT slice is a local gather.
 
-Suffix ids are 32-bit (n <= 2^32 - 2); a slice holds at most 2^30 - 2 suffixes.  The collectives are the
-text all-gather and two small all-reduces; an all-to-all is not needed because the text is replicated.
+The per-rank program is a generator that yields its collective steps, so the same code runs under
+torch.distributed (`distributed_suffix_array`) and with the ranks emulated in one process on one GPU
+(`emulate_distributed_suffix_array`: what the single-GPU tests run).
 """
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
+import time
+from dataclasses import dataclass, field
 
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import SaStats, check
+from ._lib import DsaPlan, check
 from .engine import _empty, _ptr, _scratch, _stream, byte_hist
+
+EXT_ROUNDS_MAX = 6          # extension rounds before rank doubling takes over
 
 
 def balanced_bucket_ranges(bucket_hist: np.ndarray, parts: int) -> list[tuple[int, int]]:
@@ -40,43 +47,16 @@ def balanced_bucket_ranges(bucket_hist: np.ndarray, parts: int) -> list[tuple[in
     return [(cuts[r], cuts[r + 1]) for r in range(parts)]
 
 
-def key_bucket_hist(text: torch.Tensor, begin: int, end: int, byte_hist_np: np.ndarray) -> torch.Tensor:
-    """Histogram (int64[65536], device) of the key buckets of suffixes [begin, end) of `text`."""
-    hist = torch.zeros(_lib.DIST_BUCKETS, dtype=torch.int64, device=text.device)
-    bh = np.ascontiguousarray(byte_hist_np, dtype=np.uint64)
-    check(_lib.load().hkcsa_sa_key_hist(_ptr(text), text.numel(), begin, end, bh.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                        _ptr(hist), _stream()))
-    return hist
-
-
-def build_slice(text: torch.Tensor, byte_hist_np: np.ndarray, bucket_lo: int, bucket_hi: int, capacity: int,
-                stats: SaStats | None = None, wide: bool | None = None) -> torch.Tensor:
-    """Sorted suffix ids of the suffixes in the bucket range: uint32 bit patterns in an int32 tensor, or -- for
-    texts beyond 2^32-2 symbols, or when `wide` is forced -- an int64 tensor."""
-    L = _lib.load()
-    if wide is None:
-        wide = text.numel() > _lib.DIST_MAX_N
-    if wide:
-        out = _empty(max(capacity, 1), torch.int64, text.device)
-        nbytes = L.hkcsa_sa_subset64_scratch_bytes(capacity)
-        scratch = _scratch(nbytes, text.device)
-        count = C.c_uint64(0)
-        bh = np.ascontiguousarray(byte_hist_np, dtype=np.uint64)
-        st = stats if stats is not None else SaStats()
-        check(L.hkcsa_sa_build_subset64(_ptr(text), text.numel(), bh.ctypes.data_as(C.POINTER(C.c_uint64)), bucket_lo,
-                                        bucket_hi, _ptr(out), capacity, C.byref(count), _ptr(scratch), nbytes,
-                                        _stream(), C.byref(st)))
-        return out[: count.value]
-    out = _empty(max(capacity, 1), torch.int32, text.device)
-    nbytes = L.hkcsa_sa_subset_scratch_bytes(capacity)
-    scratch = _scratch(nbytes, text.device)
-    count = C.c_uint64(0)
-    bh = np.ascontiguousarray(byte_hist_np, dtype=np.uint64)
-    st = stats if stats is not None else SaStats()
-    check(L.hkcsa_sa_build_subset(_ptr(text), text.numel(), bh.ctypes.data_as(C.POINTER(C.c_uint64)), bucket_lo,
-                                  bucket_hi, _ptr(out), capacity, C.byref(count), _ptr(scratch), nbytes, _stream(),
-                                  C.byref(st)))
-    return out[: count.value]
+def exchange_layout(hist_all: np.ndarray, parts: int):
+    """hist_all[src][bucket] -> (cuts[parts+1], cnt[src][dst], counts[dst], slice_off[parts+1]): the same on every
+    rank.  Source `s` writes its pairs for destination `d` from slot cnt[:s, d].sum() on."""
+    hist_all = np.asarray(hist_all, dtype=np.int64)
+    ranges = balanced_bucket_ranges(hist_all.sum(0), parts)
+    cuts = np.array([r[0] for r in ranges] + [hist_all.shape[1]], dtype=np.int64)
+    cnt = np.stack([hist_all[:, a:b].sum(1) for a, b in ranges], axis=1)        # [src][dst]
+    counts = cnt.sum(0)
+    slice_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return cuts, cnt, counts, slice_off
 
 
 def bwt_slice(text: torch.Tensor, sa_slice: torch.Tensor) -> torch.Tensor:
@@ -92,52 +72,282 @@ class SuffixArraySlice:
     world: int
     n: int                      # length of the whole text
     offset: int                 # global SA position of this slice's first entry
-    sa: torch.Tensor            # uint32 suffix ids (int32 storage), sorted
+    sa: torch.Tensor            # sorted suffix ids: uint32 bit patterns in int32 storage, or int64 (wide)
     bwt: torch.Tensor           # uint8, same length
     text: torch.Tensor          # the replicated text
     bucket_range: tuple
-    stats: SaStats
+    rounds: list = field(default_factory=list)        # working-set size per refinement round (this rank)
+    ext_rounds: int = 0
+    dbl_rounds: int = 0
+    phases: dict = field(default_factory=dict)        # seconds per phase (profile=True)
+    nvlink_bytes_in: int = 0                          # bytes this GPU received: text blocks + (key, id) pairs
 
     def sa_int64(self) -> torch.Tensor:
         return self.sa if self.sa.dtype == torch.int64 else self.sa.to(torch.int64) & 0xFFFFFFFF
 
 
-def distributed_suffix_array(local_block: torch.Tensor, group=None, wide: bool | None = None) -> SuffixArraySlice:
-    """local_block: this rank's contiguous part of the text (uint8, on this rank's GPU), blocks in rank order."""
+def _u64arr(vals):
+    return (C.c_uint64 * len(vals))(*[int(v) for v in vals])
+
+
+def _align(x: int, a: int = 256) -> int:
+    return (x + a - 1) // a * a
+
+
+def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: bool, ext_rounds_max: int):
+    """One rank's build as a generator.  Yields ("gather", array) -> [world, len] int64 numpy; ("text", block,
+    sizes) -> the whole text; ("symm", nbytes) -> (uint8 tensor, [address of every rank's buffer]); ("barrier",)."""
+    L = _lib.load()
+    dev = block.device
+    phases: dict = {}
+    t_last = [0.0]
+
+    def tick(name=None):
+        if not profile:
+            return
+        torch.cuda.synchronize(dev)
+        now = time.perf_counter()
+        if name is not None:
+            phases[name] = phases.get(name, 0.0) + now - t_last[0]
+        t_last[0] = now
+
+    tick()
+    # ---- 1. the text on every rank
+    sizes = (yield ("gather", np.array([block.numel()], dtype=np.int64)))[:, 0]
+    n = int(sizes.sum())
+    if n > (1 << 40):
+        raise _lib.HkcsaError(_lib.ERANGE, f"text of {n} symbols exceeds 2^40")
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    text = yield ("text", block, sizes)
+    begin, end = int(starts[rank]), int(starts[rank + 1])
+    tick("text_allgather")
+    # ---- 2. one prefix code and one set of cut points for everybody
+    bh = (yield ("gather", byte_hist(block).astype(np.int64))).sum(0).astype(np.uint64)
+    plan = DsaPlan()
+    check(L.hkcsa_dsa_plan_make(bh.ctypes.data_as(C.POINTER(C.c_uint64)), n, 1 if wide else 0, C.byref(plan)))
+    is_wide = bool(plan.wide)
+    d_hist = torch.empty(_lib.DSA_BUCKETS, dtype=torch.int64, device=dev)
+    check(L.hkcsa_dsa_bucket_hist(_ptr(text), C.byref(plan), begin, end, _ptr(d_hist), _stream()))
+    hist_all = yield ("gather", d_hist)
+    cuts, cnt, counts, slice_off = exchange_layout(hist_all, world)
+    if int(counts.max()) > _lib.MAX_N:
+        raise _lib.HkcsaError(_lib.ERANGE, f"a slice of {int(counts.max())} suffixes exceeds {_lib.MAX_N}: the buckets "
+                                           "(top 16 key bits) of this text are too uneven for this many ranks")
+    M = int(counts[rank])
+    cap = _align(max(int(counts.max()), 1), 64)
+    tick("histograms")
+    # ---- 3. symmetric workspace: receive arrays + ISA block, the same layout on every rank
+    id_bytes = 8 if is_wide else 4
+    blk = max(1, -(-n // world))                                # positions per ISA block
+    off_keys = 0
+    off_va = _align(off_keys + 8 * cap)
+    off_vb = _align(off_va + 4 * cap)
+    off_ids64 = _align(off_vb + 4 * cap)
+    off_isa = _align(off_ids64 + (8 * cap if is_wide else 0))
+    total = _align(off_isa + id_bytes * blk)
+    ws, ptrs = yield ("symm", total)
+    keys = ws[off_keys:off_keys + 8 * cap].view(torch.int64)
+    val_a = ws[off_va:off_va + 4 * cap].view(torch.int32)
+    val_b = ws[off_vb:off_vb + 4 * cap].view(torch.int32)
+    ids64 = ws[off_ids64:off_ids64 + 8 * cap].view(torch.int64) if is_wide else None
+    isa = ws[off_isa:off_isa + id_bytes * blk]
+    off_ids = off_ids64 if is_wide else off_va
+    yield ("barrier",)                                          # nobody still reads the workspace of an earlier build
+    tick("workspace")
+    # ---- 4. pack + partition + exchange in one kernel
+    d_counters = torch.empty(_lib.DSA_MAX_RANKS, dtype=torch.int64, device=dev)
+    h_cuts = (C.c_uint32 * (world + 1))(*[int(c) for c in cuts])
+    base = [int(cnt[:rank, d].sum()) for d in range(world)]
+    check(L.hkcsa_dsa_pack_exchange(_ptr(text), C.byref(plan), begin, end, world, h_cuts,
+                                    _u64arr([p + off_keys for p in ptrs]), _u64arr([p + off_ids for p in ptrs]),
+                                    _u64arr(base), _ptr(d_counters), _stream()))
+    yield ("barrier",)                                          # every pair has landed
+    tick("pack_exchange")
+    # ---- 5. local sort + refinement
+    state = C.create_string_buffer(L.hkcsa_dsa_state_bytes())
+    nscratch = L.hkcsa_dsa_scratch_bytes(cap)
+    scratch = _scratch(nscratch, dev)
+    check(L.hkcsa_dsa_begin(state, C.byref(plan), _ptr(text), _ptr(keys), _ptr(ids64) if is_wide else _ptr(val_a),
+                            _ptr(val_a), _ptr(val_b), M, cap, _ptr(scratch), nscratch, _stream()))
+    tick("sort_round0")
+    slice_ptr = L.hkcsa_dsa_slice(state) or (val_a.data_ptr())
+    off_slice = off_va if slice_ptr == val_a.data_ptr() else off_vb
+    ext_done, dbl_done, prev_all = 0, 0, None
+    isa_ready = False
+    peer_isa = _u64arr([p + off_isa for p in ptrs])
+    peer_sa = _u64arr([p + off_slice for p in ptrs])
+    peer_ids64 = _u64arr([p + off_ids64 for p in ptrs]) if is_wide else None
+    h_slice_off = _u64arr(slice_off)
+    while True:
+        m_all = int((yield ("gather", np.array([L.hkcsa_dsa_working_set(state)], dtype=np.int64))).sum())
+        if m_all == 0:
+            break
+        stalled = prev_all is not None and ext_done >= 2 and 2 * m_all > prev_all
+        prev_all = m_all
+        if not isa_ready and ext_done < ext_rounds_max and not stalled:
+            check(L.hkcsa_dsa_ext_round(state, _stream()))
+            ext_done += 1
+            tick("extension_rounds")
+            continue
+        if not isa_ready:                                       # switch to rank doubling: enter the working set
+            isa.fill_(0xFF)
+            yield ("barrier",)
+            check(L.hkcsa_dsa_isa_publish(state, world, peer_isa, blk, int(slice_off[rank]), 0, _stream()))
+            yield ("barrier",)
+            isa_ready = True
+        check(L.hkcsa_dsa_dbl_keys(state, world, peer_isa, blk, peer_sa, peer_ids64, h_slice_off, h_cuts, _stream()))
+        yield ("barrier",)                                      # every rank has read the ranks of this generation
+        check(L.hkcsa_dsa_dbl_sort(state, _stream()))
+        check(L.hkcsa_dsa_isa_publish(state, world, peer_isa, blk, int(slice_off[rank]), 1, _stream()))
+        yield ("barrier",)
+        dbl_done += 1
+        tick("doubling_rounds")
+    # ---- 6. the slice leaves the workspace; BWT of the slice
+    if is_wide:
+        sa = _empty(M, torch.int64, dev)
+        check(L.hkcsa_dsa_gather_ids64(state, _ptr(sa), _stream()))
+    else:
+        sa = (val_a if off_slice == off_va else val_b)[:M].clone()
+    sent = int(d_counters.cpu().numpy()[:world].sum())
+    if sent != end - begin:
+        raise RuntimeError(f"exchange sent {sent} pairs for a block of {end - begin} positions")
+    bw = bwt_slice(text, sa)
+    yield ("barrier",)                                          # peers may have been searching this rank's slice
+    tick("slice_and_bwt")
+    nr = C.c_uint32(0)
+    elems = (C.c_uint64 * 48)()
+    check(L.hkcsa_dsa_rounds(state, C.byref(nr), elems, 48))
+    received = (n - (end - begin)) + (M - int(cnt[rank, rank])) * (8 + id_bytes)
+    return SuffixArraySlice(rank, world, n, int(slice_off[rank]), sa, bw, text, (int(cuts[rank]), int(cuts[rank + 1])),
+                            [int(elems[r]) for r in range(min(int(nr.value), 48))], ext_done, dbl_done, phases, received)
+
+
+# ------------------------------------------------------------------ running the program: torch.distributed
+_WORKSPACES: dict = {}
+
+
+class _SymmWorkspace:
+    """One symmetric-memory allocation per process group, grown on demand and reused by later builds (allocating
+    and mapping gigabytes of peer memory costs far more than the build itself)."""
+
+    def __init__(self, nbytes: int, device, group):
+        import torch.distributed._symmetric_memory as symm
+        self.nbytes = int(nbytes)
+        self.buf = symm.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+
+def _torch_run(prog, group, device):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    dev = local_block.device
-    # 1. replicate the text
-    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-    sizes[rank] = local_block.numel()
-    dist.all_reduce(sizes, group=group)
-    sizes = sizes.cpu().tolist()
-    n = int(sum(sizes))
-    if n > (1 << 40):
-        raise _lib.HkcsaError(_lib.ERANGE, f"text of {n} symbols exceeds 2^40")
-    text = torch.empty(n, dtype=torch.uint8, device=dev)
-    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    text[starts[rank]:starts[rank + 1]] = local_block
-    for r in range(world):                                   # all-gather of unequal blocks
-        if sizes[r]:
-            dist.broadcast(text[starts[r]:starts[r + 1]], src=dist.get_global_rank(group, r) if group else r, group=group)
-    # 2. global byte histogram and key-bucket histogram
-    bh = torch.from_numpy(byte_hist(local_block).astype(np.int64)).to(dev)
-    dist.all_reduce(bh, group=group)
-    bh_np = bh.cpu().numpy().astype(np.uint64)
-    kh = key_bucket_hist(text, int(starts[rank]), int(starts[rank + 1]), bh_np)
-    dist.all_reduce(kh, group=group)
-    kh_np = kh.cpu().numpy()
-    ranges = balanced_bucket_ranges(kh_np, world)
-    counts = [int(kh_np[a:b].sum()) for a, b in ranges]
-    # 3. this rank's slice
-    lo, hi = ranges[rank]
-    st = SaStats()
-    sa = build_slice(text, bh_np, lo, hi, counts[rank], st, wide=wide)
-    assert sa.numel() == counts[rank]
-    # 4. BWT of the slice
-    return SuffixArraySlice(rank, world, n, int(sum(counts[:rank])), sa, bwt_slice(text, sa), text, (lo, hi), st)
+    ws = None
+    try:
+        req = next(prog)
+        while True:
+            kind = req[0]
+            if kind == "gather":
+                x = req[1]
+                t = x.to(torch.int64) if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(device)
+                out = torch.empty((world, t.numel()), dtype=torch.int64, device=device)
+                dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+                res = out.cpu().numpy()
+            elif kind == "text":
+                block, sizes = req[1], [int(v) for v in req[2]]
+                if len(set(sizes)) == 1:                        # equal blocks: the gathered buffer IS the text
+                    res = torch.empty(sum(sizes), dtype=torch.uint8, device=device)
+                    dist.all_gather_into_tensor(res, block.contiguous(), group=group)
+                else:                                           # one collective on padded blocks, then compaction
+                    width = max(sizes)
+                    pad = torch.zeros(width, dtype=torch.uint8, device=device)
+                    pad[: block.numel()] = block
+                    allb = torch.empty((world, width), dtype=torch.uint8, device=device)
+                    dist.all_gather_into_tensor(allb, pad, group=group)
+                    res = torch.cat([allb[r, : sizes[r]] for r in range(world)])
+            elif kind == "symm":
+                need = torch.tensor([int(req[1])], dtype=torch.int64, device=device)
+                dist.all_reduce(need, op=dist.ReduceOp.MAX, group=group)
+                need = int(need.item())
+                key = (id(group) if group is not None else 0, torch.device(device).index)
+                ws = _WORKSPACES.get(key)
+                if ws is None or ws.nbytes < need:
+                    _WORKSPACES.pop(key, None)
+                    ws = _SymmWorkspace(need + need // 8, device, group if group is not None else dist.group.WORLD)
+                    _WORKSPACES[key] = ws
+                res = (ws.buf, ws.ptrs)
+            elif kind == "barrier":
+                if ws is not None:
+                    ws.hdl.barrier()                            # device-side, on the current stream
+                else:
+                    dist.barrier(group=group)
+                res = None
+            else:
+                raise ValueError(kind)
+            req = prog.send(res)
+    except StopIteration as done:
+        return done.value
+
+
+def distributed_suffix_array(local_block: torch.Tensor, group=None, wide: bool | None = None, profile: bool = False,
+                             ext_rounds_max: int = EXT_ROUNDS_MAX) -> SuffixArraySlice:
+    """local_block: this rank's contiguous part of the text (uint8, on this rank's GPU), blocks in rank order.
+    Collective: every rank of `group` calls it.  profile=True synchronises at phase boundaries and fills
+    SuffixArraySlice.phases."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world > _lib.DSA_MAX_RANKS:
+        raise ValueError(f"at most {_lib.DSA_MAX_RANKS} ranks")
+    prog = _rank_program(dist.get_rank(group), world, local_block, wide, profile, ext_rounds_max)
+    return _torch_run(prog, group, local_block.device)
+
+
+def release_workspaces() -> None:
+    _WORKSPACES.clear()
+
+
+# ------------------------------------------------------------------ running the program: ranks emulated on one GPU
+def emulate_distributed_suffix_array(blocks, wide: bool | None = None, ext_rounds_max: int = EXT_ROUNDS_MAX,
+                                     profile: bool = False):
+    """The same per-rank programs, advanced in lockstep inside one process: `blocks` are the ranks' text blocks on
+    ONE GPU, peers' buffers are plain device buffers of the same process.  Returns the slices in rank order."""
+    world = len(blocks)
+    if not 1 <= world <= _lib.DSA_MAX_RANKS:
+        raise ValueError(f"1..{_lib.DSA_MAX_RANKS} ranks")
+    dev = blocks[0].device
+    progs = [_rank_program(r, world, blocks[r], wide, profile, ext_rounds_max) for r in range(world)]
+    reqs = [next(p) for p in progs]
+    results = [None] * world
+    live = list(range(world))
+    while live:
+        kind = reqs[live[0]][0]
+        assert all(reqs[r][0] == kind for r in live), "rank programs diverged"
+        if kind == "gather":
+            rows = [reqs[r][1].cpu().numpy() if isinstance(reqs[r][1], torch.Tensor) else np.asarray(reqs[r][1])
+                    for r in live]
+            res = [np.stack(rows).astype(np.int64)] * world
+        elif kind == "text":
+            full = torch.cat([reqs[r][1] for r in live])
+            res = [full] * world
+        elif kind == "symm":
+            need = max(int(reqs[r][1]) for r in live)
+            bufs = [torch.empty(need, dtype=torch.uint8, device=dev) for _ in live]
+            ptrs = [b.data_ptr() for b in bufs]
+            res = [(bufs[r], ptrs) for r in range(world)]
+        elif kind == "barrier":
+            res = [None] * world                                # one stream: program order is the barrier
+        else:
+            raise ValueError(kind)
+        nxt = []
+        for r in live:
+            try:
+                reqs[r] = progs[r].send(res[r])
+                nxt.append(r)
+            except StopIteration as done:
+                results[r] = done.value
+        assert not nxt or len(nxt) == len(live), "rank programs must finish together"
+        live = nxt
+    return results
 
 
 # ------------------------------------------------------------------ queries over a sliced index
@@ -242,40 +452,42 @@ def _sampled_sa_slice(sa_slice: torch.Tensor, rate: int):
 
 
 def replicate_sliced_index(sl: SuffixArraySlice, sa_sample_rate: int = 32, group=None) -> MultiSliceIndex:
-    """After distributed_suffix_array: every rank builds the wavelet tree and sampled SA of ITS slice, the blobs are
-    exchanged (one broadcast per slice: sizes differ), and every rank assembles the same MultiSliceIndex."""
+    """After distributed_suffix_array: every rank builds the wavelet tree and sampled SA of ITS slice; the plan
+    structs travel in one all-gather, the blobs (padded to the largest) in one all-gather each, and every rank
+    assembles the same MultiSliceIndex over views of the gathered buffers."""
     import torch.distributed as dist
     from .engine import DeviceWaveletTree
     world, rank, dev = sl.world, sl.rank, sl.sa.device
     wt = DeviceWaveletTree(sl.bwt)
     ssa = _sampled_sa_slice(sl.sa, sa_sample_rate) if sa_sample_rate > 0 else None
-    meta = torch.zeros(world, 3, dtype=torch.int64, device=dev)
-    meta[rank, 0] = sl.sa.numel()
-    meta[rank, 1] = wt.blob.numel()
-    meta[rank, 2] = ssa.blob.numel() if ssa is not None else 0
-    dist.all_reduce(meta, group=group)
-    meta = meta.cpu().tolist()
+    wsz, ssz = C.sizeof(_lib.WtPlan), C.sizeof(_lib.SsaPlan)
+    head = torch.zeros(24 + wsz + ssz, dtype=torch.uint8)
+    head[:24] = torch.from_numpy(np.array([sl.sa.numel(), wt.blob.numel(), ssa.blob.numel() if ssa is not None else 0],
+                                          dtype=np.int64).view(np.uint8))
+    head[24:24 + wsz] = torch.frombuffer(bytearray(bytes(wt.plan)), dtype=torch.uint8)
+    if ssa is not None:
+        head[24 + wsz:] = torch.frombuffer(bytearray(bytes(ssa.plan)), dtype=torch.uint8)
+    heads = torch.empty((world, head.numel()), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(heads, head.to(dev), group=group)
+    heads = heads.cpu().numpy()
+    meta = [heads[r, :24].view(np.int64).tolist() for r in range(world)]
     starts = [0]
     for r in range(world):
         starts.append(starts[-1] + meta[r][0])
 
-    def bcast_bytes(buf_or_none, nbytes, src):
-        t = buf_or_none if rank == src else torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        dist.broadcast(t, src=dist.get_global_rank(group, src) if group else src, group=group)
-        return t
+    def gather_blobs(mine, sizes):
+        width = (max(sizes) + 255) // 256 * 256              # rows stay 32-byte aligned (rank blocks)
+        pad = torch.zeros(width, dtype=torch.uint8, device=dev)
+        if mine is not None:
+            pad[: mine.numel()] = mine
+        allb = torch.empty((world, width), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, pad, group=group)
+        return [allb[r, : sizes[r]] for r in range(world)]
 
-    def struct_bytes(obj):
-        return torch.frombuffer(bytearray(bytes(obj)), dtype=torch.uint8).to(dev)
-
-    wt_parts, ssa_parts = [], []
-    for r in range(world):
-        pbytes = bcast_bytes(struct_bytes(wt.plan) if rank == r else None, C.sizeof(_lib.WtPlan), r)
-        plan = _lib.WtPlan.from_buffer_copy(pbytes.cpu().numpy().tobytes())
-        blob = bcast_bytes(wt.blob if rank == r else None, meta[r][1], r)
-        wt_parts.append((plan, blob))
-        if sa_sample_rate > 0:
-            sbytes = bcast_bytes(struct_bytes(ssa.plan) if rank == r else None, C.sizeof(_lib.SsaPlan), r)
-            splan = _lib.SsaPlan.from_buffer_copy(sbytes.cpu().numpy().tobytes())
-            sblob = bcast_bytes(ssa.blob if rank == r else None, meta[r][2], r)
-            ssa_parts.append((splan, sblob))
+    wt_blobs = gather_blobs(wt.blob, [m[1] for m in meta])
+    wt_parts = [(_lib.WtPlan.from_buffer_copy(heads[r, 24:24 + wsz].tobytes()), wt_blobs[r]) for r in range(world)]
+    ssa_parts = []
+    if sa_sample_rate > 0:
+        ssa_blobs = gather_blobs(ssa.blob, [m[2] for m in meta])
+        ssa_parts = [(_lib.SsaPlan.from_buffer_copy(heads[r, 24 + wsz:].tobytes()), ssa_blobs[r]) for r in range(world)]
     return MultiSliceIndex.from_parts(sl.n, starts, wt_parts, ssa_parts, sa_sample_rate)

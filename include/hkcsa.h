@@ -47,7 +47,8 @@ extern "C" {
 int         hkcsa_abi_version(void);
 const char *hkcsa_last_error(void);
 /* sizeof of the public structs (0 hkcsa_sa_stats, 1 hkcsa_wt_plan, 2 hkcsa_ssa_plan, */
-/* 3 hkcsa_prof_entry, 4 hkcsa_occ_plan) so a binding can verify its mirror.          */
+/* 3 hkcsa_prof_entry, 4 hkcsa_occ_plan, 5 hkcsa_dsa_plan) so a binding can verify   */
+/* its mirror.                                                                         */
 size_t      hkcsa_struct_size(int which);
 
 /* ------------------------------------------------------------------------ */
@@ -95,33 +96,77 @@ size_t hkcsa_sort_scratch_bytes(uint64_t n);
 int hkcsa_sort_pairs_u64(uint64_t *d_keys, uint32_t *d_vals, uint64_t *d_keys_alt, uint32_t *d_vals_alt,
                          uint64_t n, int key_bits, void *d_scratch, size_t scratch_bytes, void *stream);
 
-/* Distributed build (BASELINE config 5: a text beyond one GPU's working set; no   */
-/* reference counterpart -- the reference is single-process).  Every GPU holds the  */
-/* whole text (NCCL all-gather) and sorts the suffixes whose round-0 key falls into  */
-/* its range [bucket_lo, bucket_hi) of the 65536 buckets given by the top 16 key     */
-/* bits; the slices concatenated in rank order are the suffix array.  Groups are     */
-/* refined by extension rounds reading the text (no ranks of remote suffixes).       */
-/* Suffix ids are uint32: n <= 2^32-2; a slice holds at most HKCSA_MAX_N suffixes.   */
-/* h_byte_hist: byte histogram of the WHOLE text (uint64[256], host).                */
-#define HKCSA_DIST_BUCKETS 65536u
-int hkcsa_sa_key_hist(const uint8_t *d_text, uint64_t n, uint64_t begin, uint64_t end,
-                      const uint64_t *h_byte_hist, uint64_t *d_hist /* [HKCSA_DIST_BUCKETS] */, void *stream);
-size_t hkcsa_sa_subset_scratch_bytes(uint64_t capacity);
-/* syncs.  d_sa_out: uint32[capacity]; *h_count receives the slice length.           */
-int hkcsa_sa_build_subset(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist,
-                          uint32_t bucket_lo, uint32_t bucket_hi, uint32_t *d_sa_out, uint64_t capacity,
-                          uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
-                          hkcsa_sa_stats *h_stats);
+/* Distributed build (BASELINE config 5: a text beyond one GPU's working set; no reference counterpart -- the   */
+/* reference is single-process, but its build_suffix_array, csa/suffix_array.py:131-134, sorts ANY text and so   */
+/* does this).  One process per GPU, up to HKCSA_DSA_MAX_RANKS ranks.  The text is replicated (one all-gather);  */
+/* rank r keys the suffixes of ITS block of positions, and the kernel that packs the keys stores every (key, id) */
+/* straight into the receive arrays of the rank owning the key's bucket through peer-mapped pointers (the        */
+/* all-to-all bucket exchange is part of the pack kernel).  Each rank sorts what it received and refines its      */
+/* groups: extension rounds read the next symbols from the replicated text; whatever survives them (repetitive    */
+/* texts) is finished by rank doubling over the ranks' peer-mapped ISA blocks.  The slices concatenated in rank   */
+/* order are the suffix array.  Suffix ids are uint32 up to n = 2^32-2 and uint64 beyond (n <= 2^40); a slice     */
+/* holds at most HKCSA_MAX_N suffixes.  "peer" arrays: h_peer_x[r] is the device address, as mapped into THIS      */
+/* process, of rank r's buffer x (torch symmetric memory / cudaIpc; plain local buffers when ranks are emulated).  */
+#define HKCSA_DSA_BUCKETS 65536u
+#define HKCSA_DSA_MAX_RANKS 8
+#define HKCSA_DSA_MAX_N32 ((uint64_t)0xFFFFFFFEull)
+
+typedef struct hkcsa_dsa_plan {   /* derived from the byte histogram of the WHOLE text: identical on every rank */
+    uint64_t n;
+    uint32_t sigma;
+    uint32_t bits0;               /* width of a round-0 key (multiple of 8)                                     */
+    uint32_t k0;                  /* symbols every round-0 key is guaranteed to cover                            */
+    uint32_t passes0;             /* radix passes of the round-0 sort                                            */
+    uint32_t b_fixed;             /* bits of a fixed-width symbol code (extension rounds)                        */
+    uint32_t wide;                /* 1: suffix ids are uint64                                                    */
+    uint32_t code[257];           /* the order-preserving prefix code of round 0 ([256] = past the end)          */
+    uint8_t  len[257];
+    uint16_t fixed_code[256];     /* dense code + 1 per byte, 0 = byte does not occur                            */
+} hkcsa_dsa_plan;
+typedef struct hkcsa_dsa_state { uint64_t opaque[512]; } hkcsa_dsa_state;   /* host-side, owned by the caller   */
+
+int hkcsa_dsa_plan_make(const uint64_t *h_byte_hist, uint64_t n, int force_wide, hkcsa_dsa_plan *h_plan);
+/* d_hist[HKCSA_DSA_BUCKETS] (overwritten): suffixes of [begin, end) per bucket = top 16 bits of the round-0 key  */
+int hkcsa_dsa_bucket_hist(const uint8_t *d_text, const hkcsa_dsa_plan *h_plan, uint64_t begin, uint64_t end,
+                          uint64_t *d_hist, void *stream);
+/* Pack + partition + exchange of the suffixes of [begin, end): rank r owns buckets [h_cuts[r], h_cuts[r+1]);     */
+/* (key, id) pairs go to h_peer_keys[r] (uint64) / h_peer_ids[r] (uint32, or uint64 when plan->wide) from slot     */
+/* h_base[r] on (this source's region; the caller sizes the regions from the all-gathered bucket histograms).      */
+/* d_counters: uint64[HKCSA_DSA_MAX_RANKS], zeroed here, receives the pairs sent per destination.                  */
+int hkcsa_dsa_pack_exchange(const uint8_t *d_text, const hkcsa_dsa_plan *h_plan, uint64_t begin, uint64_t end,
+                            uint32_t world, const uint32_t *h_cuts, const uint64_t *h_peer_keys,
+                            const uint64_t *h_peer_ids, const uint64_t *h_base, uint64_t *d_counters, void *stream);
+/* Sort + refine the M received pairs.  d_keys: the received keys.  Narrow ids: d_ids == d_val_a = the received    */
+/* uint32 ids; wide: d_ids = the received uint64 ids (kept intact), d_val_a a uint32[capacity] buffer.  d_val_b:    */
+/* uint32[capacity].  The sorted slice (ids, or ordinals into d_ids when wide) ends up in d_val_a or d_val_b:      */
+/* hkcsa_dsa_slice() tells which.  `capacity` must be the same on every rank.  Every call below syncs.             */
+size_t hkcsa_dsa_state_bytes(void);
+size_t hkcsa_dsa_scratch_bytes(uint64_t capacity);
+int hkcsa_dsa_begin(hkcsa_dsa_state *state, const hkcsa_dsa_plan *h_plan, const uint8_t *d_text, uint64_t *d_keys,
+                    void *d_ids, uint32_t *d_val_a, uint32_t *d_val_b, uint64_t M, uint64_t capacity,
+                    void *d_scratch, size_t scratch_bytes, void *stream);
+uint64_t hkcsa_dsa_working_set(const hkcsa_dsa_state *state);   /* suffixes in groups that are not singletons yet  */
+uint64_t hkcsa_dsa_depth(const hkcsa_dsa_state *state);         /* symbols every group is known to share           */
+const void *hkcsa_dsa_slice(const hkcsa_dsa_state *state);
+int hkcsa_dsa_rounds(const hkcsa_dsa_state *state, uint32_t *h_rounds, uint64_t *h_round_elems, uint32_t max_rounds);
+/* one extension round (local): the same number of symbols on every rank */
+int hkcsa_dsa_ext_round(hkcsa_dsa_state *state, void *stream);
+/* Rank doubling.  ISA blocks: rank r holds the global ranks of positions [r*blk, (r+1)*blk) as uint32 (uint64 when */
+/* wide), all-ones = no entry; the caller fills them with 0xFF before the first publish.  A round is                */
+/*   hkcsa_dsa_dbl_keys (reads peers) | ranks synchronise | hkcsa_dsa_dbl_sort (local) + hkcsa_dsa_isa_publish      */
+/*   (writes peers, with_singles = 1) | ranks synchronise.                                                         */
+/* The first publish (with_singles = 0) enters the working set as it stands after the extension rounds.            */
+int hkcsa_dsa_isa_publish(hkcsa_dsa_state *state, uint32_t world, const uint64_t *h_peer_isa, uint64_t blk,
+                          uint64_t slice_offset, int with_singles, void *stream);
+int hkcsa_dsa_dbl_keys(hkcsa_dsa_state *state, uint32_t world, const uint64_t *h_peer_isa, uint64_t blk,
+                       const uint64_t *h_peer_sa, const uint64_t *h_peer_ids64, const uint64_t *h_slice_off,
+                       const uint32_t *h_cuts, void *stream);
+int hkcsa_dsa_dbl_sort(hkcsa_dsa_state *state, void *stream);
+/* wide ids: d_out[j] = id of the j-th suffix of the finished slice (uint64[M]) */
+int hkcsa_dsa_gather_ids64(const hkcsa_dsa_state *state, uint64_t *d_out, void *stream);
 /* bwt[j] = text[SA[j]-1] (text[n-1] when SA[j] == 0) for a slice of the suffix array */
 int hkcsa_bwt_slice(const uint8_t *d_text, uint64_t n, const uint32_t *d_sa_slice, uint64_t m,
                     uint8_t *d_out, void *stream);
-/* The same with 64-bit suffix ids, for texts beyond 4 GB (n <= 2^40; BASELINE config 5 is 8 GB): the sort    */
-/* moves 32-bit ordinals, the ids are gathered at the end.  d_sa_out64: uint64[capacity].                     */
-size_t hkcsa_sa_subset64_scratch_bytes(uint64_t capacity);
-int hkcsa_sa_build_subset64(const uint8_t *d_text, uint64_t n, const uint64_t *h_byte_hist,
-                            uint32_t bucket_lo, uint32_t bucket_hi, uint64_t *d_sa_out64, uint64_t capacity,
-                            uint64_t *h_count, void *d_scratch, size_t scratch_bytes, void *stream,
-                            hkcsa_sa_stats *h_stats);
 int hkcsa_bwt_slice64(const uint8_t *d_text, uint64_t n, const uint64_t *d_sa_slice, uint64_t m,
                       uint8_t *d_out, void *stream);
 

@@ -86,3 +86,23 @@ def test_balanced_bucket_ranges():
     one = np.zeros(16, dtype=np.int64); one[7] = 100                       # one giant bucket cannot be split
     r = balanced_bucket_ranges(one, 4)
     assert sum(int(one[a:b].sum()) for a, b in r) == 100
+
+
+def test_exchange_layout_regions_tile_every_destination():
+    """Host logic of the distributed build's bucket exchange: the (source, destination) count matrix derived from the
+    all-gathered bucket histograms gives every source a private region in every destination's receive array."""
+    from hkcsa.dist_sa import exchange_layout
+    rng = np.random.RandomState(3)
+    for world in (1, 2, 3, 8):
+        hist_all = rng.randint(0, 50, size=(world, 4096)).astype(np.int64)
+        hist_all[:, 100] += 5000                       # one heavy bucket
+        cuts, cnt, counts, slice_off = exchange_layout(hist_all, world)
+        assert cuts[0] == 0 and cuts[-1] == 4096 and np.all(np.diff(cuts) >= 0)
+        assert cnt.shape == (world, world) and cnt.sum() == hist_all.sum()
+        assert np.array_equal(counts, cnt.sum(0)) and slice_off[-1] == hist_all.sum()
+        for d in range(world):
+            base = [int(cnt[:s_, d].sum()) for s_ in range(world)]
+            ends = [base[s_] + int(cnt[s_, d]) for s_ in range(world)]
+            assert base[0] == 0 and ends[-1] == counts[d] and all(ends[i] == base[i + 1] for i in range(world - 1))
+        # balance: no destination exceeds the ideal share by more than the heaviest bucket
+        assert counts.max() <= hist_all.sum() / world + hist_all.sum(0).max()

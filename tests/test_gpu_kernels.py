@@ -338,44 +338,80 @@ def test_empty_and_tiny(E):
 
 
 # ------------------------------------------------------------------ distributed build, ranks emulated on one GPU
+def _emulated_build(E, text, parts, wide, ext_rounds_max=None):
+    from hkcsa import dist_sa
+    n = len(text)
+    d_text = dev(E, text)
+    bounds = [n * r // parts for r in range(parts + 1)]
+    blocks = [d_text[bounds[r]:bounds[r + 1]].clone() for r in range(parts)]
+    kw = {} if ext_rounds_max is None else {"ext_rounds_max": ext_rounds_max}
+    return dist_sa.emulate_distributed_suffix_array(blocks, wide=wide, **kw)
+
+
+def _check_slices(slices, text, wide):
+    import torch
+    want_sa = O.build_suffix_array(text)
+    want_bwt = O.bwt_transform(text, want_sa)
+    got_sa = np.concatenate([host(sl.sa_int64()) for sl in slices]).astype(np.uint32)
+    got_bwt = np.concatenate([host(sl.bwt) for sl in slices])
+    off = 0
+    for sl in slices:
+        assert sl.offset == off and sl.sa.dtype == (torch.int64 if wide else torch.int32)
+        off += sl.sa.numel()
+    assert off == len(text)
+    assert np.array_equal(got_sa, want_sa)
+    assert got_bwt.tobytes() == want_bwt.tobytes()
+
+
 @pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "runs", "rand256_50k", "dna_1m_dollar", "rand2_100k"])
 @pytest.mark.parametrize("parts", [1, 2, 3, 8])
 def test_distributed_slices_concatenate_to_the_suffix_array(E, name, parts):
-    """hkcsa.dist_sa: every 'rank' sorts the suffixes of its key-bucket range with the whole text resident;
-    the slices in rank order must be the oracle's suffix array and BWT (the collectives are exercised by
-    tools/dist_sa_check.py under torchrun)."""
-    import torch
-    from hkcsa import dist_sa
+    """hkcsa.dist_sa with the ranks emulated on one GPU (the per-rank program, the fused pack + exchange kernel,
+    the sort and the refinement are the ones torchrun executes; peers' buffers are local buffers): the slices in
+    rank order must be the oracle's suffix array and BWT.  32-bit ids, and the 64-bit path texts beyond 4 GB take."""
     text = TEXTS[name]
-    n = len(text)
+    for wide in (False, True):
+        _check_slices(_emulated_build(E, text, parts, wide), text, wide)
+
+
+@pytest.mark.parametrize("name", ["all_a_5000", "ab_period", "abc_period_tail", "fib", "repeat_block", "runs"])
+@pytest.mark.parametrize("parts", [1, 2, 5, 8])
+def test_distributed_build_sorts_repetitive_texts(E, name, parts):
+    """LCPs in the thousands: the extension rounds give up and rank doubling over the (emulated) peers' ISA blocks
+    finishes -- no text is refused."""
+    text = TEXTS[name]
+    for wide in (False, True):
+        slices = _emulated_build(E, text, parts, wide)
+        _check_slices(slices, text, wide)
+        assert max(sl.dbl_rounds for sl in slices) >= 1
+
+
+def test_distributed_build_reference_benchmark_workload(E):
+    """"mississippi$" * 1000 is the default workload of the reference's own benchmark (tests/benchmark.py:110);
+    here 20 000 copies over 4 ranks."""
+    text = b"mississippi$" * 20_000
+    _check_slices(_emulated_build(E, text, 4, False), text, False)
+
+
+@pytest.mark.parametrize("ext", [0, 1, 3])
+def test_distributed_doubling_from_any_depth(E, ext):
+    """Rank doubling may take over after any number of extension rounds (0: straight after round 0): suffixes that
+    were unique by then have no ISA entry and are ranked by the search in their owner's slice."""
+    for name in ("eng_300k", "dna_300k", "repeat_block"):
+        text = TEXTS[name]
+        _check_slices(_emulated_build(E, text, 3, False, ext_rounds_max=ext), text, False)
+    _check_slices(_emulated_build(E, TEXTS["dna_300k"], 4, True, ext_rounds_max=ext), TEXTS["dna_300k"], True)
+
+
+def test_distributed_build_ragged_blocks_and_empty_ranks(E):
+    from hkcsa import dist_sa
+    text = TEXTS["eng_300k"][:100_003]
     d_text = dev(E, text)
-    bh = E.byte_hist(d_text)
-    bounds = [n * r // parts for r in range(parts + 1)]
-    kh = sum(dist_sa.key_bucket_hist(d_text, bounds[r], bounds[r + 1], bh) for r in range(parts))
-    kh = host(kh)
-    assert int(kh.sum()) == n
-    ranges = dist_sa.balanced_bucket_ranges(kh, parts)
-    want_sa = O.build_suffix_array(text)
-    want_bwt = O.bwt_transform(text, want_sa)
-    for wide in (False, True):                     # 32-bit ids, and the 64-bit path texts beyond 4 GB take
-        got_sa, got_bwt = [], []
-        for lo, hi in ranges:
-            cap = int(kh[lo:hi].sum())
-            sl = dist_sa.build_slice(d_text, bh, lo, hi, cap, wide=wide)
-            assert sl.numel() == cap and sl.dtype == (torch.int64 if wide else torch.int32)
-            got_sa.append(host(sl).astype(np.uint32))
-            got_bwt.append(host(dist_sa.bwt_slice(d_text, sl)))
-        assert np.array_equal(np.concatenate(got_sa), want_sa)
-        assert np.concatenate(got_bwt).tobytes() == want_bwt.tobytes()
-
-
-def test_distributed_slice_rejects_hugely_repetitive_text(E):
-    from hkcsa import dist_sa, _lib
-    for name in ("all_a_5000", "repeat_block", "fib"):             # LCP in the thousands: beyond 40 extension rounds
-        d_text = dev(E, TEXTS[name])
-        bh = E.byte_hist(d_text)
-        with pytest.raises(_lib.HkcsaError, match="repetitive"):
-            dist_sa.build_slice(d_text, bh, 0, 65536, len(TEXTS[name]))
+    cuts = [0, 1, 1, 70_001, 100_003]                      # a 1-symbol block, an empty block, unaligned starts
+    blocks = [d_text[cuts[r]:cuts[r + 1]].clone() for r in range(4)]
+    _check_slices(dist_sa.emulate_distributed_suffix_array(blocks), text, False)
+    tiny = b"banana"
+    _check_slices(_emulated_build(E, tiny, 8, False), tiny, False)      # more ranks than distinct buckets
 
 
 @pytest.mark.parametrize("n", [50_000, 50_001, 50_002, 50_003, 131_073])

@@ -15,16 +15,28 @@ ap.add_argument("--verify", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--patterns", type=int, default=1_000_000)
 ap.add_argument("--wide", action="store_true", help="force 64-bit suffix ids (automatic beyond 2^32-2 symbols)")
+ap.add_argument("--sa-only", action="store_true", help="stop after the suffix array / BWT check")
+ap.add_argument("--profile", action="store_true", help="synchronise at phase boundaries and report seconds per phase")
 ap.add_argument("--props", action="store_true", help="size-independent checks (no single-GPU reference: n may exceed 2^30)")
 args = ap.parse_args()
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG", "WARN")
 dist.init_process_group("nccl", device_id=dev)
 n = args.size
-full = E.gen_text(args.kind, 42 + args.kind, n)                 # same bytes on every rank; keep only my block
-full[n - 1] = 0x24                                              # unique sentinel (the generators never emit '$'): LF walks need it
+if args.kind == 2:                                              # the reference benchmark's workload (tests/benchmark.py:110), scaled
+    reps_ = n // 12
+    n = reps_ * 12
+    full = torch.from_numpy(np.frombuffer(b"mississippi$" * reps_, dtype=np.uint8).copy()).to(dev)
+    args.sa_only = True                                         # '$' is not unique here: no LF walks on this text
+elif args.kind == 3:                                            # a 1 MB English-like block repeated: LCPs of megabytes
+    unit = E.gen_text(0, 7, 1 << 20)
+    full = unit.repeat(-(-n // (1 << 20)))[:n].contiguous()
+    full[n - 1] = 0x24
+else:
+    full = E.gen_text(args.kind, 42 + args.kind, n)             # same bytes on every rank; keep only my block
+    full[n - 1] = 0x24                                          # unique sentinel (the generators never emit '$'): LF walks need it
 lo, hi = n * rank // world, n * (rank + 1) // world
 block = full[lo:hi].clone()
 del full
@@ -32,7 +44,7 @@ torch.cuda.synchronize(); dist.barrier()
 best = None
 for _ in range(args.reps):
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-    sl = dist_sa.distributed_suffix_array(block, wide=True if args.wide else None)
+    sl = dist_sa.distributed_suffix_array(block, wide=True if args.wide else None, profile=args.profile)
     torch.cuda.synchronize(); dist.barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -51,6 +63,15 @@ if args.verify:
         bw = torch.cat([gb[r][: int(counts[r])] for r in range(world)])
         ref = E.suffix_array(sl.text)
         ok = bool(torch.equal(sa, ref)) and bool(torch.equal(bw, E.bwt(sl.text, ref)))
+if args.sa_only:
+    if rank == 0:
+        print(json.dumps({"check": "distributed_suffix_array", "world": world, "text_bytes": n, "kind": args.kind,
+                          "seconds": best, "MB_per_s": n / 1e6 / best, "slice_sizes": counts.cpu().tolist(),
+                          "rounds": sl.rounds, "ext_rounds": sl.ext_rounds, "dbl_rounds": sl.dbl_rounds,
+                          "phases_s_rank0": sl.phases, "nvlink_bytes_in_rank0": sl.nvlink_bytes_in,
+                          "verified_against_single_gpu": ok}), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0)
 # ---- the index the distributed build leaves behind: per-slice wavelet trees + sampled SAs, replicated on every
 #      rank, then the pattern batch is sharded (config 4 style) over the ranks
 from hkcsa import dist as hdist
@@ -112,7 +133,9 @@ if args.props:
 if rank == 0:
     print(json.dumps({"check": "distributed_suffix_array", "world": world, "text_bytes": n, "kind": args.kind,
                       "seconds": best, "MB_per_s": n / 1e6 / best, "slice_sizes": counts.cpu().tolist(),
-                      "rounds": int(sl.stats.rounds), "verified_against_single_gpu": ok,
+                      "rounds": sl.rounds, "ext_rounds": sl.ext_rounds, "dbl_rounds": sl.dbl_rounds,
+                      "phases_s_rank0": sl.phases, "nvlink_bytes_in_rank0": sl.nvlink_bytes_in,
+                      "verified_against_single_gpu": ok,
                       "sliced_index_build_and_replicate_s": t_index, "count_patterns": P,
                       "count_patterns_per_s": P / (float(cms.item()) / 1e3),
                       "queries_verified_against_single_gpu": q_ok, "property_checks": props_ok}), flush=True)
