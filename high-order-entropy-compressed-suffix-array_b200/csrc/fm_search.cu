@@ -128,6 +128,65 @@ __global__ void expand_ranges64_kernel(const int64_t *__restrict__ lo, const int
     }
 }
 
+// ---------------------------------------------------------------- results of a sharded batch to every rank
+// (lo, hi) of this rank's slice -> packed {lo: low 32 bits, count: high 32 bits} (a miss is lo = 0xFFFFFFFF, count 0)
+// stored at [base + p] of the result array of EVERY rank: 8 bytes per pattern instead of the 16 of (lo, hi) as int64.
+// A thread packs two patterns and issues one 16-byte store per destination; with a multicast address (NVSwitch)
+// ONE multimem.st reaches all ranks.
+struct PushDest {
+    uint64_t *out[HKCSA_MAX_PEERS];
+    uint64_t *mc;            // multicast address of the same array, or nullptr
+    uint32_t n;
+};
+__device__ __forceinline__ uint64_t pack_range(int64_t l, int64_t h)
+{
+    return l < 0 ? 0x00000000FFFFFFFFull : ((uint64_t)(uint32_t)l | ((uint64_t)(uint32_t)(h - l + 1) << 32));
+}
+__device__ __forceinline__ void multimem_st16(uint64_t *p, uint64_t a, uint64_t b)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p),
+                 "f"(__uint_as_float((uint32_t)a)), "f"(__uint_as_float((uint32_t)(a >> 32))),
+                 "f"(__uint_as_float((uint32_t)b)), "f"(__uint_as_float((uint32_t)(b >> 32))) : "memory");
+}
+__device__ __forceinline__ void multimem_st8(uint64_t *p, uint64_t a)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p),
+                 "f"(__uint_as_float((uint32_t)a)), "f"(__uint_as_float((uint32_t)(a >> 32))) : "memory");
+}
+__global__ void __launch_bounds__(256)
+ranges_push_kernel(const int64_t *__restrict__ lo, const int64_t *__restrict__ hi, uint64_t P, uint64_t base, PushDest pd)
+{
+    const uint64_t first_pair = base >> 1, pairs = ((base + P + 1) >> 1) - first_pair;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g0 = (first_pair + i) << 1;
+        const bool v0 = g0 >= base, v1 = g0 + 1 < base + P;
+        const uint64_t a = v0 ? pack_range(lo[g0 - base], hi[g0 - base]) : 0ull;
+        const uint64_t b = v1 ? pack_range(lo[g0 + 1 - base], hi[g0 + 1 - base]) : 0ull;
+        if (pd.mc) {
+            if (v0 && v1) multimem_st16(pd.mc + g0, a, b);
+            else if (v0) multimem_st8(pd.mc + g0, a);
+            else multimem_st8(pd.mc + g0 + 1, b);
+        } else {
+            for (uint32_t r = 0; r < pd.n; ++r) {
+                if (v0 && v1) *reinterpret_cast<ulonglong2 *>(pd.out[r] + g0) = make_ulonglong2(a, b);
+                else if (v0) pd.out[r][g0] = a;
+                else pd.out[r][g0 + 1] = b;
+            }
+        }
+    }
+}
+__global__ void ranges_unpack_kernel(const uint64_t *__restrict__ packed, uint64_t P, int64_t *__restrict__ lo,
+                                     int64_t *__restrict__ hi)
+{
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = packed[p];
+        const uint32_t l = (uint32_t)v, c = (uint32_t)(v >> 32);
+        const bool miss = c == 0;
+        lo[p] = miss ? -1 : (int64_t)l;
+        hi[p] = miss ? -1 : (int64_t)l + c - 1;
+    }
+}
+
 __global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ rows, uint64_t m,
                                   uint32_t *__restrict__ out)
 {
@@ -489,4 +548,39 @@ extern "C" size_t hkcsa_symbol_positions_scratch_bytes(uint64_t n)
     c.take<uint8_t>(n + 16);
     carve_sort_scratch(c, n);
     return c.total();
+}
+
+extern "C" int hkcsa_ranges_push_peers(const int64_t *d_lo, const int64_t *d_hi, uint64_t P, uint64_t out_base,
+                                       uint32_t n_peers, const uint64_t *h_peer_out, uint64_t multicast_out, void *stream)
+{
+    if (P == 0) return HKCSA_OK;
+    HK_REQUIRE(d_lo && d_hi && (h_peer_out || multicast_out), HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(n_peers <= HKCSA_MAX_PEERS && (n_peers >= 1 || multicast_out), HKCSA_EINVAL, "n_peers must be in [1, HKCSA_MAX_PEERS]");
+    PushDest pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.n = n_peers;
+    pd.mc = reinterpret_cast<uint64_t *>(static_cast<uintptr_t>(multicast_out));
+    for (uint32_t r = 0; r < n_peers && h_peer_out; ++r) {
+        HK_REQUIRE((h_peer_out[r] & 15) == 0 && h_peer_out[r], HKCSA_EINVAL, "peer arrays must be 16-byte aligned");
+        pd.out[r] = reinterpret_cast<uint64_t *>(static_cast<uintptr_t>(h_peer_out[r]));
+    }
+    HK_REQUIRE((multicast_out & 15) == 0, HKCSA_EINVAL, "multicast array must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const uint64_t pairs = (P + 2) / 2;
+    const int blocks = (int)std::min<uint64_t>((pairs + 255) / 256, (uint64_t)num_sms() * 8);
+    // algorithmic bytes: 16 B read, 8 B stored to each of the other ranks over NVLink
+    prof::Scope ps(st, prof::OTHER, P * (16 + 8ull * std::max(1u, n_peers)));
+    ranges_push_kernel<<<blocks, 256, 0, st>>>(d_lo, d_hi, P, out_base, pd);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_ranges_unpack(const uint64_t *d_packed, uint64_t P, int64_t *d_lo, int64_t *d_hi, void *stream)
+{
+    if (P == 0) return HKCSA_OK;
+    HK_REQUIRE(d_packed && d_lo && d_hi, HKCSA_EINVAL, "null pointer");
+    const int blocks = (int)std::min<uint64_t>((P + 255) / 256, (uint64_t)num_sms() * 8);
+    ranges_unpack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_packed, P, d_lo, d_hi);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
 }

@@ -180,6 +180,8 @@ SIGNATURES = {
                                      _vp, _vp, _vp]),
     "hkcsa_count_batch_peers": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(OccPlan), _vp, _u32, _vp, _vp, _u64, _u64,
                                        _u32, C.POINTER(_u64), C.POINTER(_u64), _vp]),
+    "hkcsa_ranges_push_peers": (_i32, [_vp, _vp, _u64, _u64, _u32, C.POINTER(_u64), _u64, _vp]),
+    "hkcsa_ranges_unpack": (_i32, [_vp, _u64, _vp, _vp, _vp]),
     "hkcsa_locate_rows_occ": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(OccPlan), _vp, C.POINTER(SsaPlan), _vp,
                                      _u64, _vp, _vp]),
     "hkcsa_kmer_k": (_u32, [_u32]),

@@ -157,7 +157,8 @@ class PeerRanges:
         self.hdl = symm.rendezvous(self.buf, group)
         self.world = self.hdl.world_size
         self.rank = self.hdl.rank
-        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        base = self.buf.data_ptr() - int(self.hdl.buffer_ptrs[self.rank])     # offset of the tensor in its allocation
+        ptrs = [int(p) + base for p in self.hdl.buffer_ptrs]
         self.peer_lo = (C.c_uint64 * self.world)(*ptrs)
         self.peer_hi = (C.c_uint64 * self.world)(*[p + 8 * max(self.P, 1) for p in ptrs])
 
@@ -178,10 +179,84 @@ class PeerRanges:
 def sharded_count_fused(index, pat: torch.Tensor, off: torch.Tensor, out: PeerRanges, bounds=None,
                         use_kmer_table=None):
     """Every rank holds the full batch and searches slice `rank`; the kernel stores the answers into `out` on
-    every rank.  Returns (lo, hi) of the whole batch (views of `out`)."""
+    every rank.  Returns (lo, hi) of the whole batch (views of `out`): consume or clone them before the next call
+    with the same `out` -- the call starts with a barrier, after which peers overwrite the arrays."""
     bounds = bounds if bounds is not None else shard_bounds(off, out.world)
     b, e = bounds[out.rank]
     lp, lo_ = local_slice(pat, off, b, e)
+    out.barrier()                      # every rank is done with the previous batch's answers in `out`
     index.count_batch_peers(lp, lo_, b, out.peer_lo, out.peer_hi, use_kmer_table=use_kmer_table)
     out.barrier()
     return out.lo, out.hi
+
+
+class PeerGather:
+    """Packed answers {lo: low 32 bits, count: high 32 bits} of a GLOBAL pattern batch in torch symmetric memory.
+    Every rank searches its slice into local (lo, hi) arrays and a store kernel (hkcsa_ranges_push_peers) writes the
+    packed slice into the array of every rank -- 8 bytes per pattern over NVLink, one multimem.st per 16 bytes when
+    the switch offers a multicast mapping.  The gather is pipelined against the search in chunks."""
+
+    def __init__(self, P: int, device, group=None, use_multicast: bool | None = None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.P = int(P)
+        self.buf = symm.empty(max(self.P, 2), dtype=torch.int64, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.world = self.hdl.world_size
+        self.rank = self.hdl.rank
+        base = self.buf.data_ptr() - int(self.hdl.buffer_ptrs[self.rank])        # offset of the tensor in its allocation
+        self.peer_out = (C.c_uint64 * self.world)(*[int(p) + base for p in self.hdl.buffer_ptrs])
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.multicast = (mc + base) if (mc and use_multicast is not False) else 0
+        if use_multicast and not self.multicast:
+            raise RuntimeError("no multicast mapping for the symmetric buffer on this system")
+        self._side = torch.cuda.Stream(device=device)
+
+    @property
+    def packed(self) -> torch.Tensor:
+        return self.buf[: self.P]
+
+    def unpack(self):
+        """(lo, hi) int64 of the whole batch, the format count_batch returns."""
+        from . import _lib
+        lo = torch.empty(self.P, dtype=torch.int64, device=self.buf.device)
+        hi = torch.empty_like(lo)
+        _lib.check(_lib.load().hkcsa_ranges_unpack(self.buf.data_ptr(), self.P, lo.data_ptr(), hi.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream))
+        return lo, hi
+
+
+def chunked_slices(pat: torch.Tensor, off: torch.Tensor, begin: int, end: int, chunks: int):
+    """[begin, end) of a CSR batch cut into `chunks` consecutive sub-batches: [(pat, off, first pattern)], computed
+    once per batch layout (the cut points come to the host)."""
+    out = []
+    P = end - begin
+    for c in range(chunks):
+        b, e = begin + P * c // chunks, begin + P * (c + 1) // chunks
+        if e > b:
+            p_, o_ = local_slice(pat, off, b, e)
+            out.append((p_, o_, b))
+    return out
+
+
+def sharded_count_packed(index, slices, out: PeerGather, **count_kw) -> torch.Tensor:
+    """`slices`: this rank's part of the batch as chunked_slices() cut it.  Chunk k is searched on the current stream
+    while chunk k-1 is pushed to the peers on a side stream.  Returns the packed answers of the whole batch (a view
+    of `out`: consume before the next call with the same `out`)."""
+    from . import _lib
+    L = _lib.load()
+    main = torch.cuda.current_stream()
+    side = out._side
+    out.hdl.barrier()                  # every rank is done with the previous batch's answers in `out`
+    side.wait_stream(main)
+    for p_, o_, base in slices:
+        lo, hi = index.count_batch(p_, o_, **count_kw)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.check(L.hkcsa_ranges_push_peers(lo.data_ptr(), hi.data_ptr(), lo.numel(), int(base), out.world,
+                                                 out.peer_out, out.multicast, side.cuda_stream))
+        lo.record_stream(side)
+        hi.record_stream(side)
+    main.wait_stream(side)
+    out.hdl.barrier()                  # every rank's stores have landed here
+    return out.packed

@@ -427,6 +427,14 @@ int hkcsa_count_batch_peers(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_pla
                             const hkcsa_occ_plan *h_occ_plan, const void *d_kmer_table, uint32_t k,
                             const uint8_t *d_pat, const int64_t *d_off, uint64_t P, uint64_t out_base,
                             uint32_t n_peers, const uint64_t *h_peer_lo, const uint64_t *h_peer_hi, void *stream);
+/* The gather of a sharded batch's results as a store kernel: (lo, hi) of this rank's P patterns are packed into     */
+/* 8 bytes {lo: low 32 bits, count = hi-lo+1: high 32 bits; miss: lo = 0xFFFFFFFF, count 0} and stored at             */
+/* [out_base + p] of the uint64 result array of every rank (h_peer_out[r], peer-mapped, 16-byte aligned) -- or, when  */
+/* multicast_out != 0 (the NVSwitch multicast address of the same symmetric array), by ONE multimem.st per 16 bytes   */
+/* that reaches all ranks.  hkcsa_ranges_unpack expands a packed array back to (lo, hi).                              */
+int hkcsa_ranges_push_peers(const int64_t *d_lo, const int64_t *d_hi, uint64_t P, uint64_t out_base,
+                            uint32_t n_peers, const uint64_t *h_peer_out, uint64_t multicast_out, void *stream);
+int hkcsa_ranges_unpack(const uint64_t *d_packed, uint64_t P, int64_t *d_lo, int64_t *d_hi, void *stream);
 /* hkcsa_locate_rows with the LF step (symbol + its count) read from the Occ table; same positions. */
 int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, const void *d_occ_blob,
                           const hkcsa_occ_plan *h_plan, const void *d_ssa_blob, const hkcsa_ssa_plan *h_ssa,

@@ -610,6 +610,40 @@ def test_count_batch_peers_writes_every_peer_array(E, use_occ):
         assert torch.equal(b[0], want_lo) and torch.equal(b[1], want_hi)
 
 
+def test_ranges_push_peers_packs_and_unpacks(E):
+    """hkcsa_ranges_push_peers (the result gather as a store kernel) with the "peers" being plain buffers on this
+    GPU: slices with odd and even bases, an empty slice and a one-pattern slice land packed at their place in every
+    peer array; hkcsa_ranges_unpack gives back count_batch's (lo, hi)."""
+    import ctypes as C
+    import torch
+    from hkcsa import _lib
+    L = _lib.load()
+    text = TEXTS["eng_300k"] + b"$"
+    idx = E.DeviceIndex(dev(E, text))
+    pats, off = O.gen_patterns(31, 3001, np.frombuffer(TEXTS["eng_300k"], dtype=np.uint8), 1, 40)
+    extra = [b"", b"\x01"]                                  # the whole range (count = n), and a miss
+    pats = np.concatenate([pats, np.frombuffer(b"".join(extra), dtype=np.uint8)])
+    off = np.concatenate([off, off[-1] + np.cumsum([len(e) for e in extra])])
+    P = len(off) - 1
+    d_p, d_o = torch.from_numpy(pats).cuda(), torch.from_numpy(off).cuda()
+    want_lo, want_hi = idx.count_batch(d_p, d_o, use_kmer_table=False)
+    bufs = [torch.full((P + 1,), -7, dtype=torch.int64, device="cuda") for _ in range(3)]
+    peers = (C.c_uint64 * 3)(*[b.data_ptr() for b in bufs])
+    st = torch.cuda.current_stream().cuda_stream
+    for b0, e0 in ((0, 1101), (1101, 1101), (1101, 1102), (1102, 2000), (2000, P)):
+        lo, hi = want_lo[b0:e0].contiguous(), want_hi[b0:e0].contiguous()
+        _lib.check(L.hkcsa_ranges_push_peers(lo.data_ptr(), hi.data_ptr(), e0 - b0, b0, 3, peers, 0, st))
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert int(b[P].item()) == -7                       # nothing stored past the batch
+        lo = torch.empty(P, dtype=torch.int64, device="cuda")
+        hi = torch.empty_like(lo)
+        _lib.check(L.hkcsa_ranges_unpack(b.data_ptr(), P, lo.data_ptr(), hi.data_ptr(), st))
+        assert torch.equal(lo, want_lo) and torch.equal(hi, want_hi)
+    packed = host(bufs[0][:P]).view(np.uint64)
+    assert packed[P - 2] == (np.uint64(len(text)) << np.uint64(32)) and packed[P - 1] == np.uint64(0xFFFFFFFF)
+
+
 @pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "runs", "fib"])
 def test_psi_is_the_inverse_of_lf(E, name):
     """DeviceIndex.psi(): SA[psi[i]] = SA[i] + 1 (mod n) for every row, and psi equals the concatenation of the
