@@ -18,13 +18,13 @@ class EnhancedFMIndex:
         self._E = engine
         self._smap = None
         if isinstance(text, str):
-            self.text = text + "$"                                   # :9
+            self._text0, self._text = text, None                     # self.text = text + "$" (:9), built on first access
             self._smap = engine.SymbolMap(text, extra="$")           # identity for latin-1 text
             d_text = engine.to_device_u8(self._smap.encode(text), tail=self._smap.encode("$"))
         else:                                                        # bytes / uint8 array / tensor (extension)
             import torch
             d_text = engine.to_device_u8(text, tail=b"$")
-            self.text = d_text if isinstance(text, torch.Tensor) else bytes(text) + b"$"
+            self._text0, self._text = None, (d_text if isinstance(text, torch.Tensor) else bytes(text) + b"$")
         self._idx = engine.DeviceIndex(d_text)                       # :10-12 (SA, BWT, wavelet tree = occ)
         self._sa = None
         self._bwt = None
@@ -37,6 +37,12 @@ class EnhancedFMIndex:
             self.count = {self._smap.symbol(ord(k)): v for k, v in self.count.items()}
 
     # ---- attributes of the reference, materialised on first use
+    @property
+    def text(self):
+        if self._text is None:
+            self._text = self._text0 + "$"                           # csa/enhanced_fm_index.py:9
+        return self._text
+
     @property
     def suffix_array(self):
         if self._sa is None:

@@ -202,6 +202,8 @@ SIGNATURES = {
     "hkcsa_locate_rows": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(SsaPlan), _vp, _u64, _vp, _vp]),
     "hkcsa_symbol_positions_scratch_bytes": (_sz, [_u64]),
     "hkcsa_symbol_positions": (_i32, [_vp, _u64, _vp, _vp, _vp, _sz, _vp]),
+    "hkcsa_entropy_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_entropy_from_sa": (_i32, [_vp, _u64, _vp, _u32, C.POINTER(C.c_double), _vp, _sz, _vp]),
     "hkcsa_launch_count": (C.c_ulonglong, []),
     "hkcsa_prof_enable": (_i32, [_i32]),
     "hkcsa_prof_enable_classes": (_i32, [_u32]),

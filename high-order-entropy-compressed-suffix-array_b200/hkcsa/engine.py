@@ -67,8 +67,9 @@ class SymbolMap:
 
     def __init__(self, text: str, extra: str = ""):
         self.back = None                      # identity
+        self._cache = None                    # (text, its bytes): the constructor's probe is the encoding itself
         try:
-            text.encode("latin-1")
+            self._cache = (text, text.encode("latin-1"))
         except UnicodeEncodeError:
             cps = sorted(set(text) | set(extra))
             if len(cps) > 256:
@@ -83,6 +84,9 @@ class SymbolMap:
     def encode(self, s: str):
         """bytes, or None when `s` holds a symbol outside the map (such a pattern cannot occur in the text)."""
         if self.back is None:
+            if self._cache is not None and self._cache[0] is s:
+                enc, self._cache = self._cache[1], None           # handed out once: do not pin 2x the text in memory
+                return enc
             try:
                 return s.encode("latin-1")
             except UnicodeEncodeError:
@@ -209,6 +213,26 @@ def byte_hist(sym: torch.Tensor) -> np.ndarray:
     h = torch.empty(256, dtype=torch.int64, device=sym.device)
     check(_lib.load().hkcsa_byte_hist(_ptr(sym), sym.numel(), _ptr(h), _stream()))
     return h.cpu().numpy().astype(np.uint64)
+
+
+def entropy_from_sa(text: torch.Tensor, sa: torch.Tensor, k: int) -> dict:
+    """H_k of `text` (csa/high_order_entropy.py:4-32) from its suffix array, any k >= 0: one pass over the suffix
+    array flags the runs of equal k- and (k+1)-grams.  Returns {"hk", "windows", "contexts", "grams"}."""
+    n = text.numel()
+    if n == 0 or k < 0:
+        return {"hk": 0, "windows": 0, "contexts": 0, "grams": 0}
+    if k == 0:
+        hist = byte_hist(text).astype(np.float64)
+        p = hist[hist > 0] / n
+        return {"hk": float(-(p * np.log2(p)).sum()), "windows": n, "contexts": 1, "grams": int((hist > 0).sum())}
+    if n <= k:
+        return {"hk": 0, "windows": 0, "contexts": 0, "grams": 0}
+    L = _lib.load()
+    nbytes = L.hkcsa_entropy_scratch_bytes(n)
+    scratch = _scratch(nbytes, text.device)
+    out = (C.c_double * 5)()
+    check(L.hkcsa_entropy_from_sa(_ptr(text), n, _ptr(sa), int(k), out, _ptr(scratch), nbytes, _stream()))
+    return {"hk": (out[0] - out[1]) / n, "windows": int(out[2]), "contexts": int(out[3]), "grams": int(out[4])}
 
 
 def sort_pairs_u64(keys: torch.Tensor, vals: torch.Tensor, key_bits: int = 64):
@@ -545,6 +569,12 @@ class DeviceIndex:
                                        _stream()))
         self._kmer = (table, k)
         return self._kmer
+
+    def entropy(self, k: int) -> float:
+        """H_k (bits per symbol) of the indexed text, from the suffix array of the build."""
+        if self.sa is None or self.text is None:
+            raise ValueError("H_k is computed from the text and the suffix array, which this index no longer holds")
+        return entropy_from_sa(self.text, self.sa, k)["hk"]
 
     def psi(self) -> torch.Tensor:
         """The Psi function of the compressed suffix array (Grossi-Vitter; README.md:4 of the reference): psi[i] =

