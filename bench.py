@@ -725,10 +725,17 @@ def run_ours(args):
         barrier()
         p3 = E.prof_read().get(TOP_KERNEL_CLASS)
         E.prof_enable(False)
-        c3_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev3])))
+        c3_mine = float(np.mean([a.elapsed_time(b) for a, b in ev3]))
+        c3_ms = max_over_ranks(c3_mine)
+        c3_all = [c3_mine]
+        if world > 1:
+            t_all = torch.zeros(world, dtype=torch.float64, device=dev)
+            t_all[rank] = c3_mine
+            dist.all_reduce(t_all)
+            c3_all = [round(v, 3) for v in t_all.cpu().tolist()]
         st3 = idx3.stats.sa
         c3 = {"workload": d3, "text_bytes": n3, "steps": len(ev3), "warmup": 3, "ms_per_step": c3_ms,
-              "ms_steps_this_rank": [round(a.elapsed_time(b), 3) for a, b in ev3],
+              "ms_steps_this_rank": [round(a.elapsed_time(b), 3) for a, b in ev3], "ms_per_rank": c3_all,
               "value_MBps": world * n3 / 1e6 / (c3_ms / 1e3),
               "roofline_onesweep": ({"achieved": p3["alg_bytes"] / (p3["ms"] / 1e3) / 1e9, "peak": peak,
                                      "frac": p3["alg_bytes"] / (p3["ms"] / 1e3) / 1e9 / peak, "launches": p3["launches"],
@@ -926,8 +933,9 @@ def run_ours(args):
             "wall_s_timed_region": wall,
         }
         sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-        print(json.dumps(line), flush=True)
+        # the one JSON line goes to the REAL stdout; fd 1 stays pointed at stderr so that whatever NCCL logs while the
+        # process group is torn down cannot follow the line
+        os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -69,7 +69,7 @@ class CompressedSuffixArray:
     array sampled every s = ceil((log2 n)^epsilon) text positions, so ``locate`` walks at most
     s-1 LF steps per occurrence.  The full suffix array is dropped after sampling."""
 
-    def __init__(self, text, epsilon=0.5, sa_sample_rate=None):
+    def __init__(self, text, epsilon=0.5, sa_sample_rate=None, entropy_orders=()):
         from hkcsa import engine
         self._E = engine
         self.text = text
@@ -89,10 +89,13 @@ class CompressedSuffixArray:
         # need not reach a sampled row.  Such an index keeps the full suffix array and locates through it (the
         # answers EnhancedFMIndex.find gives, csa/enhanced_fm_index.py:15-19) instead of through the samples.
         self.sentinel_unique = not has_sentinel
-        self._idx = engine.DeviceIndex(d_text, sa_sample_rate=self.sa_sample_rate, keep_sa=has_sentinel,
-                                       keep_text=False)
+        self._idx = engine.DeviceIndex(d_text, sa_sample_rate=self.sa_sample_rate, keep_sa=True, keep_text=True)
         self.n = n
-        self._hk_cache = {}
+        # H_k of the indexed text (text + '$') for the requested orders, while the suffix array still exists
+        self.entropy = {int(k): self._idx.entropy(int(k)) for k in entropy_orders}
+        self._idx.text = None
+        if not has_sentinel:
+            self._idx.sa = None                                # the full suffix array is dropped after sampling
 
     @property
     def device_index(self):
@@ -136,6 +139,20 @@ class CompressedSuffixArray:
         off, pos = self._idx.locate_batch(*self._pack(patterns), use_samples=self.sentinel_unique)
         off, pos = off.cpu().numpy(), pos.cpu().numpy()
         return [sorted(pos[off[k]:off[k + 1]].tolist()) for k in range(len(off) - 1)]
+
+    def space_report(self):
+        """Index size next to the entropy bound: bits per symbol of the query blob and of the entropy-coded levels
+        (what save(compressed=True) writes), the sampled SA, and n*H_k for the orders given at construction
+        (README.md:4-11 of the reference: "space close to the k-th order entropy")."""
+        rep = self._idx.space()
+        rep["sa_sample_rate"] = self.sa_sample_rate
+        rep["H_k_bits_per_symbol"] = dict(self.entropy)
+        rep["n_H_k_bits"] = {k: v * self.n for k, v in self.entropy.items()}
+        rep["coded_index_bits_per_symbol"] = rep["coded_level_bits_per_symbol"] + rep["sampled_sa_bits_per_symbol"]
+        return rep
+
+    def save(self, path, compressed=True):
+        self._idx.save(path, compressed=compressed)
 
     def index_bytes(self):
         """Device bytes held by the index (wavelet tree blob + sampled SA blob [+ the suffix array, kept only when

@@ -93,6 +93,7 @@ extern "C" size_t hkcsa_struct_size(int which)
         case 3: return sizeof(hkcsa_prof_entry);
         case 4: return sizeof(hkcsa_occ_plan);
         case 5: return sizeof(hkcsa_dsa_plan);
+        case 6: return sizeof(hkcsa_rrr_plan);
         default: return 0;
     }
 }

@@ -687,16 +687,9 @@ int build_markvector64(const uint64_t *d_sa, uint64_t n, uint32_t rate, RankBloc
 }
 }  // namespace hkcsa
 
-extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_blob, void *d_scratch,
-                              size_t scratch_bytes, void *stream)
+// host-side node tables of a plan -> the blob's table region.  syncs (the staging struct is reused per thread).
+static int wt_write_tables(const hkcsa_wt_plan *p, uint8_t *blob, cudaStream_t st)
 {
-    HK_REQUIRE(p && d_blob, HKCSA_EINVAL, "null pointer");
-    HK_REQUIRE(p->scratch_bytes <= scratch_bytes, HKCSA_ESCRATCH, "wavelet scratch too small");
-    HK_REQUIRE((reinterpret_cast<uintptr_t>(d_blob) & 31) == 0, HKCSA_EINVAL, "blob must be 32-byte aligned");
-    cudaStream_t st = as_stream(stream);
-    const uint64_t n = p->n;
-    uint8_t *blob = static_cast<uint8_t *>(d_blob);
-    // ---- host-side tables -> device
     static thread_local WtTables T;   // staged from pageable memory (a few KB, once per build)
     memset(&T, 0, sizeof(T));
     memcpy(T.code_of_sym, p->code_of_sym, sizeof(T.code_of_sym));
@@ -732,6 +725,52 @@ extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_bl
     WtTables *d_tab = reinterpret_cast<WtTables *>(blob + p->off_tables);
     HK_CUDA(cudaMemcpyAsync(d_tab, &T, sizeof(T), cudaMemcpyHostToDevice, st));
     HK_CUDA(cudaStreamSynchronize(st));   // T is reused by the next call on this thread
+    return HKCSA_OK;
+}
+
+// block headers, superblocks and select samples of every level from the payload bits in place; node_ones; syncs
+// once to read the ones per level (h_ones_out[levels])
+static int wt_build_dirs(const hkcsa_wt_plan *p, void *d_blob, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones,
+                         uint64_t *h_ones_out, cudaStream_t st)
+{
+    uint8_t *blob = static_cast<uint8_t *>(d_blob);
+    WtTables *d_tab = reinterpret_cast<WtTables *>(blob + p->off_tables);
+    for (uint32_t l = 0; l < p->levels; ++l) {
+        RankBlock *blocks = reinterpret_cast<RankBlock *>(blob + p->off_blocks[l]);
+        const uint64_t nblocks = rank_blocks_for(p->level_len[l]);
+        const uint64_t tiles = (nblocks + WTC_BLOCKS_PER_CTA - 1) / WTC_BLOCKS_PER_CTA;
+        prof::Scope ps(st, prof::WT_DIR, nblocks * 72);
+        wt_count_kernel<<<(uint32_t)tiles, WTC_BLOCKS_PER_CTA, 0, st>>>(blocks, nblocks, d_agg);
+        HK_LAUNCH_CHECK();
+        wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones + l);
+        HK_LAUNCH_CHECK();
+        wt_dir_fix_kernel<<<(uint32_t)((nblocks + 255) / 256), 256, 0, st>>>(
+            blocks, nblocks, d_carry, reinterpret_cast<uint64_t *>(blob + p->off_super[l]),
+            reinterpret_cast<uint32_t *>(blob + p->off_select[l]), WTC_BLOCKS_PER_CTA);
+        HK_LAUNCH_CHECK();
+    }
+    WtDev wt = make_wt_dev(d_blob, p);
+    wt_node_ones_kernel<<<p->levels, 256, 0, st>>>(wt, d_tab);
+    HK_LAUNCH_CHECK();
+    uint64_t *h_ones = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(pinned_page()) + 3072);
+    HK_CUDA(cudaMemcpyAsync(h_ones, d_ones, p->levels * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    HK_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t l = 0; l < p->levels; ++l) h_ones_out[l] = h_ones[l];
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_blob, void *d_scratch,
+                              size_t scratch_bytes, void *stream)
+{
+    HK_REQUIRE(p && d_blob, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(p->scratch_bytes <= scratch_bytes, HKCSA_ESCRATCH, "wavelet scratch too small");
+    HK_REQUIRE((reinterpret_cast<uintptr_t>(d_blob) & 31) == 0, HKCSA_EINVAL, "blob must be 32-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const uint64_t n = p->n;
+    uint8_t *blob = static_cast<uint8_t *>(d_blob);
+    int rc = wt_write_tables(p, blob, st);
+    if (rc != HKCSA_OK) return rc;
+    WtTables *d_tab = reinterpret_cast<WtTables *>(blob + p->off_tables);
     if (p->levels == 0 || n == 0) return HKCSA_OK;
     HK_REQUIRE(d_sym && d_scratch, HKCSA_EINVAL, "null pointer");
 
@@ -756,27 +795,41 @@ extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_bl
         wt_levels_kernel<<<wtiles, WTL_THREADS, 0, st>>>(d_sym, n, d_tab, d_gcnt, wtiles, lw, p->levels, p->sigma);
         HK_LAUNCH_CHECK();
     }
-    for (uint32_t l = 0; l < p->levels; ++l) {
-        RankBlock *blocks = reinterpret_cast<RankBlock *>(blob + p->off_blocks[l]);
-        const uint64_t nblocks = rank_blocks_for(p->level_len[l]);
-        const uint64_t tiles = (nblocks + WTC_BLOCKS_PER_CTA - 1) / WTC_BLOCKS_PER_CTA;
-        prof::Scope ps(st, prof::WT_DIR, nblocks * 72);
-        wt_count_kernel<<<(uint32_t)tiles, WTC_BLOCKS_PER_CTA, 0, st>>>(blocks, nblocks, d_agg);
-        HK_LAUNCH_CHECK();
-        wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones + l);
-        HK_LAUNCH_CHECK();
-        wt_dir_fix_kernel<<<(uint32_t)((nblocks + 255) / 256), 256, 0, st>>>(
-            blocks, nblocks, d_carry, reinterpret_cast<uint64_t *>(blob + p->off_super[l]),
-            reinterpret_cast<uint32_t *>(blob + p->off_select[l]), WTC_BLOCKS_PER_CTA);
-        HK_LAUNCH_CHECK();
-    }
-    WtDev wt = make_wt_dev(d_blob, p);
-    wt_node_ones_kernel<<<p->levels, 256, 0, st>>>(wt, d_tab);
-    HK_LAUNCH_CHECK();
-    uint64_t *h_ones = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(pinned_page()) + 3072);
-    HK_CUDA(cudaMemcpyAsync(h_ones, d_ones, p->levels * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    HK_CUDA(cudaStreamSynchronize(st));
-    for (uint32_t l = 0; l < p->levels; ++l) p->level_ones[l] = h_ones[l];
+    return wt_build_dirs(p, d_blob, d_agg, d_carry, d_ones, p->level_ones, st);
+}
+
+// Restoring a blob from stored level payloads (hkcsa_rrr_restore_level): _begin writes the node tables and clears the
+// level regions, the caller ORs the payload bits in, _finish rebuilds block headers, superblocks, select samples and
+// node counts and checks the ones per level against the plan.  Both sync.
+extern "C" int hkcsa_wt_restore_begin(const hkcsa_wt_plan *p, void *d_blob, void *stream)
+{
+    HK_REQUIRE(p && d_blob, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE((reinterpret_cast<uintptr_t>(d_blob) & 31) == 0, HKCSA_EINVAL, "blob must be 32-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    uint8_t *blob = static_cast<uint8_t *>(d_blob);
+    int rc = wt_write_tables(p, blob, st);
+    if (rc != HKCSA_OK) return rc;
+    if (p->levels && p->blob_bytes > p->off_blocks[0])
+        HK_CUDA(cudaMemsetAsync(blob + p->off_blocks[0], 0, p->blob_bytes - p->off_blocks[0], st));
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_wt_restore_finish(const hkcsa_wt_plan *p, void *d_blob, void *d_scratch, size_t scratch_bytes,
+                                       void *stream)
+{
+    HK_REQUIRE(p && d_blob, HKCSA_EINVAL, "null pointer");
+    if (p->levels == 0 || p->n == 0) return HKCSA_OK;
+    HK_REQUIRE(d_scratch && p->scratch_bytes <= scratch_bytes, HKCSA_ESCRATCH, "wavelet scratch too small");
+    Carver c(d_scratch);
+    const uint64_t tiles_max = rank_blocks_for(p->n) / WTC_BLOCKS_PER_CTA + 2;
+    uint32_t *d_agg = c.take<uint32_t>(tiles_max);
+    uint64_t *d_carry = c.take<uint64_t>(tiles_max);
+    uint64_t *d_ones = c.take<uint64_t>(HKCSA_MAX_LEVELS);
+    uint64_t ones[HKCSA_MAX_LEVELS];
+    int rc = wt_build_dirs(p, d_blob, d_agg, d_carry, d_ones, ones, as_stream(stream));
+    if (rc != HKCSA_OK) return rc;
+    for (uint32_t l = 0; l < p->levels; ++l)
+        HK_REQUIRE(ones[l] == p->level_ones[l], HKCSA_EINVAL, "restored level holds a different number of ones than its plan");
     return HKCSA_OK;
 }
 

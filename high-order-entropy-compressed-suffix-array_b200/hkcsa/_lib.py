@@ -113,6 +113,11 @@ class DsaPlan(C.Structure):
     ]
 
 
+class RrrPlan(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("nbits", "nblocks", "nsuper", "ones", "stream_bits", "off_super",
+                                          "off_classes", "off_stream", "blob_bytes")]
+
+
 class ProfEntry(C.Structure):
     _fields_ = [
         ("name", C.c_char * 32),
@@ -202,6 +207,15 @@ SIGNATURES = {
     "hkcsa_locate_rows": (_i32, [_vp, C.POINTER(WtPlan), _vp, C.POINTER(SsaPlan), _vp, _u64, _vp, _vp]),
     "hkcsa_symbol_positions_scratch_bytes": (_sz, [_u64]),
     "hkcsa_symbol_positions": (_i32, [_vp, _u64, _vp, _vp, _vp, _sz, _vp]),
+    "hkcsa_rrr_tables_bytes": (_sz, []),
+    "hkcsa_rrr_tables_init": (_i32, [_vp, _vp]),
+    "hkcsa_rrr_scratch_bytes": (_sz, [_u64]),
+    "hkcsa_rrr_encode": (_i32, [_vp, C.POINTER(WtPlan), _u32, _u64, _vp, C.POINTER(RrrPlan), _vp, _sz, _vp, _sz, _vp]),
+    "hkcsa_rrr_rank_batch": (_i32, [_vp, C.POINTER(RrrPlan), _vp, _vp, _u64, _vp, _vp]),
+    "hkcsa_rrr_unpack": (_i32, [_vp, C.POINTER(RrrPlan), _vp, _u64, _u64, _vp, _vp]),
+    "hkcsa_wt_restore_begin": (_i32, [C.POINTER(WtPlan), _vp, _vp]),
+    "hkcsa_rrr_restore_level": (_i32, [_vp, C.POINTER(RrrPlan), _vp, C.POINTER(WtPlan), _u32, _vp, _vp]),
+    "hkcsa_wt_restore_finish": (_i32, [C.POINTER(WtPlan), _vp, _vp, _sz, _vp]),
     "hkcsa_entropy_scratch_bytes": (_sz, [_u64]),
     "hkcsa_entropy_from_sa": (_i32, [_vp, _u64, _vp, _u32, C.POINTER(C.c_double), _vp, _sz, _vp]),
     "hkcsa_launch_count": (C.c_ulonglong, []),
@@ -231,7 +245,7 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if L.hkcsa_abi_version() != 1:
         raise ImportError("libhkcsa.so ABI version mismatch")
-    for idx, st in enumerate((SaStats, WtPlan, SsaPlan, ProfEntry, OccPlan, DsaPlan)):
+    for idx, st in enumerate((SaStats, WtPlan, SsaPlan, ProfEntry, OccPlan, DsaPlan, RrrPlan)):
         if L.hkcsa_struct_size(idx) != C.sizeof(st):
             raise ImportError(f"struct layout mismatch for {st.__name__}: "
                               f"C {L.hkcsa_struct_size(idx)} vs ctypes {C.sizeof(st)}")

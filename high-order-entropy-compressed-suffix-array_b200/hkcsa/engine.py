@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import HkcsaError, OccPlan, SaStats, SsaPlan, WtPlan, check
+from ._lib import HkcsaError, OccPlan, RrrPlan, SaStats, SsaPlan, WtPlan, check
 
 ENG96, DNA4 = 0, 1
 
@@ -368,6 +368,85 @@ class DeviceWaveletTree:
         return out
 
 
+# ------------------------------------------------------------------ entropy-coded bit-vectors (csrc/rrr.cu)
+_RRR_TABLES: dict = {}
+
+
+def rrr_tables(device) -> torch.Tensor:
+    """The class / offset tables of the 15-bit block code, one copy per device."""
+    key = torch.device(device).index
+    if key not in _RRR_TABLES:
+        L = _lib.load()
+        t = torch.empty(L.hkcsa_rrr_tables_bytes(), dtype=torch.uint8, device=device)
+        check(L.hkcsa_rrr_tables_init(_ptr(t), _stream()))
+        _RRR_TABLES[key] = t
+    return _RRR_TABLES[key]
+
+
+class RrrVector:
+    """A level of a wavelet tree (or a stand-alone DeviceBitVector) in the class/offset code: n*H_0 + o(n) bits,
+    rank answered on the coded form, decodable bit for bit."""
+
+    def __init__(self, plan: RrrPlan, blob: torch.Tensor):
+        self.plan, self.blob = plan, blob
+
+    @classmethod
+    def encode(cls, wt: "DeviceWaveletTree", level: int, nbits: int | None = None) -> "RrrVector":
+        L = _lib.load()
+        nbits = wt.level_len(level) if nbits is None else int(nbits)
+        tab = rrr_tables(wt.device)
+        plan = RrrPlan()
+        nscr = L.hkcsa_rrr_scratch_bytes(nbits)
+        scratch = _scratch(nscr, wt.device)
+        check(L.hkcsa_rrr_encode(_ptr(wt.blob), C.byref(wt.plan), level, nbits, _ptr(tab), C.byref(plan), None, 0,
+                                 _ptr(scratch), nscr, _stream()))
+        blob = torch.empty(max(int(plan.blob_bytes), 256), dtype=torch.uint8, device=wt.device)
+        check(L.hkcsa_rrr_encode(_ptr(wt.blob), C.byref(wt.plan), level, nbits, _ptr(tab), C.byref(plan), _ptr(blob),
+                                 blob.numel(), _ptr(scratch), nscr, _stream()))
+        return cls(plan, blob[: max(int(plan.blob_bytes), 1)])
+
+    @property
+    def nbits(self) -> int:
+        return int(self.plan.nbits)
+
+    @property
+    def coded_bits(self) -> int:
+        """4 class bits per block + the offset stream + 128 bits per superblock."""
+        return 4 * int(self.plan.nblocks) + int(self.plan.stream_bits) + 128 * int(self.plan.nsuper)
+
+    def rank(self, pos) -> torch.Tensor:
+        pos = (pos.to(device=self.blob.device, dtype=torch.int64).contiguous() if isinstance(pos, torch.Tensor)
+               else torch.as_tensor(np.asarray(pos, dtype=np.int64), device=self.blob.device))
+        out = torch.empty_like(pos)
+        check(_lib.load().hkcsa_rrr_rank_batch(_ptr(self.blob), C.byref(self.plan), _ptr(rrr_tables(self.blob.device)),
+                                               _ptr(pos), pos.numel(), _ptr(out), _stream()))
+        return out
+
+    def bits(self, begin: int = 0, count: int | None = None) -> torch.Tensor:
+        count = self.nbits - begin if count is None else count
+        out = _empty(count, torch.uint8, self.blob.device)
+        check(_lib.load().hkcsa_rrr_unpack(_ptr(self.blob), C.byref(self.plan), _ptr(rrr_tables(self.blob.device)),
+                                           begin, count, _ptr(out), _stream()))
+        return out
+
+
+def wt_from_coded_levels(plan: WtPlan, coded: list, device) -> DeviceWaveletTree:
+    """Rebuild the query blob of a wavelet tree from its RRR-coded levels: node tables from the plan, payload bits
+    decoded in place, block headers / superblocks / select samples recomputed (checked against the plan's counts)."""
+    L = _lib.load()
+    wt = DeviceWaveletTree.__new__(DeviceWaveletTree)
+    wt.device, wt.n, wt.hist, wt.plan = torch.device(device), int(plan.n), None, plan
+    wt.blob = torch.empty(int(plan.blob_bytes), dtype=torch.uint8, device=device)
+    check(L.hkcsa_wt_restore_begin(C.byref(plan), _ptr(wt.blob), _stream()))
+    tab = rrr_tables(device)
+    for level, vec in enumerate(coded):
+        check(L.hkcsa_rrr_restore_level(_ptr(vec.blob), C.byref(vec.plan), _ptr(tab), C.byref(plan), level,
+                                        _ptr(wt.blob), _stream()))
+    scratch = _scratch(plan.scratch_bytes, device)
+    check(L.hkcsa_wt_restore_finish(C.byref(plan), _ptr(wt.blob), _ptr(scratch), int(plan.scratch_bytes), _stream()))
+    return wt
+
+
 class DeviceBitVector(DeviceWaveletTree):
     """Stand-alone rank/select bit-vector (SuccinctRankSelect, csa/wavelet_tree.py:5-25): a one-level
     plan whose level 0 is the bitmap.  `bits`: uint8 device tensor, one byte per bit."""
@@ -526,12 +605,37 @@ class DeviceIndex:
         return self
 
     # -- persistence (the reference never writes its index to disk: SURVEY.md section 5; next-row 3)
-    def save(self, path: str) -> None:
-        """Write the query structures (wavelet-tree blob + plan, sampled SA) to one .npz file.  The blob is
-        stored exactly as it lives in HBM, so loading is a single host->device copy."""
+    def coded_levels(self) -> list:
+        """Every wavelet-tree level in the class/offset code (csrc/rrr.cu), cached."""
+        if getattr(self, "_coded", None) is None:
+            self._coded = [RrrVector.encode(self.wt, l) for l in range(self.wt.levels)]
+        return self._coded
+
+    def space(self) -> dict:
+        """Bits per symbol of the index: the query blob as it lives in HBM, and the entropy-coded form save() writes."""
+        n = max(self.n, 1)
+        coded = self.coded_levels()
+        ssa_bits = 8 * int(self.ssa.blob.numel()) if self.ssa is not None else 0
+        return {"n": self.n, "levels": self.wt.levels,
+                "query_blob_bits_per_symbol": 8.0 * self.wt.blob.numel() / n,
+                "raw_level_bits_per_symbol": sum(self.wt.level_len(l) for l in range(self.wt.levels)) / n,
+                "coded_level_bits_per_symbol": sum(v.coded_bits for v in coded) / n,
+                "coded_bits_per_level": [v.coded_bits for v in coded],
+                "sampled_sa_bits_per_symbol": ssa_bits / n}
+
+    def save(self, path: str, compressed: bool = False) -> None:
+        """Write the query structures to one .npz file.  compressed=False: the wavelet-tree blob exactly as it lives
+        in HBM (loading is a single host->device copy).  compressed=True: every level in the class/offset code
+        (n*H_0 of the level + o(n) bits; over the levels of a BWT: n*H_k + o(n)); load() decodes the payload bits
+        in place and rebuilds the rank directories -- the restored blob is bit-identical."""
         parts = {"n": np.array([self.n], dtype=np.int64),
-                 "wt_plan": np.frombuffer(bytes(self.wt.plan), dtype=np.uint8),
-                 "wt_blob": self.wt.blob.cpu().numpy()}
+                 "wt_plan": np.frombuffer(bytes(self.wt.plan), dtype=np.uint8)}
+        if compressed:
+            for l, vec in enumerate(self.coded_levels()):
+                parts[f"rrr_plan_{l}"] = np.frombuffer(bytes(vec.plan), dtype=np.uint8)
+                parts[f"rrr_blob_{l}"] = vec.blob.cpu().numpy()
+        else:
+            parts["wt_blob"] = self.wt.blob.cpu().numpy()
         if self.ssa is not None:
             parts["ssa_plan"] = np.frombuffer(bytes(self.ssa.plan), dtype=np.uint8)
             parts["ssa_blob"] = self.ssa.blob.cpu().numpy()
@@ -543,7 +647,15 @@ class DeviceIndex:
         device = device or _require_cuda()
         z = np.load(path)
         plan = WtPlan.from_buffer_copy(z["wt_plan"].tobytes())
-        blob = torch.from_numpy(z["wt_blob"]).to(device)
+        if "wt_blob" in z.files:
+            blob = torch.from_numpy(z["wt_blob"]).to(device)
+        else:
+            coded = []
+            for l in range(int(plan.levels)):
+                rp = RrrPlan.from_buffer_copy(z[f"rrr_plan_{l}"].tobytes())
+                rb = torch.from_numpy(z[f"rrr_blob_{l}"]).to(device)
+                coded.append(RrrVector(rp, rb))
+            blob = wt_from_coded_levels(plan, coded, device).blob
         ssa = None
         if "ssa_plan" in z.files:
             ssa = SampledSA(SsaPlan.from_buffer_copy(z["ssa_plan"].tobytes()), torch.from_numpy(z["ssa_blob"]).to(device))

@@ -47,8 +47,8 @@ extern "C" {
 int         hkcsa_abi_version(void);
 const char *hkcsa_last_error(void);
 /* sizeof of the public structs (0 hkcsa_sa_stats, 1 hkcsa_wt_plan, 2 hkcsa_ssa_plan, */
-/* 3 hkcsa_prof_entry, 4 hkcsa_occ_plan, 5 hkcsa_dsa_plan) so a binding can verify   */
-/* its mirror.                                                                         */
+/* 3 hkcsa_prof_entry, 4 hkcsa_occ_plan, 5 hkcsa_dsa_plan, 6 hkcsa_rrr_plan) so a    */
+/* binding can verify its mirror.                                                     */
 size_t      hkcsa_struct_size(int which);
 
 /* ------------------------------------------------------------------------ */
@@ -367,6 +367,47 @@ int hkcsa_multi_locate_rows(const void *d_desc, const uint64_t *d_rows, uint64_t
 size_t hkcsa_symbol_positions_scratch_bytes(uint64_t n);
 int hkcsa_symbol_positions(const uint8_t *d_bwt, uint64_t n, uint32_t *d_pos, uint64_t *d_start,
                            void *d_scratch, size_t scratch_bytes, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* Entropy-coded bit-vectors with rank on the coded form (no working reference   */
+/* counterpart: WaveletTree.compress keeps Golomb run codes that cannot be       */
+/* decoded -- zero runs are not coded, csa/wavelet_tree.py:40-63 -- and          */
+/* decompress returns '', :158-200).  Class/offset code of Raman-Raman-Rao with   */
+/* 15-bit blocks: per block a 4-bit class (its popcount) and the index of the     */
+/* pattern inside its class in ceil(log2 C(15, c)) bits; per 64 blocks the ones   */
+/* and the offset-stream position before them.  n H_0 + o(n) bits per vector;     */
+/* over the wavelet-tree levels of a BWT that is the n H_k + o(n) index.          */
+/* ------------------------------------------------------------------------ */
+typedef struct hkcsa_rrr_plan {
+    uint64_t nbits, nblocks, nsuper;
+    uint64_t ones;           /* ones in the vector                               */
+    uint64_t stream_bits;    /* length of the offset stream                      */
+    uint64_t off_super, off_classes, off_stream;
+    uint64_t blob_bytes;
+} hkcsa_rrr_plan;
+size_t hkcsa_rrr_tables_bytes(void);
+int hkcsa_rrr_tables_init(void *d_tables, void *stream);              /* syncs */
+size_t hkcsa_rrr_scratch_bytes(uint64_t nbits);
+/* Encodes bits [0, nbits) of `level` of a wavelet-tree blob.  Two calls: d_out == NULL sizes the code (fills   */
+/* *h_plan), otherwise writes it (h_plan->blob_bytes bytes, 32-byte aligned, out_capacity >= that).  syncs.      */
+int hkcsa_rrr_encode(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan, uint32_t level, uint64_t nbits,
+                     const void *d_tables, hkcsa_rrr_plan *h_plan, void *d_out, size_t out_capacity,
+                     void *d_scratch, size_t scratch_bytes, void *stream);
+/* SuccinctRankSelect.rank (csa/wavelet_tree.py:14-15) on the coded form: ones in bits [0, i) */
+int hkcsa_rrr_rank_batch(const void *d_rrr, const hkcsa_rrr_plan *h_plan, const void *d_tables,
+                         const uint64_t *d_pos, uint64_t m, uint64_t *d_out, void *stream);
+/* bits [begin, begin + count) decoded to one byte per bit */
+int hkcsa_rrr_unpack(const void *d_rrr, const hkcsa_rrr_plan *h_plan, const void *d_tables, uint64_t begin,
+                     uint64_t count, uint8_t *d_out, void *stream);
+/* Restoring a wavelet-tree blob from coded levels: hkcsa_wt_restore_begin writes the node tables and clears the  */
+/* level regions, hkcsa_rrr_restore_level decodes a level's payload bits in place, hkcsa_wt_restore_finish        */
+/* rebuilds block headers, superblocks, select samples and node counts (scratch: plan->scratch_bytes) and checks  */
+/* the ones per level against the plan.                                                                           */
+int hkcsa_wt_restore_begin(const hkcsa_wt_plan *h_plan, void *d_blob, void *stream);
+int hkcsa_rrr_restore_level(const void *d_rrr, const hkcsa_rrr_plan *h_plan, const void *d_tables,
+                            const hkcsa_wt_plan *h_wt_plan, uint32_t level, void *d_wt_blob, void *stream);
+int hkcsa_wt_restore_finish(const hkcsa_wt_plan *h_plan, void *d_blob, void *d_scratch, size_t scratch_bytes,
+                            void *stream);
 
 /* ------------------------------------------------------------------------ */
 /* k-th order empirical entropy -- replaces calculate_high_order_entropy,       */
