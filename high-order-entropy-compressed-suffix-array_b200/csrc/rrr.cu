@@ -8,7 +8,7 @@
 //   block b (15 bits)   class c = popcount (4 bits, packed two per byte)
 //                       offset  = index of the 15-bit pattern among the C(15, c) patterns of its class,
 //                                 ceil(log2 C(15, c)) bits in one bit stream
-//   superblock (64 blocks = 960 bits)  {ones before it, bit position of its first offset}
+//   superblock (64 blocks = 960 bits)  {ones before it, bit position of its first offset}: 2 x 32 bits
 //
 // rank(i) reads one superblock entry, the 32 class bytes of the superblock (one sector), one offset and one table
 // entry -- it never expands the vector.  decode restores the level payload bit for bit (save / load round trip).
@@ -34,9 +34,9 @@ struct RrrTables {
     uint8_t cls_bits[16];
 };
 
-struct RrrSuper {
-    uint64_t ones;                // ones before the superblock
-    uint64_t bitpos;              // position of the superblock's first offset in the stream
+struct RrrSuper {                 // 8 bytes per 960 bits (a vector holds at most HKCSA_MAX_N < 2^30 bits)
+    uint32_t ones;                // ones before the superblock
+    uint32_t bitpos;              // position of the superblock's first offset in the stream
 };
 
 struct RrrDev {
@@ -120,7 +120,7 @@ rrr_scan_kernel(const uint64_t *__restrict__ sb_ones, const uint64_t *__restrict
         __syncthreads();
         uint64_t pa = s_ca, pb = s_cb;
         for (uint32_t w = 0; w < warp; ++w) { pa += s_a[w]; pb += s_b[w]; }
-        if (i < nsuper) { super[i].ones = pa + xa - a; super[i].bitpos = pb + xb - b; }
+        if (i < nsuper) { super[i].ones = (uint32_t)(pa + xa - a); super[i].bitpos = (uint32_t)(pb + xb - b); }
         __syncthreads();
         if (tid == 1023) { s_ca = pa + xa; s_cb = pb + xb; }
         __syncthreads();
@@ -318,6 +318,7 @@ extern "C" int hkcsa_rrr_encode(const void *d_wt_blob, const hkcsa_wt_plan *h_wt
 {
     HK_REQUIRE(d_wt_blob && h_wt && d_tables && h_plan && d_scratch, HKCSA_EINVAL, "null pointer");
     HK_REQUIRE(level < h_wt->levels && nbits <= h_wt->level_len[level], HKCSA_EINVAL, "level / nbits out of range");
+    HK_REQUIRE(nbits <= HKCSA_MAX_N + 1, HKCSA_ERANGE, "vector exceeds HKCSA_MAX_N bits (32-bit superblock entries)");
     HK_REQUIRE(!d_out || (reinterpret_cast<uintptr_t>(d_out) & 31) == 0, HKCSA_EINVAL, "output must be 32-byte aligned");
     cudaStream_t st = as_stream(stream);
     rrr_layout(h_plan, nbits, 0, 0);

@@ -411,8 +411,8 @@ class RrrVector:
 
     @property
     def coded_bits(self) -> int:
-        """4 class bits per block + the offset stream + 128 bits per superblock."""
-        return 4 * int(self.plan.nblocks) + int(self.plan.stream_bits) + 128 * int(self.plan.nsuper)
+        """4 class bits per block + the offset stream + 64 bits per superblock of 960 bits."""
+        return 4 * int(self.plan.nblocks) + int(self.plan.stream_bits) + 64 * int(self.plan.nsuper)
 
     def rank(self, pos) -> torch.Tensor:
         pos = (pos.to(device=self.blob.device, dtype=torch.int64).contiguous() if isinstance(pos, torch.Tensor)

@@ -375,7 +375,7 @@ int hkcsa_symbol_positions(const uint8_t *d_bwt, uint64_t n, uint32_t *d_pos, ui
 /* decompress returns '', :158-200).  Class/offset code of Raman-Raman-Rao with   */
 /* 15-bit blocks: per block a 4-bit class (its popcount) and the index of the     */
 /* pattern inside its class in ceil(log2 C(15, c)) bits; per 64 blocks the ones   */
-/* and the offset-stream position before them.  n H_0 + o(n) bits per vector;     */
+/* and the offset-stream position before them (2 x 32 bits).  n H_0 + o(n) bits per vector;     */
 /* over the wavelet-tree levels of a BWT that is the n H_k + o(n) index.          */
 /* ------------------------------------------------------------------------ */
 typedef struct hkcsa_rrr_plan {

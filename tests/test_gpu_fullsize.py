@@ -42,6 +42,30 @@ def test_build_and_query_at_baseline_size(E, kind, seed, n):
     assert got.tolist() == [fm.rank(int(c), int(i)) for c, i in zip(sym, pos)]
     ap = rng.randint(0, n + 1, 5000).astype(np.int64)
     assert np.array_equal(idx.wt.access(ap).cpu().numpy(), want_bwt[ap])
+    # ---- every level of the reference's wavelet tree (the left spine, csa/wavelet_tree.py:72-100) and its
+    #      rank_support (:9-12) bit for bit at full size; select (:17-25) at 2 000 ranks per level
+    _, spine = O.wt_spine(want_bwt)
+    assert len(spine) >= 2 and len(spine[0]) == n + 1
+    for level, bits in enumerate(spine):
+        n_l = len(bits)
+        assert n_l <= idx.wt.level_len(level)
+        got_bits = idx.wt.bv_bits(level, 0, n_l).cpu().numpy()
+        assert np.array_equal(got_bits, bits), f"level {level} bits"
+        del got_bits
+        rs = O.rank_support(bits)
+        got_rs = idx.wt.bv_rank_range(level, 0, n_l + 1).cpu().numpy().astype(np.uint32)
+        assert np.array_equal(got_rs, rs), f"level {level} rank_support"
+        del got_rs
+        ones = int(rs[-1])
+        ks = np.unique(np.concatenate([[1, min(2, max(ones, 1)), max(ones, 1)], rng.randint(1, max(ones, 1) + 1, 2000)])).astype(np.int64)
+        ks = ks[ks <= max(ones, 0)] if ones else ks[:0]
+        if len(ks):
+            got_sel = idx.wt.bv_select(level, ks).cpu().numpy()
+            want_sel = np.searchsorted(rs, ks, side="left")          # smallest p with rank(p) >= k
+            # a level holds more nodes than the reference's left-most one: select answers inside the spine prefix
+            assert np.array_equal(got_sel, want_sel), f"level {level} select"
+            assert want_sel.tolist()[:3] == [O.select(rs, int(k)) for k in ks[:3]]
+        del rs
     # ---- count against the oracle on 20 k patterns; locate round trip
     pats, off = O.gen_patterns(44, 20_000, h_text[:n])
     d_p, d_o = torch.from_numpy(pats).cuda(), torch.from_numpy(off).cuda()

@@ -440,6 +440,77 @@ def test_index_save_load_round_trip(E, tmp_path):
     assert torch.equal(o1, o2) and torch.equal(p1, p2)
 
 
+@pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "runs", "rand256_50k", "all_a_5000", "fib", "rand2_100k"])
+def test_rrr_coded_levels_rank_and_round_trip(E, name):
+    """csrc/rrr.cu: every wavelet-tree level in the class/offset code -- rank on the coded form equals rank on the
+    plain level at block / superblock boundaries and random positions, and decoding gives the level back bit for bit."""
+    import torch
+    seq = TEXTS[name]
+    wt = E.DeviceWaveletTree(dev(E, seq))
+    rng = np.random.RandomState(7)
+    for level in range(wt.levels):
+        n_l = wt.level_len(level)
+        vec = E.RrrVector.encode(wt, level)
+        assert vec.nbits == n_l and int(vec.plan.ones) == wt.level_ones(level)
+        want_bits = host(wt.bv_bits(level, 0, n_l))
+        assert np.array_equal(host(vec.bits()), want_bits)
+        if n_l > 2000:
+            assert np.array_equal(host(vec.bits(959, 1000)), want_bits[959:1959])       # a range across superblocks
+        edge = [0, 1, 14, 15, 16, 959, 960, 961, n_l - 1, n_l, n_l + 5]
+        pos = np.unique(np.clip(np.concatenate([edge, rng.randint(0, n_l + 1, 3000)]), 0, None)).astype(np.int64)
+        want = np.concatenate([[0], np.cumsum(want_bits, dtype=np.int64)])[np.minimum(pos, n_l)]
+        assert np.array_equal(host(vec.rank(pos)), want)
+        assert np.array_equal(host(wt.bv_rank(level, np.minimum(pos, n_l))), want)
+    # a sparse and a dense stand-alone vector: the code is far below / slightly above one bit per bit
+    for p_one, lo, hi in ((0.01, 0.3, 0.4), (0.5, 1.0, 1.25)):       # 4 / 15 class bits + 64 / 960 + the offsets
+        bits = (rng.random_sample(200_003) < p_one).astype(np.uint8)
+        bv = E.DeviceBitVector(torch.from_numpy(bits).cuda())
+        vec = E.RrrVector.encode(bv, 0)
+        assert np.array_equal(host(vec.bits()), bits)
+        assert lo < vec.coded_bits / len(bits) < hi
+
+
+@pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "runs", "all_a_5000"])
+def test_index_save_compressed_load_round_trip(E, tmp_path, name):
+    """save(compressed=True) writes the coded levels; load() decodes them in place and rebuilds the rank directories:
+    the restored query blob is bit-identical to the original and answers identically."""
+    import os
+    import torch
+    text = TEXTS[name] + b"$"
+    idx = E.DeviceIndex(dev(E, text), sa_sample_rate=16)
+    plain, coded = str(tmp_path / "plain.npz"), str(tmp_path / "coded.npz")
+    idx.save(plain)
+    idx.save(coded, compressed=True)
+    back = E.DeviceIndex.load(coded)
+    assert torch.equal(back.wt.blob, idx.wt.blob)
+    pats, off = O.gen_patterns(5, 2000, np.frombuffer(TEXTS[name], dtype=np.uint8), 1, 30)
+    d_p, d_o = torch.from_numpy(pats).cuda(), torch.from_numpy(off).cuda()
+    a, b = idx.count_batch(d_p, d_o), back.count_batch(d_p, d_o)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    o1, p1 = idx.locate_batch(d_p, d_o, use_samples=True)
+    o2, p2 = back.locate_batch(d_p, d_o)
+    assert torch.equal(o1, o2) and torch.equal(p1, p2)
+    sp = idx.space()
+    assert sp["coded_level_bits_per_symbol"] > 0 and len(sp["coded_bits_per_level"]) == idx.wt.levels
+    if name in ("runs", "all_a_5000"):                       # long runs: far below the raw level bits
+        assert sp["coded_level_bits_per_symbol"] < 0.6 * max(sp["raw_level_bits_per_symbol"], 1e-9) or idx.wt.levels == 0
+
+
+def test_compressed_suffix_array_space_report_next_to_entropy(E):
+    """CompressedSuffixArray.space_report(): index bits per symbol next to n*H_k (the reference's README.md:4-11 claim
+    'space close to the k-th order entropy' made measurable).  On the order-3 Markov text H_3 << H_0 and the coded
+    wavelet tree of the BWT sits between them."""
+    from csa.csa import CompressedSuffixArray
+    text = O.gen_text(O.ENG96, 42, 300_000).tobytes().decode("latin-1")
+    csa = CompressedSuffixArray(text, entropy_orders=(0, 1, 2, 3, 4))
+    rep = csa.space_report()
+    H = rep["H_k_bits_per_symbol"]
+    assert H[0] > H[1] > H[2] > H[3] >= H[4] > 0
+    assert rep["n_H_k_bits"][3] == pytest.approx(H[3] * csa.n)
+    assert H[3] * 0.9 < rep["coded_level_bits_per_symbol"] < rep["raw_level_bits_per_symbol"]
+    assert csa.locate(text[1000:1012]) == sorted(i for i in range(len(text)) if text.startswith(text[1000:1012], i))
+
+
 @pytest.mark.parametrize("name,parts", [("eng_300k", 3), ("dna_300k", 8), ("rand2_100k", 2), ("dna_1m_dollar", 5), ("runs", 4)])
 def test_multi_slice_index_matches_single_index(E, name, parts):
     """hkcsa.dist_sa.MultiSliceIndex (the index a distributed build leaves behind) must answer exactly like the
