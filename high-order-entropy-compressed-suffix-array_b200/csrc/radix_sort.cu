@@ -215,39 +215,28 @@ struct __align__(16) OsSmem {
     uint64_t bar;
 };
 
-// lanes of the warp holding the same 8-bit digit.  MODE 0: match.any (cost grows with the number of
-// distinct digits in the warp); MODE 1: eight ballots, one per digit bit (fixed cost).
-template <int MODE>
+// lanes of the warp holding the same 8-bit digit: eight ballots, one per digit bit (fixed cost; match.any costs ~37
+// ADU cycles at ~30 distinct digits per warp and only wins below ~8 distinct values).  Spelled in PTX -- test, vote,
+// conditional complement, and: ptxas turns the eight bit tests of an item into one R2P, 3.2 instructions per digit
+// bit where the C++ form (shift, and, two compares, select, and) compiles to six.
 __device__ __forceinline__ uint32_t digit_peers(uint32_t d)
 {
-    if (MODE == 0) return __match_any_sync(0xffffffffu, d);
-    if (MODE == 2) {       // same ballots, spelled in PTX: test, vote, conditional complement, and -- four
-                           // instructions per bit (the C++ form compiles to six: shift, and, two compares, select, and)
-        uint32_t peers = 0xffffffffu;
-#pragma unroll
-        for (int bit = 0; bit < 8; ++bit) {
-            uint32_t x;
-            asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                         "and.b32 t, %1, %2;\n\t"
-                         "setp.ne.u32 p, t, 0;\n\t"
-                         "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
-                         "@!p not.b32 %0, %0;\n\t}"
-                         : "=r"(x) : "r"(d), "r"(1u << bit));
-            peers &= x;
-        }
-        return peers;
-    }
     uint32_t peers = 0xffffffffu;
 #pragma unroll
     for (int bit = 0; bit < 8; ++bit) {
-        const bool one = (d >> bit) & 1u;
-        const uint32_t b = __ballot_sync(0xffffffffu, one);
-        peers &= one ? b : ~b;
+        uint32_t x;
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                     "and.b32 t, %1, %2;\n\t"
+                     "setp.ne.u32 p, t, 0;\n\t"
+                     "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+                     "@!p not.b32 %0, %0;\n\t}"
+                     : "=r"(x) : "r"(d), "r"(1u << bit));
+        peers &= x;
     }
     return peers;
 }
 
-template <int THREADS, int MIN_CTAS, int MODE, bool IDENT>
+template <int THREADS, int MIN_CTAS, bool IDENT>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout, const uint32_t *__restrict__ vin,
                   uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
@@ -305,7 +294,7 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
         val[k] = ident ? tile_base + local : S.vals[local];
         const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
         dr[k] = d << 16;
-        peers[k] = digit_peers<MODE>(d);
+        peers[k] = digit_peers(d);
     }
     const uint32_t lt = lanemask_lt();
 #pragma unroll
@@ -396,191 +385,6 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     }
 }
 
-// ---------------------------------------------------------------------------
-// Persistent variant: every CTA loops over tiles taken from the ticket counter and keeps two TMA stages,
-// so the bulk copy of the next tile is in flight while the current one is ranked, staged and written out.
-// Deadlock-free: a CTA works on its tiles in ticket order, so the lowest unfinished tile is always being
-// processed and only looks back at finished tiles.
-// ---------------------------------------------------------------------------
-template <int THREADS>
-struct __align__(16) OsSmemP {
-    static constexpr int TILE = THREADS * OS_IPT;
-    static constexpr int WARPS = THREADS / 32;
-    uint64_t keys[2][TILE];
-    uint32_t vals[2][TILE];
-    uint16_t whist[WARPS][RADIX];
-    uint32_t gbase[RADIX];
-    uint32_t wsum[32];
-    uint32_t cur_tile, next_tile;
-    uint64_t bar[2];
-};
-
-template <int THREADS>
-__device__ __forceinline__ void os_issue_tile(OsSmemP<THREADS> &S, int stage, const uint64_t *kin, const uint32_t *vin,
-                                              uint32_t n, uint32_t tile)
-{
-    constexpr int TILE = OsSmemP<THREADS>::TILE;
-    const uint32_t tile_base = tile * (uint32_t)TILE;
-    const uint32_t nvalid = min((uint32_t)TILE, n - tile_base);
-    const uint32_t nk16 = nvalid & ~1u, nv16 = nvalid & ~3u;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this stage are done
-    mbar_expect_tx(&S.bar[stage], nk16 * 8u + nv16 * 4u);
-    if (nk16) bulk_g2s(S.keys[stage], kin + tile_base, nk16 * 8u, &S.bar[stage]);
-    if (nv16) bulk_g2s(S.vals[stage], vin + tile_base, nv16 * 4u, &S.bar[stage]);
-}
-
-template <int THREADS, int MIN_CTAS, int MODE>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS)
-onesweep64_persistent_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
-                             const uint32_t *__restrict__ vin, uint32_t *__restrict__ vout, uint32_t n, int shift,
-                             const uint32_t *__restrict__ digit_base, uint32_t *lookback, uint32_t *ticket,
-                             uint32_t tiles)
-{
-    using Smem = OsSmemP<THREADS>;
-    constexpr int TILE = Smem::TILE;
-    constexpr int WARPS = Smem::WARPS;
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-
-    if (tid == 0) {
-        mbar_init(&S.bar[0], 1);
-        mbar_init(&S.bar[1], 1);
-        const uint32_t t0 = atomicAdd(ticket, 1u);
-        S.cur_tile = t0;
-        if (t0 < tiles) os_issue_tile<THREADS>(S, 0, kin, vin, n, t0);
-    }
-    __syncthreads();
-
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t tile = S.cur_tile;
-        if (tile >= tiles) break;
-        const int st = it & 1;
-        const uint32_t parity = (it >> 1) & 1u;
-        // prefetch the next tile into the other stage (its previous contents were written out last iteration)
-        if (tid == 0) {
-            const uint32_t tn = atomicAdd(ticket, 1u);
-            S.next_tile = tn;
-            if (tn < tiles) os_issue_tile<THREADS>(S, st ^ 1, kin, vin, n, tn);
-        }
-        for (int i = tid; i < WARPS * RADIX / 2; i += THREADS) reinterpret_cast<uint32_t *>(&S.whist[0][0])[i] = 0;
-        const uint32_t tile_base = tile * (uint32_t)TILE;
-        const uint32_t nvalid = min((uint32_t)TILE, n - tile_base);
-        const uint32_t nk16 = nvalid & ~1u, nv16 = nvalid & ~3u;
-        uint64_t *Sk = S.keys[st];
-        uint32_t *Sv = S.vals[st];
-        mbar_wait(&S.bar[st], parity);
-        if (tid == 0 && nk16 < nvalid) Sk[nk16] = kin[tile_base + nk16];
-        if (tid < 4 && nv16 + tid < nvalid) Sv[nv16 + tid] = vin[tile_base + nv16 + tid];
-        __syncthreads();
-
-        uint64_t key[OS_IPT];
-        uint32_t val[OS_IPT];
-        uint32_t peers[OS_IPT];
-        uint16_t rnk[OS_IPT];
-        const uint32_t wbase = warp * 32u * OS_IPT + lane;
-#pragma unroll
-        for (int k = 0; k < OS_IPT; ++k) {
-            const uint32_t local = wbase + k * 32u;
-            const bool valid = local < nvalid;
-            key[k] = valid ? Sk[local] : ~0ULL;
-            val[k] = Sv[local];
-            const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
-            peers[k] = digit_peers<MODE>(d);
-        }
-#pragma unroll
-        for (int k = 0; k < OS_IPT; ++k) {
-            const bool valid = (wbase + k * 32u) < nvalid;
-            const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
-            const uint32_t leader = __ffs(peers[k]) - 1;
-            uint32_t before = 0;
-            uint16_t *cnt = &S.whist[warp][d];
-            if (lane == leader) {
-                before = *cnt;
-                *cnt = (uint16_t)(before + __popc(peers[k]));
-            }
-            before = __shfl_sync(0xffffffffu, before, leader);
-            rnk[k] = (uint16_t)(before + __popc(peers[k] & lanemask_lt()));
-            __syncwarp();
-        }
-        __syncthreads();
-
-        uint32_t bt = 0;
-        if (tid < RADIX) {
-            uint32_t run = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                const uint32_t c = S.whist[w][tid];
-                S.whist[w][tid] = (uint16_t)run;
-                run += c;
-            }
-            bt = run;
-            st_volatile_u32(&lookback[(size_t)tile * RADIX + tid], (tile == 0 ? LB_INC : LB_AGG) | bt);
-        }
-        uint32_t wtotal;
-        const uint32_t ex = warp_excl_sum(bt, wtotal);
-        if (lane == 0) S.wsum[warp] = wtotal;
-        __syncthreads();
-        uint32_t wprefix = 0;
-        for (uint32_t w = 0; w < warp && w < RADIX / 32; ++w) wprefix += S.wsum[w];
-        const uint32_t bexcl = ex + wprefix;
-        if (tid < RADIX) {
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) S.whist[w][tid] = (uint16_t)(S.whist[w][tid] + bexcl);
-        }
-        __syncthreads();
-
-#pragma unroll
-        for (int k = 0; k < OS_IPT; ++k) {
-            const bool valid = (wbase + k * 32u) < nvalid;
-            const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 0xFFu) : 255u;
-            const uint32_t slot = (uint32_t)S.whist[warp][d] + rnk[k];
-            Sk[slot] = key[k];
-            Sv[slot] = val[k];
-        }
-
-        if (tid < RADIX) {
-            uint32_t excl = 0;
-            if (tile > 0) {
-                int64_t t = (int64_t)tile - 1;
-                bool done = false;
-                while (!done) {
-                    uint32_t v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        v[j] = (t - j >= 0) ? ld_volatile_u32(&lookback[(size_t)(t - j) * RADIX + tid]) : LB_INC;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (done) break;
-                        const uint32_t flag = v[j] >> 30;
-                        if (flag == 0) break;
-                        excl += v[j] & LB_VAL;
-                        --t;
-                        if (flag == 2) done = true;
-                    }
-                }
-                st_volatile_u32(&lookback[(size_t)tile * RADIX + tid], LB_INC | (excl + bt));
-            }
-            S.gbase[tid] = digit_base[tid] + excl - bexcl;
-        }
-        __syncthreads();
-
-#pragma unroll
-        for (int k = 0; k < OS_IPT; ++k) {
-            const uint32_t i = k * THREADS + tid;
-            if (i < nvalid) {
-                const uint64_t kk = Sk[i];
-                const uint32_t g = S.gbase[(uint32_t)(kk >> shift) & 0xFFu] + i;
-                kout[g] = kk;
-                vout[g] = Sv[i];
-            }
-        }
-        __syncthreads();                      // stage `st` fully consumed; next_tile visible
-        if (tid == 0) S.cur_tile = S.next_tile;
-        __syncthreads();
-    }
-}
-
 template <typename KeyT, int VAL_MODE, int THREADS, int IPT>
 static constexpr size_t onesweep_smem()
 {
@@ -650,19 +454,14 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
     return cudaGetLastError();
 }
 
-// Variant selection (HKCSA_OS_VARIANT, read once; measured on B200, profiles/r01_onesweep_variants.txt):
-// 7 (default) = 384 threads x 8, 3 CTAs/SM (3072 pairs per tile, 56 registers), ballot ranking spelled in PTX
-// (3.2 instructions per digit bit); 6 = the same with 512 threads, 2 CTAs/SM (0.729 vs 0.715 ms per pass);
-// 2 = 512 threads with the ballots in C++ (6 instructions per bit: 0.78 ms per pass); 0 = same with match.any
-// ranking (faster only when a digit takes < ~8 distinct values); 1 = 256 threads x 8, 4 CTAs/SM, match.any.
-template <int THREADS, int MIN_CTAS, int MODE>
+template <int THREADS, int MIN_CTAS>
 static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n, int passes,
                                   const SortScratch &s, cudaStream_t st, bool identity_vals)
 {
     using Smem = OsSmem<THREADS>;
     constexpr size_t smem = sizeof(Smem) + 128;
-    auto kern = onesweep64_kernel<THREADS, MIN_CTAS, MODE, false>;
-    auto kern_ident = onesweep64_kernel<THREADS, MIN_CTAS, MODE, true>;
+    auto kern = onesweep64_kernel<THREADS, MIN_CTAS, false>;
+    auto kern_ident = onesweep64_kernel<THREADS, MIN_CTAS, true>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -697,62 +496,18 @@ static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint
     return cudaSuccess;
 }
 
-static cudaError_t run_onesweep64_persistent(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n,
-                                             int passes, const SortScratch &s, cudaStream_t st)
-{
-    constexpr int THREADS = 512;
-    using Smem = OsSmemP<THREADS>;
-    constexpr size_t smem = sizeof(Smem) + 128;
-    auto kern = onesweep64_persistent_kernel<THREADS, 2, 1>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    const uint32_t tiles = (n + Smem::TILE - 1) / Smem::TILE;
-    const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)num_sms() * 2);
-    uint64_t *kin = k0, *kout = k1;
-    uint32_t *vin = v0, *vout = v1;
-    for (int p = 0; p < passes; ++p) {
-        cudaError_t e = cudaMemsetAsync(s.lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), st);
-        if (e != cudaSuccess) return e;
-        {
-            prof::Scope ps(st, prof::ONESWEEP_U64, (uint64_t)n * 24);
-            kern<<<grid, THREADS, smem, st>>>(kin, kout, vin, vout, n, 8 * p, s.base + p * RADIX, s.lookback,
-                                              s.ticket + p, tiles);
-            count_launch();
-        }
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        uint64_t *tk = kin; kin = kout; kout = tk;
-        uint32_t *tv = vin; vin = vout; vout = tv;
-    }
-    return cudaSuccess;
-}
-
 cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n,
                                  int passes, const SortScratch &s, cudaStream_t st, bool identity_vals)
 {
     if (n == 0 || passes <= 0) return cudaSuccess;
-    static int variant = -1;
-    if (variant < 0) {
-        const char *e = getenv("HKCSA_OS_VARIANT");
-        variant = e ? atoi(e) : 7;
-    }
     radix_scan_kernel<<<passes, RADIX, 0, st>>>(s.hist, s.base);
     count_launch();
     cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    if (variant == 5 && !identity_vals) return run_onesweep64_persistent(k0, v0, k1, v1, n, passes, s, st);
-    if (variant == 1) return run_onesweep64<256, 4, 0>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
-    if (variant == 3) return run_onesweep64<256, 4, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
-    if (variant == 4) return run_onesweep64<384, 3, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
-    if (variant == 0) return run_onesweep64<512, 2, 0>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
-    if (variant == 2) return run_onesweep64<512, 2, 1>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
-    if (variant == 8) return run_onesweep64<256, 4, 2>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
-    if (variant == 6) return run_onesweep64<512, 2, 2>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
-    return run_onesweep64<384, 3, 2>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+    // 384 threads x 8 pairs, 3 CTAs per SM, ballots spelled in PTX: the fastest of the shapes measured on B200
+    // (profiles/r01_onesweep_variants.txt keeps the numbers of the others: 256 x 8 / 512 x 8, match.any ranking,
+    // C++ ballots, a persistent two-stage kernel)
+    return run_onesweep64<384, 3>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
 }
 
 cudaError_t radix_partition_bytes(const uint8_t *d_in, uint8_t *d_out, uint32_t *d_pos_out, uint32_t n,
