@@ -238,6 +238,19 @@ class _SymmWorkspace:
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
 
 
+def _all_gather_rows(t: torch.Tensor, world: int, group) -> torch.Tensor:
+    """[world, len] from one row per rank: one collective (NCCL), or the list form for gloo (CPU tests)."""
+    import torch.distributed as dist
+    t = t.contiguous()
+    if t.is_cuda:
+        out = torch.empty((world, t.numel()), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    return torch.stack(parts)
+
+
 def _torch_run(prog, group, device):
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -250,20 +263,16 @@ def _torch_run(prog, group, device):
             if kind == "gather":
                 x = req[1]
                 t = x.to(torch.int64) if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(device)
-                out = torch.empty((world, t.numel()), dtype=torch.int64, device=device)
-                dist.all_gather_into_tensor(out, t.contiguous(), group=group)
-                res = out.cpu().numpy()
+                res = _all_gather_rows(t, world, group).cpu().numpy()
             elif kind == "text":
                 block, sizes = req[1], [int(v) for v in req[2]]
                 if len(set(sizes)) == 1:                        # equal blocks: the gathered buffer IS the text
-                    res = torch.empty(sum(sizes), dtype=torch.uint8, device=device)
-                    dist.all_gather_into_tensor(res, block.contiguous(), group=group)
+                    res = _all_gather_rows(block, world, group).reshape(-1)
                 else:                                           # one collective on padded blocks, then compaction
                     width = max(sizes)
                     pad = torch.zeros(width, dtype=torch.uint8, device=device)
                     pad[: block.numel()] = block
-                    allb = torch.empty((world, width), dtype=torch.uint8, device=device)
-                    dist.all_gather_into_tensor(allb, pad, group=group)
+                    allb = _all_gather_rows(pad, world, group)
                     res = torch.cat([allb[r, : sizes[r]] for r in range(world)])
             elif kind == "symm":
                 need = torch.tensor([int(req[1])], dtype=torch.int64, device=device)

@@ -106,3 +106,43 @@ def test_exchange_layout_regions_tile_every_destination():
             assert base[0] == 0 and ends[-1] == counts[d] and all(ends[i] == base[i + 1] for i in range(world - 1))
         # balance: no destination exceeds the ideal share by more than the heaviest bucket
         assert counts.max() <= hist_all.sum() / world + hist_all.sum(0).max()
+
+
+def _program_worker(rank, world, port, out):
+    """The collective steps of the distributed build's rank program (hkcsa.dist_sa._torch_run) over gloo: a toy
+    program yields the same requests the real one does -- sizes, text blocks (ragged and equal), histograms, barrier."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hkcsa import dist_sa
+        full = O.gen_text(O.ENG96, 3, 10_000 + world)
+        cuts_ragged = [0] + [1000 * (r + 1) + r for r in range(world - 1)] + [len(full)]
+        cuts_equal = [len(full) // world * r for r in range(world)] + [len(full) // world * world]
+
+        def program():
+            got = {}
+            for name, cuts in (("ragged", cuts_ragged), ("equal", cuts_equal)):
+                block = torch.from_numpy(full[cuts[rank]:cuts[rank + 1]].copy())
+                sizes = (yield ("gather", np.array([block.numel()], dtype=np.int64)))[:, 0]
+                text = yield ("text", block, sizes)
+                got[name] = (sizes.tolist(), text.numpy().copy())
+            hist = np.bincount(full[cuts_ragged[rank]:cuts_ragged[rank + 1]], minlength=256).astype(np.int64)
+            got["hist"] = (yield ("gather", torch.from_numpy(hist))).sum(0)
+            yield ("barrier",)
+            return got
+
+        got = dist_sa._torch_run(program(), None, torch.device("cpu"))
+        ok = got["ragged"][0] == list(np.diff(cuts_ragged)) and np.array_equal(got["ragged"][1], full)
+        ok = ok and np.array_equal(got["equal"][1], full[: cuts_equal[-1]])
+        ok = ok and np.array_equal(got["hist"], np.bincount(full, minlength=256))
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_rank_program_collectives_gloo(world):
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_program_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {r: 1 for r in range(world)}

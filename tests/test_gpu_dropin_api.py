@@ -371,11 +371,21 @@ def test_reference_benchmark_harness_runs_on_the_package(capsys, monkeypatch):
     out = capsys.readouterr().out
     assert "Benchmark Summary" in out and sorted(res.pattern_times) == [5, 10, 50, 100, 500, 1000], which
     assert res.construction_time > 0 and res.total_time >= res.construction_time
-    # what locate returns is what a scan of the indexed text finds
+    # The benchmark text holds '$' itself, so the appended sentinel is not unique and backward search is the
+    # reference's recurrence on a BWT whose rows are suffixes, not rotations (it reports e.g. one spurious row for
+    # "mississippi$mi"): locate must return exactly what the reference-parity EnhancedFMIndex.find returns ...
+    from csa.enhanced_fm_index import EnhancedFMIndex
     csa, _, _ = bench.benchmark_construction(text)
+    fm = EnhancedFMIndex(text)
     for q in ("ssi", "mississippi$mi", text[7:507], "$m", "x"):
         locs, _, _ = bench.benchmark_pattern_search(csa, q)
-        assert locs == [i for i in range(len(text)) if text.startswith(q, i)], q
+        assert locs == sorted(fm.find(q)), q
+    # ... and on the same text with a sentinel-free separator, what a plain scan finds
+    clean = text.replace("$", "#")
+    csa2, _, _ = bench.benchmark_construction(clean)
+    for q in ("ssi", "mississippi#mi", clean[7:507], "#m", "x"):
+        locs, _, _ = bench.benchmark_pattern_search(csa2, q)
+        assert locs == [i for i in range(len(clean)) if clean.startswith(q, i)], q
 
 
 def test_main_demo_matches_reference_output(capsys):
