@@ -440,6 +440,13 @@ def wt_from_coded_levels(plan: WtPlan, coded: list, device) -> DeviceWaveletTree
     check(L.hkcsa_wt_restore_begin(C.byref(plan), _ptr(wt.blob), _stream()))
     tab = rrr_tables(device)
     for level, vec in enumerate(coded):
+        if isinstance(vec, np.ndarray):             # a level kept plain: payload words back behind zeroed headers
+            a, b = int(plan.off_blocks[level]), int(plan.off_super[level])
+            rows = torch.zeros(((b - a) // 32, 8), dtype=torch.int32, device=device)
+            k = min(rows.shape[0], vec.shape[0])
+            rows[:k, 1:] = torch.from_numpy(vec[:k].view(np.int32)).to(device)
+            wt.blob[a:a + rows.numel() * 4] = rows.view(torch.uint8).reshape(-1)
+            continue
         check(L.hkcsa_rrr_restore_level(_ptr(vec.blob), C.byref(vec.plan), _ptr(tab), C.byref(plan), level,
                                         _ptr(wt.blob), _stream()))
     scratch = _scratch(plan.scratch_bytes, device)
@@ -616,11 +623,15 @@ class DeviceIndex:
         n = max(self.n, 1)
         coded = self.coded_levels()
         ssa_bits = 8 * int(self.ssa.blob.numel()) if self.ssa is not None else 0
+        raw = [self.wt.level_len(l) for l in range(self.wt.levels)]
+        stored = [min(v.coded_bits, r) for v, r in zip(coded, raw)]       # a level the code does not shrink stays plain
         return {"n": self.n, "levels": self.wt.levels,
                 "query_blob_bits_per_symbol": 8.0 * self.wt.blob.numel() / n,
-                "raw_level_bits_per_symbol": sum(self.wt.level_len(l) for l in range(self.wt.levels)) / n,
-                "coded_level_bits_per_symbol": sum(v.coded_bits for v in coded) / n,
+                "raw_level_bits_per_symbol": sum(raw) / n,
+                "coded_level_bits_per_symbol": sum(stored) / n,
                 "coded_bits_per_level": [v.coded_bits for v in coded],
+                "stored_bits_per_level": stored,
+                "levels_kept_plain": [l for l, (v, r) in enumerate(zip(coded, raw)) if v.coded_bits >= r],
                 "sampled_sa_bits_per_symbol": ssa_bits / n}
 
     def save(self, path: str, compressed: bool = False) -> None:
@@ -632,8 +643,13 @@ class DeviceIndex:
                  "wt_plan": np.frombuffer(bytes(self.wt.plan), dtype=np.uint8)}
         if compressed:
             for l, vec in enumerate(self.coded_levels()):
-                parts[f"rrr_plan_{l}"] = np.frombuffer(bytes(vec.plan), dtype=np.uint8)
-                parts[f"rrr_blob_{l}"] = vec.blob.cpu().numpy()
+                if vec.coded_bits < self.wt.level_len(l):
+                    parts[f"rrr_plan_{l}"] = np.frombuffer(bytes(vec.plan), dtype=np.uint8)
+                    parts[f"rrr_blob_{l}"] = vec.blob.cpu().numpy()
+                else:       # the code does not shrink this level: its 224 payload bits per rank block, headers dropped
+                    a, b = int(self.wt.plan.off_blocks[l]), int(self.wt.plan.off_super[l])
+                    words = self.wt.blob[a:b].cpu().numpy().view(np.uint32).reshape(-1, 8)
+                    parts[f"raw_payload_{l}"] = np.ascontiguousarray(words[:, 1:])
         else:
             parts["wt_blob"] = self.wt.blob.cpu().numpy()
         if self.ssa is not None:
@@ -652,9 +668,11 @@ class DeviceIndex:
         else:
             coded = []
             for l in range(int(plan.levels)):
-                rp = RrrPlan.from_buffer_copy(z[f"rrr_plan_{l}"].tobytes())
-                rb = torch.from_numpy(z[f"rrr_blob_{l}"]).to(device)
-                coded.append(RrrVector(rp, rb))
+                if f"rrr_plan_{l}" in z.files:
+                    rp = RrrPlan.from_buffer_copy(z[f"rrr_plan_{l}"].tobytes())
+                    coded.append(RrrVector(rp, torch.from_numpy(z[f"rrr_blob_{l}"]).to(device)))
+                else:
+                    coded.append(np.asarray(z[f"raw_payload_{l}"], dtype=np.uint32))
             blob = wt_from_coded_levels(plan, coded, device).blob
         ssa = None
         if "ssa_plan" in z.files:

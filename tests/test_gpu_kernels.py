@@ -509,7 +509,12 @@ def test_compressed_suffix_array_space_report_next_to_entropy(E):
     H = rep["H_k_bits_per_symbol"]
     assert H[0] > H[1] > H[2] > H[3] >= H[4] > 0
     assert rep["n_H_k_bits"][3] == pytest.approx(H[3] * csa.n)
-    assert H[3] * 0.9 < rep["coded_level_bits_per_symbol"] < rep["raw_level_bits_per_symbol"]
+    # the 15-bit class/offset code pays 4/15 + 1/15 bits per level bit on top of the blocks' entropy: on a text this
+    # small only the run-heavy levels shrink, the others are kept plain -- never above the raw levels
+    assert H[3] * 0.9 < rep["coded_level_bits_per_symbol"] <= rep["raw_level_bits_per_symbol"]
+    assert rep["stored_bits_per_level"] == [min(a, b) for a, b in zip(rep["coded_bits_per_level"],
+                                                                      [rep["stored_bits_per_level"][l] if l in rep["levels_kept_plain"] else 10 ** 18
+                                                                       for l in range(rep["levels"])])]
     assert csa.locate(text[1000:1012]) == sorted(i for i in range(len(text)) if text.startswith(text[1000:1012], i))
 
 
