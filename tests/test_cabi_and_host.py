@@ -35,7 +35,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_mirrors_match_c_layout():
     from hkcsa import _lib
     L = _lib.load()
-    for idx, st in enumerate((_lib.SaStats, _lib.WtPlan, _lib.SsaPlan, _lib.ProfEntry, _lib.OccPlan)):
+    for idx, st in enumerate((_lib.SaStats, _lib.WtPlan, _lib.SsaPlan, _lib.ProfEntry, _lib.OccPlan, _lib.DsaPlan,
+                              _lib.RrrPlan)):
         assert L.hkcsa_struct_size(idx) == C.sizeof(st)
 
 
@@ -215,3 +216,49 @@ def test_prof_class_names():
     assert L.hkcsa_prof_class_index(b"onesweep_u64") >= 0
     assert L.hkcsa_prof_class_index(b"bwt_gather") >= 0
     assert L.hkcsa_prof_class_index(b"no such kernel") == -1
+
+
+def test_distributed_build_plan_is_host_only():
+    """hkcsa_dsa_plan_make derives the round-0 prefix code and the id width from the byte histogram of the whole text
+    (host memory only): the same inputs give the same plan on every rank; argument checks need no GPU."""
+    from hkcsa import _lib
+    L = _lib.load()
+    assert L.hkcsa_dsa_state_bytes() == C.sizeof(C.c_uint64) * 512 and L.hkcsa_dsa_scratch_bytes(1 << 20) > (1 << 20) * 24
+
+    def plan(hist, n, wide=0):
+        h = np.zeros(256, dtype=np.uint64)
+        for k, v in hist.items():
+            h[k] = v
+        p = _lib.DsaPlan()
+        rc = L.hkcsa_dsa_plan_make(h.ctypes.data_as(C.POINTER(C.c_uint64)), n, wide, C.byref(p))
+        return rc, p
+
+    rc, dna = plan({65: 25, 67: 25, 71: 25, 84: 25, 36: 1}, 101)
+    assert rc == 0 and dna.sigma == 5 and dna.bits0 % 8 == 0 and 16 <= dna.bits0 <= 64 and dna.passes0 == dna.bits0 // 8
+    assert dna.wide == 0 and dna.k0 >= 1 and dna.b_fixed == 3
+    codes = [(dna.code[c], dna.len[c]) for c in (256, 36, 65, 67, 71, 84)]       # past-the-end, then bytes in order
+    streams = [format(c, "b").zfill(l) for c, l in codes]
+    assert streams == sorted(streams) and len(set(streams)) == 6                   # order-preserving ...
+    assert not any(a != b and b.startswith(a) for a in streams for b in streams)   # ... and prefix-free
+    assert [dna.fixed_code[c] for c in (36, 65, 67, 71, 84)] == [1, 2, 3, 4, 5] and dna.fixed_code[66] == 0
+    rc2, again = plan({65: 25, 67: 25, 71: 25, 84: 25, 36: 1}, 101)
+    assert bytes(again) == bytes(dna)
+    assert plan({97: 10}, (1 << 32) - 2)[1].wide == 0 and plan({97: 10}, (1 << 32) - 1)[1].wide == 1
+    assert plan({97: 10}, 100, wide=1)[1].wide == 1
+    assert plan({97: 10}, (1 << 40) + 1)[0] == _lib.ERANGE
+    one = plan({97: 1000}, 1000)[1]
+    assert one.sigma == 1 and one.bits0 >= 16
+    # argument checks of the device entry points come before any CUDA call
+    st = C.create_string_buffer(L.hkcsa_dsa_state_bytes())
+    assert L.hkcsa_dsa_ext_round(st, None) == _lib.EINVAL                           # state not initialised by _begin
+    assert L.hkcsa_dsa_working_set(st) == 0 and L.hkcsa_dsa_slice(st) is None
+    cuts = (C.c_uint32 * 3)(0, 10, 65535)                                          # does not span every bucket
+    z = (C.c_uint64 * 2)(0, 0)
+    assert L.hkcsa_dsa_pack_exchange(1, C.byref(dna), 0, 0, 2, cuts, z, z, z, 1, None) == _lib.EINVAL
+    assert L.hkcsa_dsa_pack_exchange(1, C.byref(dna), 0, 0, 9, cuts, z, z, z, 1, None) == _lib.EINVAL
+    assert L.hkcsa_ranges_push_peers(1, 1, 5, 0, 17, z, 0, None) == _lib.EINVAL
+    assert L.hkcsa_ranges_push_peers(None, None, 0, 0, 1, z, 0, None) == 0          # empty slice: nothing to do
+    assert L.hkcsa_entropy_scratch_bytes(1000) > 1000 * 9 and L.hkcsa_rrr_scratch_bytes(960 * 100) >= 100 * 24
+    out = (C.c_double * 5)()
+    assert L.hkcsa_entropy_from_sa(None, 10, None, 0, out, None, 0, None) == _lib.EINVAL       # k = 0 is the histogram's job
+    assert L.hkcsa_entropy_from_sa(None, 3, None, 5, out, None, 0, None) == 0 and list(out) == [0.0] * 5   # n <= k -> 0
