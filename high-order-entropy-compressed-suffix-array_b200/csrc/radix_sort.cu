@@ -164,7 +164,7 @@ onesweep_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uin
 // flight), ranked from shared memory, staged in digit order in a second
 // shared buffer and written out as coalesced runs.
 // ---------------------------------------------------------------------------
-constexpr int OS_IPT = 8;
+constexpr int OS_IPT = 8;            // default pairs per thread
 #ifndef OS_LB_BATCH
 #define OS_LB_BATCH 8
 #endif
@@ -202,9 +202,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 
 // Shared memory of one CTA.  The TMA destination doubles as the digit-ordered staging buffer: by the
 // time the tile is staged every thread holds its keys and values in registers.
-template <int THREADS>
+template <int THREADS, int IPT = OS_IPT>
 struct __align__(16) OsSmem {
-    static constexpr int TILE = THREADS * OS_IPT;
+    static constexpr int TILE = THREADS * IPT;
     static constexpr int WARPS = THREADS / 32;
     uint64_t keys[TILE];
     uint32_t vals[TILE];
@@ -236,13 +236,13 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d)
     return peers;
 }
 
-template <int THREADS, int MIN_CTAS, bool IDENT>
+template <int THREADS, int MIN_CTAS, bool IDENT, int IPT = OS_IPT>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout, const uint32_t *__restrict__ vin,
                   uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
                   uint32_t *lookback, uint32_t *ticket, uint32_t *__restrict__ lookback_next)
 {
-    using Smem = OsSmem<THREADS>;
+    using Smem = OsSmem<THREADS, IPT>;
     constexpr int TILE = Smem::TILE;
     constexpr int WARPS = Smem::WARPS;
     static_assert(THREADS >= RADIX, "one thread per digit");
@@ -282,13 +282,13 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
 
     // ---- rank inside the warp (warp-striped: lane l, item k <-> tile offset warp*32*IPT + k*32 + l)
     //      Slots past the end of the array read as all-ones keys: digit 255 at every shift, ranked last.
-    uint64_t key[OS_IPT];
-    uint32_t val[OS_IPT];
-    uint32_t peers[OS_IPT];
-    uint32_t dr[OS_IPT];          // digit << 16 | rank of the item among the warp's items with that digit
-    const uint32_t wbase = warp * 32u * OS_IPT + lane;
+    uint64_t key[IPT];
+    uint32_t val[IPT];
+    uint32_t peers[IPT];
+    uint32_t dr[IPT];          // digit << 16 | rank of the item among the warp's items with that digit
+    const uint32_t wbase = warp * 32u * IPT + lane;
 #pragma unroll
-    for (int k = 0; k < OS_IPT; ++k) {
+    for (int k = 0; k < IPT; ++k) {
         const uint32_t local = wbase + k * 32u;
         key[k] = (local < nvalid) ? S.keys[local] : ~0ULL;
         val[k] = ident ? tile_base + local : S.vals[local];
@@ -298,7 +298,7 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     }
     const uint32_t lt = lanemask_lt();
 #pragma unroll
-    for (int k = 0; k < OS_IPT; ++k) {
+    for (int k = 0; k < IPT; ++k) {
         // the lowest lane of a digit group adds the group to the warp's counter; everybody reads the counter back
         // and takes its place from the end: rank = counter - #(peers at or above me)
         uint16_t *cnt = &S.whist[warp][dr[k] >> 16];
@@ -338,7 +338,7 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
 
     // ---- stage (key, value) in digit order
 #pragma unroll
-    for (int k = 0; k < OS_IPT; ++k) {
+    for (int k = 0; k < IPT; ++k) {
         const uint32_t slot = (uint32_t)S.whist[warp][dr[k] >> 16] + (dr[k] & 0xFFFFu);
         S.keys[slot] = key[k];
         S.vals[slot] = val[k];
@@ -374,7 +374,7 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
 
     // ---- coalesced write-out: consecutive threads take consecutive sorted slots
 #pragma unroll
-    for (int k = 0; k < OS_IPT; ++k) {
+    for (int k = 0; k < IPT; ++k) {
         const uint32_t i = k * THREADS + tid;
         if (i < nvalid) {
             const uint64_t kk = S.keys[i];
@@ -454,14 +454,14 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
     return cudaGetLastError();
 }
 
-template <int THREADS, int MIN_CTAS>
+template <int THREADS, int MIN_CTAS, int IPT = OS_IPT>
 static cudaError_t run_onesweep64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint32_t n, int passes,
                                   const SortScratch &s, cudaStream_t st, bool identity_vals)
 {
-    using Smem = OsSmem<THREADS>;
+    using Smem = OsSmem<THREADS, IPT>;
     constexpr size_t smem = sizeof(Smem) + 128;
-    auto kern = onesweep64_kernel<THREADS, MIN_CTAS, false>;
-    auto kern_ident = onesweep64_kernel<THREADS, MIN_CTAS, true>;
+    auto kern = onesweep64_kernel<THREADS, MIN_CTAS, false, IPT>;
+    auto kern_ident = onesweep64_kernel<THREADS, MIN_CTAS, true, IPT>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -507,6 +507,20 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
     // 384 threads x 8 pairs, 3 CTAs per SM, ballots spelled in PTX: the fastest of the shapes measured on B200
     // (profiles/r01_onesweep_variants.txt keeps the numbers of the others: 256 x 8 / 512 x 8, match.any ranking,
     // C++ ballots, a persistent two-stage kernel)
+#ifdef HKCSA_OS_SHAPES      // experiment build: tile shapes selectable at run time (tools/sort_probe.py)
+    static int shape = -1;
+    if (shape < 0) { const char *e = getenv("HKCSA_OS_SHAPE"); shape = e ? atoi(e) : 0; }
+    switch (shape) {
+        case 1: return run_onesweep64<256, 4, 12>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 2: return run_onesweep64<256, 3, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 3: return run_onesweep64<384, 2, 12>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 4: return run_onesweep64<512, 2, 12>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 5: return run_onesweep64<384, 4, 6>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 6: return run_onesweep64<256, 5, 8>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 7: return run_onesweep64<320, 4, 8>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        default: break;
+    }
+#endif
     return run_onesweep64<384, 3>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
 }
 

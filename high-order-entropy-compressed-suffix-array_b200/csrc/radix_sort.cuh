@@ -48,18 +48,34 @@ __device__ __forceinline__ void hist_add_key(uint32_t *s_hist, uint64_t key, int
         }
     }
 }
-// Same contract, for keys in no particular order (round 0): one uniformity test on the whole key (runs of one
-// symbol) instead of one per digit; otherwise plain shared-memory atomics.
-__device__ __forceinline__ void hist_add_key_unsorted(uint32_t *s_hist, uint64_t key, int passes, bool valid)
+// one shared-memory atomic per digit, the digit taken from the key's 32-bit halves already scaled to a byte offset
+// (shift + mask: two instructions per digit, no 64-bit shifts, no per-pass loop test)
+template <int PASSES>
+__device__ __forceinline__ void hist_add_digits(uint32_t *s_hist, uint64_t key)
+{
+    const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+    char *base = reinterpret_cast<char *>(s_hist);
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+        const uint32_t half = p < 4 ? lo : hi;
+        const int sh = 8 * (p & 3);
+        const uint32_t off = (sh >= 2 ? (half >> (sh >= 2 ? sh - 2 : 0)) : (half << 2)) & 0x3FCu;      // digit * 4
+        atomicAdd(reinterpret_cast<uint32_t *>(base + p * RADIX * 4 + off), 1u);
+    }
+}
+// Same contract as hist_add_key, for keys in no particular order (round 0), PASSES known at compile time: one
+// uniformity test on the whole key (runs of one symbol) instead of one per digit; otherwise plain shared-memory atomics.
+template <int PASSES>
+__device__ __forceinline__ void hist_add_key_unsorted(uint32_t *s_hist, uint64_t key, bool valid)
 {
     const uint64_t key0 = __shfl_sync(0xffffffffu, key, 0);
     const bool uniform = __all_sync(0xffffffffu, !valid || key == key0);
     if (uniform) {
         const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, valid));
         if (lane_id() == 0 && nvalid)
-            for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * RADIX + ((uint32_t)(key0 >> (8 * p)) & 0xFFu)], nvalid);
+            for (int p = 0; p < PASSES; ++p) atomicAdd(&s_hist[p * RADIX + ((uint32_t)(key0 >> (8 * p)) & 0xFFu)], nvalid);
     } else if (valid) {
-        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * RADIX + ((uint32_t)(key >> (8 * p)) & 0xFFu)], 1u);
+        hist_add_digits<PASSES>(s_hist, key);
     }
 }
 __device__ __forceinline__ void hist_zero(uint32_t *s_hist, int passes)

@@ -149,10 +149,14 @@ cudaError_t byte_hist(const uint8_t *d_text, uint64_t n, uint64_t *d_hist, cudaS
 // at that position's bit offset -- three shared loads and two funnel shifts, whatever the number of symbols
 // the key covers.  Keys are produced warp-striped so the stores are fully coalesced.  The suffix ids are not
 // written at all: the first radix pass takes "value = index" (radix_sort_pairs_u64, identity_vals).
+// PASSES = radix passes of round 0 = key bits / 8, a template parameter: the key shift and the digit histogram of
+// every pass (the bulk of the kernel's instructions: one shared atomic per key and pass) are straight-line code.
+template <int PASSES>
 __global__ void __launch_bounds__(PACK_THREADS, 6)
-sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, int bits, int passes,
-                uint64_t *__restrict__ keys, uint32_t *__restrict__ ghist)
+sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, uint64_t *__restrict__ keys,
+                uint32_t *__restrict__ ghist)
 {
+    constexpr int bits = 8 * PASSES, passes = PASSES;
     __shared__ __align__(16) uint16_t s_off[PACK_TILE];
     __shared__ uint32_t s_stream[PACK_STREAM_WORDS];
     __shared__ uint32_t s_hist[8 * RADIX];
@@ -196,7 +200,7 @@ sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, int 
         const uint64_t key = (((uint64_t)hi << 32) | lo) >> (64 - bits);
         const bool valid = g < n;
         if (valid) keys[g] = key;
-        hist_add_key_unsorted(s_hist, key, passes, valid);
+        hist_add_key_unsorted<PASSES>(s_hist, key, valid);
     }
     __syncthreads();
     hist_flush(s_hist, ghist, passes);
@@ -714,7 +718,15 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     {
         const uint32_t blocks = (N + PACK_TILE - 1) / PACK_TILE;
         prof::Scope ps(st, prof::SA_PACK0, (uint64_t)N * 9);
-        sa_pack0_kernel<<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, bits0, passes0, ka, B.sort.hist);
+        switch (passes0) {
+            case 2: sa_pack0_kernel<2><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
+            case 3: sa_pack0_kernel<3><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
+            case 4: sa_pack0_kernel<4><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
+            case 5: sa_pack0_kernel<5><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
+            case 6: sa_pack0_kernel<6><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
+            case 7: sa_pack0_kernel<7><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
+            default: sa_pack0_kernel<8><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
+        }
         HK_LAUNCH_CHECK();
     }
     HK_CUDA(radix_sort_pairs_u64(ka, va, kb, vb, N, passes0, B.sort, st, /*identity_vals=*/true));

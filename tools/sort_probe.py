@@ -14,6 +14,9 @@ cases = {
     "4 values per digit": (torch.randint(0, 2**62, (n,), dtype=torch.int64, device="cuda", generator=g) & 0x0303030303030303),
     "16 values per digit": (torch.randint(0, 2**62, (n,), dtype=torch.int64, device="cuda", generator=g) & 0x0F0F0F0F0F0F0F0F),
 }
+only = os.environ.get("CASES")
+if only:
+    cases = {k: v for k, v in cases.items() if any(w in k for w in only.split(","))}
 for name, keys in cases.items():
     vals = torch.arange(n, dtype=torch.int32, device="cuda")
     for rep in range(2):
