@@ -287,6 +287,8 @@ onesweep64_kernel(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     uint32_t peers[IPT];
     uint32_t dr[IPT];          // digit << 16 | rank of the item among the warp's items with that digit
     const uint32_t wbase = warp * 32u * IPT + lane;
+    // all ballots first (they are independent), then the counter updates: batching the ballots by 8 to shorten the
+    // live range of the peer masks was measured slower (0.649 vs 0.622 ms per pass at 512 x 16)
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const uint32_t local = wbase + k * 32u;
@@ -504,9 +506,8 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
     count_launch();
     cudaError_t e = cudaMemsetAsync(s.ticket, 0, 64 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    // 384 threads x 8 pairs, 3 CTAs per SM, ballots spelled in PTX: the fastest of the shapes measured on B200
-    // (profiles/r01_onesweep_variants.txt keeps the numbers of the others: 256 x 8 / 512 x 8, match.any ranking,
-    // C++ ballots, a persistent two-stage kernel)
+    // ballots spelled in PTX; profiles/r01_onesweep_variants.txt keeps the numbers of the round-1 alternatives
+    // (256 x 8 / 512 x 8, match.any ranking, C++ ballots, a persistent two-stage kernel)
 #ifdef HKCSA_OS_SHAPES      // experiment build: tile shapes selectable at run time (tools/sort_probe.py)
     static int shape = -1;
     if (shape < 0) { const char *e = getenv("HKCSA_OS_SHAPE"); shape = e ? atoi(e) : 0; }
@@ -518,9 +519,30 @@ cudaError_t radix_sort_pairs_u64(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint3
         case 5: return run_onesweep64<384, 4, 6>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
         case 6: return run_onesweep64<256, 5, 8>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
         case 7: return run_onesweep64<320, 4, 8>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 8: return run_onesweep64<256, 2, 24>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 9: return run_onesweep64<256, 3, 20>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 10: return run_onesweep64<384, 2, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 11: return run_onesweep64<512, 2, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 12: return run_onesweep64<512, 1, 24>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 13: return run_onesweep64<256, 4, 14>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 14: return run_onesweep64<256, 2, 32>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 15: return run_onesweep64<320, 3, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 16: return run_onesweep64<448, 2, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 17: return run_onesweep64<512, 2, 12>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 18: return run_onesweep64<1024, 1, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 19: return run_onesweep64<768, 1, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 20: return run_onesweep64<480, 2, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 21: return run_onesweep64<416, 2, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 22: return run_onesweep64<448, 2, 18>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
+        case 23: return run_onesweep64<384, 2, 20>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
         default: break;
     }
 #endif
+    // Large arrays: 448 threads x 16 pairs = 7168 pairs per tile, 2 CTAs per SM -- the per-tile work (256-digit prefix
+    // over the warps, look-back, five block barriers) is spread over 2.3x the pairs of the 384 x 8 tile: 0.621 vs 0.720 ms
+    // per pass of 10^8 pairs (profiles/r02_onesweep_shapes.txt; 512 x 16: 0.627, 384 x 16: 0.638, 256 x 16 x 3 CTAs: 0.648,
+    // 256 x 24: 0.638, 20+ pairs per thread: slower).  Small arrays keep the 3072-pair tile so that every SM gets tiles.
+    if (n >= (1u << 22)) return run_onesweep64<448, 2, 16>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
     return run_onesweep64<384, 3>(k0, v0, k1, v1, n, passes, s, st, identity_vals);
 }
 
