@@ -30,6 +30,9 @@ namespace hkcsa {
 
 constexpr int DSA_BUCKET_BITS = 16;
 constexpr int DSA_MAX_WORLD = HKCSA_DSA_MAX_RANKS;
+// 64-bit suffix ids (n <= 2^40) travel with the BWT symbol of their suffix in the top byte: the source rank has
+// text[i - 1] at hand when it packs suffix i, so the owner's BWT slice needs no random gather over the whole text
+constexpr uint64_t DSA_ID_MASK = (1ull << 56) - 1ull;
 
 struct DsaDest {                       // kernel parameter of the exchange
     uint64_t *keys[DSA_MAX_WORLD];     // receive arrays of every rank (peer-mapped)
@@ -148,7 +151,9 @@ dsa_pack_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin, ui
             const uint32_t j = warp * (32u * PACK_IPT) + e * 32u + lane;
             const uint32_t slot = s_first[dest] + (ds[e] & 0xFFFFu);
             s_keys[slot] = key[e];
-            s_ids[slot] = (IdT)(base + j);
+            const uint64_t g = base + j;
+            if (WIDE) s_ids[slot] = (IdT)(g | ((uint64_t)text[g ? g - 1 : n - 1] << 56));
+            else s_ids[slot] = (IdT)g;
         }
     }
     __syncthreads();
@@ -192,7 +197,7 @@ dsa_keybuild_ext_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__res
         const bool valid = j < m;
         uint64_t key = 0;
         if (valid) {
-            const uint64_t g = (ids64 ? ids64[cidx[j]] : (uint64_t)cidx[j]) + depth;
+            const uint64_t g = (ids64 ? (ids64[cidx[j]] & DSA_ID_MASK) : (uint64_t)cidx[j]) + depth;
             key = ((uint64_t)cgrp[j] << eb) | pack_from_text(text, n, g, s_code, b, ke);
             keys[j] = key;
         }
@@ -250,7 +255,7 @@ __device__ uint64_t dsa_remote_rank(const DsaPeers &pp, const uint8_t *__restric
     while (lo < hi) {
         const uint64_t mid = lo + ((hi - lo) >> 1);
         uint64_t s = ld_sys(sa + mid);
-        if (WIDE) s = ld_sys(pp.ids64[r] + s);
+        if (WIDE) s = ld_sys(pp.ids64[r] + s) & DSA_ID_MASK;
         if (s == t) return pp.slice_off[r] + mid;
         if (suffix_less(text, n, s, t)) lo = mid + 1; else hi = mid;
     }
@@ -276,7 +281,7 @@ dsa_keybuild_dbl_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__res
         const bool valid = j < m;
         uint64_t key = 0;
         if (valid) {
-            const uint64_t id = WIDE ? ids64[cidx[j]] : (uint64_t)cidx[j];
+            const uint64_t id = WIDE ? (ids64[cidx[j]] & DSA_ID_MASK) : (uint64_t)cidx[j];
             const uint64_t t = id + h;
             uint64_t k2 = 0;
             if (t < n) {
@@ -306,14 +311,14 @@ dsa_isa_publish_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__rest
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (uint64_t j = t0; j < m_keep; j += stride) {
-        const uint64_t id = WIDE ? ids64[cidx[j]] : (uint64_t)cidx[j];
+        const uint64_t id = WIDE ? (ids64[cidx[j]] & DSA_ID_MASK) : (uint64_t)cidx[j];
         const uint64_t owner = id / pp.blk;
         static_cast<IsaT *>(pp.isa[owner])[id - owner * pp.blk] = (IsaT)(slice_off + cgrp[j]);
     }
     for (uint64_t j = t0; j < m_sorted; j += stride) {
         const uint32_t f = flags[j >> 3];                     // bit e: head, bit 8 + e: singleton (seg_reduce_kernel)
         if ((f >> (SEG_IPT + (j & 7u))) & 1u) {
-            const uint64_t id = WIDE ? ids64[sidx[j]] : (uint64_t)sidx[j];
+            const uint64_t id = WIDE ? (ids64[sidx[j]] & DSA_ID_MASK) : (uint64_t)sidx[j];
             const uint64_t owner = id / pp.blk;
             static_cast<IsaT *>(pp.isa[owner])[id - owner * pp.blk] = (IsaT)(slice_off + (pos ? pos[j] : (uint32_t)j));
         }
@@ -330,11 +335,15 @@ __global__ void bwt_slice_kernel(const uint8_t *__restrict__ text, uint64_t n, c
     out[j] = text[v ? v - 1 : n - 1];
 }
 
+// the finished slice with 64-bit ids: id and BWT symbol of the j-th suffix from ONE random read
 __global__ void gather_ids64_kernel(const uint64_t *__restrict__ ids64, const uint32_t *__restrict__ ord, uint64_t m,
-                                    uint64_t *__restrict__ out)
+                                    uint64_t *__restrict__ out, uint8_t *__restrict__ out_bwt)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < m) out[j] = ids64[ord[j]];
+    if (j >= m) return;
+    const uint64_t v = ids64[ord[j]];
+    out[j] = v & DSA_ID_MASK;
+    if (out_bwt) out_bwt[j] = (uint8_t)(v >> 56);
 }
 
 // ---------------------------------------------------------------- host state of one rank's slice
@@ -718,13 +727,14 @@ extern "C" int hkcsa_dsa_dbl_sort(hkcsa_dsa_state *state, void *stream)
 }
 
 // 64-bit ids: out[j] = ids[ordinal[j]] for the finished slice
-extern "C" int hkcsa_dsa_gather_ids64(const hkcsa_dsa_state *state, uint64_t *d_out, void *stream)
+extern "C" int hkcsa_dsa_gather_ids64(const hkcsa_dsa_state *state, uint64_t *d_out, uint8_t *d_out_bwt, void *stream)
 {
     const DsaState *S = reinterpret_cast<const DsaState *>(state);
     HK_REQUIRE(S && S->magic == DSA_MAGIC && S->wide, HKCSA_EINVAL, "bad state (64-bit ids only)");
     if (S->M == 0) return HKCSA_OK;
     HK_REQUIRE(d_out, HKCSA_EINVAL, "null pointer");
-    gather_ids64_kernel<<<(uint32_t)((S->M + 255) / 256), 256, 0, as_stream(stream)>>>(S->ids64, S->sa, S->M, d_out);
+    prof::Scope ps(as_stream(stream), prof::BWT_GATHER, S->M * 21);
+    gather_ids64_kernel<<<(uint32_t)((S->M + 255) / 256), 256, 0, as_stream(stream)>>>(S->ids64, S->sa, S->M, d_out, d_out_bwt);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

@@ -154,7 +154,7 @@ SIGNATURES = {
     "hkcsa_dsa_dbl_keys": (_i32, [_vp, _u32, C.POINTER(_u64), _u64, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64),
                                   C.POINTER(_u32), _vp]),
     "hkcsa_dsa_dbl_sort": (_i32, [_vp, _vp]),
-    "hkcsa_dsa_gather_ids64": (_i32, [_vp, _vp, _vp]),
+    "hkcsa_dsa_gather_ids64": (_i32, [_vp, _vp, _vp, _vp]),
     "hkcsa_bwt_slice": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp]),
     "hkcsa_bwt_slice64": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp]),
     "hkcsa_ssa_build64": (_i32, [_vp, C.POINTER(SsaPlan), _vp, _vp, _sz, _vp]),

@@ -203,15 +203,16 @@ def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: boo
         dbl_done += 1
         tick("doubling_rounds")
     # ---- 6. the slice leaves the workspace; BWT of the slice
-    if is_wide:
+    if is_wide:                     # ids and BWT symbols arrive together (the symbol rides in the id's top byte)
         sa = _empty(M, torch.int64, dev)
-        check(L.hkcsa_dsa_gather_ids64(state, _ptr(sa), _stream()))
+        bw = _empty(M, torch.uint8, dev)
+        check(L.hkcsa_dsa_gather_ids64(state, _ptr(sa), _ptr(bw), _stream()))
     else:
         sa = (val_a if off_slice == off_va else val_b)[:M].clone()
+        bw = bwt_slice(text, sa)
     sent = int(d_counters.cpu().numpy()[:world].sum())
     if sent != end - begin:
         raise RuntimeError(f"exchange sent {sent} pairs for a block of {end - begin} positions")
-    bw = bwt_slice(text, sa)
     yield ("barrier",)                                          # peers may have been searching this rank's slice
     tick("slice_and_bwt")
     nr = C.c_uint32(0)
