@@ -654,6 +654,31 @@ extern "C" int hkcsa_dsa_ext_round(hkcsa_dsa_state *state, void *stream)
     return dsa_sort_refine(S, passes, st);
 }
 
+// One refinement round without a radix sort or communication: every group of at most GS_MAX suffixes is ordered by
+// comparing the replicated text beyond the current depth (group_local_keys).  Meant for the first round after
+// hkcsa_dsa_begin, when nearly all groups hold two or three suffixes.  The depth does not advance.
+extern "C" int hkcsa_dsa_group_round(hkcsa_dsa_state *state, void *stream)
+{
+    DsaState *Sp = dsa_state(state);
+    HK_REQUIRE(Sp, HKCSA_EINVAL, "bad state");
+    DsaState &S = *Sp;
+    if (S.m == 0) return HKCSA_OK;
+    cudaStream_t st = as_stream(stream);
+    const uint32_t m = (uint32_t)S.m;
+    if (S.round > 1) S.vother = S.sidx;                 // the sorted ids consumed by the last refinement: free again
+    S.pcur ^= 1;
+    S.pos = S.posbuf[S.pcur];
+    {
+        prof::Scope ps(st, prof::SA_KEYBUILD, (uint64_t)m * 48);
+        HK_CUDA(group_local_keys(S.cidx, S.grp, m, S.text, S.n, S.depth, S.ids64, S.kx, st));
+    }
+    S.skey = S.kx;
+    S.sidx = S.cidx;
+    S.vfree = S.vother;
+    { uint64_t *t = S.kx; S.kx = S.ky; S.ky = t; }      // kx never holds the keys being refined
+    return dsa_refine(S, st);
+}
+
 extern "C" int hkcsa_dsa_isa_publish(hkcsa_dsa_state *state, uint32_t world, const uint64_t *h_peer_isa, uint64_t blk,
                                      uint64_t slice_offset, int with_singles, void *stream)
 {

@@ -518,6 +518,88 @@ seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict_
     }
 }
 
+// ---------------------------------------------------------------- group-local refinement (no radix sort)
+// After round 0 nearly all surviving groups hold two or three suffixes.  Sorting them with seven or eight radix
+// passes over the whole working set is out of proportion: here the thread of a group's first element loads the
+// group's suffix ids, orders them by comparing the text directly from the known depth on (up to GS_DEPTH more
+// symbols; the end of the text is smallest), writes them back in order and gives every element the key
+// (group start << 32 | number of its sub-group): equal keys = still tied within GS_DEPTH symbols.  The usual
+// seg_reduce / seg_scan / seg_apply then refine on these keys.  Groups above GS_MAX elements are left alone (one key
+// for the whole group): they go to the next regular round, whose depth therefore stays where it was.
+__global__ void group_key_init_kernel(const uint32_t *__restrict__ cgrp, uint32_t m, uint64_t *__restrict__ keys)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) keys[j] = (uint64_t)cgrp[j] << 32;
+}
+
+// -1 / 0 / +1: order of suffixes a and b beyond the `depth` symbols they share, 0 = tied within GS_DEPTH symbols
+__device__ __forceinline__ int suffix_cmp_from(const uint8_t *__restrict__ text, uint64_t n, uint64_t a, uint64_t b,
+                                               uint64_t depth)
+{
+    uint64_t pa = a + depth, pb = b + depth;
+    for (int q = 0; q < GS_DEPTH; ++q, ++pa, ++pb) {
+        if (pa >= n || pb >= n) {
+            if (pa >= n && pb >= n) return a > b ? -1 : 1;      // both ended: the shorter suffix (larger id) is smaller
+            return pa >= n ? -1 : 1;
+        }
+        const uint32_t ca = text[pa], cb = text[pb];
+        if (ca != cb) return ca < cb ? -1 : 1;
+    }
+    return 0;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256)
+group_sort_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp, uint32_t m,
+                  const uint8_t *__restrict__ text, uint64_t n, uint64_t depth, const uint64_t *__restrict__ ids64,
+                  uint64_t *__restrict__ keys)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t g = cgrp[j];
+    if (j > 0 && cgrp[j - 1] == g) return;                      // not the first element of its group
+    uint32_t s = 1;
+    while (s <= GS_MAX && j + s < m && cgrp[j + s] == g) ++s;
+    if (s > GS_MAX || s < 2) return;                            // large group: keys stay (g << 32) for every member
+    uint32_t v[GS_MAX];                                         // cidx entries (suffix ids, or ordinals when WIDE)
+    uint64_t id[GS_MAX];
+    for (uint32_t i = 0; i < s; ++i) {
+        v[i] = cidx[j + i];
+        id[i] = WIDE ? (ids64[v[i]] & ((1ull << 56) - 1ull)) : (uint64_t)v[i];
+    }
+    for (uint32_t i = 1; i < s; ++i) {                          // insertion sort: groups are tiny
+        const uint32_t xv = v[i];
+        const uint64_t xi = id[i];
+        uint32_t k = i;
+        while (k > 0 && suffix_cmp_from(text, n, xi, id[k - 1], depth) < 0) {
+            v[k] = v[k - 1];
+            id[k] = id[k - 1];
+            --k;
+        }
+        v[k] = xv;
+        id[k] = xi;
+    }
+    uint32_t sub = 0;
+    for (uint32_t i = 0; i < s; ++i) {
+        if (i > 0 && suffix_cmp_from(text, n, id[i - 1], id[i], depth) != 0) ++sub;
+        cidx[j + i] = v[i];
+        keys[j + i] = ((uint64_t)g << 32) | sub;
+    }
+}
+
+cudaError_t group_local_keys(uint32_t *cidx, const uint32_t *cgrp, uint32_t m, const uint8_t *text, uint64_t n,
+                             uint64_t depth, const uint64_t *ids64, uint64_t *keys, cudaStream_t st)
+{
+    if (m == 0) return cudaSuccess;
+    const uint32_t blocks = (m + 255) / 256;
+    group_key_init_kernel<<<blocks, 256, 0, st>>>(cgrp, m, keys);
+    count_launch();
+    if (ids64) group_sort_kernel<true><<<blocks, 256, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+    else group_sort_kernel<false><<<blocks, 256, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- the last, tiny rounds in one CTA
 // Once at most FIN_MAX suffixes are left (C2: 6 after two rounds, C3: 20) a round of the general path is ~25 launches
 // and two host round trips for nothing.  One CTA finishes the job on its own: key build (same look-ups), bitonic sort
@@ -827,6 +909,18 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         pcur ^= 1;
         pos = B.pos[pcur];
         uint32_t *vx = cidx, *vy = vother;
+        if (round == 1 && (uint64_t)m * 2 <= n && !getenv("HKCSA_NO_GROUP_ROUND")) {
+            // Round 1 without a radix sort: the survivors of round 0 sit in groups of two or three; each small group
+            // is ordered by comparing text beyond the k0 symbols its members share.  The depth does not advance
+            // (large groups are untouched), every survivor gets its rank scattered by the refinement that follows.
+            prof::Scope ps(st, prof::SA_KEYBUILD, (uint64_t)m * 48);
+            HK_CUDA(group_local_keys(vx, B.grp, m, d_text, n, std::min<uint64_t>(h, n), nullptr, kx, st));
+            skey = kx; sidx = vx; vfree = vy;
+            stats.round_elems[round] = m;
+            stats.round_passes[round] = 0;                      // 0 passes = refined without a radix sort
+            stats.alg_bytes += (uint64_t)m * 48;
+            continue;
+        }
         const int bits = b1 + b2;
         const int passes = (bits + 7) / 8;
         HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));

@@ -123,6 +123,14 @@ __device__ __forceinline__ void pack_emit8(uint32_t *s_stream, uint16_t *s_off8,
 
 cudaError_t byte_hist(const uint8_t *d_text, uint64_t n, uint64_t *d_hist, cudaStream_t st);
 
+// ---------------------------------------------------------------- group-local refinement (suffix_array.cu)
+constexpr int GS_MAX = 16;       // groups up to this size are ordered by one thread
+constexpr int GS_DEPTH = 64;     // symbols compared beyond the depth the group shares
+// keys[j] = (cgrp[j] << 32 | sub-group) with every group of at most GS_MAX elements reordered in place (cidx) by text
+// comparison from `depth` on; ids64 != nullptr: cidx holds ordinals into ids64 (low 56 bits = suffix id)
+cudaError_t group_local_keys(uint32_t *cidx, const uint32_t *cgrp, uint32_t m, const uint8_t *text, uint64_t n,
+                             uint64_t depth, const uint64_t *ids64, uint64_t *keys, cudaStream_t st);
+
 // ---------------------------------------------------------------- segmented rank update (suffix_array.cu)
 __global__ void __launch_bounds__(SEG_THREADS) seg_reduce_kernel(const uint64_t *__restrict__ skey, uint32_t m, uint32_t *__restrict__ agg_head,
                                   uint32_t *__restrict__ agg_keep, uint16_t *__restrict__ flags);

@@ -149,6 +149,7 @@ SIGNATURES = {
     "hkcsa_dsa_depth": (_u64, [_vp]),
     "hkcsa_dsa_slice": (_vp, [_vp]),
     "hkcsa_dsa_rounds": (_i32, [_vp, C.POINTER(_u32), C.POINTER(_u64), _u32]),
+    "hkcsa_dsa_group_round": (_i32, [_vp, _vp]),
     "hkcsa_dsa_ext_round": (_i32, [_vp, _vp]),
     "hkcsa_dsa_isa_publish": (_i32, [_vp, _u32, C.POINTER(_u64), _u64, _u64, _i32, _vp]),
     "hkcsa_dsa_dbl_keys": (_i32, [_vp, _u32, C.POINTER(_u64), _u64, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64),

@@ -94,7 +94,8 @@ def _align(x: int, a: int = 256) -> int:
     return (x + a - 1) // a * a
 
 
-def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: bool, ext_rounds_max: int):
+def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: bool, ext_rounds_max: int,
+                  group_round: bool = True):
     """One rank's build as a generator.  Yields ("gather", array) -> [world, len] int64 numpy; ("text", block,
     sizes) -> the whole text; ("symm", nbytes) -> (uint8 tensor, [address of every rank's buffer]); ("barrier",)."""
     L = _lib.load()
@@ -174,6 +175,7 @@ def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: boo
     off_slice = off_va if slice_ptr == val_a.data_ptr() else off_vb
     ext_done, dbl_done, prev_all = 0, 0, None
     isa_ready = False
+    group_round_due = group_round
     peer_isa = _u64arr([p + off_isa for p in ptrs])
     peer_sa = _u64arr([p + off_slice for p in ptrs])
     peer_ids64 = _u64arr([p + off_ids64 for p in ptrs]) if is_wide else None
@@ -182,6 +184,14 @@ def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: boo
         m_all = int((yield ("gather", np.array([L.hkcsa_dsa_working_set(state)], dtype=np.int64))).sum())
         if m_all == 0:
             break
+        if group_round_due:
+            # first: every small group ordered by direct text comparison, no radix sort, no communication -- after
+            # round 0 nearly all groups hold two or three suffixes.  Skipped for repetitive texts (most suffixes tied).
+            group_round_due = False
+            if 2 * m_all <= n:
+                check(L.hkcsa_dsa_group_round(state, _stream()))
+                tick("group_round")
+                continue
         stalled = prev_all is not None and ext_done >= 2 and 2 * m_all > prev_all
         prev_all = m_all
         if not isa_ready and ext_done < ext_rounds_max and not stalled:
@@ -300,7 +310,7 @@ def _torch_run(prog, group, device):
 
 
 def distributed_suffix_array(local_block: torch.Tensor, group=None, wide: bool | None = None, profile: bool = False,
-                             ext_rounds_max: int = EXT_ROUNDS_MAX) -> SuffixArraySlice:
+                             ext_rounds_max: int = EXT_ROUNDS_MAX, group_round: bool = True) -> SuffixArraySlice:
     """local_block: this rank's contiguous part of the text (uint8, on this rank's GPU), blocks in rank order.
     Collective: every rank of `group` calls it.  profile=True synchronises at phase boundaries and fills
     SuffixArraySlice.phases."""
@@ -308,7 +318,7 @@ def distributed_suffix_array(local_block: torch.Tensor, group=None, wide: bool |
     world = dist.get_world_size(group)
     if world > _lib.DSA_MAX_RANKS:
         raise ValueError(f"at most {_lib.DSA_MAX_RANKS} ranks")
-    prog = _rank_program(dist.get_rank(group), world, local_block, wide, profile, ext_rounds_max)
+    prog = _rank_program(dist.get_rank(group), world, local_block, wide, profile, ext_rounds_max, group_round)
     return _torch_run(prog, group, local_block.device)
 
 
@@ -318,14 +328,14 @@ def release_workspaces() -> None:
 
 # ------------------------------------------------------------------ running the program: ranks emulated on one GPU
 def emulate_distributed_suffix_array(blocks, wide: bool | None = None, ext_rounds_max: int = EXT_ROUNDS_MAX,
-                                     profile: bool = False):
+                                     profile: bool = False, group_round: bool = True):
     """The same per-rank programs, advanced in lockstep inside one process: `blocks` are the ranks' text blocks on
     ONE GPU, peers' buffers are plain device buffers of the same process.  Returns the slices in rank order."""
     world = len(blocks)
     if not 1 <= world <= _lib.DSA_MAX_RANKS:
         raise ValueError(f"1..{_lib.DSA_MAX_RANKS} ranks")
     dev = blocks[0].device
-    progs = [_rank_program(r, world, blocks[r], wide, profile, ext_rounds_max) for r in range(world)]
+    progs = [_rank_program(r, world, blocks[r], wide, profile, ext_rounds_max, group_round) for r in range(world)]
     reqs = [next(p) for p in progs]
     results = [None] * world
     live = list(range(world))

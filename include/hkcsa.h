@@ -149,6 +149,9 @@ uint64_t hkcsa_dsa_working_set(const hkcsa_dsa_state *state);   /* suffixes in g
 uint64_t hkcsa_dsa_depth(const hkcsa_dsa_state *state);         /* symbols every group is known to share           */
 const void *hkcsa_dsa_slice(const hkcsa_dsa_state *state);
 int hkcsa_dsa_rounds(const hkcsa_dsa_state *state, uint32_t *h_rounds, uint64_t *h_round_elems, uint32_t max_rounds);
+/* one round without a radix sort (local): groups of up to 16 suffixes are ordered by comparing the replicated text  */
+/* beyond the current depth (up to 64 symbols); the depth does not advance.  Meant for the first round after _begin. */
+int hkcsa_dsa_group_round(hkcsa_dsa_state *state, void *stream);
 /* one extension round (local): the same number of symbols on every rank */
 int hkcsa_dsa_ext_round(hkcsa_dsa_state *state, void *stream);
 /* Rank doubling.  ISA blocks: rank r holds the global ranks of positions [r*blk, (r+1)*blk) as uint32 (uint64 when */
