@@ -14,4 +14,9 @@ ncu --set full --clock-control none -k regex:"dsa_keybuild_dbl|dsa_isa_publish" 
 echo new2 rc=$?
 ncu --set full --clock-control none -k regex:"hk_count|hk_heads|hk_sum|rrr_|ranges_push" -c 14 -o gpurun_out/r02_hk_rrr_push python tools/profile_r02.py > gpurun_out/ncu_new3.log 2>&1
 echo new3 rc=$?
-ls -la gpurun_out/*.ncu-rep
+for r in r02_build_others r02_dsa_pack r02_dsa_dbl r02_hk_rrr_push; do
+  python tools/ncu_summary.py gpurun_out/$r.ncu-rep gpurun_out/$r.txt && rm -f gpurun_out/$r.ncu-rep
+done
+python tools/ncu_summary.py gpurun_out/r02_onesweep.ncu-rep gpurun_out/r02_onesweep.txt
+ncu -i gpurun_out/r02_onesweep.ncu-rep --page source --csv > gpurun_out/r02_onesweep_source.csv 2>/dev/null
+ls -la gpurun_out/ | head -40; du -sh gpurun_out
