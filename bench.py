@@ -582,7 +582,7 @@ def run_ours(args):
     roofline = None
     traffic = None
     try:   # DRAM bytes per pair from the committed ncu --set full capture, scaled to this run's average launch
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f)["onesweep64_kernel"]
         per_pair = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["pairs_in_profiled_launch"]
         if one and one["launches"]:
@@ -594,7 +594,7 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": "onesweep64_kernel (one 8-bit LSD radix pass, 24 B per (u64,u32) pair)",
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "profiles/r01_traffic.json: dram bytes per pair of one ncu --set full capture of this "
+                    "traffic_source": "profiles/r02_traffic.json: dram bytes per pair of one ncu --set full capture of this "
                                       "kernel, scaled to this run's average launch (not measured in this run)",
                     "alg_bytes_per_launch": one["alg_bytes"] / one["launches"],
                     "launches": one["launches"], "avg_launch_ms": one["ms"] / one["launches"],

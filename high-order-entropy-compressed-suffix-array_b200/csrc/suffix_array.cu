@@ -835,6 +835,21 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     uint32_t *vfree = B.val[1];                        // free value buffer (receives the compacted ids)
     uint32_t *vother = B.val[0];                       // the round-0 sort's other value buffer: free from here on
 
+    bool lazy_index_due = false;
+    // the look-up structures over the sorted round-0 keys (lz.keys0): built on first use -- when the group-local
+    // round finishes the job no look-up ever happens
+    auto build_lazy_index = [&]() -> int {
+        if (!lazy_index_due) return HKCSA_OK;
+        lazy_index_due = false;
+        const uint32_t nbuckets = 1u << bucket_bits;
+        prof::Scope ps(st, prof::OTHER, (uint64_t)nbuckets * 8);
+        sa_bucket_index_kernel<<<(nbuckets + 1 + 255) / 256, 256, 0, st>>>(lz.keys0, N, lz.shift, nbuckets, B.bucket);
+        HK_LAUNCH_CHECK();
+        const uint32_t nsamp = (uint32_t)(((uint64_t)N + (1u << LAZY_SAMPLE_SHIFT) - 1) >> LAZY_SAMPLE_SHIFT);
+        sa_key_samples_kernel<<<(nsamp + 255) / 256, 256, 0, st>>>(lz.keys0, N, B.samples);
+        HK_LAUNCH_CHECK();
+        return HKCSA_OK;
+    };
     while (true) {
         // ---- refine ranks from the sorted keys
         const uint32_t tiles = (m + SEG_TILE - 1) / SEG_TILE;
@@ -858,14 +873,8 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
             lz.keys0 = skey;
             lz.bucket = B.bucket;
             scatter_all = false;
-            const uint32_t nbuckets = 1u << bucket_bits;
-            prof::Scope ps(st, prof::OTHER, (uint64_t)nbuckets * 8);
-            sa_bucket_index_kernel<<<(nbuckets + 1 + 255) / 256, 256, 0, st>>>(skey, N, lz.shift, nbuckets, B.bucket);
-            HK_LAUNCH_CHECK();
             lz.samples = B.samples;
-            const uint32_t nsamp = (uint32_t)(((uint64_t)N + (1u << LAZY_SAMPLE_SHIFT) - 1) >> LAZY_SAMPLE_SHIFT);
-            sa_key_samples_kernel<<<(nsamp + 255) / 256, 256, 0, st>>>(skey, N, B.samples);
-            HK_LAUNCH_CHECK();
+            lazy_index_due = true;          // bucket index + key samples are built when a look-up round actually comes
         }
         uint32_t *cpos = B.pos[pcur ^ 1];
         uint32_t *cidx = vfree;
@@ -888,6 +897,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         if (m_next <= (uint32_t)FIN_MAX) {
             // the few suffixes left are finished by one CTA: no more launches per round, no more host round trips
             lz.first_round = (round == 1) ? 1 : 0;
+            if (int rc = build_lazy_index()) return rc;
             prof::Scope ps(st, prof::OTHER, (uint64_t)m_next * 32);
             sa_finish_small_kernel<<<1, FIN_MAX, 0, st>>>(cidx, B.grp, cpos, m_next, N, std::min<uint64_t>(h, n), d_sa,
                                                           B.rank, lz, ac);
@@ -925,6 +935,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         const int passes = (bits + 7) / 8;
         HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
         lz.first_round = (round == 1) ? 1 : 0;
+        if (int rc = build_lazy_index()) return rc;
         {
             const int blocks = (int)std::min<uint64_t>(((uint64_t)m + 255) / 256, (uint64_t)num_sms() * 16);
             prof::Scope ps(st, prof::SA_KEYBUILD, (uint64_t)m * 20);
