@@ -2,6 +2,7 @@
 //   pos = SA[i] - 1; if pos < 0: pos = n - 1; bwt[i] = text[pos].
 #include "common.cuh"
 #include "prof.cuh"
+#include "suffix_array.cuh"
 #include <stdlib.h>
 
 namespace hkcsa {
@@ -62,16 +63,9 @@ bwt_gather_scalar_kernel(const uint8_t *__restrict__ text, const uint32_t *__res
     bwt[i] = text[v ? (uint64_t)v - 1 : n - 1];
 }
 
-}  // namespace hkcsa
-
-using namespace hkcsa;
-
-extern "C" int hkcsa_bwt(const uint8_t *d_text, const uint32_t *d_sa, uint64_t n, uint8_t *d_bwt, void *stream)
+int bwt_gather(const uint8_t *d_text, const uint32_t *d_sa, uint64_t n, uint8_t *d_bwt, cudaStream_t st)
 {
     if (n == 0) return HKCSA_OK;
-    HK_REQUIRE(d_text && d_sa && d_bwt, HKCSA_EINVAL, "null pointer");
-    HK_REQUIRE(n <= HKCSA_MAX_N, HKCSA_ERANGE, "n exceeds HKCSA_MAX_N");
-    cudaStream_t st = as_stream(stream);
     if (((reinterpret_cast<uintptr_t>(d_sa) & 15) | (reinterpret_cast<uintptr_t>(d_bwt) & 7)) != 0) {
         // views at odd offsets: plain element-wise gather
         prof::Scope ps(st, prof::BWT_GATHER, n * 6);
@@ -99,4 +93,16 @@ extern "C" int hkcsa_bwt(const uint8_t *d_text, const uint32_t *d_sa, uint64_t n
     }
     HK_CUDA(cudaGetLastError());
     return HKCSA_OK;
+}
+
+}  // namespace hkcsa
+
+using namespace hkcsa;
+
+extern "C" int hkcsa_bwt(const uint8_t *d_text, const uint32_t *d_sa, uint64_t n, uint8_t *d_bwt, void *stream)
+{
+    if (n == 0) return HKCSA_OK;
+    HK_REQUIRE(d_text && d_sa && d_bwt, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(n <= HKCSA_MAX_N, HKCSA_ERANGE, "n exceeds HKCSA_MAX_N");
+    return bwt_gather(d_text, d_sa, n, d_bwt, as_stream(stream));
 }

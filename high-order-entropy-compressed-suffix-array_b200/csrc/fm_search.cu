@@ -11,10 +11,13 @@
 
 namespace hkcsa {
 
+// wavelet.cu: mark bit-vector + directory + samples of the sampled suffix array in one pass over d_sa
 int build_markvector(const uint32_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
-                     uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st);
+                     uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, uint32_t *d_state,
+                     uint32_t *d_samples, cudaStream_t st);
 int build_markvector64(const uint64_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
-                       uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st);
+                       uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, uint32_t *d_state,
+                       uint32_t *d_samples, cudaStream_t st);
 
 constexpr int COUNT_THREADS = 256;
 
@@ -192,37 +195,6 @@ __global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32
 {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q < m) out[q] = src[rows[q]];
-}
-
-// samples[rank1(marks, j)] = SA[j] / rate for marked rows.  A thread takes four consecutive rows (one 16-byte load
-// for 32-bit ids): a quarter of the threads and CTAs of the one-row-per-thread form.
-template <typename IdT>
-__device__ __forceinline__ void ssa_fill_one(IdT v, uint64_t j, uint32_t rate, bool pow2, int sh, const BitVec &marks,
-                                             uint32_t *__restrict__ samples)
-{
-    if (pow2) {                                   // power-of-two rate: no division per entry
-        if ((v & (IdT)(rate - 1u)) == 0) samples[bv_rank(marks, j)] = (uint32_t)(v >> sh);
-    } else if (v % rate == 0) {
-        samples[bv_rank(marks, j)] = (uint32_t)(v / rate);
-    }
-}
-template <typename IdT>
-__global__ void __launch_bounds__(256)
-ssa_fill_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, BitVec marks, uint32_t *__restrict__ samples)
-{
-    const uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (j0 >= n) return;
-    const bool pow2 = (rate & (rate - 1u)) == 0;
-    const int sh = __ffs(rate) - 1;
-    if (sizeof(IdT) == 4 && j0 + 4 <= n && (reinterpret_cast<uintptr_t>(sa) & 15) == 0) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(sa + j0);
-        ssa_fill_one<IdT>((IdT)q.x, j0, rate, pow2, sh, marks, samples);
-        ssa_fill_one<IdT>((IdT)q.y, j0 + 1, rate, pow2, sh, marks, samples);
-        ssa_fill_one<IdT>((IdT)q.z, j0 + 2, rate, pow2, sh, marks, samples);
-        ssa_fill_one<IdT>((IdT)q.w, j0 + 3, rate, pow2, sh, marks, samples);
-    } else {
-        for (uint64_t j = j0; j < n && j < j0 + 4; ++j) ssa_fill_one<IdT>(sa[j], j, rate, pow2, sh, marks, samples);
-    }
 }
 
 // position of row j: walk LF until a marked row, pos = sample * rate + steps.
@@ -403,6 +375,7 @@ extern "C" int hkcsa_ssa_plan_make(uint64_t n, uint32_t rate, hkcsa_ssa_plan *p)
     c.take<uint64_t>(tiles);
     c.take<uint64_t>(8);
     c.take<uint32_t>(select_samples_for(n));
+    c.take<uint32_t>(tiles + 1);
     p->scratch_bytes = c.total();
     return HKCSA_OK;
 }
@@ -434,22 +407,17 @@ static int ssa_build_t(const IdT *d_sa, const hkcsa_ssa_plan *p, void *d_blob, v
     uint64_t *d_carry = c.take<uint64_t>(tiles);
     uint64_t *d_ones = c.take<uint64_t>(8);
     uint32_t *d_sel = c.take<uint32_t>(select_samples_for(n));
+    uint32_t *d_state = c.take<uint32_t>(tiles + 1);
     uint8_t *blob = static_cast<uint8_t *>(d_blob);
-    prof::Scope ps(st, prof::SSA_BUILD, n * 10);
-    const uint32_t grid = (uint32_t)(((n + 3) / 4 + 255) / 256);      // four rows per thread
-    BitVec marks;
-    marks.blocks = reinterpret_cast<const RankBlock *>(blob + p->off_blocks);
-    marks.super = reinterpret_cast<const uint64_t *>(blob + p->off_super);
-    marks.len = n;
+    // one pass: ids read once (+ the marked ones again from cache), mark blocks and samples written
+    prof::Scope ps(st, prof::SSA_BUILD, n * sizeof(IdT) + n / 7 + (n / p->rate) * (4 + sizeof(IdT)));
     RankBlock *blocks = reinterpret_cast<RankBlock *>(blob + p->off_blocks);
     uint64_t *super = reinterpret_cast<uint64_t *>(blob + p->off_super);
-    int rc;
-    if constexpr (sizeof(IdT) == 8) rc = build_markvector64(d_sa, n, p->rate, blocks, super, d_sel, d_agg, d_carry, d_ones, st);
-    else rc = build_markvector(d_sa, n, p->rate, blocks, super, d_sel, d_agg, d_carry, d_ones, st);
-    if (rc != HKCSA_OK) return rc;
-    ssa_fill_kernel<IdT><<<grid, 256, 0, st>>>(d_sa, n, p->rate, marks, reinterpret_cast<uint32_t *>(blob + p->off_samples));
-    HK_LAUNCH_CHECK();
-    return HKCSA_OK;
+    uint32_t *samples = reinterpret_cast<uint32_t *>(blob + p->off_samples);
+    if constexpr (sizeof(IdT) == 8)
+        return build_markvector64(d_sa, n, p->rate, blocks, super, d_sel, d_agg, d_carry, d_ones, d_state, samples, st);
+    else
+        return build_markvector(d_sa, n, p->rate, blocks, super, d_sel, d_agg, d_carry, d_ones, d_state, samples, st);
 }
 
 extern "C" int hkcsa_ssa_build(const uint32_t *d_sa, const hkcsa_ssa_plan *p, void *d_blob, void *d_scratch,

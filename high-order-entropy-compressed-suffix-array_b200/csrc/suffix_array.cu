@@ -64,7 +64,7 @@ bool build_alpha_code(const uint64_t *h_hist, AlphaCode &ac, double &avg_len, in
     return true;
 }
 
-void make_round0_plan(const uint64_t *h_hist, Round0Plan &p)
+void make_round0_plan(const uint64_t *h_hist, Round0Plan &p, bool want_carry)
 {
     uint32_t sigma = 0;
     for (int ch = 0; ch < 256; ++ch)
@@ -85,6 +85,11 @@ void make_round0_plan(const uint64_t *h_hist, Round0Plan &p)
     const int k_target = 64 / b;
     int bits0 = 8 * (int)ceil(k_target * avg_len / 8.0 - 1e-9);
     bits0 = std::max(16, std::min(64, bits0));
+    // HKCSA_CARRY56=1: a 64-bit plan settles for 56 bits so that the BWT symbol can ride in the top byte -- one radix
+    // pass less and no gather afterwards, but more survivors in round 1.  Measured on the 200 MB English-like text
+    // (C3): 21.4 M survivors instead of 5.1 M, 17.2 ms instead of 16.4 ms -- so it is off unless asked for.
+    const char *c56 = getenv("HKCSA_CARRY56");
+    if (want_carry && bits0 > 56 && c56 && atoi(c56)) bits0 = 56;
     if (const char *e = getenv("HKCSA_BITS0")) bits0 = std::max(16, std::min(64, 8 * (atoi(e) / 8)));   // tuning knob
     p.sigma = sigma;
     p.b = b;
@@ -151,11 +156,15 @@ cudaError_t byte_hist(const uint8_t *d_text, uint64_t n, uint64_t *d_hist, cudaS
 // written at all: the first radix pass takes "value = index" (radix_sort_pairs_u64, identity_vals).
 // PASSES = radix passes of round 0 = key bits / 8, a template parameter: the key shift and the digit histogram of
 // every pass (the bulk of the kernel's instructions: one shared atomic per key and pass) are straight-line code.
-template <int PASSES>
+// CARRY: the symbol before the suffix (its BWT symbol, csa/bwt.py:6-11) rides in the top byte of the key, above
+// the sorted bits (keys of at most 56 bits): the sort delivers the BWT in suffix-array order and nobody has to gather
+// text[SA[i] - 1] at random afterwards.
+template <int PASSES, bool CARRY>
 __global__ void __launch_bounds__(PACK_THREADS, 6)
 sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, uint64_t *__restrict__ keys,
                 uint32_t *__restrict__ ghist)
 {
+    static_assert(!CARRY || PASSES <= 7, "the carried symbol needs the top byte of the key");
     constexpr int bits = 8 * PASSES, passes = PASSES;
     __shared__ __align__(16) uint16_t s_off[PACK_TILE];
     __shared__ uint32_t s_stream[PACK_STREAM_WORDS];
@@ -199,7 +208,10 @@ sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, uint
         const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
         const uint64_t key = (((uint64_t)hi << 32) | lo) >> (64 - bits);
         const bool valid = g < n;
-        if (valid) keys[g] = key;
+        if (valid) {
+            if (CARRY) keys[g] = key | ((uint64_t)__ldg(text + (g ? g - 1 : (uint64_t)n - 1)) << 56);   // an L1 hit: the tile was just read
+            else keys[g] = key;
+        }
         hist_add_key_unsorted<PASSES>(s_hist, key, valid);
     }
     __syncthreads();
@@ -223,6 +235,7 @@ struct LazyRank {
                                // so the rank array is neither written in round 0 nor read here
     int bits;                  // width of a round-0 key
     int shift;                 // key >> shift = bucket id
+    uint64_t mask;             // the sorted bits of a round-0 key (the top byte may carry the BWT symbol)
 };
 
 constexpr int LAZY_BUCKET_BITS = 20;
@@ -231,16 +244,17 @@ constexpr int LAZY_BUCKET_BITS = 20;
 // steps -- inside 64 consecutive keys = four lines -- go to DRAM.
 constexpr int LAZY_SAMPLE_SHIFT = 6;
 
-__global__ void sa_key_samples_kernel(const uint64_t *__restrict__ keys0, uint32_t n, uint64_t *__restrict__ samples)
+__global__ void sa_key_samples_kernel(const uint64_t *__restrict__ keys0, uint32_t n, uint64_t mask,
+                                      uint64_t *__restrict__ samples)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (((uint64_t)j << LAZY_SAMPLE_SHIFT) < n) samples[j] = keys0[(uint64_t)j << LAZY_SAMPLE_SHIFT];
+    if (((uint64_t)j << LAZY_SAMPLE_SHIFT) < n) samples[j] = keys0[(uint64_t)j << LAZY_SAMPLE_SHIFT] & mask;
 }
 
 // bucket[v] = lower_bound(keys0, v << shift) for v in [0, nbuckets]: one binary search per bucket
 // boundary (2^20 searches whose upper levels stay in L2), not a pass over the keys
-__global__ void sa_bucket_index_kernel(const uint64_t *__restrict__ keys0, uint32_t n, int shift, uint32_t nbuckets,
-                                       uint32_t *__restrict__ bucket)
+__global__ void sa_bucket_index_kernel(const uint64_t *__restrict__ keys0, uint32_t n, int shift, uint64_t mask,
+                                       uint32_t nbuckets, uint32_t *__restrict__ bucket)
 {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v > nbuckets) return;
@@ -249,7 +263,7 @@ __global__ void sa_bucket_index_kernel(const uint64_t *__restrict__ keys0, uint3
     const uint64_t key = (uint64_t)v << shift;
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (__ldg(keys0 + mid) < key) lo = mid + 1; else hi = mid;
+        if ((__ldg(keys0 + mid) & mask) < key) lo = mid + 1; else hi = mid;
     }
     bucket[v] = lo;
 }
@@ -280,10 +294,10 @@ __device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const u
     }
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (__ldg(lz.keys0 + mid) < key) lo = mid + 1; else hi = mid;
+        if ((__ldg(lz.keys0 + mid) & lz.mask) < key) lo = mid + 1; else hi = mid;
     }
     if (lz.first_round) return lo;
-    const bool shared_group = (lo + 1 < n) && (__ldg(lz.keys0 + lo + 1) == key);
+    const bool shared_group = (lo + 1 < n) && ((__ldg(lz.keys0 + lo + 1) & lz.mask) == key);
     if (!shared_group) return lo;
     return COHERENT ? *reinterpret_cast<const volatile uint32_t *>(rank + t) : rank[t];
 }
@@ -327,8 +341,9 @@ sa_keybuild_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict
 //   non-singletons are compacted into (cpos, cidx, cgrp) for the next round.
 // Three phases (tile reduce, scan of tile aggregates, apply) -- no spinning.
 
-__device__ __forceinline__ void seg_flags(const uint64_t *__restrict__ skey, uint32_t m, uint32_t j0,
-                                          bool head[SEG_IPT], bool single[SEG_IPT])
+// `mask` = the key bits that were sorted on; *carried = the top bytes of the thread's eight keys, first key lowest
+__device__ __forceinline__ void seg_flags(const uint64_t *__restrict__ skey, uint32_t m, uint32_t j0, uint64_t mask,
+                                          bool head[SEG_IPT], bool single[SEG_IPT], uint64_t *carried)
 {
     // thread owns j0 .. j0+SEG_IPT-1 (blocked): four 16-byte loads; the keys just outside (j0-1 and
     // j0+SEG_IPT) come from the neighbouring lanes, only the warp's two edge lanes load them.
@@ -353,6 +368,14 @@ __device__ __forceinline__ void seg_flags(const uint64_t *__restrict__ skey, uin
     if (lane == 31) next = (j0 + SEG_IPT < m) ? skey[j0 + SEG_IPT] : 0ULL;
     k[0] = prev;
     k[SEG_IPT + 1] = next;
+    if (carried) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int e = 0; e < SEG_IPT; ++e) c |= (k[1 + e] >> 56) << (8 * e);
+        *carried = c;
+    }
+#pragma unroll
+    for (int e = 0; e < SEG_IPT + 2; ++e) k[e] &= mask;
 #pragma unroll
     for (int e = 0; e < SEG_IPT; ++e) {
         const uint32_t j = j0 + e;
@@ -366,13 +389,24 @@ __device__ __forceinline__ void seg_flags(const uint64_t *__restrict__ skey, uin
 
 __global__ void __launch_bounds__(SEG_THREADS)
 seg_reduce_kernel(const uint64_t *__restrict__ skey, uint32_t m, uint32_t *__restrict__ agg_head,
-                  uint32_t *__restrict__ agg_keep, uint16_t *__restrict__ flags)
+                  uint32_t *__restrict__ agg_keep, uint16_t *__restrict__ flags, uint64_t mask,
+                  uint8_t *__restrict__ carried_out)
 {
     __shared__ uint32_t s_h[SEG_THREADS / 32], s_k[SEG_THREADS / 32];
     const uint32_t tid = threadIdx.x;
     const uint32_t j0 = blockIdx.x * SEG_TILE + tid * SEG_IPT;
     bool head[SEG_IPT], single[SEG_IPT];
-    seg_flags(skey, m, j0, head, single);
+    uint64_t carried = 0;
+    seg_flags(skey, m, j0, mask, head, single, carried_out ? &carried : nullptr);
+    if (carried_out) {
+        // round 0 with the BWT symbol in the top byte of the key: row j of the BWT is the top byte of sorted key j
+        // (rows of suffixes that are not yet in their final slot are written again by the round that places them)
+        if (j0 + SEG_IPT <= m && (reinterpret_cast<uintptr_t>(carried_out) & 7) == 0) {
+            *reinterpret_cast<uint64_t *>(carried_out + j0) = carried;
+        } else {
+            for (int e = 0; e < SEG_IPT && j0 + e < m; ++e) carried_out[j0 + e] = (uint8_t)(carried >> (8 * e));
+        }
+    }
     uint32_t lasthead = 0, keep = 0;   // lasthead = (index of last head) + 1, 0 = none
     uint32_t f = 0;
 #pragma unroll
@@ -456,7 +490,8 @@ seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict_
                  const uint32_t *__restrict__ pos /* nullptr = identity */, uint32_t m,
                  const uint32_t *__restrict__ carry_head, const uint32_t *__restrict__ carry_keep,
                  uint32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint32_t *__restrict__ cpos,
-                 uint32_t *__restrict__ cidx, uint32_t *__restrict__ cgrp, bool write_sa, bool scatter_all)
+                 uint32_t *__restrict__ cidx, uint32_t *__restrict__ cgrp, bool write_sa, bool scatter_all,
+                 const uint8_t *__restrict__ text, uint32_t n, uint8_t *__restrict__ bwt)
 {
     __shared__ uint32_t s_h[SEG_THREADS / 32], s_k[SEG_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -507,7 +542,10 @@ seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict_
         // round 0 with lazy ranks needs the suffix id of survivors only: most of the id stream is never read
         const bool need_id = write_sa || scatter_all || !single[e];
         const uint32_t s = need_id ? sidx[j] : 0u;
-        if (write_sa) sa[p] = s;
+        if (write_sa) {
+            sa[p] = s;
+            if (bwt) bwt[p] = text[s ? s - 1u : n - 1u];         // BWT rows carried by round 0: this slot's row follows its suffix
+        }
         if (rank && (scatter_all || !single[e])) rank[s] = cur_grp;
         if (!single[e]) {
             cpos[slot] = p;
@@ -610,7 +648,8 @@ constexpr int FIN_MAX = 1024;
 __global__ void __launch_bounds__(FIN_MAX)
 sa_finish_small_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp,
                        const uint32_t *__restrict__ cpos, uint32_t m, uint32_t n, uint64_t h, uint32_t *sa,
-                       uint32_t *rank, LazyRank lz, AlphaCode ac)
+                       uint32_t *rank, LazyRank lz, AlphaCode ac, const uint8_t *__restrict__ text,
+                       uint8_t *__restrict__ bwt)
 {
     __shared__ uint64_t s_key[FIN_MAX];
     __shared__ uint32_t s_idx[FIN_MAX], s_grp[FIN_MAX], s_pos[FIN_MAX], s_aux[FIN_MAX];
@@ -679,6 +718,7 @@ sa_finish_small_kernel(const uint32_t *__restrict__ cidx, const uint32_t *__rest
         __syncthreads();                                        // every thread has read s_pos / s_key
         if (in) {
             sa[p] = idx;
+            if (bwt) bwt[p] = text[idx ? idx - 1u : n - 1u];
             *reinterpret_cast<volatile uint32_t *>(rank + idx) = newgrp;
         }
         if (keep) {
@@ -756,8 +796,12 @@ extern "C" int hkcsa_byte_hist(const uint8_t *d_sym, uint64_t n, uint64_t *d_his
     return HKCSA_OK;
 }
 
-extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, void *d_scratch,
-                              size_t scratch_bytes, void *stream, hkcsa_sa_stats *h_stats)
+// d_bwt != nullptr: the BWT (csa/bwt.py:3-13) is produced along with the suffix array.  With round-0 keys of at most
+// 56 bits the symbol before each suffix rides through the sort in the top byte of its key, seg_reduce_kernel writes the
+// rows as it reads the sorted keys, and the rounds that move a suffix to its final slot rewrite that slot's row; with
+// 64-bit keys the phased gather of bwt.cu runs after the build.
+static int sa_build_impl(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint8_t *d_bwt, void *d_scratch,
+                         size_t scratch_bytes, void *stream, hkcsa_sa_stats *h_stats)
 {
     hkcsa_sa_stats stats;
     memset(&stats, 0, sizeof(stats));
@@ -781,7 +825,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     HK_CUDA(cudaMemcpyAsync(h_hist, B.hist64, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     HK_CUDA(cudaStreamSynchronize(st));
     static thread_local Round0Plan r0;
-    make_round0_plan(h_hist, r0);
+    make_round0_plan(h_hist, r0, /*want_carry=*/d_bwt != nullptr);
     const AlphaCode &ac = r0.ac;
     const uint32_t sigma = r0.sigma;
     const int max_len = r0.max_len, bits0 = r0.bits0, k0 = r0.k0, passes0 = r0.passes0;
@@ -789,6 +833,10 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     memcpy(stats.byte_hist, h_hist, sizeof(stats.byte_hist));
     stats.bits_per_symbol = (uint32_t)max_len;
     stats.k0 = (uint32_t)k0;
+    stats.key_bits0 = (uint32_t)bits0;
+    const bool carry = d_bwt != nullptr && bits0 <= 56;
+    stats.bwt_carried = carry ? 1u : 0u;
+    const uint64_t mask0 = bits0 >= 64 ? ~0ULL : ((1ULL << bits0) - 1ULL);
 
     const uint32_t N = (uint32_t)n;
     HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
@@ -800,15 +848,16 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     {
         const uint32_t blocks = (N + PACK_TILE - 1) / PACK_TILE;
         prof::Scope ps(st, prof::SA_PACK0, (uint64_t)N * 9);
+#define HK_PACK0(P)                                                                                              \
+    case P:                                                                                                       \
+        if (carry) sa_pack0_kernel<P, true><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist);     \
+        else sa_pack0_kernel<P, false><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist);          \
+        break;
         switch (passes0) {
-            case 2: sa_pack0_kernel<2><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
-            case 3: sa_pack0_kernel<3><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
-            case 4: sa_pack0_kernel<4><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
-            case 5: sa_pack0_kernel<5><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
-            case 6: sa_pack0_kernel<6><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
-            case 7: sa_pack0_kernel<7><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
-            default: sa_pack0_kernel<8><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
+            HK_PACK0(2) HK_PACK0(3) HK_PACK0(4) HK_PACK0(5) HK_PACK0(6) HK_PACK0(7)
+            default: sa_pack0_kernel<8, false><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, ka, B.sort.hist); break;
         }
+#undef HK_PACK0
         HK_LAUNCH_CHECK();
     }
     HK_CUDA(radix_sort_pairs_u64(ka, va, kb, vb, N, passes0, B.sort, st, /*identity_vals=*/true));
@@ -831,6 +880,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
     lz.text = nullptr; lz.keys0 = nullptr; lz.bucket = nullptr; lz.samples = nullptr; lz.first_round = 0; lz.bits = bits0;
     const int bucket_bits = std::min(LAZY_BUCKET_BITS, bits0);
     lz.shift = bits0 - bucket_bits;
+    lz.mask = mask0;
     uint64_t *kx = nullptr, *ky = nullptr;             // key ping-pong of the later rounds
     uint32_t *vfree = B.val[1];                        // free value buffer (receives the compacted ids)
     uint32_t *vother = B.val[0];                       // the round-0 sort's other value buffer: free from here on
@@ -843,10 +893,11 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         lazy_index_due = false;
         const uint32_t nbuckets = 1u << bucket_bits;
         prof::Scope ps(st, prof::OTHER, (uint64_t)nbuckets * 8);
-        sa_bucket_index_kernel<<<(nbuckets + 1 + 255) / 256, 256, 0, st>>>(lz.keys0, N, lz.shift, nbuckets, B.bucket);
+        sa_bucket_index_kernel<<<(nbuckets + 1 + 255) / 256, 256, 0, st>>>(lz.keys0, N, lz.shift, lz.mask, nbuckets,
+                                                                           B.bucket);
         HK_LAUNCH_CHECK();
         const uint32_t nsamp = (uint32_t)(((uint64_t)N + (1u << LAZY_SAMPLE_SHIFT) - 1) >> LAZY_SAMPLE_SHIFT);
-        sa_key_samples_kernel<<<(nsamp + 255) / 256, 256, 0, st>>>(lz.keys0, N, B.samples);
+        sa_key_samples_kernel<<<(nsamp + 255) / 256, 256, 0, st>>>(lz.keys0, N, lz.mask, B.samples);
         HK_LAUNCH_CHECK();
         return HKCSA_OK;
     };
@@ -854,8 +905,10 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         // ---- refine ranks from the sorted keys
         const uint32_t tiles = (m + SEG_TILE - 1) / SEG_TILE;
         {
-            prof::Scope ps(st, prof::SEG_REDUCE, (uint64_t)m * 8 + m / 4);
-            seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, m, B.agg_head, B.agg_keep, B.flags);
+            const bool emit = carry && round == 0;      // round 0: the sorted keys deliver the BWT
+            prof::Scope ps(st, prof::SEG_REDUCE, (uint64_t)m * 8 + m / 4 + (emit ? m : 0));
+            seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(skey, m, B.agg_head, B.agg_keep, B.flags,
+                                                             round == 0 ? mask0 : ~0ULL, emit ? d_bwt : nullptr);
             HK_LAUNCH_CHECK();
         }
         {
@@ -886,7 +939,8 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
             // lower bound), and round 1's own scatter covers every survivor before round 2 reads the array
             uint32_t *rank_out = (round == 0 && !scatter_all) ? nullptr : B.rank;
             seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(B.flags, sidx, pos, m, B.agg_head, B.agg_keep, d_sa, rank_out,
-                                                           cpos, cidx, B.grp, round != 0, scatter_all);
+                                                           cpos, cidx, B.grp, round != 0, scatter_all, d_text, N,
+                                                           carry ? d_bwt : nullptr);
             HK_LAUNCH_CHECK();
         }
         stats.alg_bytes += (uint64_t)m * 8 + m / 2 + (uint64_t)m_next * 20 + ((round != 0 || scatter_all) ? (uint64_t)m * 12 : 0);
@@ -900,7 +954,7 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
             if (int rc = build_lazy_index()) return rc;
             prof::Scope ps(st, prof::OTHER, (uint64_t)m_next * 32);
             sa_finish_small_kernel<<<1, FIN_MAX, 0, st>>>(cidx, B.grp, cpos, m_next, N, std::min<uint64_t>(h, n), d_sa,
-                                                          B.rank, lz, ac);
+                                                          B.rank, lz, ac, d_text, carry ? d_bwt : nullptr);
             HK_LAUNCH_CHECK();
             stats.round_elems[round] = m_next;
             stats.round_passes[round] = 0;                      // 0 passes = finished in shared memory
@@ -953,6 +1007,21 @@ extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa,
         h *= 2;
     }
     stats.rounds = round;
+    if (carry) stats.alg_bytes += n;
     if (h_stats) *h_stats = stats;
+    if (d_bwt && !carry) return bwt_gather(d_text, d_sa, n, d_bwt, st);
     return HKCSA_OK;
+}
+
+extern "C" int hkcsa_sa_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, void *d_scratch,
+                              size_t scratch_bytes, void *stream, hkcsa_sa_stats *h_stats)
+{
+    return sa_build_impl(d_text, n, d_sa, nullptr, d_scratch, scratch_bytes, stream, h_stats);
+}
+
+extern "C" int hkcsa_sa_bwt_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint8_t *d_bwt, void *d_scratch,
+                                  size_t scratch_bytes, void *stream, hkcsa_sa_stats *h_stats)
+{
+    HK_REQUIRE(d_bwt != nullptr || n == 0, HKCSA_EINVAL, "null pointer");
+    return sa_build_impl(d_text, n, d_sa, d_bwt, d_scratch, scratch_bytes, stream, h_stats);
 }

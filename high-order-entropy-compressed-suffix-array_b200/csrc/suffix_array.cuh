@@ -39,7 +39,12 @@ struct Round0Plan {
     int k0;         // symbols every key is guaranteed to cover
     int passes0;    // radix passes of round 0
 };
-void make_round0_plan(const uint64_t *h_hist, Round0Plan &p);
+// want_carry: the caller wants the BWT symbol carried in the top byte of the key (single-GPU builder with a BWT
+// output): with HKCSA_CARRY56=1 a plan that would use all 64 bits settles for 56
+void make_round0_plan(const uint64_t *h_hist, Round0Plan &p, bool want_carry = false);
+
+// bwt[i] = text[SA[i] - 1] (wrapping to text[n - 1]) by the phased gather of bwt.cu
+int bwt_gather(const uint8_t *d_text, const uint32_t *d_sa, uint64_t n, uint8_t *d_bwt, cudaStream_t st);
 
 // first `bits` bits of the code stream of the suffix whose symbols are produced by next_sym(t), t = 0, 1, ...
 template <typename NextSym>
@@ -132,14 +137,17 @@ cudaError_t group_local_keys(uint32_t *cidx, const uint32_t *cgrp, uint32_t m, c
                              uint64_t depth, const uint64_t *ids64, uint64_t *keys, cudaStream_t st);
 
 // ---------------------------------------------------------------- segmented rank update (suffix_array.cu)
+// mask = the key bits that were sorted on; carried_out != nullptr: byte j = top byte of sorted key j
 __global__ void __launch_bounds__(SEG_THREADS) seg_reduce_kernel(const uint64_t *__restrict__ skey, uint32_t m, uint32_t *__restrict__ agg_head,
-                                  uint32_t *__restrict__ agg_keep, uint16_t *__restrict__ flags);
+                                  uint32_t *__restrict__ agg_keep, uint16_t *__restrict__ flags, uint64_t mask,
+                                  uint8_t *__restrict__ carried_out);
 __global__ void __launch_bounds__(1024) seg_scan_kernel(uint32_t *__restrict__ agg_head, uint32_t *__restrict__ agg_keep, uint32_t tiles,
                                 uint32_t *__restrict__ out_m);
 __global__ void __launch_bounds__(SEG_THREADS, 6) seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict__ sidx,
                                  const uint32_t *__restrict__ pos /* nullptr = identity */, uint32_t m,
                                  const uint32_t *__restrict__ carry_head, const uint32_t *__restrict__ carry_keep,
                                  uint32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint32_t *__restrict__ cpos,
-                                 uint32_t *__restrict__ cidx, uint32_t *__restrict__ cgrp, bool write_sa, bool scatter_all);
+                                 uint32_t *__restrict__ cidx, uint32_t *__restrict__ cgrp, bool write_sa, bool scatter_all,
+                                 const uint8_t *__restrict__ text, uint32_t n, uint8_t *__restrict__ bwt);
 
 }  // namespace hkcsa

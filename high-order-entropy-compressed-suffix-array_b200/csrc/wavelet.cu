@@ -614,27 +614,75 @@ int build_bitvector(const uint8_t *d_sym, uint64_t len, const uint8_t *d_lut_bit
 }
 }  // namespace hkcsa
 
-// Mark bit-vector of the sampled suffix array, bit j = (SA[j] % rate == 0), packed straight from the suffix
-// array with warp ballots (no byte flags in between) + its directory.
+// Sampled suffix array in ONE pass over the suffix array: mark bit-vector (bit j = SA[j] % rate == 0) packed into rank
+// blocks, and the samples SA[j] / rate of the marked rows written in row order.  A thread takes four consecutive rows
+// per step (one 16-byte load for 32-bit ids); the flag nibbles of eight lanes are OR-ed into the 32-bit word of their
+// rows with three shuffles.  The sample slot of a marked row = marks in earlier tiles (decoupled look-back over one
+// counter per tile, tiles handed out by a ticket) + marks before it in the tile (prefix over the tile's words); the
+// marked entries -- one in `rate` -- are read a second time from L1/L2, so the suffix array comes from DRAM once.
 namespace hkcsa {
+constexpr int SSA_STEPS = WTP_SYMS / (WTP_THREADS * 4);      // 14 steps of 1024 rows
+static_assert(WTP_SYMS % (WTP_THREADS * 4) == 0, "tile shape");
+constexpr int SSA_WORDS = WTP_SYMS / 32;                     // 448 words = 64 blocks x 7
+
+template <typename IdT>
+__device__ __forceinline__ void ssa_load4(const IdT *__restrict__ sa, uint64_t n, uint64_t r0, bool aligned16, IdT v[4])
+{
+    if (r0 + 4 <= n && aligned16) {
+        if constexpr (sizeof(IdT) == 4) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(sa + r0);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(sa + r0);
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(sa + r0 + 2);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (r0 + e < n) ? sa[r0 + e] : (IdT)1;      // 1 % rate != 0 unless rate == 1: masked below
+    }
+}
+
 template <typename IdT>
 __global__ void __launch_bounds__(WTP_THREADS)
-ssa_mark_pack_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, RankBlock *__restrict__ blocks,
-                     uint64_t nblocks, uint32_t *__restrict__ agg)
+ssa_mark_sample_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, RankBlock *__restrict__ blocks,
+                       uint64_t nblocks, uint32_t *__restrict__ agg, uint32_t *state, uint32_t *ticket,
+                       uint32_t *__restrict__ samples)
 {
-    __shared__ uint32_t s_words[WTP_BLOCKS_PER_CTA * 7];
+    __shared__ uint32_t s_words[SSA_WORDS];
+    __shared__ uint32_t s_pref[SSA_WORDS];
     __shared__ uint32_t s_wsum[2];
+    __shared__ uint32_t s_tile, s_total, s_base;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint64_t row_base = (uint64_t)blockIdx.x * WTP_SYMS;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t row_base = (uint64_t)tile * WTP_SYMS;
     const bool pow2 = (rate & (rate - 1u)) == 0;      // power-of-two rate: no division per entry
-    for (uint32_t it = 0; it < WTP_SYMS / WTP_THREADS; ++it) {
-        const uint64_t row = row_base + it * WTP_THREADS + tid;
-        const bool flag = row < n && (pow2 ? ((sa[row] & (IdT)(rate - 1u)) == 0) : (sa[row] % rate == 0));
-        const uint32_t w = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) s_words[it * (WTP_THREADS / 32) + warp] = w;
+    const int sh = __ffs(rate) - 1;
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(sa) & 15) == 0;
+    uint64_t nibs = 0;                                // this thread's four flags of every step
+#pragma unroll
+    for (int it = 0; it < SSA_STEPS; ++it) {
+        const uint64_t r0 = row_base + (uint64_t)it * (WTP_THREADS * 4) + tid * 4u;
+        IdT v[4];
+        ssa_load4<IdT>(sa, n, r0, aligned16, v);
+        uint32_t nib = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool f = (r0 + e < n) && (pow2 ? ((v[e] & (IdT)(rate - 1u)) == 0) : (v[e] % rate == 0));
+            nib |= (f ? 1u : 0u) << e;
+        }
+        nibs |= (uint64_t)nib << (4 * it);
+        uint32_t x = nib << (4u * (lane & 7u));
+        x |= __shfl_xor_sync(0xffffffffu, x, 1);
+        x |= __shfl_xor_sync(0xffffffffu, x, 2);
+        x |= __shfl_xor_sync(0xffffffffu, x, 4);
+        if ((lane & 7u) == 0) s_words[it * (WTP_THREADS / 8) + warp * 4 + (lane >> 3)] = x;
     }
     __syncthreads();
-    const uint64_t gb = (uint64_t)blockIdx.x * WTP_BLOCKS_PER_CTA + tid;
+    // threads 0..63: one rank block each (7 words), block headers relative to the tile, prefix of every word
+    const uint64_t gb = (uint64_t)tile * WTP_BLOCKS_PER_CTA + tid;
     uint32_t w[7] = {0, 0, 0, 0, 0, 0, 0};
     uint32_t cnt = 0;
     if (tid < WTP_BLOCKS_PER_CTA) {
@@ -647,6 +695,9 @@ ssa_mark_pack_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, Rank
     __syncthreads();
     if (tid < WTP_BLOCKS_PER_CTA) {
         const uint32_t rel = ex + ((tid >= 32) ? s_wsum[0] : 0u);
+        uint32_t run = rel;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) { s_pref[tid * 7 + t] = run; run += __popc(w[t]); }
         if (gb < nblocks) {
             uint4 lo4, hi4;
             lo4.x = rel; lo4.y = w[0]; lo4.z = w[1]; lo4.w = w[2];
@@ -655,18 +706,68 @@ ssa_mark_pack_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, Rank
             dst[0] = lo4;
             dst[1] = hi4;
         }
-        if (tid == WTP_BLOCKS_PER_CTA - 1) agg[blockIdx.x] = rel + cnt;
+        if (tid == WTP_BLOCKS_PER_CTA - 1) {
+            agg[tile] = rel + cnt;
+            s_total = rel + cnt;
+            st_volatile_u32(&state[tile], (tile == 0 ? LB_INC : LB_AGG) | (rel + cnt));
+        }
+    }
+    __syncthreads();
+    // marks in earlier tiles: warp 0 looks back 32 tiles per round trip
+    if (warp == 0) {
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                const int64_t mine = t - lane;
+                const uint32_t v = mine >= 0 ? ld_volatile_u32(&state[mine]) : LB_INC;
+                const uint32_t flag = v >> 30;
+                const uint32_t not_ready = __ballot_sync(0xffffffffu, flag == 0);
+                const uint32_t inc = __ballot_sync(0xffffffffu, flag == 2);
+                // usable lanes: below the first unpublished one, up to and including the first inclusive one
+                uint32_t upto = not_ready ? (uint32_t)(__ffs(not_ready) - 1) : 32u;
+                bool done = false;
+                if (inc && (uint32_t)(__ffs(inc) - 1) < upto) { upto = (uint32_t)__ffs(inc); done = true; }
+                const uint32_t part = __reduce_add_sync(0xffffffffu, lane < upto ? (v & LB_VAL) : 0u);
+                excl += part;
+                t -= upto;
+                if (done) break;
+            }
+            if (lane == 0) st_volatile_u32(&state[tile], LB_INC | (excl + s_total));
+        }
+        if (lane == 0) s_base = excl;
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+    if (nibs == 0) return;
+#pragma unroll
+    for (int it = 0; it < SSA_STEPS; ++it) {
+        uint32_t nib = (uint32_t)(nibs >> (4 * it)) & 0xFu;
+        if (nib == 0) continue;
+        const uint32_t local = it * (WTP_THREADS * 4) + tid * 4u;       // first of the four rows inside the tile
+        const uint32_t q = local >> 5;
+        const uint32_t word = s_words[q];
+        const uint32_t pre = base + s_pref[q];
+        while (nib) {
+            const uint32_t e = __ffs(nib) - 1;
+            nib &= nib - 1;
+            const uint32_t bit = (local & 31u) + e;
+            const IdT v = sa[row_base + local + e];
+            samples[pre + __popc(word & ((1u << bit) - 1u))] = pow2 ? (uint32_t)(v >> sh) : (uint32_t)(v / rate);
+        }
     }
 }
 
 template <typename IdT>
 static int build_markvector_t(const IdT *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
-                              uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st)
+                              uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, uint32_t *d_state,
+                              uint32_t *d_samples, cudaStream_t st)
 {
-    static_assert(WTP_SYMS % WTP_THREADS == 0 && WTP_THREADS % 32 == 0, "tile shape");
     const uint64_t nblocks = rank_blocks_for(n);
     const uint64_t tiles = (nblocks + WTP_BLOCKS_PER_CTA - 1) / WTP_BLOCKS_PER_CTA;
-    ssa_mark_pack_kernel<IdT><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg);
+    HK_CUDA(cudaMemsetAsync(d_state, 0, (tiles + 1) * sizeof(uint32_t), st));       // [tiles] look-back states + the ticket
+    ssa_mark_sample_kernel<IdT><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg, d_state,
+                                                                         d_state + tiles, d_samples);
     HK_LAUNCH_CHECK();
     wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones);
     HK_LAUNCH_CHECK();
@@ -676,14 +777,18 @@ static int build_markvector_t(const IdT *d_sa, uint64_t n, uint32_t rate, RankBl
     return HKCSA_OK;
 }
 int build_markvector(const uint32_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
-                     uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st)
+                     uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, uint32_t *d_state,
+                     uint32_t *d_samples, cudaStream_t st)
 {
-    return build_markvector_t<uint32_t>(d_sa, n, rate, d_blocks, d_super, d_select, d_agg, d_carry, d_ones, st);
+    return build_markvector_t<uint32_t>(d_sa, n, rate, d_blocks, d_super, d_select, d_agg, d_carry, d_ones, d_state,
+                                        d_samples, st);
 }
 int build_markvector64(const uint64_t *d_sa, uint64_t n, uint32_t rate, RankBlock *d_blocks, uint64_t *d_super,
-                       uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, cudaStream_t st)
+                       uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, uint32_t *d_state,
+                       uint32_t *d_samples, cudaStream_t st)
 {
-    return build_markvector_t<uint64_t>(d_sa, n, rate, d_blocks, d_super, d_select, d_agg, d_carry, d_ones, st);
+    return build_markvector_t<uint64_t>(d_sa, n, rate, d_blocks, d_super, d_select, d_agg, d_carry, d_ones, d_state,
+                                        d_samples, st);
 }
 }  // namespace hkcsa
 

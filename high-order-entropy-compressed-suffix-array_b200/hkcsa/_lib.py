@@ -42,6 +42,8 @@ class SaStats(C.Structure):
         ("round_elems", C.c_uint64 * 40),
         ("round_passes", C.c_uint32 * 40),
         ("byte_hist", C.c_uint64 * 256),
+        ("key_bits0", C.c_uint32),
+        ("bwt_carried", C.c_uint32),
     ]
 
 
@@ -138,6 +140,7 @@ SIGNATURES = {
     "hkcsa_gen_pattern_bytes": (_i32, [_u64, _u64, _vp, _u64, _vp, _u32, _vp, _vp, _vp]),
     "hkcsa_sa_scratch_bytes": (_sz, [_u64]),
     "hkcsa_sa_build": (_i32, [_vp, _u64, _vp, _vp, _sz, _vp, C.POINTER(SaStats)]),
+    "hkcsa_sa_bwt_build": (_i32, [_vp, _u64, _vp, _vp, _vp, _sz, _vp, C.POINTER(SaStats)]),
     "hkcsa_dsa_plan_make": (_i32, [C.POINTER(_u64), _u64, _i32, C.POINTER(DsaPlan)]),
     "hkcsa_dsa_bucket_hist": (_i32, [_vp, C.POINTER(DsaPlan), _u64, _u64, _vp, _vp]),
     "hkcsa_dsa_pack_exchange": (_i32, [_vp, C.POINTER(DsaPlan), _u64, _u64, _u32, C.POINTER(_u32), C.POINTER(_u64),

@@ -198,6 +198,24 @@ def suffix_array(text: torch.Tensor, stats: SaStats | None = None) -> torch.Tens
     return sa
 
 
+def suffix_array_bwt(text: torch.Tensor, stats: SaStats | None = None):
+    """build_suffix_array + bwt_transform, the pair EnhancedFMIndex.__init__ runs (csa/enhanced_fm_index.py:10-11),
+    in one call -> (int32[n], uint8[n]): with round-0 keys of at most 56 bits the BWT comes out of the sort."""
+    L = _lib.load()
+    n = text.numel()
+    if n > _lib.MAX_N:
+        raise HkcsaError(_lib.ERANGE, f"text of {n} symbols exceeds the single-GPU limit {_lib.MAX_N}")
+    sa = _empty(n, torch.int32, text.device)
+    out = _empty(n, torch.uint8, text.device)
+    if n == 0:
+        return sa, out
+    nbytes = L.hkcsa_sa_scratch_bytes(n)
+    scratch = _scratch(nbytes, text.device)
+    st = stats if stats is not None else SaStats()
+    check(L.hkcsa_sa_bwt_build(_ptr(text), n, _ptr(sa), _ptr(out), _ptr(scratch), nbytes, _stream(), C.byref(st)))
+    return sa, out
+
+
 def bwt(text: torch.Tensor, sa: torch.Tensor) -> torch.Tensor:
     """bwt_transform (csa/bwt.py:3-13) -> uint8[n]."""
     n = text.numel()
@@ -538,7 +556,9 @@ class DeviceIndex:
         self.device = text.device
         self.n = text.numel()
         self.stats = BuildStats(n=self.n)
-        self.sa = suffix_array(text, self.stats.sa)
+        # suffix array and BWT in one call: the symbol before each suffix rides through the round-0 sort in the top
+        # byte of its key when the key leaves it free (no gather over the text afterwards)
+        self.sa, self.bwt = suffix_array_bwt(text, self.stats.sa)
         side = None
         if host_sa is not None or host_bwt is not None:
             side = _aux_stream(self.device, "copy")
@@ -556,15 +576,12 @@ class DeviceIndex:
         if sa_sample_rate > 0:
             sa_done = torch.cuda.Event()
             sa_done.record(main)
-        # the BWT gather goes out first: the host-side set-up of the side stream must not delay the main stream
-        # BWT gather and wavelet tree are the critical path of the tail; with a sampled SA being built beside
-        # them they run on a high-priority stream, so the block scheduler serves them first and the sampled-SA
-        # kernels fill what is left (the tree build alone: 2.6 ms at C3; sharing the SMs evenly: 3.4 ms)
+        # the wavelet tree is the critical path of the tail; with a sampled SA being built beside it, it runs on a
+        # high-priority stream, so the block scheduler serves it first and the sampled-SA kernels fill what is left
+        # (the tree build alone: 2.6 ms at C3; sharing the SMs evenly: 3.4 ms)
         crit = _aux_stream(self.device, "critical", priority=-1) if sa_sample_rate > 0 else main
         if crit is not main:
             crit.wait_stream(main)
-        with torch.cuda.stream(crit):
-            self.bwt = bwt(text, self.sa)
         if sa_sample_rate > 0:
             ssa_stream = _aux_stream(self.device, "ssa")
             ssa_stream.wait_event(sa_done)
@@ -582,10 +599,9 @@ class DeviceIndex:
             self.wt = DeviceWaveletTree(self.bwt, hist=hist)
         if crit is not main:
             main.wait_stream(crit)
-            for t in (text, self.sa):
+            for t in (text, self.sa, self.bwt):
                 t.record_stream(crit)
-            for t in (self.bwt, self.wt.blob):
-                t.record_stream(main)
+            self.wt.blob.record_stream(main)
         if ssa_stream is not None:
             main.wait_stream(ssa_stream)
             self.ssa.blob.record_stream(main)

@@ -82,6 +82,8 @@ typedef struct hkcsa_sa_stats {
     uint32_t round_passes[40];  /* radix passes per round                       */
     uint64_t byte_hist[256];    /* occurrences per byte value (the BWT has the  */
                                 /* same histogram: hkcsa_wt_plan_from_hist)     */
+    uint32_t key_bits0;         /* sorted bits of a round-0 key                 */
+    uint32_t bwt_carried;       /* 1: the BWT came out of the round-0 sort      */
 } hkcsa_sa_stats;
 
 size_t hkcsa_sa_scratch_bytes(uint64_t n);
@@ -180,6 +182,16 @@ int hkcsa_bwt_slice64(const uint8_t *d_text, uint64_t n, const uint64_t *d_sa_sl
 /*     bwt[i] = text[SA[i]-1], text[n-1] when SA[i] == 0.                       */
 /* ------------------------------------------------------------------------ */
 int hkcsa_bwt(const uint8_t *d_text, const uint32_t *d_sa, uint64_t n, uint8_t *d_bwt, void *stream);
+
+/* K1 + K2 in one call -- the pair EnhancedFMIndex.__init__ runs back to back,   */
+/* csa/enhanced_fm_index.py:10-11 (build_suffix_array, then bwt_transform).       */
+/* Same contract as hkcsa_sa_build plus d_bwt: uint8[n].  When the round-0 key    */
+/* leaves its top byte free (<= 56 sorted bits) the symbol before each suffix     */
+/* rides through the radix sort in that byte and the BWT is written while the     */
+/* sorted keys are read -- no random gather over the text; otherwise the gather   */
+/* of hkcsa_bwt runs after the build.  Identical outputs either way.  syncs.      */
+int hkcsa_sa_bwt_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint8_t *d_bwt,
+                       void *d_scratch, size_t scratch_bytes, void *stream, hkcsa_sa_stats *h_stats);
 
 /* Byte histogram: the raw counts under build_count, utils/utils.py:16-24.      */
 /* d_hist: uint64[256] (overwritten).                                           */

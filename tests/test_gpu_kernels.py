@@ -1,6 +1,7 @@
 """GPU parity tests, kernel by kernel, through the C-ABI (hkcsa.engine -> libhkcsa.so)
 against the CPU oracle and the golden fixtures frozen from the reference."""
 import numpy as np
+import torch
 import pytest
 
 from conftest import golden_case_names
@@ -127,6 +128,57 @@ def test_sa_bwt_oracle(E, name):
     assert np.array_equal(got, want), f"first mismatch at {np.flatnonzero(got != want)[:5]}"
     assert st.rounds >= 1
     assert host(E.bwt(d_text, sa)).tobytes() == O.bwt_transform(text, want).tobytes()
+
+
+@pytest.mark.parametrize("env", [{}, {"HKCSA_CARRY56": "1"}, {"HKCSA_BITS0": "24"}, {"HKCSA_BITS0": "56", "HKCSA_NO_GROUP_ROUND": "1"}])
+@pytest.mark.parametrize("name", list(TEXTS))
+def test_sa_bwt_one_call(E, name, env, monkeypatch):
+    """hkcsa_sa_bwt_build: the BWT symbol rides in the top byte of the round-0 key (keys of at most 56 bits) or the
+    gather runs after the build (64-bit keys, unless HKCSA_CARRY56=1 trims them to 56); narrow keys leave many suffixes to the later
+    rounds, whose slots get their BWT rows rewritten."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    text = TEXTS[name]
+    d_text = dev(E, text)
+    st = E.SaStats()
+    sa, got = E.suffix_array_bwt(d_text, st)
+    want = O.build_suffix_array(text)
+    assert np.array_equal(host(sa).astype(np.uint32), want)
+    assert host(got).tobytes() == O.bwt_transform(text, want).tobytes()
+    if env:
+        assert st.bwt_carried == 1 and st.key_bits0 <= 56
+    else:
+        assert st.bwt_carried == (1 if st.key_bits0 <= 56 else 0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 4095, 4097, 100_003])
+def test_sa_bwt_one_call_ragged_sizes(E, n):
+    for kind in (O.ENG96, O.DNA4):
+        text = O.gen_text(kind, 3 + n % 5, n).tobytes()
+        sa, got = E.suffix_array_bwt(dev(E, text))
+        want = O.build_suffix_array(text)
+        assert np.array_equal(host(sa).astype(np.uint32), want)
+        assert host(got).tobytes() == O.bwt_transform(text, want).tobytes()
+
+
+@pytest.mark.parametrize("rate", [1, 3, 4, 32, 1000])
+@pytest.mark.parametrize("n", [1, 31, 224, 14336, 14337, 100_003, 1_000_001])
+def test_sampled_sa_one_pass(E, n, rate):
+    """Marks and samples of the sampled suffix array from one pass over the suffix array (look-back over tiles of
+    14336 rows): samples = SA[j] / rate of the rows with SA[j] % rate == 0, in row order; marks rank-consistent."""
+    rng = np.random.RandomState(n % 1000 + rate)
+    perm = rng.permutation(n).astype(np.int32)
+    ssa = E.build_sampled_sa(torch.from_numpy(perm).cuda(), rate)
+    marked = perm % rate == 0
+    want = (perm[marked] // rate).astype(np.uint32)
+    assert int(ssa.plan.n_samples) == want.size
+    blob = host(ssa.blob)
+    off = int(ssa.plan.off_samples)
+    got = blob[off:off + 4 * want.size].view(np.uint32)
+    assert np.array_equal(got, want)
+    bits = np.unpackbits(blob[int(ssa.plan.off_blocks):int(ssa.plan.off_super)].reshape(-1, 32)[:, 4:], axis=1,
+                         bitorder="little").reshape(-1)[:n]
+    assert np.array_equal(bits.astype(bool), marked)
 
 
 def test_byte_hist(E):
