@@ -212,17 +212,31 @@ struct LevelWords {
     uint32_t *w[HKCSA_MAX_LEVELS];   // rank blocks of each level viewed as uint32[8] per block
 };
 
+// The CTA's tile as root-to-leaf PATHS (WtTables::path_of_sym), one byte per element: the bit of an element at level l
+// is bit 7 - l of its path and its node is the top l bits, so the level loop needs no table look-up per element.  At
+// level l the tile is ordered by the top l path bits (stable); the elements sharing them are one contiguous run
+// [S, E) -- an internal node, or a leaf reached earlier whose remaining path bits are zero, so that splitting it moves
+// nothing.  Per level:
+//   A  bits: warp w owns tile positions [1024 w, 1024 w + 1024) as 32 rows of 32; one ballot per row gives the row's
+//      word of bits (lane r of the warp keeps row r's word); ones before every row by a block scan of the popcounts;
+//   B  emit: each internal node's run of bits goes to its place in the level's bit-vector (funnel-shifted to the
+//      destination alignment; whole words stored, edge words OR-ed);
+//   C  split: per run one table entry {split point M - ones before the run, ones before the run}; an element moves to
+//      M + (ones before it inside the run) or to its position minus that count.  The lanes of a row read the same
+//      entry (broadcast) and write two consecutive byte streams: no bank conflicts to speak of.
+// Slots past the end of the text hold path 0xFF: they stay at the tail of the last run on every level and are never
+// emitted (the runs' lengths come from the tile histogram, which does not count them).
 __global__ void __launch_bounds__(WTL_THREADS, WTL_MIN_CTAS)
 wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__restrict__ tab,
                  const uint32_t *__restrict__ gpre, uint32_t tiles, LevelWords lv, uint32_t levels, uint32_t sigma)
 {
     __shared__ __align__(16) uint8_t s_a[WTL_TILE];
     __shared__ __align__(16) uint8_t s_b[WTL_TILE];
-    __shared__ uint32_t s_bits[WTL_THREADS + 1];
-    __shared__ uint32_t s_wpre[WTL_THREADS + 1];
-    __shared__ uint32_t s_tcum[257], s_gcum[257];
-    __shared__ uint64_t s_ent[256];
-    __shared__ uint8_t s_code[256];
+    __shared__ uint32_t s_bits[WTL_THREADS + 1];      // word r = bits of tile positions [32 r, 32 r + 32)
+    __shared__ uint32_t s_wpre[WTL_THREADS + 1];      // ones before word r
+    __shared__ uint32_t s_tcum[257], s_gcum[257];     // per path x: elements with a smaller path in this tile / in earlier tiles
+    __shared__ uint32_t s_ent[128];
+    __shared__ uint8_t s_path[256];
     __shared__ uint32_t s_scan[2][8];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -230,15 +244,15 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
     const uint64_t base = (uint64_t)tile * WTL_TILE;
     const uint32_t nv = (uint32_t)min((uint64_t)WTL_TILE, n - base);
 
-    s_code[tid] = tab->code8_of_sym[tid];
-    // tile-local and global (earlier tiles) counts per code -> exclusive prefixes over codes
-    uint32_t cnt = 0, pre = 0;
-    if (tid < sigma) {
-        const uint32_t *row = gpre + (size_t)tid * (tiles + 1);
-        pre = row[tile];
-        cnt = row[tile + 1] - pre;
-    }
+    s_path[tid] = tab->path_of_sym[tid];
     {
+        uint32_t cnt = 0, pre = 0;
+        const uint32_t c = tab->code_of_path[tid];
+        if (c < sigma) {
+            const uint32_t *row = gpre + (size_t)c * (tiles + 1);
+            pre = row[tile];
+            cnt = row[tile + 1] - pre;
+        }
         uint32_t t1, t2;
         const uint32_t e1 = warp_excl_sum(cnt, t1);
         const uint32_t e2 = warp_excl_sum(pre, t2);
@@ -251,7 +265,7 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
         if (tid == 255) { s_tcum[256] = p1 + e1 + cnt; s_gcum[256] = p2 + e2 + pre; }
     }
     if (tid == 0) s_bits[WTL_THREADS] = 0;
-    // symbols -> codes, original order
+    // symbols -> paths, original order (32 consecutive symbols per thread: two 16-byte loads)
     {
         const uint8_t *src = sym + base + (uint64_t)tid * WTL_EPT;
         const bool vec = ((reinterpret_cast<uintptr_t>(sym) & 15) == 0) && (tid * WTL_EPT + WTL_EPT <= nv);
@@ -264,84 +278,54 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
                 uint32_t o4[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    o4[j] = (uint32_t)s_code[w4[j] & 0xFF] | ((uint32_t)s_code[(w4[j] >> 8) & 0xFF] << 8) |
-                            ((uint32_t)s_code[(w4[j] >> 16) & 0xFF] << 16) | ((uint32_t)s_code[w4[j] >> 24] << 24);
+                    o4[j] = (uint32_t)s_path[w4[j] & 0xFF] | ((uint32_t)s_path[(w4[j] >> 8) & 0xFF] << 8) |
+                            ((uint32_t)s_path[(w4[j] >> 16) & 0xFF] << 16) | ((uint32_t)s_path[w4[j] >> 24] << 24);
                 reinterpret_cast<uint4 *>(s_a + tid * WTL_EPT)[h] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
             }
         } else {
             for (uint32_t k = 0; k < WTL_EPT; ++k) {
                 const uint32_t i = tid * WTL_EPT + k;
-                if (i < nv) s_a[i] = s_code[src[k]];
+                s_a[i] = (i < nv) ? s_path[src[k]] : (uint8_t)0xFF;
             }
         }
     }
     __syncthreads();
 
-    // Per level and code, one packed table entry: run start S (14 bits) | split M (14) | ones before
-    // the run Ps (14) | mid code (8) | alive (1) -- one 64-bit shared load per element.
     uint8_t *cur = s_a, *nxt = s_b;
+    const uint32_t lt = lanemask_lt();
     for (uint32_t l = 0; l < levels; ++l) {
-        // (i) per code: alive at this level, split point, start of its node's run in the tile
-        uint64_t my_entry = 0;
-        {
-            const uint32_t c = tid;
-            const bool alive = c < sigma && tab->depth[c] > l;
-            if (alive) {
-                const uint32_t lo = tab->node_lo[l][c];
-                const uint32_t hi = (uint32_t)tab->node_hi1[l][c] + 1;
-                const uint32_t mid = lo + (hi - lo) / 2;
-                my_entry = (uint64_t)s_tcum[lo] | ((uint64_t)s_tcum[mid] << 14) | ((uint64_t)mid << 42) | (1ull << 50);
-            }
-            s_ent[c] = my_entry;
+        const uint32_t shift = 7u - l;
+        // ---- A: the words of bits of this warp's 32 rows; lane r keeps row r's word
+        const uint8_t *wrow = cur + warp * 1024u + lane;
+        uint32_t myword = 0;
+#pragma unroll 8
+        for (uint32_t r = 0; r < 32; ++r) {
+            const uint32_t pth = wrow[r * 32u];
+            const uint32_t word = __ballot_sync(0xffffffffu, (pth >> shift) & 1u);
+            if (lane == r) myword = word;
         }
-        __syncthreads();
-        // this thread's 32 codes, kept in registers for the whole level
-        uint32_t cw[8];
-        {
-            const uint4 x0 = reinterpret_cast<const uint4 *>(cur + tid * WTL_EPT)[0];
-            const uint4 x1 = reinterpret_cast<const uint4 *>(cur + tid * WTL_EPT)[1];
-            cw[0] = x0.x; cw[1] = x0.y; cw[2] = x0.z; cw[3] = x0.w;
-            cw[4] = x1.x; cw[5] = x1.y; cw[6] = x1.z; cw[7] = x1.w;
-        }
-        const uint32_t i_base = tid * WTL_EPT;
-        const uint32_t n_mine = (i_base >= nv) ? 0u : min((uint32_t)WTL_EPT, nv - i_base);
-        // (ii) this thread's word of bits in the current order + tile-wide prefix of ones
-        uint32_t w = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < WTL_EPT; ++k) {
-            if (k < n_mine) {
-                const uint32_t c = (cw[k >> 2] >> ((k & 3u) * 8u)) & 0xFFu;
-                const uint64_t e = s_ent[c];
-                const uint32_t mid = (uint32_t)(e >> 42) & 0xFFu;
-                if ((e >> 50) && c >= mid) w |= 1u << k;
-            }
-        }
-        s_bits[tid] = w;
+        s_bits[tid] = myword;
         {
             uint32_t wt;
-            const uint32_t ex = warp_excl_sum(__popc(w), wt);
+            const uint32_t ex = warp_excl_sum(__popc(myword), wt);
             if (lane == 31) s_scan[0][warp] = wt;
             __syncthreads();
-            uint32_t p = 0;
-            for (uint32_t q = 0; q < warp; ++q) p += s_scan[0][q];
+            uint32_t p = 0, tot = 0;
+            for (uint32_t q = 0; q < WTL_THREADS / 32; ++q) { if (q < warp) p += s_scan[0][q]; tot += s_scan[0][q]; }
             s_wpre[tid] = p + ex;
+            if (tid == 0) s_wpre[WTL_THREADS] = tot;
         }
         __syncthreads();
-        // (iii) ones before the start of each code's run, merged into its entry
-        if (my_entry) {
-            const uint32_t sidx = (uint32_t)my_entry & 0x3FFFu;
-            const uint32_t ps = s_wpre[sidx >> 5] + __popc(s_bits[sidx >> 5] & ((1u << (sidx & 31u)) - 1u));
-            s_ent[tid] = my_entry | ((uint64_t)ps << 28);
-        }
-        // (iv) emit every node's run of bits into the level (warps take nodes round-robin)
+        // ---- B: every internal node's run of bits into the level (warps take nodes round-robin)
         {
             const uint32_t nnodes = tab->lvl_nodes[l];
             uint32_t *words = lv.w[l];
             for (uint32_t k = warp; k < nnodes; k += WTL_THREADS / 32) {
                 const uint32_t lo = tab->lvl_lo[l][k], hi = (uint32_t)tab->lvl_hi1[l][k] + 1;
-                const uint32_t s0 = s_tcum[lo], r = s_tcum[hi] - s0;
+                const uint32_t x0 = tab->path_of_code[lo], x1 = tab->path_of_code[hi];
+                const uint32_t s0 = s_tcum[x0], r = s_tcum[x1] - s0;
                 if (r == 0) continue;
-                const uint32_t D = (tab->node_start[l][lo] & NODE_START_MASK) + (s_gcum[hi] - s_gcum[lo]);
+                const uint32_t D = (tab->node_start[l][lo] & NODE_START_MASK) + (s_gcum[x1] - s_gcum[x0]);
                 const uint32_t q0 = D >> 5, q1 = (D + r - 1) >> 5;
                 for (uint32_t q = q0 + lane; q <= q1; q += 32) {
                     const uint32_t lo_bit = max(q << 5, D), hi_bit = min((q << 5) + 32u, D + r);
@@ -359,23 +343,29 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
             }
         }
         if (l + 1 == levels) break;
-        __syncthreads();   // entries complete
-        // (v) stable split of every run by its bit -> order by level l+1 node
-        const uint32_t wp = s_wpre[tid];
-#pragma unroll
-        for (uint32_t k = 0; k < WTL_EPT; ++k) {
-            if (k < n_mine) {
-                const uint32_t i = i_base + k;
-                const uint32_t c = (cw[k >> 2] >> ((k & 3u) * 8u)) & 0xFFu;
-                const uint64_t e = s_ent[c];
-                uint32_t dst = i;                      // codes that are leaves already keep their slot
-                if (e >> 50) {
-                    const uint32_t M = (uint32_t)(e >> 14) & 0x3FFFu;
-                    const uint32_t ps = (uint32_t)(e >> 28) & 0x3FFFu;
-                    const uint32_t ones_before = wp + __popc(w & ((1u << k) - 1u)) - ps;
-                    dst = ((w >> k) & 1u) ? M + ones_before : i - ones_before;
-                }
-                nxt[dst] = (uint8_t)c;
+        // ---- C: stable split of every run by its bit -> order by the top l + 1 path bits
+        if (tid < (1u << l)) {
+            const uint32_t x_lo = tid << (shift + 1u);
+            const uint32_t S = s_tcum[x_lo], M = s_tcum[x_lo + (1u << shift)];
+            const uint32_t ps = s_wpre[S >> 5] + __popc(s_bits[S >> 5] & ((1u << (S & 31u)) - 1u));
+            s_ent[tid] = (M - ps) | (ps << 16);
+        }
+        __syncthreads();
+        {
+            uint8_t *wout = nxt;
+            const uint32_t row0 = warp * 32u;
+            const uint32_t mypre = s_wpre[tid];
+#pragma unroll 4
+            for (uint32_t r = 0; r < 32; ++r) {
+                const uint32_t i = (row0 + r) * 32u + lane;
+                const uint32_t pth = cur[i];
+                const uint32_t word = __shfl_sync(0xffffffffu, myword, r);
+                const uint32_t pre = __shfl_sync(0xffffffffu, mypre, r);
+                const uint32_t e = s_ent[pth >> (shift + 1u)];
+                const uint32_t ob = pre + __popc(word & lt);              // ones before this element in the tile order
+                const uint32_t ps = e >> 16;
+                const uint32_t dst = ((word >> lane) & 1u) ? (e & 0xFFFFu) + ob : i + ps - ob;
+                wout[dst] = (uint8_t)pth;
             }
         }
         __syncthreads();
@@ -388,12 +378,33 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
 constexpr int WTC_BLOCKS_PER_CTA = 256;
 static_assert(HKCSA_SUPER_BLOCKS % WTC_BLOCKS_PER_CTA == 0, "superblocks must start on a CTA tile");
 
+// The directories of ALL levels in three launches (count, scan, fix) instead of three per level: the tiles of 256 rank
+// blocks of every level are numbered consecutively (tile0[l] = first tile of level l) in agg / carry.
+struct DirLevels {
+    RankBlock *blocks[HKCSA_MAX_LEVELS];
+    uint64_t *super[HKCSA_MAX_LEVELS];
+    uint32_t *select[HKCSA_MAX_LEVELS];
+    uint64_t nblocks[HKCSA_MAX_LEVELS];
+    uint32_t tile0[HKCSA_MAX_LEVELS + 1];
+    uint32_t levels;
+};
+
+__device__ __forceinline__ uint32_t dir_level_of_tile(const DirLevels &D, uint32_t tile)
+{
+    uint32_t l = 0;
+    while (l + 1 < D.levels && tile >= D.tile0[l + 1]) ++l;
+    return l;
+}
+
 __global__ void __launch_bounds__(WTC_BLOCKS_PER_CTA)
-wt_count_kernel(RankBlock *__restrict__ blocks, uint64_t nblocks, uint32_t *__restrict__ agg)
+wt_count_all_kernel(DirLevels D, uint32_t *__restrict__ agg)
 {
     __shared__ uint32_t s_w[8];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint64_t g = (uint64_t)blockIdx.x * WTC_BLOCKS_PER_CTA + tid;
+    const uint32_t l = dir_level_of_tile(D, blockIdx.x);
+    RankBlock *blocks = D.blocks[l];
+    const uint64_t nblocks = D.nblocks[l];
+    const uint64_t g = (uint64_t)(blockIdx.x - D.tile0[l]) * WTC_BLOCKS_PER_CTA + tid;
     uint32_t cnt = 0;
     if (g < nblocks) {
         const RankBlock b = load_block(blocks + g);
@@ -407,6 +418,66 @@ wt_count_kernel(RankBlock *__restrict__ blocks, uint64_t nblocks, uint32_t *__re
     for (uint32_t q = 0; q < warp; ++q) p += s_w[q];
     if (g < nblocks) reinterpret_cast<uint32_t *>(blocks + g)[0] = p + ex;
     if (tid == WTC_BLOCKS_PER_CTA - 1) agg[blockIdx.x] = p + ex + cnt;
+}
+
+// CTA l: exclusive scan of level l's tile totals -> carry (same numbering); ones of the level -> ones_out[l]
+__global__ void __launch_bounds__(1024)
+wt_dir_scan_all_kernel(DirLevels D, const uint32_t *__restrict__ agg, uint64_t *__restrict__ carry,
+                       uint64_t *__restrict__ ones_out)
+{
+    __shared__ uint64_t s_w[32];
+    __shared__ uint64_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t l = blockIdx.x;
+    const uint32_t t0 = D.tile0[l], tiles = D.tile0[l + 1] - t0;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < tiles; base += 1024) {
+        const uint32_t t = base + tid;
+        const uint64_t v = (t < tiles) ? agg[t0 + t] : 0ull;
+        uint64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o) x += y;
+        }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        uint64_t pre = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) pre += s_w[w];
+        if (t < tiles) carry[t0 + t] = pre + x - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = pre + x;
+        __syncthreads();
+    }
+    if (tid == 0) ones_out[l] = s_carry;
+}
+
+__global__ void __launch_bounds__(WTC_BLOCKS_PER_CTA)
+wt_dir_fix_all_kernel(DirLevels D, const uint64_t *__restrict__ carry)
+{
+    const uint32_t l = dir_level_of_tile(D, blockIdx.x);
+    const uint32_t t = blockIdx.x - D.tile0[l];
+    const uint64_t g = (uint64_t)t * WTC_BLOCKS_PER_CTA + threadIdx.x;
+    if (g >= D.nblocks[l]) return;
+    RankBlock *blocks = D.blocks[l];
+    const uint64_t *lcarry = carry + D.tile0[l];
+    const RankBlock b = load_block(blocks + g);
+    const uint32_t rel = (uint32_t)(b.w[0] & 0xFFFFFFFFu);
+    const uint64_t abs_before = lcarry[t] + rel;
+    const uint64_t sb = g / HKCSA_SUPER_BLOCKS;
+    const uint64_t sb_abs = lcarry[sb * (HKCSA_SUPER_BLOCKS / WTC_BLOCKS_PER_CTA)];
+    reinterpret_cast<uint32_t *>(blocks + g)[0] = (uint32_t)(abs_before - sb_abs);
+    if (g % HKCSA_SUPER_BLOCKS == 0) D.super[l][sb] = sb_abs;
+    const uint32_t cnt = block_rank(b, HKCSA_BLOCK_BITS);
+    if (cnt) {
+        const uint64_t ts = (abs_before + HKCSA_SELECT_SAMPLE - 1) / HKCSA_SELECT_SAMPLE;
+        const uint64_t k = 1 + ts * HKCSA_SELECT_SAMPLE;
+        if (k <= abs_before + cnt) {
+            const uint32_t bit = block_select(b, (uint32_t)(k - abs_before));
+            D.select[l][ts] = (uint32_t)(g * HKCSA_BLOCK_BITS + bit);
+        }
+    }
 }
 
 // node_ones[l][code] = rank1(level l, start of code's node)
@@ -580,7 +651,7 @@ extern "C" int hkcsa_wt_plan_from_hist(const uint64_t h_hist[256], hkcsa_wt_plan
     Carver c(nullptr);
     const uint64_t wtiles = (n + WTL_TILE - 1) / WTL_TILE;
     c.take<uint32_t>((uint64_t)(sigma ? sigma : 1) * (wtiles + 1));
-    const uint64_t tiles = rank_blocks_for(n) / WTC_BLOCKS_PER_CTA + 2;
+    const uint64_t tiles = HKCSA_MAX_LEVELS * (rank_blocks_for(n) / WTC_BLOCKS_PER_CTA + 2);   // directory tiles of all levels
     c.take<uint32_t>(tiles);
     c.take<uint64_t>(tiles);
     c.take<uint64_t>(HKCSA_MAX_LEVELS);
@@ -827,6 +898,15 @@ static int wt_write_tables(const hkcsa_wt_plan *p, uint8_t *blob, cudaStream_t s
         }
     }
     for (int ch = 0; ch < 256; ++ch) T.code8_of_sym[ch] = (p->code_of_sym[ch] == 0xFFFF) ? 0 : (uint8_t)p->code_of_sym[ch];
+    memset(T.code_of_path, 0xFF, sizeof(T.code_of_path));
+    for (uint32_t c = 0; c < p->sigma; ++c) {
+        uint32_t path = 0;
+        for (uint32_t l = 0; l < p->depth[c]; ++l) path |= (uint32_t)(p->node_bit[l][c] ? 1u : 0u) << (7 - l);
+        T.path_of_code[c] = (uint16_t)path;
+        T.code_of_path[path] = (uint16_t)c;
+        T.path_of_sym[p->sym_of_code[c]] = (uint8_t)path;
+    }
+    T.path_of_code[p->sigma] = 256;
     WtTables *d_tab = reinterpret_cast<WtTables *>(blob + p->off_tables);
     HK_CUDA(cudaMemcpyAsync(d_tab, &T, sizeof(T), cudaMemcpyHostToDevice, st));
     HK_CUDA(cudaStreamSynchronize(st));   // T is reused by the next call on this thread
@@ -840,18 +920,25 @@ static int wt_build_dirs(const hkcsa_wt_plan *p, void *d_blob, uint32_t *d_agg, 
 {
     uint8_t *blob = static_cast<uint8_t *>(d_blob);
     WtTables *d_tab = reinterpret_cast<WtTables *>(blob + p->off_tables);
+    DirLevels D;
+    memset(&D, 0, sizeof(D));
+    D.levels = p->levels;
+    uint64_t all_blocks = 0;
     for (uint32_t l = 0; l < p->levels; ++l) {
-        RankBlock *blocks = reinterpret_cast<RankBlock *>(blob + p->off_blocks[l]);
-        const uint64_t nblocks = rank_blocks_for(p->level_len[l]);
-        const uint64_t tiles = (nblocks + WTC_BLOCKS_PER_CTA - 1) / WTC_BLOCKS_PER_CTA;
-        prof::Scope ps(st, prof::WT_DIR, nblocks * 72);
-        wt_count_kernel<<<(uint32_t)tiles, WTC_BLOCKS_PER_CTA, 0, st>>>(blocks, nblocks, d_agg);
+        D.blocks[l] = reinterpret_cast<RankBlock *>(blob + p->off_blocks[l]);
+        D.super[l] = reinterpret_cast<uint64_t *>(blob + p->off_super[l]);
+        D.select[l] = reinterpret_cast<uint32_t *>(blob + p->off_select[l]);
+        D.nblocks[l] = rank_blocks_for(p->level_len[l]);
+        D.tile0[l + 1] = D.tile0[l] + (uint32_t)((D.nblocks[l] + WTC_BLOCKS_PER_CTA - 1) / WTC_BLOCKS_PER_CTA);
+        all_blocks += D.nblocks[l];
+    }
+    if (D.tile0[p->levels]) {
+        prof::Scope ps(st, prof::WT_DIR, all_blocks * 72);
+        wt_count_all_kernel<<<D.tile0[p->levels], WTC_BLOCKS_PER_CTA, 0, st>>>(D, d_agg);
         HK_LAUNCH_CHECK();
-        wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones + l);
+        wt_dir_scan_all_kernel<<<p->levels, 1024, 0, st>>>(D, d_agg, d_carry, d_ones);
         HK_LAUNCH_CHECK();
-        wt_dir_fix_kernel<<<(uint32_t)((nblocks + 255) / 256), 256, 0, st>>>(
-            blocks, nblocks, d_carry, reinterpret_cast<uint64_t *>(blob + p->off_super[l]),
-            reinterpret_cast<uint32_t *>(blob + p->off_select[l]), WTC_BLOCKS_PER_CTA);
+        wt_dir_fix_all_kernel<<<D.tile0[p->levels], WTC_BLOCKS_PER_CTA, 0, st>>>(D, d_carry);
         HK_LAUNCH_CHECK();
     }
     WtDev wt = make_wt_dev(d_blob, p);
@@ -882,7 +969,7 @@ extern "C" int hkcsa_wt_build(const uint8_t *d_sym, hkcsa_wt_plan *p, void *d_bl
     Carver c(d_scratch);
     const uint32_t wtiles = (uint32_t)((n + WTL_TILE - 1) / WTL_TILE);
     uint32_t *d_gcnt = c.take<uint32_t>((uint64_t)p->sigma * (wtiles + 1));
-    const uint64_t tiles_max = rank_blocks_for(n) / WTC_BLOCKS_PER_CTA + 2;
+    const uint64_t tiles_max = HKCSA_MAX_LEVELS * (rank_blocks_for(n) / WTC_BLOCKS_PER_CTA + 2);
     uint32_t *d_agg = c.take<uint32_t>(tiles_max);
     uint64_t *d_carry = c.take<uint64_t>(tiles_max);
     uint64_t *d_ones = c.take<uint64_t>(HKCSA_MAX_LEVELS);
@@ -926,7 +1013,7 @@ extern "C" int hkcsa_wt_restore_finish(const hkcsa_wt_plan *p, void *d_blob, voi
     if (p->levels == 0 || p->n == 0) return HKCSA_OK;
     HK_REQUIRE(d_scratch && p->scratch_bytes <= scratch_bytes, HKCSA_ESCRATCH, "wavelet scratch too small");
     Carver c(d_scratch);
-    const uint64_t tiles_max = rank_blocks_for(p->n) / WTC_BLOCKS_PER_CTA + 2;
+    const uint64_t tiles_max = HKCSA_MAX_LEVELS * (rank_blocks_for(p->n) / WTC_BLOCKS_PER_CTA + 2);
     uint32_t *d_agg = c.take<uint32_t>(tiles_max);
     uint64_t *d_carry = c.take<uint64_t>(tiles_max);
     uint64_t *d_ones = c.take<uint64_t>(HKCSA_MAX_LEVELS);

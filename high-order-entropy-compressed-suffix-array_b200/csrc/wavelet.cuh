@@ -23,6 +23,11 @@ struct WtTables {
     uint8_t lvl_lo[HKCSA_MAX_LEVELS][128];      // per (level, node k): first code
     uint8_t lvl_hi1[HKCSA_MAX_LEVELS][128];     // per (level, node k): last code
     uint32_t lvl_nodes[HKCSA_MAX_LEVELS];
+    // root-to-leaf paths: bit 7 - l of a path = the bit the symbol takes at level l, zeros below its leaf.  Paths order
+    // like the codes, the level-l node of a symbol is the top l bits of its path.
+    uint8_t path_of_sym[256];                   // byte -> path (present symbols only)
+    uint16_t path_of_code[260];                 // [sigma] = 256
+    uint16_t code_of_path[256];                 // 0xFFFF: no symbol has this path
 };
 
 struct WtDev {
