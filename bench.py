@@ -270,8 +270,7 @@ def run_dist_build(args, world, rank, dev, barrier, max_over_ranks, sum_over_ran
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            sa1 = E.suffix_array(one)
-            bw1 = E.bwt(one, sa1)
+            sa1, bw1 = E.suffix_array_bwt(one)
             b.record()
             torch.cuda.synchronize()
             if it:
@@ -336,7 +335,7 @@ def run_dist_build(args, world, rank, dev, barrier, max_over_ranks, sum_over_ran
             "text_bytes": n_big, "n_gpus": world, "suffix_id_bits": 64 if sl.sa.dtype == torch.int64 else 32,
             "ms": ms, "ms_runs": times, "MBps": n_big / 1e6 / (ms / 1e3),
             "single_gpu": {"text_bytes": per_rank, "ms": single_ms, "MBps": per_rank / 1e6 / (single_ms / 1e3),
-                           "what": "hkcsa_sa_build + hkcsa_bwt of one rank's share on one GPU, same run"},
+                           "what": "hkcsa_sa_bwt_build (suffix array + BWT) of one rank's share on one GPU, same run"},
             "fraction_of_linear": (n_big / ms) / (world * per_rank / single_ms),
             "phases_ms_max_over_ranks": phases,
             "phases_note": "from one extra run that synchronises at every phase boundary (not the timed runs)",
@@ -914,7 +913,7 @@ def run_ours(args):
                             "blob), wall clock incl. final sync; the full suffix array is shipped by e2e_full_sa"},
             "e2e_full_sa": {"value": world * nbytes / 1e6 / (e2e_full_ms / 1e3), "unit": "MB/s", "ms_per_step": e2e_full_ms,
                             "h2d_bytes_per_step": n, "d2h_bytes_per_step": 5 * n,
-                            "what": "the same with D2H of SA (4n) + BWT (n) on a side stream overlapping the build tail"},
+                            "what": "the same with D2H of SA (4n) + BWT (n) as well (what round 1 shipped)"},
             "e2e_api": e2e_api,
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": roofline,

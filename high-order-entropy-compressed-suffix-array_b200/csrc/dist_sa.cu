@@ -49,14 +49,17 @@ __device__ __forceinline__ uint32_t dsa_dest_of(const uint32_t *cuts, uint32_t w
     return d;
 }
 
-// MODE 0: histogram of the buckets (top 16 key bits) of suffixes [begin, end).
+// MODE 0: histogram of the buckets (top 16 key bits) of suffixes [begin, end) -- of every tile_stride-th tile.
 // MODE 1: (key, id) of every suffix of [begin, end) stored into the receive arrays of the rank owning its bucket.
+// MODE 2: suffixes of [begin, end) per destination rank (counters[d]): the exact region sizes of the exchange when
+//         the cut points came from a sampled histogram.
 // Keys are produced exactly as in sa_pack0_kernel (code words of the tile in one shared bit stream, key = the
 // 64-bit window at the symbol's bit offset), so both modes and the single-GPU builder agree on every key.
 template <int MODE, bool WIDE>
 __global__ void __launch_bounds__(PACK_THREADS, 4)
 dsa_pack_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin, uint64_t end, AlphaCode ac, int bits,
-                DsaDest dd, unsigned long long *__restrict__ counters, unsigned long long *__restrict__ bucket_hist)
+                DsaDest dd, unsigned long long *__restrict__ counters, unsigned long long *__restrict__ bucket_hist,
+                uint32_t tile_stride)
 {
     using IdT = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
     __shared__ __align__(16) uint16_t s_off[PACK_TILE];
@@ -81,7 +84,7 @@ dsa_pack_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin, ui
     }
     if (tid <= DSA_MAX_WORLD) s_cuts[tid] = dd.cuts[tid];
     __syncthreads();
-    const uint64_t base = begin + (uint64_t)blockIdx.x * PACK_TILE;
+    const uint64_t base = begin + (uint64_t)blockIdx.x * tile_stride * PACK_TILE;
     const bool aligned8 = (reinterpret_cast<uintptr_t>(text + base) & 7) == 0;
     uint32_t cl[PACK_IPT], cl2[PACK_IPT];
     s_tot[tid] = pack_load8(text, n, base + (uint64_t)tid * PACK_IPT, aligned8, s_tab, cl);
@@ -135,6 +138,10 @@ dsa_pack_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin, ui
     }
     if (MODE == 0) return;
     __syncthreads();
+    if (MODE == 2) {
+        if (tid < dd.world && s_cnt[tid]) atomicAdd(&counters[tid], (unsigned long long)s_cnt[tid]);
+        return;
+    }
     if (tid < dd.world) {
         uint32_t pre = 0;
         for (uint32_t d = 0; d < tid; ++d) pre += s_cnt[d];
@@ -336,14 +343,40 @@ __global__ void bwt_slice_kernel(const uint8_t *__restrict__ text, uint64_t n, c
 }
 
 // the finished slice with 64-bit ids: id and BWT symbol of the j-th suffix from ONE random read
-__global__ void gather_ids64_kernel(const uint64_t *__restrict__ ids64, const uint32_t *__restrict__ ord, uint64_t m,
-                                    uint64_t *__restrict__ out, uint8_t *__restrict__ out_bwt)
+// Four consecutive rows per thread: one 16-byte load of ordinals, four independent random 8-byte reads in flight
+// (the gather is bound by the rate of random requests), 2 x 16 bytes of ids and 4 BWT bytes stored.
+__global__ void __launch_bounds__(256)
+gather_ids64_kernel(const uint64_t *__restrict__ ids64, const uint32_t *__restrict__ ord, uint64_t m,
+                    uint64_t *__restrict__ out, uint8_t *__restrict__ out_bwt)
 {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const uint64_t v = ids64[ord[j]];
-    out[j] = v & DSA_ID_MASK;
-    if (out_bwt) out_bwt[j] = (uint8_t)(v >> 56);
+    const uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= m) return;
+    const bool full = j0 + 4 <= m && ((reinterpret_cast<uintptr_t>(ord) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    uint32_t o[4] = {0, 0, 0, 0};
+    if (full) {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(ord + j0));
+        o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+    } else {
+        for (int e = 0; e < 4; ++e) if (j0 + e < m) o[e] = ord[j0 + e];
+    }
+    uint64_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (j0 + e < m) ? __ldg(ids64 + o[e]) : 0ull;
+    if (full) {
+        __stcs(reinterpret_cast<ulonglong2 *>(out + j0), make_ulonglong2(v[0] & DSA_ID_MASK, v[1] & DSA_ID_MASK));
+        __stcs(reinterpret_cast<ulonglong2 *>(out + j0 + 2), make_ulonglong2(v[2] & DSA_ID_MASK, v[3] & DSA_ID_MASK));
+        if (out_bwt) {
+            const uint32_t w = (uint32_t)(v[0] >> 56) | ((uint32_t)(v[1] >> 56) << 8) | ((uint32_t)(v[2] >> 56) << 16) |
+                               ((uint32_t)(v[3] >> 56) << 24);
+            if ((reinterpret_cast<uintptr_t>(out_bwt) & 3) == 0) *reinterpret_cast<uint32_t *>(out_bwt + j0) = w;
+            else for (int e = 0; e < 4; ++e) out_bwt[j0 + e] = (uint8_t)(w >> (8 * e));
+        }
+    } else {
+        for (int e = 0; e < 4 && j0 + e < m; ++e) {
+            out[j0 + e] = v[e] & DSA_ID_MASK;
+            if (out_bwt) out_bwt[j0 + e] = (uint8_t)(v[e] >> 56);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- host state of one rank's slice
@@ -487,10 +520,12 @@ static void plan_codes(const hkcsa_dsa_plan *p, AlphaCode &ac, CodeMap *map)
     if (map) memcpy(map->code, p->fixed_code, sizeof(map->code));
 }
 
-extern "C" int hkcsa_dsa_bucket_hist(const uint8_t *d_text, const hkcsa_dsa_plan *p, uint64_t begin, uint64_t end,
-                                     uint64_t *d_hist, void *stream)
+// tile_stride > 1: only every tile_stride-th tile of 2048 positions is counted (cut points from a sample; the exact
+// region sizes then come from hkcsa_dsa_dest_counts)
+extern "C" int hkcsa_dsa_bucket_hist_sampled(const uint8_t *d_text, const hkcsa_dsa_plan *p, uint64_t begin, uint64_t end,
+                                             uint32_t tile_stride, uint64_t *d_hist, void *stream)
 {
-    HK_REQUIRE(d_text && p && d_hist, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(d_text && p && d_hist && tile_stride >= 1, HKCSA_EINVAL, "bad argument");
     HK_REQUIRE(begin <= end && end <= p->n, HKCSA_ERANGE, "range");
     cudaStream_t st = as_stream(stream);
     HK_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)HKCSA_DSA_BUCKETS * sizeof(uint64_t), st));
@@ -499,12 +534,47 @@ extern "C" int hkcsa_dsa_bucket_hist(const uint8_t *d_text, const hkcsa_dsa_plan
     plan_codes(p, ac, nullptr);
     DsaDest dd;
     memset(&dd, 0, sizeof(dd));
+    const uint64_t tiles = (end - begin + PACK_TILE - 1) / PACK_TILE;
+    const uint64_t blocks = (tiles + tile_stride - 1) / tile_stride;
+    HK_REQUIRE(blocks <= 0x7FFFFFFFull, HKCSA_ERANGE, "block of positions too large for one launch");
+    prof::Scope ps(st, prof::SA_PACK0, (end - begin) / tile_stride);
+    dsa_pack_kernel<0, false><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd,
+                                                                       nullptr,
+                                                                       reinterpret_cast<unsigned long long *>(d_hist),
+                                                                       tile_stride);
+    HK_LAUNCH_CHECK();
+    return HKCSA_OK;
+}
+
+extern "C" int hkcsa_dsa_bucket_hist(const uint8_t *d_text, const hkcsa_dsa_plan *p, uint64_t begin, uint64_t end,
+                                     uint64_t *d_hist, void *stream)
+{
+    return hkcsa_dsa_bucket_hist_sampled(d_text, p, begin, end, 1, d_hist, stream);
+}
+
+// suffixes of [begin, end) per destination rank under the cut points h_cuts -> d_counts[HKCSA_DSA_MAX_RANKS]
+extern "C" int hkcsa_dsa_dest_counts(const uint8_t *d_text, const hkcsa_dsa_plan *p, uint64_t begin, uint64_t end,
+                                     uint32_t world, const uint32_t *h_cuts, uint64_t *d_counts, void *stream)
+{
+    HK_REQUIRE(d_text && p && h_cuts && d_counts, HKCSA_EINVAL, "null pointer");
+    HK_REQUIRE(world >= 1 && world <= (uint32_t)DSA_MAX_WORLD, HKCSA_EINVAL, "1..HKCSA_DSA_MAX_RANKS ranks");
+    HK_REQUIRE(begin <= end && end <= p->n, HKCSA_ERANGE, "range");
+    HK_REQUIRE(h_cuts[0] == 0 && h_cuts[world] == HKCSA_DSA_BUCKETS, HKCSA_EINVAL, "cuts must span every bucket");
+    cudaStream_t st = as_stream(stream);
+    HK_CUDA(cudaMemsetAsync(d_counts, 0, DSA_MAX_WORLD * sizeof(uint64_t), st));
+    if (begin == end) return HKCSA_OK;
+    static thread_local AlphaCode ac;
+    plan_codes(p, ac, nullptr);
+    DsaDest dd;
+    memset(&dd, 0, sizeof(dd));
+    for (uint32_t r = 0; r <= world; ++r) dd.cuts[r] = h_cuts[r];
+    dd.world = world;
     const uint64_t blocks = (end - begin + PACK_TILE - 1) / PACK_TILE;
     HK_REQUIRE(blocks <= 0x7FFFFFFFull, HKCSA_ERANGE, "block of positions too large for one launch");
     prof::Scope ps(st, prof::SA_PACK0, end - begin);
-    dsa_pack_kernel<0, false><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd,
-                                                                       nullptr,
-                                                                       reinterpret_cast<unsigned long long *>(d_hist));
+    dsa_pack_kernel<2, false><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd,
+                                                                       reinterpret_cast<unsigned long long *>(d_counts),
+                                                                       nullptr, 1);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }
@@ -539,9 +609,9 @@ extern "C" int hkcsa_dsa_pack_exchange(const uint8_t *d_text, const hkcsa_dsa_pl
     prof::Scope ps(st, prof::SA_PACK0, (end - begin) * (p->wide ? 17 : 13));
     unsigned long long *cnt = reinterpret_cast<unsigned long long *>(d_counters);
     if (p->wide)
-        dsa_pack_kernel<1, true><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd, cnt, nullptr);
+        dsa_pack_kernel<1, true><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd, cnt, nullptr, 1);
     else
-        dsa_pack_kernel<1, false><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd, cnt, nullptr);
+        dsa_pack_kernel<1, false><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd, cnt, nullptr, 1);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }
@@ -759,7 +829,7 @@ extern "C" int hkcsa_dsa_gather_ids64(const hkcsa_dsa_state *state, uint64_t *d_
     if (S->M == 0) return HKCSA_OK;
     HK_REQUIRE(d_out, HKCSA_EINVAL, "null pointer");
     prof::Scope ps(as_stream(stream), prof::BWT_GATHER, S->M * 21);
-    gather_ids64_kernel<<<(uint32_t)((S->M + 255) / 256), 256, 0, as_stream(stream)>>>(S->ids64, S->sa, S->M, d_out, d_out_bwt);
+    gather_ids64_kernel<<<(uint32_t)((S->M + 1023) / 1024), 256, 0, as_stream(stream)>>>(S->ids64, S->sa, S->M, d_out, d_out_bwt);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

@@ -580,6 +580,19 @@ wt_access_kernel(WtDev wt, const uint64_t *__restrict__ pos, uint64_t m, uint8_t
 // ------------------------------------------------------------------ host side
 using namespace hkcsa;
 
+// scratch of hkcsa_wt_build: per-symbol tile counts, directory tile aggregates and carries of all levels, ones per level
+static size_t wt_scratch_for(uint64_t n, uint32_t sigma)
+{
+    Carver c(nullptr);
+    const uint64_t wtiles = (n + WTL_TILE - 1) / WTL_TILE;
+    c.take<uint32_t>((uint64_t)(sigma ? sigma : 1) * (wtiles + 1));
+    const uint64_t tiles = HKCSA_MAX_LEVELS * (rank_blocks_for(n) / WTC_BLOCKS_PER_CTA + 2);
+    c.take<uint32_t>(tiles);
+    c.take<uint64_t>(tiles);
+    c.take<uint64_t>(HKCSA_MAX_LEVELS);
+    return c.total();
+}
+
 extern "C" int hkcsa_wt_plan_from_hist(const uint64_t h_hist[256], hkcsa_wt_plan *p)
 {
     HK_REQUIRE(h_hist && p, HKCSA_EINVAL, "null pointer");
@@ -647,17 +660,23 @@ extern "C" int hkcsa_wt_plan_from_hist(const uint64_t h_hist[256], hkcsa_wt_plan
         off = align_up(off + select_samples_for(bits) * sizeof(uint32_t), 256);
     }
     p->blob_bytes = off;
-    // scratch: per-symbol tile counts, directory tile aggregates and carries, ones per level
-    Carver c(nullptr);
-    const uint64_t wtiles = (n + WTL_TILE - 1) / WTL_TILE;
-    c.take<uint32_t>((uint64_t)(sigma ? sigma : 1) * (wtiles + 1));
-    const uint64_t tiles = HKCSA_MAX_LEVELS * (rank_blocks_for(n) / WTC_BLOCKS_PER_CTA + 2);   // directory tiles of all levels
-    c.take<uint32_t>(tiles);
-    c.take<uint64_t>(tiles);
-    c.take<uint64_t>(HKCSA_MAX_LEVELS);
-    p->scratch_bytes = c.total();
+    p->scratch_bytes = wt_scratch_for(n, sigma);
     return HKCSA_OK;
 }
+
+// the largest blob / scratch a plan over n symbols can ask for (256 symbols, 8 levels): what a caller allocates
+// before the byte histogram is known (hkcsa_index_build)
+extern "C" size_t hkcsa_wt_blob_bound(uint64_t n)
+{
+    uint64_t off = align_up(sizeof(WtTables), 256);
+    for (uint32_t l = 0; l < HKCSA_MAX_LEVELS; ++l) {
+        off = align_up(off + rank_blocks_for(n) * sizeof(RankBlock), 256);
+        off = align_up(off + super_for(n) * sizeof(uint64_t), 256);
+        off = align_up(off + select_samples_for(n) * sizeof(uint32_t), 256);
+    }
+    return off;
+}
+extern "C" size_t hkcsa_wt_scratch_bound(uint64_t n) { return wt_scratch_for(n, 256); }
 
 // Builds one packed bit-vector with its directory from a byte sequence and a
 // byte -> bit table (shared by the wavelet levels and the sampled-SA marks).
@@ -863,7 +882,7 @@ int build_markvector64(const uint64_t *d_sa, uint64_t n, uint32_t rate, RankBloc
 }
 }  // namespace hkcsa
 
-// host-side node tables of a plan -> the blob's table region.  syncs (the staging struct is reused per thread).
+// host-side node tables of a plan -> the blob's table region
 static int wt_write_tables(const hkcsa_wt_plan *p, uint8_t *blob, cudaStream_t st)
 {
     static thread_local WtTables T;   // staged from pageable memory (a few KB, once per build)
@@ -908,8 +927,9 @@ static int wt_write_tables(const hkcsa_wt_plan *p, uint8_t *blob, cudaStream_t s
     }
     T.path_of_code[p->sigma] = 256;
     WtTables *d_tab = reinterpret_cast<WtTables *>(blob + p->off_tables);
+    // pageable source: the call returns once T has been copied to the driver's staging buffer (no wait for the
+    // stream), so T may be reused by the next call on this thread and the host goes on enqueueing the build
     HK_CUDA(cudaMemcpyAsync(d_tab, &T, sizeof(T), cudaMemcpyHostToDevice, st));
-    HK_CUDA(cudaStreamSynchronize(st));   // T is reused by the next call on this thread
     return HKCSA_OK;
 }
 

@@ -141,8 +141,14 @@ SIGNATURES = {
     "hkcsa_sa_scratch_bytes": (_sz, [_u64]),
     "hkcsa_sa_build": (_i32, [_vp, _u64, _vp, _vp, _sz, _vp, C.POINTER(SaStats)]),
     "hkcsa_sa_bwt_build": (_i32, [_vp, _u64, _vp, _vp, _vp, _sz, _vp, C.POINTER(SaStats)]),
+    "hkcsa_wt_blob_bound": (_sz, [_u64]),
+    "hkcsa_wt_scratch_bound": (_sz, [_u64]),
+    "hkcsa_index_build": (_i32, [_vp, _u64, _vp, _vp, _vp, _sz, C.POINTER(WtPlan), _vp, _sz, _vp, _sz,
+                                 C.POINTER(SsaPlan), _vp, _vp, _sz, _vp, _vp, _vp, C.POINTER(SaStats)]),
     "hkcsa_dsa_plan_make": (_i32, [C.POINTER(_u64), _u64, _i32, C.POINTER(DsaPlan)]),
     "hkcsa_dsa_bucket_hist": (_i32, [_vp, C.POINTER(DsaPlan), _u64, _u64, _vp, _vp]),
+    "hkcsa_dsa_bucket_hist_sampled": (_i32, [_vp, C.POINTER(DsaPlan), _u64, _u64, C.c_uint32, _vp, _vp]),
+    "hkcsa_dsa_dest_counts": (_i32, [_vp, C.POINTER(DsaPlan), _u64, _u64, C.c_uint32, C.POINTER(C.c_uint32), _vp, _vp]),
     "hkcsa_dsa_pack_exchange": (_i32, [_vp, C.POINTER(DsaPlan), _u64, _u64, _u32, C.POINTER(_u32), C.POINTER(_u64),
                                        C.POINTER(_u64), C.POINTER(_u64), _vp, _vp]),
     "hkcsa_dsa_state_bytes": (_sz, []),

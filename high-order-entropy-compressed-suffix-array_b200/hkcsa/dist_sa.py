@@ -59,6 +59,18 @@ def exchange_layout(hist_all: np.ndarray, parts: int):
     return cuts, cnt, counts, slice_off
 
 
+def exchange_layout_from_counts(cuts, cnt: np.ndarray):
+    """The same from cut points chosen on a sampled histogram and the exact cnt[src][dst] counted under them."""
+    cnt = np.asarray(cnt, dtype=np.int64)
+    counts = cnt.sum(0)
+    slice_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return np.asarray(cuts, dtype=np.int64), cnt, counts, slice_off
+
+
+HIST_SAMPLE_MIN = 1 << 24      # blocks of at least this many positions take their cut points from a sampled histogram
+HIST_SAMPLE_STRIDE = 8         # ... of every 8th tile of 2048 positions
+
+
 def bwt_slice(text: torch.Tensor, sa_slice: torch.Tensor) -> torch.Tensor:
     out = _empty(sa_slice.numel(), torch.uint8, text.device)
     fn = _lib.load().hkcsa_bwt_slice64 if sa_slice.dtype == torch.int64 else _lib.load().hkcsa_bwt_slice
@@ -95,7 +107,7 @@ def _align(x: int, a: int = 256) -> int:
 
 
 def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: bool, ext_rounds_max: int,
-                  group_round: bool = True):
+                  group_round: bool = True, hist_stride: int | None = None):
     """One rank's build as a generator.  Yields ("gather", array) -> [world, len] int64 numpy; ("text", block,
     sizes) -> the whole text; ("symm", nbytes) -> (uint8 tensor, [address of every rank's buffer]); ("barrier",)."""
     L = _lib.load()
@@ -128,9 +140,24 @@ def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: boo
     check(L.hkcsa_dsa_plan_make(bh.ctypes.data_as(C.POINTER(C.c_uint64)), n, 1 if wide else 0, C.byref(plan)))
     is_wide = bool(plan.wide)
     d_hist = torch.empty(_lib.DSA_BUCKETS, dtype=torch.int64, device=dev)
-    check(L.hkcsa_dsa_bucket_hist(_ptr(text), C.byref(plan), begin, end, _ptr(d_hist), _stream()))
-    hist_all = yield ("gather", d_hist)
-    cuts, cnt, counts, slice_off = exchange_layout(hist_all, world)
+    # the exact bucket histogram costs one global atomic per suffix; big blocks histogram a sample of their tiles for
+    # the cut points and count their suffixes per owner under those cuts in a second, atomics-free pass (the regions
+    # of the exchange must be sized exactly)
+    stride = hist_stride if hist_stride is not None else (HIST_SAMPLE_STRIDE if int(sizes.max()) >= HIST_SAMPLE_MIN else 1)
+    if stride > 1:
+        check(L.hkcsa_dsa_bucket_hist_sampled(_ptr(text), C.byref(plan), begin, end, stride, _ptr(d_hist), _stream()))
+        hist_all = yield ("gather", d_hist)
+        ranges = balanced_bucket_ranges(np.asarray(hist_all, dtype=np.int64).sum(0), world)
+        cuts0 = [r[0] for r in ranges] + [_lib.DSA_BUCKETS]
+        d_cnt = torch.empty(_lib.DSA_MAX_RANKS, dtype=torch.int64, device=dev)
+        check(L.hkcsa_dsa_dest_counts(_ptr(text), C.byref(plan), begin, end, world,
+                                      (C.c_uint32 * (world + 1))(*[int(c) for c in cuts0]), _ptr(d_cnt), _stream()))
+        cnt_all = (yield ("gather", d_cnt))[:, :world]
+        cuts, cnt, counts, slice_off = exchange_layout_from_counts(cuts0, cnt_all)
+    else:
+        check(L.hkcsa_dsa_bucket_hist(_ptr(text), C.byref(plan), begin, end, _ptr(d_hist), _stream()))
+        hist_all = yield ("gather", d_hist)
+        cuts, cnt, counts, slice_off = exchange_layout(hist_all, world)
     if int(counts.max()) > _lib.MAX_N:
         raise _lib.HkcsaError(_lib.ERANGE, f"a slice of {int(counts.max())} suffixes exceeds {_lib.MAX_N}: the buckets "
                                            "(top 16 key bits) of this text are too uneven for this many ranks")
@@ -310,7 +337,8 @@ def _torch_run(prog, group, device):
 
 
 def distributed_suffix_array(local_block: torch.Tensor, group=None, wide: bool | None = None, profile: bool = False,
-                             ext_rounds_max: int = EXT_ROUNDS_MAX, group_round: bool = True) -> SuffixArraySlice:
+                             ext_rounds_max: int = EXT_ROUNDS_MAX, group_round: bool = True,
+                             hist_stride: int | None = None) -> SuffixArraySlice:
     """local_block: this rank's contiguous part of the text (uint8, on this rank's GPU), blocks in rank order.
     Collective: every rank of `group` calls it.  profile=True synchronises at phase boundaries and fills
     SuffixArraySlice.phases."""
@@ -318,7 +346,7 @@ def distributed_suffix_array(local_block: torch.Tensor, group=None, wide: bool |
     world = dist.get_world_size(group)
     if world > _lib.DSA_MAX_RANKS:
         raise ValueError(f"at most {_lib.DSA_MAX_RANKS} ranks")
-    prog = _rank_program(dist.get_rank(group), world, local_block, wide, profile, ext_rounds_max, group_round)
+    prog = _rank_program(dist.get_rank(group), world, local_block, wide, profile, ext_rounds_max, group_round, hist_stride)
     return _torch_run(prog, group, local_block.device)
 
 
@@ -328,14 +356,14 @@ def release_workspaces() -> None:
 
 # ------------------------------------------------------------------ running the program: ranks emulated on one GPU
 def emulate_distributed_suffix_array(blocks, wide: bool | None = None, ext_rounds_max: int = EXT_ROUNDS_MAX,
-                                     profile: bool = False, group_round: bool = True):
+                                     profile: bool = False, group_round: bool = True, hist_stride: int | None = None):
     """The same per-rank programs, advanced in lockstep inside one process: `blocks` are the ranks' text blocks on
     ONE GPU, peers' buffers are plain device buffers of the same process.  Returns the slices in rank order."""
     world = len(blocks)
     if not 1 <= world <= _lib.DSA_MAX_RANKS:
         raise ValueError(f"1..{_lib.DSA_MAX_RANKS} ranks")
     dev = blocks[0].device
-    progs = [_rank_program(r, world, blocks[r], wide, profile, ext_rounds_max, group_round) for r in range(world)]
+    progs = [_rank_program(r, world, blocks[r], wide, profile, ext_rounds_max, group_round, hist_stride) for r in range(world)]
     reqs = [next(p) for p in progs]
     results = [None] * world
     live = list(range(world))

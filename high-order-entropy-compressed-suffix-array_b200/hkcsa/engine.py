@@ -553,58 +553,67 @@ class DeviceIndex:
         array and the BWT; the copies run on a side stream and overlap the rest of the build.  The
         caller synchronises (torch.cuda.synchronize()) before reading them."""
         _require_cuda()
-        self.device = text.device
-        self.n = text.numel()
-        self.stats = BuildStats(n=self.n)
-        # suffix array and BWT in one call: the symbol before each suffix rides through the round-0 sort in the top
-        # byte of its key when the key leaves it free (no gather over the text afterwards)
-        self.sa, self.bwt = suffix_array_bwt(text, self.stats.sa)
+        L = _lib.load()
+        dev = self.device = text.device
+        n = self.n = text.numel()
+        self.stats = BuildStats(n=n)
+        if n > _lib.MAX_N:
+            raise HkcsaError(_lib.ERANGE, f"text of {n} symbols exceeds the single-GPU limit {_lib.MAX_N}")
+        # Every buffer is in place before the first kernel: the whole build is ONE library call (hkcsa_index_build:
+        # suffix array + BWT, then the wavelet tree on a high-priority stream beside the sampled suffix array), so no
+        # Python runs while the GPU could be working.  The tree's shape depends on the byte histogram, which the call
+        # computes itself: the blob is allocated at the bound for n symbols and trimmed to the plan's size afterwards.
+        main = torch.cuda.current_stream()
+        self.sa = _empty(n, torch.int32, dev)
+        self.bwt = _empty(n, torch.uint8, dev)
+        sa_bytes = L.hkcsa_sa_scratch_bytes(n)
+        sa_scratch = _scratch(sa_bytes, dev)
+        blob_cap, wt_cap = int(L.hkcsa_wt_blob_bound(n)), int(L.hkcsa_wt_scratch_bound(n))
+        blob = torch.empty(blob_cap, dtype=torch.uint8, device=dev)       # zeroed by the build
+        wt_scratch = _scratch(wt_cap, dev)
+        wt = DeviceWaveletTree.__new__(DeviceWaveletTree)
+        wt.device, wt.n, wt.plan = dev, n, WtPlan()
+        self.ssa = None
+        ssa_plan = ssa_blob = ssa_scratch = None
+        crit = ssa_stream = main
+        if sa_sample_rate > 0:
+            ssa_plan = SsaPlan()
+            check(L.hkcsa_ssa_plan_make(n, sa_sample_rate, C.byref(ssa_plan)))
+            ssa_blob = torch.zeros(int(ssa_plan.blob_bytes), dtype=torch.uint8, device=dev)
+            ssa_scratch = _scratch(ssa_plan.scratch_bytes, dev)
+            # the tree is the critical path of the tail: on a high-priority stream the block scheduler serves it first
+            # and the sampled-SA kernel fills what is left (tree alone 2.6 ms at C3; sharing the SMs evenly 3.4 ms)
+            crit = _aux_stream(dev, "critical", priority=-1)
+            ssa_stream = _aux_stream(dev, "ssa")
+        check(L.hkcsa_index_build(_ptr(text), n, _ptr(self.sa), _ptr(self.bwt), _ptr(sa_scratch), sa_bytes,
+                                  C.byref(wt.plan), _ptr(blob), blob_cap, _ptr(wt_scratch), wt_cap,
+                                  C.byref(ssa_plan) if ssa_plan is not None else None, _ptr(ssa_blob), _ptr(ssa_scratch),
+                                  int(ssa_plan.scratch_bytes) if ssa_plan is not None else 0,
+                                  main.cuda_stream, crit.cuda_stream if crit is not main else None,
+                                  ssa_stream.cuda_stream if ssa_stream is not main else None, C.byref(self.stats.sa)))
+        if crit is not main:
+            for t in (self.bwt, blob, wt_scratch):
+                t.record_stream(crit)
+            for t in (self.sa, ssa_blob, ssa_scratch):
+                t.record_stream(ssa_stream)
+        used = int(wt.plan.blob_bytes)
+        # keep exactly the plan's bytes: a view while most of the bound is in use, a copy (and the bound released) otherwise
+        wt.blob = blob[:used] if 4 * used >= 3 * blob_cap else blob[:used].clone()
+        wt.hist = np.ctypeslib.as_array(self.stats.sa.byte_hist).copy()
+        self.wt = wt
+        if ssa_plan is not None:
+            self.ssa = SampledSA(ssa_plan, ssa_blob)
         side = None
         if host_sa is not None or host_bwt is not None:
-            side = _aux_stream(self.device, "copy")
-        if host_sa is not None:
-            side.wait_stream(torch.cuda.current_stream())
+            side = _aux_stream(dev, "copy")
+            side.wait_stream(main)
             with torch.cuda.stream(side):
-                host_sa.copy_(self.sa, non_blocking=True)
+                if host_sa is not None:
+                    host_sa.copy_(self.sa, non_blocking=True)
+                if host_bwt is not None:
+                    host_bwt.copy_(self.bwt, non_blocking=True)
             self.sa.record_stream(side)        # keep_sa=False must not hand the buffer back while the copy runs
-        # the sampled SA depends on the suffix array only: build it on a second stream while the BWT and the
-        # wavelet tree are built on this one
-        main = torch.cuda.current_stream()
-        ssa_stream = None
-        self.ssa = None
-        sa_done = None
-        if sa_sample_rate > 0:
-            sa_done = torch.cuda.Event()
-            sa_done.record(main)
-        # the wavelet tree is the critical path of the tail; with a sampled SA being built beside it, it runs on a
-        # high-priority stream, so the block scheduler serves it first and the sampled-SA kernels fill what is left
-        # (the tree build alone: 2.6 ms at C3; sharing the SMs evenly: 3.4 ms)
-        crit = _aux_stream(self.device, "critical", priority=-1) if sa_sample_rate > 0 else main
-        if crit is not main:
-            crit.wait_stream(main)
-        if sa_sample_rate > 0:
-            ssa_stream = _aux_stream(self.device, "ssa")
-            ssa_stream.wait_event(sa_done)
-            with torch.cuda.stream(ssa_stream):
-                self.ssa = build_sampled_sa(self.sa, sa_sample_rate)
-            self.sa.record_stream(ssa_stream)
-        if host_bwt is not None:
-            side.wait_stream(crit)
-            with torch.cuda.stream(side):
-                host_bwt.copy_(self.bwt, non_blocking=True)
             self.bwt.record_stream(side)
-        # the BWT is a permutation of the text: the byte histogram of the suffix-array build serves the tree
-        hist = np.ctypeslib.as_array(self.stats.sa.byte_hist).copy() if self.n else None
-        with torch.cuda.stream(crit):
-            self.wt = DeviceWaveletTree(self.bwt, hist=hist)
-        if crit is not main:
-            main.wait_stream(crit)
-            for t in (text, self.sa, self.bwt):
-                t.record_stream(crit)
-            self.wt.blob.record_stream(main)
-        if ssa_stream is not None:
-            main.wait_stream(ssa_stream)
-            self.ssa.blob.record_stream(main)
         self._side = side
         self.text = text if keep_text else None
         if not keep_sa:

@@ -131,6 +131,13 @@ int hkcsa_dsa_plan_make(const uint64_t *h_byte_hist, uint64_t n, int force_wide,
 /* d_hist[HKCSA_DSA_BUCKETS] (overwritten): suffixes of [begin, end) per bucket = top 16 bits of the round-0 key  */
 int hkcsa_dsa_bucket_hist(const uint8_t *d_text, const hkcsa_dsa_plan *h_plan, uint64_t begin, uint64_t end,
                           uint64_t *d_hist, void *stream);
+/* The same over every tile_stride-th tile of 2048 positions only: cut points from a sample (one global atomic per  */
+/* suffix is what the exact histogram costs).  The exact sizes of the exchange regions then come from              */
+/* hkcsa_dsa_dest_counts: d_counts[HKCSA_DSA_MAX_RANKS] (overwritten) = suffixes of [begin, end) per owner rank.    */
+int hkcsa_dsa_bucket_hist_sampled(const uint8_t *d_text, const hkcsa_dsa_plan *h_plan, uint64_t begin, uint64_t end,
+                                  uint32_t tile_stride, uint64_t *d_hist, void *stream);
+int hkcsa_dsa_dest_counts(const uint8_t *d_text, const hkcsa_dsa_plan *h_plan, uint64_t begin, uint64_t end,
+                          uint32_t world, const uint32_t *h_cuts, uint64_t *d_counts, void *stream);
 /* Pack + partition + exchange of the suffixes of [begin, end): rank r owns buckets [h_cuts[r], h_cuts[r+1]);     */
 /* (key, id) pairs go to h_peer_keys[r] (uint64) / h_peer_ids[r] (uint32, or uint64 when plan->wide) from slot     */
 /* h_base[r] on (this source's region; the caller sizes the regions from the all-gathered bucket histograms).      */
@@ -353,6 +360,25 @@ int hkcsa_gather_u32(const uint32_t *d_src, const uint32_t *d_rows, uint64_t m, 
 int hkcsa_locate_rows(const void *d_wt_blob, const hkcsa_wt_plan *h_plan, const void *d_ssa_blob,
                       const hkcsa_ssa_plan *h_ssa, const uint32_t *d_rows, uint64_t m,
                       uint32_t *d_out_pos, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* The constructor in one call -- EnhancedFMIndex.__init__,                    */
+/* csa/enhanced_fm_index.py:8-13 (suffix array, BWT, occ / count): suffix array */
+/* + BWT on `stream` (hkcsa_sa_bwt_build), then the wavelet tree over the BWT   */
+/* on `stream_tree` and the sampled suffix array on `stream_ssa` side by side   */
+/* (NULL = `stream`); on return `stream` waits for both.  h_ssa_plan NULL = no  */
+/* sampled SA.  The tree's shape depends on the byte histogram, which the call  */
+/* computes itself: the caller sizes d_wt_blob / d_wt_scratch with the bounds   */
+/* below, the plan filled into h_wt_plan says how much of the blob is used.     */
+/* No host-language code runs between the refinement rounds and the tree        */
+/* kernels -- the GPU does not wait for the caller there.  syncs.               */
+size_t hkcsa_wt_blob_bound(uint64_t n);
+size_t hkcsa_wt_scratch_bound(uint64_t n);
+int hkcsa_index_build(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint8_t *d_bwt, void *d_sa_scratch,
+                      size_t sa_scratch_bytes, hkcsa_wt_plan *h_wt_plan, void *d_wt_blob, size_t wt_blob_cap,
+                      void *d_wt_scratch, size_t wt_scratch_cap, const hkcsa_ssa_plan *h_ssa_plan,
+                      void *d_ssa_blob, void *d_ssa_scratch, size_t ssa_scratch_bytes, void *stream,
+                      void *stream_tree, void *stream_ssa, hkcsa_sa_stats *h_stats);
 
 /* Sampled SA of a SLICE of the suffix array (distributed build): the number of marked rows of a slice is  */
 /* not ceil(m / rate), the caller passes it (count of SA[j] % rate == 0 in the slice).                        */

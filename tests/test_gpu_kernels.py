@@ -438,6 +438,20 @@ def test_distributed_build_sorts_repetitive_texts(E, name, parts):
         assert max(sl.dbl_rounds for sl in slices) >= 1
 
 
+@pytest.mark.parametrize("name", ["eng_300k", "dna_1m_dollar", "runs", "rand256_50k"])
+@pytest.mark.parametrize("parts,stride", [(2, 2), (3, 8), (8, 5)])
+def test_distributed_build_with_sampled_cut_points(E, name, parts, stride):
+    """Cut points from a histogram over every stride-th tile only, region sizes counted exactly under those cuts
+    (hkcsa_dsa_bucket_hist_sampled + hkcsa_dsa_dest_counts): what blocks of 16 M positions and more do."""
+    from hkcsa import dist_sa
+    text = TEXTS[name]
+    d_text = dev(E, text)
+    n = len(text)
+    cuts = [n * r // parts for r in range(parts + 1)]
+    blocks = [d_text[cuts[r]:cuts[r + 1]].clone() for r in range(parts)]
+    _check_slices(dist_sa.emulate_distributed_suffix_array(blocks, hist_stride=stride), text, False)
+
+
 def test_distributed_build_reference_benchmark_workload(E):
     """"mississippi$" * 1000 is the default workload of the reference's own benchmark (tests/benchmark.py:110);
     here 20 000 copies over 4 ranks."""
