@@ -232,8 +232,7 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
 {
     __shared__ __align__(16) uint8_t s_a[WTL_TILE];
     __shared__ __align__(16) uint8_t s_b[WTL_TILE];
-    __shared__ uint32_t s_bits[WTL_THREADS + 1];      // word r = bits of tile positions [32 r, 32 r + 32)
-    __shared__ uint32_t s_wpre[WTL_THREADS + 1];      // ones before word r
+    __shared__ uint2 s_wp[WTL_THREADS + 1];           // row r: .x = bits of tile positions [32 r, 32 r + 32), .y = ones before them
     __shared__ uint32_t s_tcum[257], s_gcum[257];     // per path x: elements with a smaller path in this tile / in earlier tiles
     __shared__ uint32_t s_ent[128];
     __shared__ uint8_t s_path[256];
@@ -264,7 +263,7 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
         s_gcum[tid] = p2 + e2;
         if (tid == 255) { s_tcum[256] = p1 + e1 + cnt; s_gcum[256] = p2 + e2 + pre; }
     }
-    if (tid == 0) s_bits[WTL_THREADS] = 0;
+    if (tid == 0) s_wp[WTL_THREADS].x = 0;
     // symbols -> paths, original order (32 consecutive symbols per thread: two 16-byte loads)
     {
         const uint8_t *src = sym + base + (uint64_t)tid * WTL_EPT;
@@ -292,28 +291,29 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
     __syncthreads();
 
     uint8_t *cur = s_a, *nxt = s_b;
-    const uint32_t lt = lanemask_lt();
+    const uint32_t lt = lanemask_lt(), lanebit = 1u << lane;
     for (uint32_t l = 0; l < levels; ++l) {
         const uint32_t shift = 7u - l;
-        // ---- A: the words of bits of this warp's 32 rows; lane r keeps row r's word
+        // ---- A: the words of bits of this warp's 32 rows (lane 0 files each), ones before every row
         const uint8_t *wrow = cur + warp * 1024u + lane;
-        uint32_t myword = 0;
+        uint2 *wp_row = s_wp + warp * 32u;
 #pragma unroll 8
         for (uint32_t r = 0; r < 32; ++r) {
             const uint32_t pth = wrow[r * 32u];
             const uint32_t word = __ballot_sync(0xffffffffu, (pth >> shift) & 1u);
-            if (lane == r) myword = word;
+            if (lane == 0) wp_row[r].x = word;
         }
-        s_bits[tid] = myword;
+        __syncwarp();
         {
+            const uint32_t myword = s_wp[tid].x;
             uint32_t wt;
             const uint32_t ex = warp_excl_sum(__popc(myword), wt);
             if (lane == 31) s_scan[0][warp] = wt;
             __syncthreads();
             uint32_t p = 0, tot = 0;
             for (uint32_t q = 0; q < WTL_THREADS / 32; ++q) { if (q < warp) p += s_scan[0][q]; tot += s_scan[0][q]; }
-            s_wpre[tid] = p + ex;
-            if (tid == 0) s_wpre[WTL_THREADS] = tot;
+            s_wp[tid].y = p + ex;
+            if (tid == 0) s_wp[WTL_THREADS].y = tot;
         }
         __syncthreads();
         // ---- B: every internal node's run of bits into the level (warps take nodes round-robin)
@@ -332,7 +332,7 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
                     const uint32_t nb = hi_bit - lo_bit;
                     const uint32_t i0 = s0 + (lo_bit - D);
                     const uint32_t wi = i0 >> 5, sh = i0 & 31u;
-                    const uint64_t x = (uint64_t)s_bits[wi] | ((uint64_t)s_bits[wi + 1] << 32);
+                    const uint64_t x = (uint64_t)s_wp[wi].x | ((uint64_t)s_wp[wi + 1].x << 32);
                     uint32_t v = (uint32_t)(x >> sh);
                     if (nb < 32) v &= (1u << nb) - 1u;
                     const uint32_t out = v << (lo_bit - (q << 5));
@@ -347,24 +347,21 @@ wt_levels_kernel(const uint8_t *__restrict__ sym, uint64_t n, const WtTables *__
         if (tid < (1u << l)) {
             const uint32_t x_lo = tid << (shift + 1u);
             const uint32_t S = s_tcum[x_lo], M = s_tcum[x_lo + (1u << shift)];
-            const uint32_t ps = s_wpre[S >> 5] + __popc(s_bits[S >> 5] & ((1u << (S & 31u)) - 1u));
+            const uint2 wp = s_wp[S >> 5];
+            const uint32_t ps = wp.y + __popc(wp.x & ((1u << (S & 31u)) - 1u));
             s_ent[tid] = (M - ps) | (ps << 16);
         }
         __syncthreads();
         {
             uint8_t *wout = nxt;
-            const uint32_t row0 = warp * 32u;
-            const uint32_t mypre = s_wpre[tid];
-#pragma unroll 4
+            const uint32_t i0 = warp * 1024u + lane;
+#pragma unroll 8
             for (uint32_t r = 0; r < 32; ++r) {
-                const uint32_t i = (row0 + r) * 32u + lane;
-                const uint32_t pth = cur[i];
-                const uint32_t word = __shfl_sync(0xffffffffu, myword, r);
-                const uint32_t pre = __shfl_sync(0xffffffffu, mypre, r);
+                const uint32_t pth = wrow[r * 32u];
+                const uint2 wp = wp_row[r];                               // the row's word and the ones before it: a broadcast
                 const uint32_t e = s_ent[pth >> (shift + 1u)];
-                const uint32_t ob = pre + __popc(word & lt);              // ones before this element in the tile order
-                const uint32_t ps = e >> 16;
-                const uint32_t dst = ((word >> lane) & 1u) ? (e & 0xFFFFu) + ob : i + ps - ob;
+                const uint32_t ob = wp.y + __popc(wp.x & lt);             // ones before this element in the tile order
+                const uint32_t dst = (wp.x & lanebit) ? (e & 0xFFFFu) + ob : (i0 + r * 32u) + (e >> 16) - ob;
                 wout[dst] = (uint8_t)pth;
             }
         }
@@ -716,6 +713,19 @@ static_assert(WTP_SYMS % (WTP_THREADS * 4) == 0, "tile shape");
 constexpr int SSA_WORDS = WTP_SYMS / 32;                     // 448 words = 64 blocks x 7
 
 template <typename IdT>
+__device__ __forceinline__ void ssa_load4_fast(const IdT *__restrict__ p, IdT v[4])
+{
+    if constexpr (sizeof(IdT) == 4) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(p);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+
+template <typename IdT>
 __device__ __forceinline__ void ssa_load4(const IdT *__restrict__ sa, uint64_t n, uint64_t r0, bool aligned16, IdT v[4])
 {
     if (r0 + 4 <= n && aligned16) {
@@ -733,7 +743,41 @@ __device__ __forceinline__ void ssa_load4(const IdT *__restrict__ sa, uint64_t n
     }
 }
 
-template <typename IdT>
+// the flags of the tile's rows: every thread's four flags per step (returned), the words of 32 rows into s_words
+template <typename IdT, bool POW2, bool FAST>
+__device__ __forceinline__ uint64_t ssa_flag_steps(const IdT *__restrict__ sa, uint64_t n, uint64_t row_base, uint32_t rate,
+                                                   IdT mask, bool aligned16, uint32_t *s_words)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t nib_shift = 4u * (lane & 7u);
+    uint32_t *my_word = &s_words[warp * 4 + (lane >> 3)];
+    const IdT *p = sa + row_base + tid * 4u;
+    uint64_t nibs = 0;
+#pragma unroll
+    for (int it = 0; it < SSA_STEPS; ++it) {
+        IdT v[4];
+        if (FAST) ssa_load4_fast<IdT>(p + it * (WTP_THREADS * 4), v);
+        else ssa_load4<IdT>(sa, n, row_base + (uint64_t)it * (WTP_THREADS * 4) + tid * 4u, aligned16, v);
+        uint32_t nib = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool hit = POW2 ? ((v[e] & mask) == 0) : (v[e] % rate == 0);
+            const bool f = hit && (FAST || row_base + (uint64_t)it * (WTP_THREADS * 4) + tid * 4u + e < n);
+            nib |= (f ? 1u : 0u) << e;
+        }
+        nibs |= (uint64_t)nib << (4 * it);
+        uint32_t x = nib << nib_shift;
+        x |= __shfl_xor_sync(0xffffffffu, x, 1);
+        x |= __shfl_xor_sync(0xffffffffu, x, 2);
+        x |= __shfl_xor_sync(0xffffffffu, x, 4);
+        if ((lane & 7u) == 0) my_word[it * (WTP_THREADS / 8)] = x;
+    }
+    return nibs;
+}
+
+// POW2: the rate is a power of two -- a mask and a shift per entry instead of a division (a run-time test inside the
+// loop made the compiler evaluate both forms for every entry: 37 instructions per row)
+template <typename IdT, bool POW2>
 __global__ void __launch_bounds__(WTP_THREADS)
 ssa_mark_sample_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, RankBlock *__restrict__ blocks,
                        uint64_t nblocks, uint32_t *__restrict__ agg, uint32_t *state, uint32_t *ticket,
@@ -748,28 +792,13 @@ ssa_mark_sample_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, Ra
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t row_base = (uint64_t)tile * WTP_SYMS;
-    const bool pow2 = (rate & (rate - 1u)) == 0;      // power-of-two rate: no division per entry
     const int sh = __ffs(rate) - 1;
+    const IdT mask = (IdT)(rate - 1u);
     const bool aligned16 = (reinterpret_cast<uintptr_t>(sa) & 15) == 0;
-    uint64_t nibs = 0;                                // this thread's four flags of every step
-#pragma unroll
-    for (int it = 0; it < SSA_STEPS; ++it) {
-        const uint64_t r0 = row_base + (uint64_t)it * (WTP_THREADS * 4) + tid * 4u;
-        IdT v[4];
-        ssa_load4<IdT>(sa, n, r0, aligned16, v);
-        uint32_t nib = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const bool f = (r0 + e < n) && (pow2 ? ((v[e] & (IdT)(rate - 1u)) == 0) : (v[e] % rate == 0));
-            nib |= (f ? 1u : 0u) << e;
-        }
-        nibs |= (uint64_t)nib << (4 * it);
-        uint32_t x = nib << (4u * (lane & 7u));
-        x |= __shfl_xor_sync(0xffffffffu, x, 1);
-        x |= __shfl_xor_sync(0xffffffffu, x, 2);
-        x |= __shfl_xor_sync(0xffffffffu, x, 4);
-        if ((lane & 7u) == 0) s_words[it * (WTP_THREADS / 8) + warp * 4 + (lane >> 3)] = x;
-    }
+    const bool fast = aligned16 && row_base + WTP_SYMS <= n;     // every tile but the last: no bounds checks
+    // this thread's four flags of every step
+    const uint64_t nibs = fast ? ssa_flag_steps<IdT, POW2, true>(sa, n, row_base, rate, mask, aligned16, s_words)
+                               : ssa_flag_steps<IdT, POW2, false>(sa, n, row_base, rate, mask, aligned16, s_words);
     __syncthreads();
     // threads 0..63: one rank block each (7 words), block headers relative to the tile, prefix of every word
     const uint64_t gb = (uint64_t)tile * WTP_BLOCKS_PER_CTA + tid;
@@ -843,7 +872,7 @@ ssa_mark_sample_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, Ra
             nib &= nib - 1;
             const uint32_t bit = (local & 31u) + e;
             const IdT v = sa[row_base + local + e];
-            samples[pre + __popc(word & ((1u << bit) - 1u))] = pow2 ? (uint32_t)(v >> sh) : (uint32_t)(v / rate);
+            samples[pre + __popc(word & ((1u << bit) - 1u))] = POW2 ? (uint32_t)(v >> sh) : (uint32_t)(v / rate);
         }
     }
 }
@@ -856,8 +885,12 @@ static int build_markvector_t(const IdT *d_sa, uint64_t n, uint32_t rate, RankBl
     const uint64_t nblocks = rank_blocks_for(n);
     const uint64_t tiles = (nblocks + WTP_BLOCKS_PER_CTA - 1) / WTP_BLOCKS_PER_CTA;
     HK_CUDA(cudaMemsetAsync(d_state, 0, (tiles + 1) * sizeof(uint32_t), st));       // [tiles] look-back states + the ticket
-    ssa_mark_sample_kernel<IdT><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg, d_state,
-                                                                         d_state + tiles, d_samples);
+    if ((rate & (rate - 1u)) == 0)
+        ssa_mark_sample_kernel<IdT, true><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg,
+                                                                                   d_state, d_state + tiles, d_samples);
+    else
+        ssa_mark_sample_kernel<IdT, false><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg,
+                                                                                    d_state, d_state + tiles, d_samples);
     HK_LAUNCH_CHECK();
     wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones);
     HK_LAUNCH_CHECK();
