@@ -121,6 +121,21 @@ extern "C" int hkcsa_prof_reset(void)
     prof::g_used = 0;
     return HKCSA_OK;
 }
+// every bracketed launch in recording order: start / end in ms relative to the first record's start, and its class
+extern "C" int hkcsa_prof_timeline(float *h_start_ms, float *h_end_ms, int *h_class, int max_entries, int *h_n)
+{
+    HK_REQUIRE(h_start_ms && h_end_ms && h_class && h_n, HKCSA_EINVAL, "null pointer");
+    const int n = prof::g_used < max_entries ? prof::g_used : max_entries;
+    for (int i = 0; i < n; ++i) {
+        HK_CUDA(cudaEventSynchronize(prof::g_rec[i].b));
+        HK_CUDA(cudaEventElapsedTime(&h_start_ms[i], prof::g_rec[0].a, prof::g_rec[i].a));
+        HK_CUDA(cudaEventElapsedTime(&h_end_ms[i], prof::g_rec[0].a, prof::g_rec[i].b));
+        h_class[i] = prof::g_rec[i].cls;
+    }
+    *h_n = n;
+    return HKCSA_OK;
+}
+
 extern "C" int hkcsa_prof_read(hkcsa_prof_entry *h_out, int max_entries, int *h_n)
 {
     HK_REQUIRE(h_out && h_n && max_entries >= prof::NUM_CLASSES, HKCSA_EINVAL, "need room for every class");

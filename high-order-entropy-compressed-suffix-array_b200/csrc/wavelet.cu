@@ -701,12 +701,14 @@ int build_bitvector(const uint8_t *d_sym, uint64_t len, const uint8_t *d_lut_bit
 }
 }  // namespace hkcsa
 
-// Sampled suffix array in ONE pass over the suffix array: mark bit-vector (bit j = SA[j] % rate == 0) packed into rank
-// blocks, and the samples SA[j] / rate of the marked rows written in row order.  A thread takes four consecutive rows
-// per step (one 16-byte load for 32-bit ids); the flag nibbles of eight lanes are OR-ed into the 32-bit word of their
-// rows with three shuffles.  The sample slot of a marked row = marks in earlier tiles (decoupled look-back over one
-// counter per tile, tiles handed out by a ticket) + marks before it in the tile (prefix over the tile's words); the
-// marked entries -- one in `rate` -- are read a second time from L1/L2, so the suffix array comes from DRAM once.
+// Sampled suffix array with the suffix array streamed ONCE: `ssa_mark_pack_kernel` packs the mark bit-vector (bit j =
+// SA[j] % rate == 0) into rank blocks -- a thread takes four consecutive rows per step (one 16-byte load for 32-bit
+// ids), the flag nibbles of eight lanes are OR-ed into the 32-bit word of their rows with three shuffles --, the
+// single-CTA scan turns the tile totals into carries, and `ssa_fix_sample_kernel` finishes the directory and writes
+// the samples SA[j] / rate of the marked rows in row order: the thread of a rank block knows the marks before it and
+// reads only the marked entries again (one in `rate`).  (A single kernel with a decoupled look-back over one counter
+// per 14336-row tile was measured first: its chain of inclusive prefixes advances 32 tiles per L2 round trip, 218 hops
+// for C2 = 0.25 ms whatever the bandwidth.)
 namespace hkcsa {
 constexpr int SSA_STEPS = WTP_SYMS / (WTP_THREADS * 4);      // 14 steps of 1024 rows
 static_assert(WTP_SYMS % (WTP_THREADS * 4) == 0, "tile shape");
@@ -779,28 +781,21 @@ __device__ __forceinline__ uint64_t ssa_flag_steps(const IdT *__restrict__ sa, u
 // loop made the compiler evaluate both forms for every entry: 37 instructions per row)
 template <typename IdT, bool POW2>
 __global__ void __launch_bounds__(WTP_THREADS)
-ssa_mark_sample_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, RankBlock *__restrict__ blocks,
-                       uint64_t nblocks, uint32_t *__restrict__ agg, uint32_t *state, uint32_t *ticket,
-                       uint32_t *__restrict__ samples)
+ssa_mark_pack_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, RankBlock *__restrict__ blocks,
+                     uint64_t nblocks, uint32_t *__restrict__ agg)
 {
     __shared__ uint32_t s_words[SSA_WORDS];
-    __shared__ uint32_t s_pref[SSA_WORDS];
     __shared__ uint32_t s_wsum[2];
-    __shared__ uint32_t s_tile, s_total, s_base;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile = blockIdx.x;
     const uint64_t row_base = (uint64_t)tile * WTP_SYMS;
-    const int sh = __ffs(rate) - 1;
     const IdT mask = (IdT)(rate - 1u);
     const bool aligned16 = (reinterpret_cast<uintptr_t>(sa) & 15) == 0;
     const bool fast = aligned16 && row_base + WTP_SYMS <= n;     // every tile but the last: no bounds checks
-    // this thread's four flags of every step
-    const uint64_t nibs = fast ? ssa_flag_steps<IdT, POW2, true>(sa, n, row_base, rate, mask, aligned16, s_words)
-                               : ssa_flag_steps<IdT, POW2, false>(sa, n, row_base, rate, mask, aligned16, s_words);
+    if (fast) ssa_flag_steps<IdT, POW2, true>(sa, n, row_base, rate, mask, aligned16, s_words);
+    else ssa_flag_steps<IdT, POW2, false>(sa, n, row_base, rate, mask, aligned16, s_words);
     __syncthreads();
-    // threads 0..63: one rank block each (7 words), block headers relative to the tile, prefix of every word
+    // threads 0..63: one rank block each (7 words), block headers relative to the tile
     const uint64_t gb = (uint64_t)tile * WTP_BLOCKS_PER_CTA + tid;
     uint32_t w[7] = {0, 0, 0, 0, 0, 0, 0};
     uint32_t cnt = 0;
@@ -814,9 +809,6 @@ ssa_mark_sample_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, Ra
     __syncthreads();
     if (tid < WTP_BLOCKS_PER_CTA) {
         const uint32_t rel = ex + ((tid >= 32) ? s_wsum[0] : 0u);
-        uint32_t run = rel;
-#pragma unroll
-        for (int t = 0; t < 7; ++t) { s_pref[tid * 7 + t] = run; run += __popc(w[t]); }
         if (gb < nblocks) {
             uint4 lo4, hi4;
             lo4.x = rel; lo4.y = w[0]; lo4.z = w[1]; lo4.w = w[2];
@@ -825,54 +817,49 @@ ssa_mark_sample_kernel(const IdT *__restrict__ sa, uint64_t n, uint32_t rate, Ra
             dst[0] = lo4;
             dst[1] = hi4;
         }
-        if (tid == WTP_BLOCKS_PER_CTA - 1) {
-            agg[tile] = rel + cnt;
-            s_total = rel + cnt;
-            st_volatile_u32(&state[tile], (tile == 0 ? LB_INC : LB_AGG) | (rel + cnt));
-        }
+        if (tid == WTP_BLOCKS_PER_CTA - 1) agg[tile] = rel + cnt;
     }
-    __syncthreads();
-    // marks in earlier tiles: warp 0 looks back 32 tiles per round trip
-    if (warp == 0) {
-        uint32_t excl = 0;
-        if (tile > 0) {
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                const int64_t mine = t - lane;
-                const uint32_t v = mine >= 0 ? ld_volatile_u32(&state[mine]) : LB_INC;
-                const uint32_t flag = v >> 30;
-                const uint32_t not_ready = __ballot_sync(0xffffffffu, flag == 0);
-                const uint32_t inc = __ballot_sync(0xffffffffu, flag == 2);
-                // usable lanes: below the first unpublished one, up to and including the first inclusive one
-                uint32_t upto = not_ready ? (uint32_t)(__ffs(not_ready) - 1) : 32u;
-                bool done = false;
-                if (inc && (uint32_t)(__ffs(inc) - 1) < upto) { upto = (uint32_t)__ffs(inc); done = true; }
-                const uint32_t part = __reduce_add_sync(0xffffffffu, lane < upto ? (v & LB_VAL) : 0u);
-                excl += part;
-                t -= upto;
-                if (done) break;
-            }
-            if (lane == 0) st_volatile_u32(&state[tile], LB_INC | (excl + s_total));
-        }
-        if (lane == 0) s_base = excl;
+}
+
+// wt_dir_fix_kernel for the mark vector, and the samples: the thread of a rank block knows the marks before it (tile
+// carry + header) and walks the block's set bits in row order: samples[marks before + k] = SA[row] / rate.  Only the
+// marked entries are read again -- one in `rate`, 7 per block at rate 32 -- so the suffix array is streamed once.
+template <typename IdT, bool POW2>
+__global__ void __launch_bounds__(256)
+ssa_fix_sample_kernel(RankBlock *__restrict__ blocks, uint64_t nblocks, const uint64_t *__restrict__ carry,
+                      uint64_t *__restrict__ super, uint32_t *__restrict__ select_samples, const IdT *__restrict__ sa,
+                      uint32_t rate, uint32_t *__restrict__ samples)
+{
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nblocks) return;
+    const RankBlock b = load_block(blocks + g);
+    const uint32_t rel = (uint32_t)(b.w[0] & 0xFFFFFFFFu);
+    const uint64_t abs_before = carry[g / WTP_BLOCKS_PER_CTA] + rel;
+    const uint64_t sb = g / HKCSA_SUPER_BLOCKS;
+    const uint64_t sb_abs = carry[sb * (HKCSA_SUPER_BLOCKS / WTP_BLOCKS_PER_CTA)];
+    reinterpret_cast<uint32_t *>(blocks + g)[0] = (uint32_t)(abs_before - sb_abs);
+    if (g % HKCSA_SUPER_BLOCKS == 0) super[sb] = sb_abs;
+    const uint32_t cnt = block_rank(b, HKCSA_BLOCK_BITS);
+    if (cnt == 0) return;
+    const uint64_t ts = (abs_before + HKCSA_SELECT_SAMPLE - 1) / HKCSA_SELECT_SAMPLE;
+    const uint64_t ksel = 1 + ts * HKCSA_SELECT_SAMPLE;
+    if (ksel <= abs_before + cnt) {
+        const uint32_t bit = block_select(b, (uint32_t)(ksel - abs_before));
+        select_samples[ts] = (uint32_t)(g * HKCSA_BLOCK_BITS + bit);
     }
-    __syncthreads();
-    const uint32_t base = s_base;
-    if (nibs == 0) return;
+    const int sh = __ffs(rate) - 1;
+    const IdT *row0 = sa + g * HKCSA_BLOCK_BITS;
+    uint32_t *out = samples + abs_before;
+    uint32_t k = 0;
 #pragma unroll
-    for (int it = 0; it < SSA_STEPS; ++it) {
-        uint32_t nib = (uint32_t)(nibs >> (4 * it)) & 0xFu;
-        if (nib == 0) continue;
-        const uint32_t local = it * (WTP_THREADS * 4) + tid * 4u;       // first of the four rows inside the tile
-        const uint32_t q = local >> 5;
-        const uint32_t word = s_words[q];
-        const uint32_t pre = base + s_pref[q];
-        while (nib) {
-            const uint32_t e = __ffs(nib) - 1;
-            nib &= nib - 1;
-            const uint32_t bit = (local & 31u) + e;
-            const IdT v = sa[row_base + local + e];
-            samples[pre + __popc(word & ((1u << bit) - 1u))] = POW2 ? (uint32_t)(v >> sh) : (uint32_t)(v / rate);
+    for (int q = 0; q < 4; ++q) {
+        uint64_t x = q ? b.w[q] : (b.w[0] >> 32);          // payload bit j of the block = bit 32 + j of the 256
+        const int base = q ? 64 * q - 32 : 0;
+        while (x) {
+            const int bit = __ffsll((long long)x) - 1;
+            x &= x - 1;
+            const IdT v = row0[base + bit];
+            out[k++] = POW2 ? (uint32_t)(v >> sh) : (uint32_t)(v / rate);
         }
     }
 }
@@ -882,20 +869,18 @@ static int build_markvector_t(const IdT *d_sa, uint64_t n, uint32_t rate, RankBl
                               uint32_t *d_select, uint32_t *d_agg, uint64_t *d_carry, uint64_t *d_ones, uint32_t *d_state,
                               uint32_t *d_samples, cudaStream_t st)
 {
+    (void)d_state;
     const uint64_t nblocks = rank_blocks_for(n);
     const uint64_t tiles = (nblocks + WTP_BLOCKS_PER_CTA - 1) / WTP_BLOCKS_PER_CTA;
-    HK_CUDA(cudaMemsetAsync(d_state, 0, (tiles + 1) * sizeof(uint32_t), st));       // [tiles] look-back states + the ticket
-    if ((rate & (rate - 1u)) == 0)
-        ssa_mark_sample_kernel<IdT, true><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg,
-                                                                                   d_state, d_state + tiles, d_samples);
-    else
-        ssa_mark_sample_kernel<IdT, false><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg,
-                                                                                    d_state, d_state + tiles, d_samples);
+    const bool pow2 = (rate & (rate - 1u)) == 0;
+    if (pow2) ssa_mark_pack_kernel<IdT, true><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg);
+    else ssa_mark_pack_kernel<IdT, false><<<(uint32_t)tiles, WTP_THREADS, 0, st>>>(d_sa, n, rate, d_blocks, nblocks, d_agg);
     HK_LAUNCH_CHECK();
     wt_dir_scan_kernel<<<1, 1024, 0, st>>>(d_agg, tiles, d_carry, d_ones);
     HK_LAUNCH_CHECK();
-    wt_dir_fix_kernel<<<(uint32_t)((nblocks + 255) / 256), 256, 0, st>>>(d_blocks, nblocks, d_carry, d_super, d_select,
-                                                                         WTP_BLOCKS_PER_CTA);
+    const uint32_t grid = (uint32_t)((nblocks + 255) / 256);
+    if (pow2) ssa_fix_sample_kernel<IdT, true><<<grid, 256, 0, st>>>(d_blocks, nblocks, d_carry, d_super, d_select, d_sa, rate, d_samples);
+    else ssa_fix_sample_kernel<IdT, false><<<grid, 256, 0, st>>>(d_blocks, nblocks, d_carry, d_super, d_select, d_sa, rate, d_samples);
     HK_LAUNCH_CHECK();
     return HKCSA_OK;
 }

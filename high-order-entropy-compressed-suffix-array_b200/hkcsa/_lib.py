@@ -234,6 +234,7 @@ SIGNATURES = {
     "hkcsa_prof_class_index": (_i32, [C.c_char_p]),
     "hkcsa_prof_reset": (_i32, []),
     "hkcsa_prof_read": (_i32, [C.POINTER(ProfEntry), _i32, C.POINTER(_i32)]),
+    "hkcsa_prof_timeline": (_i32, [_vp, _vp, _vp, C.c_int, _vp]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@ to a sampled SA (CompressedSuffixArray.locate).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -585,6 +586,13 @@ class DeviceIndex:
             # and the sampled-SA kernel fills what is left (tree alone 2.6 ms at C3; sharing the SMs evenly 3.4 ms)
             crit = _aux_stream(dev, "critical", priority=-1)
             ssa_stream = _aux_stream(dev, "ssa")
+            tail = os.environ.get("HKCSA_TAIL", "")              # experiment knob: how the tail shares the GPU
+            if tail == "flat":
+                crit = main
+            elif tail == "serial":
+                crit = ssa_stream = main
+            elif tail == "ssa_high":
+                crit, ssa_stream = _aux_stream(dev, "ssa"), _aux_stream(dev, "critical", priority=-1)
         check(L.hkcsa_index_build(_ptr(text), n, _ptr(self.sa), _ptr(self.bwt), _ptr(sa_scratch), sa_bytes,
                                   C.byref(wt.plan), _ptr(blob), blob_cap, _ptr(wt_scratch), wt_cap,
                                   C.byref(ssa_plan) if ssa_plan is not None else None, _ptr(ssa_blob), _ptr(ssa_scratch),

@@ -489,6 +489,8 @@ int hkcsa_prof_enable_classes(uint32_t class_mask);
 int hkcsa_prof_class_index(const char *name);
 int hkcsa_prof_reset(void);
 int hkcsa_prof_read(hkcsa_prof_entry *h_out, int max_entries, int *h_n);
+/* every bracketed launch in recording order: start / end (ms after the first record's start) and class index    */
+int hkcsa_prof_timeline(float *h_start_ms, float *h_end_ms, int *h_class, int max_entries, int *h_n);
 
 /* ------------------------------------------------------------------------ */
 /* Sampled Occ table (optional second rank structure): the reference's dense occ[c][i] (build_occ,          */
