@@ -15,6 +15,7 @@
 #include "radix_sort.cuh"
 #include "suffix_array.cuh"
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace hkcsa {
@@ -225,6 +226,262 @@ sa_pack0_kernel(const uint8_t *__restrict__ text, uint32_t n, AlphaCode ac, uint
     hist_flush(s_hist, ghist, passes);
 }
 
+// ---------------------------------------------------------------- round 0 keys from the k-gram code
+// digits of the 8 symbols a thread owns, as one 8-byte word (positions past the end: digit 0)
+__device__ __forceinline__ uint2 gram_digits8(const uint8_t *__restrict__ text, uint64_t n, uint64_t p0, bool aligned8,
+                                              const uint8_t *s_digit)
+{
+    uint32_t d[8];
+    if (aligned8 && p0 + 8 <= n) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2 *>(text + p0));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = s_digit[((e < 4 ? a.x : a.y) >> (8 * (e & 3))) & 0xFFu];
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = (p0 + e < n) ? (uint32_t)s_digit[text[p0 + e]] : 0u;
+    }
+    return make_uint2(d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24), d[4] | (d[5] << 8) | (d[6] << 16) | (d[7] << 24));
+}
+
+// the grams starting at the 8 positions from j0 (digits in shared memory), by a rolling base-B number
+__device__ __forceinline__ void gram_roll8(const uint8_t *s_dig, uint32_t j0, uint32_t k, uint32_t B, uint32_t pw, uint32_t g[8])
+{
+    uint32_t cur = 0;
+    for (uint32_t q = 0; q < k; ++q) cur = cur * B + s_dig[j0 + q];
+    g[0] = cur;
+#pragma unroll
+    for (int e = 1; e < 8; ++e) {
+        cur = (cur - (uint32_t)s_dig[j0 + e - 1] * pw) * B + s_dig[j0 + e - 1 + k];
+        g[e] = cur;
+    }
+}
+
+// sampled k-gram histogram: CTA b counts the grams of tile b * stride (2048 positions) with global atomics
+__global__ void __launch_bounds__(PACK_THREADS)
+gram_hist_kernel(const uint8_t *__restrict__ text, uint32_t n, GramCode gc, uint32_t stride, uint32_t *__restrict__ gh)
+{
+    __shared__ uint8_t s_digit[256];
+    __shared__ __align__(8) uint8_t s_dig[PACK_TILE + 16];
+    const uint32_t tid = threadIdx.x;
+    s_digit[tid] = gc.digit[tid];
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * stride * PACK_TILE;
+    const bool aligned8 = (reinterpret_cast<uintptr_t>(text) & 7) == 0;
+    const uint64_t p0 = base + (uint64_t)tid * PACK_IPT;
+    reinterpret_cast<uint2 *>(s_dig)[tid] = gram_digits8(text, n, p0, aligned8, s_digit);
+    if (tid < 2) reinterpret_cast<uint2 *>(s_dig)[PACK_THREADS + tid] = gram_digits8(text, n, base + PACK_TILE + tid * 8u, aligned8, s_digit);
+    __syncthreads();
+    uint32_t g[8];
+    gram_roll8(s_dig, tid * PACK_IPT, gc.k, gc.B, gc.pw, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (p0 + e < n) atomicAdd(&gh[g[e]], 1u);
+}
+
+// one CTA: w[g] = 16 * count + s (s = max(1, samples / G): the unseen grams together weigh 1/16 of the seen ones, which
+// bounds every code length by log2(17 G) + 2 <= 23 bits), cum[] = exclusive prefix sums, cum[G] = total weight
+__global__ void __launch_bounds__(1024)
+gram_scan_kernel(const uint32_t *__restrict__ gh, uint32_t G, uint64_t *__restrict__ cum, double *__restrict__ stats)
+{
+    __shared__ uint64_t s_w[32];
+    __shared__ uint64_t s_smooth;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // every thread owns `per` consecutive grams (a multiple of 4: 16-byte loads)
+    const uint32_t per = ((G + 1023) / 1024 + 3) & ~3u;
+    const uint32_t g0 = tid * per;
+    uint64_t cnt = 0;
+    for (uint32_t q = 0; q < per; q += 4) {
+        if (g0 + q + 4 <= G) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(gh + g0 + q);
+            cnt += (uint64_t)v.x + v.y + v.z + v.w;
+        } else {
+            for (uint32_t r = 0; r < 4; ++r) if (g0 + q + r < G) cnt += gh[g0 + q + r];
+        }
+    }
+    uint64_t x = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    uint64_t pre = 0, tot = 0;
+    for (uint32_t w = 0; w < 32; ++w) { if (w < warp) pre += s_w[w]; tot += s_w[w]; }
+    if (tid == 0) {
+        s_smooth = tot / G > 1 ? tot / G : 1;
+        stats[0] = (double)tot;         // samples
+        stats[1] = 0;                   // sum of count * len            (gram_assign_kernel)
+        stats[2] = 0;                   // longest code word
+        stats[3] = 0;                   // failures
+        stats[4] = 0;                   // sum of count * log2(samples / count)
+        stats[5] = 0;                   // sum of count * log2(samples / count)^2
+        stats[6] = 0;                   // sum of count * log2(count of the (k-1)-prefix / count): information of the k-th
+        stats[7] = 0;                   // ... and its square                                      symbol given k - 1
+    }
+    __syncthreads();
+    const uint64_t smooth = s_smooth;
+    const uint32_t mine = g0 < G ? min(per, G - g0) : 0u;
+    // exclusive prefix of the weights: 16 * (counts before) + smooth * (grams before)
+    uint64_t run = 16ull * (pre + x - cnt) + smooth * (uint64_t)min(g0, G);
+    for (uint32_t q = 0; q < mine; ++q) {
+        cum[g0 + q] = run;
+        run += 16ull * gh[g0 + q] + smooth;
+    }
+    if (tid == 1023) cum[G] = 16ull * tot + smooth * (uint64_t)G;
+}
+
+// every leaf walks down from the root: a node [lo, hi) splits where its two halves weigh most alike (binary search on
+// cum); left = 0, right = 1.  All leaves of a node compute the same split, so the codes are prefix-free and ordered.
+__global__ void __launch_bounds__(64)
+gram_assign_kernel(const uint64_t *__restrict__ cum, const uint32_t *__restrict__ gh, uint32_t G, uint32_t B,
+                   uint32_t *__restrict__ tab, double *__restrict__ stats)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t len = 0, code = 0;
+    bool ok = true;
+    if (g < G) {
+        uint32_t lo = 0, hi = G;
+        uint64_t clo = 0, chi = cum[G];
+        while (hi - lo > 1) {
+            const uint64_t target = clo + chi;                  // twice the midpoint weight
+            uint32_t a = lo + 1, b = hi - 1;                     // smallest sp in [lo + 1, hi - 1] with 2 cum[sp] >= target
+            while (a < b) {
+                const uint32_t mid = a + ((b - a) >> 1);
+                if (2 * cum[mid] >= target) b = mid; else a = mid + 1;
+            }
+            uint32_t sp = a;
+            if (sp > lo + 1) {
+                const uint64_t hi_d = 2 * cum[sp] >= target ? 2 * cum[sp] - target : target - 2 * cum[sp];
+                const uint64_t lo_d = target - 2 * cum[sp - 1];   // 2 cum[sp - 1] < target
+                if (lo_d <= hi_d) sp = sp - 1;
+            }
+            if (g < sp) { hi = sp; chi = cum[sp]; code <<= 1; }
+            else { lo = sp; clo = cum[sp]; code = (code << 1) | 1u; }
+            if (++len > (uint32_t)GRAM_MAX_LEN) { ok = false; break; }
+        }
+        if (len == 0) len = 1;                                  // a single leaf (G == 1)
+        tab[g] = ok ? ((code << (32 - len)) | len) : 0u;        // code word left-aligned above the 5 length bits
+    }
+    // statistics over the sample: code bits, longest code word, failures, mean and second moment of the information
+    const double c = (g < G) ? (double)gh[g] : 0.0;
+    double wl = ok ? c * len : 0.0, i1 = 0.0, i2 = 0.0, c1 = 0.0, c2 = 0.0;
+    if (c > 0.0) {
+        const double lp = log2(stats[0] / c);
+        i1 = c * lp;
+        i2 = c * lp * lp;
+        // the grams sharing this one's first k - 1 digits are the B consecutive table entries around it
+        const uint32_t first = g - g % B;
+        double cp = 0.0;
+        for (uint32_t q = 0; q < B; ++q) cp += (double)gh[first + q];
+        const double lc = log2(cp / c);
+        c1 = c * lc;
+        c2 = c * lc * lc;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        wl += __shfl_down_sync(0xffffffffu, wl, o);
+        i1 += __shfl_down_sync(0xffffffffu, i1, o);
+        i2 += __shfl_down_sync(0xffffffffu, i2, o);
+        c1 += __shfl_down_sync(0xffffffffu, c1, o);
+        c2 += __shfl_down_sync(0xffffffffu, c2, o);
+    }
+    uint32_t ml = (g < G) ? len : 0u;
+    ml = __reduce_max_sync(0xffffffffu, ml);
+    const uint32_t bad = __popc(__ballot_sync(0xffffffffu, g < G && !ok));
+    if ((threadIdx.x & 31u) == 0) {
+        if (wl > 0.0) atomicAdd(&stats[1], wl);
+        if (i1 > 0.0) { atomicAdd(&stats[4], i1); atomicAdd(&stats[5], i2); }
+        if (c1 > 0.0) { atomicAdd(&stats[6], c1); atomicAdd(&stats[7], c2); }
+        // max over non-negative doubles through their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long *>(&stats[2]), (unsigned long long)__double_as_longlong((double)ml));
+        if (bad) atomicAdd(&stats[3], (double)bad);
+    }
+}
+
+// key[i] = the first `bits` bits of code(gram at i) code(gram at i + k) ...  Per tile: (1) the digits of the tile's
+// symbols (+ the look-ahead a key can reach) into shared memory; (2) the gram at every position by a rolling base-B
+// number, its table entry -- a 4-byte load whose hot part (the grams that occur: 16 KB for DNA) stays in L1 -- into
+// shared memory; (3) a key = the entries at i, i + k, i + 2k, ... OR-ed in at the bits consumed so far (the code word
+// sits left-aligned in the entry: one 64-bit shift per gram).  Persistent, digit histograms fused, BWT symbol in the
+// top byte as in sa_pack0_kernel.
+constexpr int GRAM_LOOK = GRAM_PER_KEY * GRAM_MAX_K;            // positions a key can reach beyond its own
+template <int PASSES, bool CARRY>
+__global__ void __launch_bounds__(PACK_THREADS, 6)
+sa_pack0_gram_kernel(const uint8_t *__restrict__ text, uint32_t n, GramCode gc, uint64_t *__restrict__ keys,
+                     uint32_t *__restrict__ ghist)
+{
+    static_assert(!CARRY || PASSES <= 7, "the carried symbol needs the top byte of the key");
+    constexpr int bits = 8 * PASSES;
+    constexpr int LOOK_THREADS = GRAM_LOOK / PACK_IPT;            // 16 threads also take a look-ahead group
+    __shared__ uint32_t s_cl[PACK_TILE + GRAM_LOOK];
+    __shared__ uint32_t s_hist[8 * RADIX];
+    __shared__ __align__(8) uint8_t s_dig[PACK_TILE + GRAM_LOOK + 16];
+    __shared__ uint8_t s_digit[256];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    s_digit[tid] = gc.digit[tid];
+    hist_zero(s_hist, PASSES);
+    const bool aligned8 = (reinterpret_cast<uintptr_t>(text) & 7) == 0;
+    const uint32_t k = gc.k, B = gc.B, pw = gc.pw;
+    const uint32_t tiles = (n + PACK_TILE - 1) / PACK_TILE;
+    __syncthreads();
+    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t base = (uint64_t)tile * PACK_TILE;
+        reinterpret_cast<uint2 *>(s_dig)[tid] = gram_digits8(text, n, base + (uint64_t)tid * PACK_IPT, aligned8, s_digit);
+        if (tid < LOOK_THREADS + 2)
+            reinterpret_cast<uint2 *>(s_dig)[PACK_THREADS + tid] =
+                gram_digits8(text, n, base + PACK_TILE + (uint64_t)tid * PACK_IPT, aligned8, s_digit);
+        __syncthreads();
+        {
+            uint32_t g[8], c[8];
+            gram_roll8(s_dig, tid * PACK_IPT, k, B, pw, g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) c[e] = __ldg(gc.tab + g[e]);
+            uint4 *dst = reinterpret_cast<uint4 *>(s_cl + tid * PACK_IPT);
+            dst[0] = make_uint4(c[0], c[1], c[2], c[3]);
+            dst[1] = make_uint4(c[4], c[5], c[6], c[7]);
+            if (tid < LOOK_THREADS) {
+                gram_roll8(s_dig, PACK_TILE + tid * PACK_IPT, k, B, pw, g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) c[e] = __ldg(gc.tab + g[e]);
+                uint4 *dl = reinterpret_cast<uint4 *>(s_cl + PACK_TILE + tid * PACK_IPT);
+                dl[0] = make_uint4(c[0], c[1], c[2], c[3]);
+                dl[1] = make_uint4(c[4], c[5], c[6], c[7]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < PACK_IPT; ++e) {
+            const uint32_t j = warp * (32u * PACK_IPT) + e * 32u + lane;
+            const uint64_t gpos = base + j;
+            uint64_t acc = 0;
+            uint32_t used = 0;
+            const uint32_t *p = s_cl + j;
+            // three grams without a test (3 x 27 bits cannot run past bit 63 of the shift count's range), then until
+            // the key is full: most keys of the DNA workload take four
+#pragma unroll
+            for (int t = 0; t < 3; ++t, p += k) {
+                const uint32_t c = *p;
+                acc |= ((uint64_t)(c & ~GRAM_LEN_MASK) << 32) >> used;
+                used += c & GRAM_LEN_MASK;
+            }
+#pragma unroll 1
+            for (int t = 3; t < GRAM_PER_KEY && used < (uint32_t)bits; ++t, p += k) {
+                const uint32_t c = *p;
+                acc |= ((uint64_t)(c & ~GRAM_LEN_MASK) << 32) >> used;
+                used += c & GRAM_LEN_MASK;
+            }
+            const uint64_t key = acc >> (64 - bits);
+            const bool valid = gpos < n;
+            if (valid) {
+                if (CARRY) keys[gpos] = key | ((uint64_t)__ldg(text + (gpos ? gpos - 1 : (uint64_t)n - 1)) << 56);
+                else keys[gpos] = key;
+            }
+            hist_add_key_unsorted<PASSES>(s_hist, key, valid);
+        }
+        __syncthreads();      // the next tile overwrites the digits and the entries
+    }
+    hist_flush(s_hist, ghist, PASSES);
+}
+
 // ---------------------------------------------------------------- later rounds: key build
 // key[j] = (group start << b2) | (rank(idx + h) + 1), low part 0 when idx + h >= n.
 //
@@ -243,6 +500,7 @@ struct LazyRank {
     int bits;                  // width of a round-0 key
     int shift;                 // key >> shift = bucket id
     uint64_t mask;             // the sorted bits of a round-0 key (the top byte may carry the BWT symbol)
+    GramCode gram;             // gram.tab != nullptr: round-0 keys come from the k-gram code
 };
 
 constexpr int LAZY_BUCKET_BITS = 20;
@@ -280,10 +538,11 @@ template <bool COHERENT = false>
 __device__ __forceinline__ uint32_t lazy_rank_lookup(const LazyRank &lz, const uint32_t *s_code, const uint8_t *s_len,
                                                      uint32_t n, uint32_t t, const uint32_t *rank)
 {
-    const uint64_t key = alpha_pack(s_code, s_len, lz.bits, [&](int q) {
-        const uint64_t g = (uint64_t)t + q;
-        return g < n ? (uint32_t)lz.text[g] : 256u;
-    });
+    const uint64_t key = lz.gram.tab ? gram_key(lz.gram, lz.text, n, t, lz.bits)
+                                     : alpha_pack(s_code, s_len, lz.bits, [&](int q) {
+                                           const uint64_t g = (uint64_t)t + q;
+                                           return g < n ? (uint32_t)lz.text[g] : 256u;
+                                       });
     const uint32_t v = (uint32_t)(key >> lz.shift);
     uint32_t lo = __ldg(lz.bucket + v), hi = __ldg(lz.bucket + v + 1);
     if (hi - lo > (2u << LAZY_SAMPLE_SHIFT)) {
@@ -776,6 +1035,8 @@ struct SaBuffers {
     uint64_t *hist64;
     uint32_t *bucket;
     uint64_t *samples;
+    uint32_t *gram_tab, *gram_hist;
+    uint64_t *gram_cum, *gram_stats;
     SortScratch sort;
 };
 
@@ -798,6 +1059,10 @@ SaBuffers carve_sa(Carver &c, uint64_t n)
     b.hist64 = c.take<uint64_t>(256);
     b.bucket = c.take<uint32_t>((1u << LAZY_BUCKET_BITS) + 2);
     b.samples = c.take<uint64_t>((n >> LAZY_SAMPLE_SHIFT) + 2);
+    b.gram_tab = c.take<uint32_t>(GRAM_MAX_G);
+    b.gram_hist = c.take<uint32_t>(GRAM_MAX_G);
+    b.gram_cum = c.take<uint64_t>(GRAM_MAX_G + 1);
+    b.gram_stats = c.take<uint64_t>(8);
     b.sort = carve_sort_scratch(c, n);
     return b;
 }
@@ -849,6 +1114,78 @@ static int sa_build_impl(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint
     make_round0_plan(h_hist, r0, /*want_carry=*/d_bwt != nullptr);
     const AlphaCode &ac = r0.ac;
     const uint32_t sigma = r0.sigma;
+    const uint32_t N = (uint32_t)n;
+    // ---- the k-gram code (suffix_array.cuh): sampled gram histogram -> code built on the device -> its statistics
+    //      decide the key width.  Small texts and failures keep the per-symbol code of the plan above.
+    GramCode &gc = r0.gram;
+    gc.tab = nullptr;
+    {
+        SaBuffers &B_ = B;
+        const char *e = getenv("HKCSA_GRAM");
+        const uint32_t B = sigma + 1;
+        uint32_t k = 1, G = B;
+        while (k < (uint32_t)GRAM_MAX_K && (uint64_t)G * B <= (uint64_t)GRAM_MAX_G) { G *= B; ++k; }
+        if (n >= 1024 && k >= (uint32_t)GRAM_MIN_K && !(e && atoi(e) == 0)) {
+            memset(gc.digit, 0, sizeof(gc.digit));
+            uint32_t dgt = 0;
+            for (int ch = 0; ch < 256; ++ch)
+                if (h_hist[ch]) gc.digit[ch] = (uint8_t)++dgt;      // k >= 4 means B <= 19
+            gc.k = k; gc.B = B; gc.G = G;
+            gc.pw = 1;
+            for (uint32_t q = 1; q < k; ++q) gc.pw *= B;
+            const uint32_t tiles = (N + PACK_TILE - 1) / PACK_TILE;
+            const uint32_t stride = std::max<uint32_t>(1, tiles / 256);           // about half a million samples at most
+            double *h_gs = reinterpret_cast<double *>(pin + 2560);
+            HK_CUDA(cudaMemsetAsync(B_.gram_hist, 0, (size_t)G * sizeof(uint32_t), st));
+            {
+                prof::Scope ps(st, prof::OTHER, (uint64_t)N / stride + (uint64_t)G * 24);
+                gram_hist_kernel<<<(tiles + stride - 1) / stride, PACK_THREADS, 0, st>>>(d_text, N, gc, stride, B_.gram_hist);
+                HK_LAUNCH_CHECK();
+                gram_scan_kernel<<<1, 1024, 0, st>>>(B_.gram_hist, G, B_.gram_cum, reinterpret_cast<double *>(B_.gram_stats));
+                HK_LAUNCH_CHECK();
+                gram_assign_kernel<<<(G + 63) / 64, 64, 0, st>>>(B_.gram_cum, B_.gram_hist, G, B, B_.gram_tab,
+                                                                 reinterpret_cast<double *>(B_.gram_stats));
+                HK_LAUNCH_CHECK();
+            }
+            HK_CUDA(cudaMemcpyAsync(h_gs, B_.gram_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            HK_CUDA(cudaStreamSynchronize(st));
+            if (h_gs[0] > 0 && h_gs[3] == 0 && h_gs[2] >= 1 && h_gs[2] <= (double)GRAM_MAX_LEN) {
+                gc.tab = B_.gram_tab;
+                const double samples = h_gs[0];
+                const double gram_len = h_gs[1] / samples;                          // mean code bits per gram
+                const double mu = h_gs[4] / samples;                                // information per gram: mean ...
+                const double var = std::max(1e-9, h_gs[5] / samples - mu * mu);     // ... and variance
+                const int gram_max_len = (int)h_gs[2];
+                const int min_bits = std::max(16, 8 * ((gram_max_len + 7) / 8));    // a key holds at least one whole gram
+                const double h_rate = h_gs[6] / samples;                            // information of a symbol given the k - 1 before it
+                const double h_var = std::max(1e-9, h_gs[7] / samples - h_rate * h_rate);
+                // Key width: the narrowest whose predicted survivors stay under 0.5 % of the suffixes.  A key of `cand`
+                // code bits covers s = cand * k / gram_len symbols; their information is about normal with the first
+                // gram's marginal mean / variance plus, per further symbol, the conditional ones (the text's entropy
+                // rate at order k - 1: the marginal statistics of DNA 6-grams are nearly flat, the skew sits in the
+                // conditionals).  A suffix survives round 0 when its key is likelier than 1 / n.  A survivor costs
+                // about as much as 40 elements of a radix pass, so a pass is worth dropping while it adds less than
+                // 2.5 % survivors; the prediction ran 4x low on the DNA workload, hence 0.5 %.
+                int bits = 64;
+                for (int cand = min_bits; cand <= 64; cand += 8) {
+                    const double more = std::max(0.0, cand * (double)k / gram_len - k);
+                    const double z = (log2((double)n) - (mu + more * h_rate)) / sqrt(var + more * h_var);
+                    if (0.5 * erfc(-z / sqrt(2.0)) <= 0.005) { bits = cand; break; }
+                }
+                if (getenv("HKCSA_DEBUG_PLAN"))
+                    fprintf(stderr, "[hkcsa] gram code: k=%u B=%u G=%u samples=%.0f len/gram=%.3f max_len=%d info/gram=%.3f var=%.3f "
+                            "rate=%.3f var=%.3f -> bits0=%d\n", k, B, G, samples, gram_len, gram_max_len, mu, var, h_rate, h_var, bits);
+                const char *c56 = getenv("HKCSA_CARRY56");
+                if (d_bwt && bits > 56 && c56 && atoi(c56)) bits = 56;
+                if (const char *eb = getenv("HKCSA_BITS0")) bits = std::max(min_bits, std::min(64, 8 * (atoi(eb) / 8)));
+                r0.bits0 = bits;
+                r0.max_len = gram_max_len;
+                r0.k0 = (int)k * std::max(1, std::min(GRAM_PER_KEY, bits / gram_max_len));
+                r0.passes0 = bits / 8;
+            }
+        }
+    }
+    stats.gram_k = gc.tab ? gc.k : 0;
     const int max_len = r0.max_len, bits0 = r0.bits0, k0 = r0.k0, passes0 = r0.passes0;
     stats.sigma = sigma;
     memcpy(stats.byte_hist, h_hist, sizeof(stats.byte_hist));
@@ -859,7 +1196,6 @@ static int sa_build_impl(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint
     stats.bwt_carried = carry ? 1u : 0u;
     const uint64_t mask0 = bits0 >= 64 ? ~0ULL : ((1ULL << bits0) - 1ULL);
 
-    const uint32_t N = (uint32_t)n;
     HK_CUDA(cudaMemsetAsync(B.sort.hist, 0, 8 * RADIX * sizeof(uint32_t), st));
     // Round 0.  The value ping-pong is (d_sa, val[0]) arranged so the sorted suffix ids land in d_sa:
     // the suffix array of round 0 needs no extra copy.
@@ -869,6 +1205,18 @@ static int sa_build_impl(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint
     {
         const uint32_t blocks = std::min<uint32_t>((N + PACK_TILE - 1) / PACK_TILE, (uint32_t)num_sms() * 6u);
         prof::Scope ps(st, prof::SA_PACK0, (uint64_t)N * 9);
+        if (gc.tab) {
+#define HK_PACKG(P)                                                                                                 \
+    case P:                                                                                                          \
+        if (carry) sa_pack0_gram_kernel<P, true><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, gc, ka, B.sort.hist);  \
+        else sa_pack0_gram_kernel<P, false><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, gc, ka, B.sort.hist);       \
+        break;
+            switch (passes0) {
+                HK_PACKG(2) HK_PACKG(3) HK_PACKG(4) HK_PACKG(5) HK_PACKG(6) HK_PACKG(7)
+                default: sa_pack0_gram_kernel<8, false><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, gc, ka, B.sort.hist); break;
+            }
+#undef HK_PACKG
+        } else {
 #define HK_PACK0(P)                                                                                              \
     case P:                                                                                                       \
         if (carry) sa_pack0_kernel<P, true><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, (uint32_t)max_len, ka, B.sort.hist);     \
@@ -879,6 +1227,7 @@ static int sa_build_impl(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint
             default: sa_pack0_kernel<8, false><<<blocks, PACK_THREADS, 0, st>>>(d_text, N, ac, (uint32_t)max_len, ka, B.sort.hist); break;
         }
 #undef HK_PACK0
+        }
         HK_LAUNCH_CHECK();
     }
     HK_CUDA(radix_sort_pairs_u64(ka, va, kb, vb, N, passes0, B.sort, st, /*identity_vals=*/true));
@@ -902,6 +1251,7 @@ static int sa_build_impl(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint
     const int bucket_bits = std::min(LAZY_BUCKET_BITS, bits0);
     lz.shift = bits0 - bucket_bits;
     lz.mask = mask0;
+    lz.gram = gc;
     uint64_t *kx = nullptr, *ky = nullptr;             // key ping-pong of the later rounds
     uint32_t *vfree = B.val[1];                        // free value buffer (receives the compacted ids)
     uint32_t *vother = B.val[0];                       // the round-0 sort's other value buffer: free from here on

@@ -44,6 +44,8 @@ class SaStats(C.Structure):
         ("byte_hist", C.c_uint64 * 256),
         ("key_bits0", C.c_uint32),
         ("bwt_carried", C.c_uint32),
+        ("gram_k", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
