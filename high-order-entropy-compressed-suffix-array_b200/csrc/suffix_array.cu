@@ -278,85 +278,82 @@ gram_hist_kernel(const uint8_t *__restrict__ text, uint32_t n, GramCode gc, uint
         if (p0 + e < n) atomicAdd(&gh[g[e]], 1u);
 }
 
-// one CTA: w[g] = 16 * count + s (s = max(1, samples / G): the unseen grams together weigh 1/16 of the seen ones, which
-// bounds every code length by log2(17 G) + 2 <= 23 bits), cum[] = exclusive prefix sums, cum[G] = total weight
+// Weights w[g] = 16 * count + smooth (smooth = max(1, samples / G): the unseen grams together weigh 1/16 of the seen
+// ones, which bounds every code length by log2(17 G) + 2 <= 23 bits).  CTA c scans chunk c of 4096 grams: cum[] =
+// exclusive prefix sums inside the chunk, ctot[c] = the chunk's weight; gram_assign_kernel adds the chunks before.
+constexpr int GRAM_CHUNK = 4096;
+constexpr int GRAM_MAX_CHUNKS = GRAM_MAX_G / GRAM_CHUNK;
 __global__ void __launch_bounds__(1024)
-gram_scan_kernel(const uint32_t *__restrict__ gh, uint32_t G, uint64_t *__restrict__ cum, double *__restrict__ stats)
+gram_scan_kernel(const uint32_t *__restrict__ gh, uint32_t G, uint64_t smooth, uint64_t *__restrict__ cum,
+                 uint64_t *__restrict__ ctot)
 {
     __shared__ uint64_t s_w[32];
-    __shared__ uint64_t s_smooth;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    // every thread owns `per` consecutive grams (a multiple of 4: 16-byte loads)
-    const uint32_t per = ((G + 1023) / 1024 + 3) & ~3u;
-    const uint32_t g0 = tid * per;
-    uint64_t cnt = 0;
-    for (uint32_t q = 0; q < per; q += 4) {
-        if (g0 + q + 4 <= G) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(gh + g0 + q);
-            cnt += (uint64_t)v.x + v.y + v.z + v.w;
-        } else {
-            for (uint32_t r = 0; r < 4; ++r) if (g0 + q + r < G) cnt += gh[g0 + q + r];
-        }
+    const uint32_t g0 = blockIdx.x * GRAM_CHUNK + tid * 4u;
+    uint64_t w[4] = {0, 0, 0, 0};
+    if (g0 + 4 <= G && (G & 3u) == 0) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(gh + g0);
+        w[0] = 16ull * v.x + smooth; w[1] = 16ull * v.y + smooth; w[2] = 16ull * v.z + smooth; w[3] = 16ull * v.w + smooth;
+    } else {
+        for (int q = 0; q < 4; ++q) if (g0 + q < G) w[q] = 16ull * gh[g0 + q] + smooth;
     }
-    uint64_t x = cnt;
+    const uint64_t sum = w[0] + w[1] + w[2] + w[3];
+    uint64_t x = sum;
     for (int o = 1; o < 32; o <<= 1) {
         const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= (uint32_t)o) x += y;
     }
     if (lane == 31) s_w[warp] = x;
     __syncthreads();
-    uint64_t pre = 0, tot = 0;
-    for (uint32_t w = 0; w < 32; ++w) { if (w < warp) pre += s_w[w]; tot += s_w[w]; }
-    if (tid == 0) {
-        s_smooth = tot / G > 1 ? tot / G : 1;
-        stats[0] = (double)tot;         // samples
-        stats[1] = 0;                   // sum of count * len            (gram_assign_kernel)
-        stats[2] = 0;                   // longest code word
-        stats[3] = 0;                   // failures
-        stats[4] = 0;                   // sum of count * log2(samples / count)
-        stats[5] = 0;                   // sum of count * log2(samples / count)^2
-        stats[6] = 0;                   // sum of count * log2(count of the (k-1)-prefix / count): information of the k-th
-        stats[7] = 0;                   // ... and its square                                      symbol given k - 1
+    uint64_t pre = 0;
+    for (uint32_t q = 0; q < warp; ++q) pre += s_w[q];
+    uint64_t run = pre + x - sum;
+    for (int q = 0; q < 4; ++q) {
+        if (g0 + q < G) cum[g0 + q] = run;
+        run += w[q];
     }
-    __syncthreads();
-    const uint64_t smooth = s_smooth;
-    const uint32_t mine = g0 < G ? min(per, G - g0) : 0u;
-    // exclusive prefix of the weights: 16 * (counts before) + smooth * (grams before)
-    uint64_t run = 16ull * (pre + x - cnt) + smooth * (uint64_t)min(g0, G);
-    for (uint32_t q = 0; q < mine; ++q) {
-        cum[g0 + q] = run;
-        run += 16ull * gh[g0 + q] + smooth;
-    }
-    if (tid == 1023) cum[G] = 16ull * tot + smooth * (uint64_t)G;
+    if (tid == 1023) ctot[blockIdx.x] = pre + x;
 }
 
 // every leaf walks down from the root: a node [lo, hi) splits where its two halves weigh most alike (binary search on
 // cum); left = 0, right = 1.  All leaves of a node compute the same split, so the codes are prefix-free and ordered.
 __global__ void __launch_bounds__(64)
-gram_assign_kernel(const uint64_t *__restrict__ cum, const uint32_t *__restrict__ gh, uint32_t G, uint32_t B,
-                   uint32_t *__restrict__ tab, double *__restrict__ stats)
+gram_assign_kernel(const uint64_t *__restrict__ cum, const uint64_t *__restrict__ ctot, const uint32_t *__restrict__ gh,
+                   uint32_t G, uint32_t B, double samples, uint32_t *__restrict__ tab, double *__restrict__ stats)
 {
+    __shared__ uint64_t s_off[GRAM_MAX_CHUNKS + 1];
+    const uint32_t nchunks = (G + GRAM_CHUNK - 1) / GRAM_CHUNK;
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (uint32_t c = 0; c < nchunks; ++c) { s_off[c] = run; run += ctot[c]; }
+        s_off[nchunks] = run;
+    }
+    __syncthreads();
+    // global exclusive prefix at x (x == G: the total weight)
+    auto cumv = [&](uint32_t x) -> uint64_t { return x >= G ? s_off[nchunks] : cum[x] + s_off[x / GRAM_CHUNK]; };
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t len = 0, code = 0;
     bool ok = true;
     if (g < G) {
         uint32_t lo = 0, hi = G;
-        uint64_t clo = 0, chi = cum[G];
+        uint64_t clo = 0, chi = cumv(G);
         while (hi - lo > 1) {
             const uint64_t target = clo + chi;                  // twice the midpoint weight
             uint32_t a = lo + 1, b = hi - 1;                     // smallest sp in [lo + 1, hi - 1] with 2 cum[sp] >= target
             while (a < b) {
                 const uint32_t mid = a + ((b - a) >> 1);
-                if (2 * cum[mid] >= target) b = mid; else a = mid + 1;
+                if (2 * cumv(mid) >= target) b = mid; else a = mid + 1;
             }
             uint32_t sp = a;
+            uint64_t csp = cumv(sp);
             if (sp > lo + 1) {
-                const uint64_t hi_d = 2 * cum[sp] >= target ? 2 * cum[sp] - target : target - 2 * cum[sp];
-                const uint64_t lo_d = target - 2 * cum[sp - 1];   // 2 cum[sp - 1] < target
-                if (lo_d <= hi_d) sp = sp - 1;
+                const uint64_t cpr = cumv(sp - 1);                // 2 cum[sp - 1] < target
+                const uint64_t hi_d = 2 * csp >= target ? 2 * csp - target : target - 2 * csp;
+                const uint64_t lo_d = target - 2 * cpr;
+                if (lo_d <= hi_d) { sp = sp - 1; csp = cpr; }
             }
-            if (g < sp) { hi = sp; chi = cum[sp]; code <<= 1; }
-            else { lo = sp; clo = cum[sp]; code = (code << 1) | 1u; }
+            if (g < sp) { hi = sp; chi = csp; code <<= 1; }
+            else { lo = sp; clo = csp; code = (code << 1) | 1u; }
             if (++len > (uint32_t)GRAM_MAX_LEN) { ok = false; break; }
         }
         if (len == 0) len = 1;                                  // a single leaf (G == 1)
@@ -366,7 +363,7 @@ gram_assign_kernel(const uint64_t *__restrict__ cum, const uint32_t *__restrict_
     const double c = (g < G) ? (double)gh[g] : 0.0;
     double wl = ok ? c * len : 0.0, i1 = 0.0, i2 = 0.0, c1 = 0.0, c2 = 0.0;
     if (c > 0.0) {
-        const double lp = log2(stats[0] / c);
+        const double lp = log2(samples / c);
         i1 = c * lp;
         i2 = c * lp * lp;
         // the grams sharing this one's first k - 1 digits are the B consecutive table entries around it
@@ -1061,7 +1058,7 @@ SaBuffers carve_sa(Carver &c, uint64_t n)
     b.samples = c.take<uint64_t>((n >> LAZY_SAMPLE_SHIFT) + 2);
     b.gram_tab = c.take<uint32_t>(GRAM_MAX_G);
     b.gram_hist = c.take<uint32_t>(GRAM_MAX_G);
-    b.gram_cum = c.take<uint64_t>(GRAM_MAX_G + 1);
+    b.gram_cum = c.take<uint64_t>(GRAM_MAX_G + 8 + GRAM_MAX_CHUNKS + 8);      // per-chunk prefix sums, then the chunk totals
     b.gram_stats = c.take<uint64_t>(8);
     b.sort = carve_sort_scratch(c, n);
     return b;
@@ -1137,21 +1134,27 @@ static int sa_build_impl(const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint
             const uint32_t stride = std::max<uint32_t>(1, tiles / 256);           // about half a million samples at most
             double *h_gs = reinterpret_cast<double *>(pin + 2560);
             HK_CUDA(cudaMemsetAsync(B_.gram_hist, 0, (size_t)G * sizeof(uint32_t), st));
+            HK_CUDA(cudaMemsetAsync(B_.gram_stats, 0, 8 * sizeof(uint64_t), st));
+            // the sampled positions: every stride-th tile of 2048
+            uint64_t nsamp = 0;
+            for (uint32_t t = 0; t < tiles; t += stride) nsamp += std::min<uint64_t>(PACK_TILE, n - (uint64_t)t * PACK_TILE);
+            const uint64_t smooth = std::max<uint64_t>(1, nsamp / G);
+            uint64_t *d_ctot = B_.gram_cum + GRAM_MAX_G + 8;
             {
                 prof::Scope ps(st, prof::OTHER, (uint64_t)N / stride + (uint64_t)G * 24);
                 gram_hist_kernel<<<(tiles + stride - 1) / stride, PACK_THREADS, 0, st>>>(d_text, N, gc, stride, B_.gram_hist);
                 HK_LAUNCH_CHECK();
-                gram_scan_kernel<<<1, 1024, 0, st>>>(B_.gram_hist, G, B_.gram_cum, reinterpret_cast<double *>(B_.gram_stats));
+                gram_scan_kernel<<<(G + GRAM_CHUNK - 1) / GRAM_CHUNK, 1024, 0, st>>>(B_.gram_hist, G, smooth, B_.gram_cum, d_ctot);
                 HK_LAUNCH_CHECK();
-                gram_assign_kernel<<<(G + 63) / 64, 64, 0, st>>>(B_.gram_cum, B_.gram_hist, G, B, B_.gram_tab,
-                                                                 reinterpret_cast<double *>(B_.gram_stats));
+                gram_assign_kernel<<<(G + 63) / 64, 64, 0, st>>>(B_.gram_cum, d_ctot, B_.gram_hist, G, B, (double)nsamp,
+                                                                 B_.gram_tab, reinterpret_cast<double *>(B_.gram_stats));
                 HK_LAUNCH_CHECK();
             }
             HK_CUDA(cudaMemcpyAsync(h_gs, B_.gram_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
             HK_CUDA(cudaStreamSynchronize(st));
-            if (h_gs[0] > 0 && h_gs[3] == 0 && h_gs[2] >= 1 && h_gs[2] <= (double)GRAM_MAX_LEN) {
+            if (nsamp > 0 && h_gs[3] == 0 && h_gs[2] >= 1 && h_gs[2] <= (double)GRAM_MAX_LEN) {
                 gc.tab = B_.gram_tab;
-                const double samples = h_gs[0];
+                const double samples = (double)nsamp;
                 const double gram_len = h_gs[1] / samples;                          // mean code bits per gram
                 const double mu = h_gs[4] / samples;                                // information per gram: mean ...
                 const double var = std::max(1e-9, h_gs[5] / samples - mu * mu);     // ... and variance

@@ -130,7 +130,8 @@ def test_sa_bwt_oracle(E, name):
     assert host(E.bwt(d_text, sa)).tobytes() == O.bwt_transform(text, want).tobytes()
 
 
-@pytest.mark.parametrize("env", [{}, {"HKCSA_CARRY56": "1"}, {"HKCSA_BITS0": "24"}, {"HKCSA_BITS0": "56", "HKCSA_NO_GROUP_ROUND": "1"}])
+@pytest.mark.parametrize("env", [{}, {"HKCSA_CARRY56": "1"}, {"HKCSA_BITS0": "24"}, {"HKCSA_BITS0": "56", "HKCSA_NO_GROUP_ROUND": "1"},
+                                 {"HKCSA_GRAM": "0", "HKCSA_CARRY56": "1"}])
 @pytest.mark.parametrize("name", list(TEXTS))
 def test_sa_bwt_one_call(E, name, env, monkeypatch):
     """hkcsa_sa_bwt_build: the BWT symbol rides in the top byte of the round-0 key (keys of at most 56 bits) or the
@@ -149,6 +150,30 @@ def test_sa_bwt_one_call(E, name, env, monkeypatch):
         assert st.bwt_carried == 1 and st.key_bits0 <= 56
     else:
         assert st.bwt_carried == (1 if st.key_bits0 <= 56 else 0)
+
+
+@pytest.mark.parametrize("name", ["dna_300k", "dna_1m_dollar", "rand2_100k", "runs", "fib", "all_a_5000", "ab_period", "eng_300k"])
+def test_round0_key_code_over_grams(E, name, monkeypatch):
+    """Small alphabets key round 0 with the order-preserving code over k-grams (k >= 4; built on the device from a
+    sampled gram histogram), larger ones with the per-symbol code; HKCSA_GRAM=0 forces the latter.  Same suffix array
+    either way, and narrow keys (many survivors: the lazy look-ups recompute gram keys from the text) agree too."""
+    text = TEXTS[name]
+    d_text = dev(E, text)
+    want = O.build_suffix_array(text)
+    st = E.SaStats()
+    sa = E.suffix_array(d_text, st)
+    assert np.array_equal(host(sa).astype(np.uint32), want)
+    sigma = len(set(text))
+    assert (st.gram_k >= 4) == (sigma <= 18), (st.gram_k, sigma)
+    monkeypatch.setenv("HKCSA_GRAM", "0")
+    st0 = E.SaStats()
+    assert np.array_equal(host(E.suffix_array(d_text, st0)).astype(np.uint32), want) and st0.gram_k == 0
+    monkeypatch.delenv("HKCSA_GRAM")
+    for bits, extra in (("24", {}), ("32", {"HKCSA_NO_GROUP_ROUND": "1"})):
+        monkeypatch.setenv("HKCSA_BITS0", bits)
+        for k, v in extra.items():
+            monkeypatch.setenv(k, v)
+        assert np.array_equal(host(E.suffix_array(d_text)).astype(np.uint32), want)
 
 
 @pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 4095, 4097, 100_003])
