@@ -7,7 +7,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-fil
 echo launches rc=$?
 ncu --set full --clock-control none --import-source on -k regex:onesweep64 -s 8 -c 2 -o gpurun_out/r02s2_onesweep $CMD > gpurun_out/ncu_onesweep.log 2>&1
 echo onesweep rc=$?
-ncu --set full --clock-control none -k regex:"sa_pack0|seg_apply|seg_reduce|seg_scan|wt_levels|wt_tile_hist|wt_count_all|wt_dir_fix_all|ssa_mark_sample|group_sort" -s 0 -c 14 -o gpurun_out/r02s2_build_others $CMD > gpurun_out/ncu_others.log 2>&1
+ncu --set full --clock-control none -k regex:"sa_pack0|gram_|seg_apply|seg_reduce|seg_scan|wt_levels|wt_tile_hist|wt_count_all|wt_dir_fix_all|ssa_mark_pack|ssa_fix_sample|group_sort" -s 0 -c 18 -o gpurun_out/r02s2_build_others $CMD > gpurun_out/ncu_others.log 2>&1
 echo others rc=$?
 CMD3="python bench.py --workload c3 --steps 1 --warmup 1 --no-queries --no-cpu-baseline"
 ncu --set full --clock-control none -k regex:"wt_levels|wt_tile_hist|bwt_gather|sa_keybuild|seg_apply|sa_pack0" -s 0 -c 10 -o gpurun_out/r02s2_build_c3 $CMD3 > gpurun_out/ncu_c3.log 2>&1
