@@ -344,8 +344,9 @@ def run_dist_build(args, world, rank, dev, barrier, max_over_ranks, sum_over_ran
                        "frac_of_900GBps_over_whole_build": bytes_in / (ms / 1e3) / 1e9 / NVLINK_GBS,
                        "exchange_phase_GBps": ((bytes_in - (n_big - blk.numel())) / (phases["pack_exchange"] / 1e3) / 1e9
                                                if phases.get("pack_exchange") else None),
-                       "text_allgather_GBps": ((n_big - blk.numel()) / (phases["text_allgather"] / 1e3) / 1e9
-                                               if phases.get("text_allgather") else None)},
+                       "text_allgather": "in-place all-gather left running on NCCL's stream beside the histograms, the "
+                                         "exchange and the round-0 sort; phases text_allgather / text_wait = its set-up "
+                                         "and what was left of it when the refinement rounds needed the text"},
             "properties_at_full_size": props, "properties_ok": ok_props,
         })
         assert ok_props, f"distributed build failed its full-size checks: {props}"

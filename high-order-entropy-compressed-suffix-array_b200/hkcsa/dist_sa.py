@@ -67,6 +67,8 @@ def exchange_layout_from_counts(cuts, cnt: np.ndarray):
     return np.asarray(cuts, dtype=np.int64), cnt, counts, slice_off
 
 
+EDGE_HEAD, EDGE_TAIL = 2304, 8  # bytes of the next / previous block a rank's own kernels may read: the last tile of 2048
+                                # positions + 64 symbols of look-ahead past the block's end; the byte before its start
 HIST_SAMPLE_MIN = 1 << 24      # blocks of at least this many positions take their cut points from a sampled histogram
 HIST_SAMPLE_STRIDE = 8         # ... of every 8th tile of 2048 positions
 
@@ -108,8 +110,9 @@ def _align(x: int, a: int = 256) -> int:
 
 def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: bool, ext_rounds_max: int,
                   group_round: bool = True, hist_stride: int | None = None):
-    """One rank's build as a generator.  Yields ("gather", array) -> [world, len] int64 numpy; ("text", block,
-    sizes) -> the whole text; ("symm", nbytes) -> (uint8 tensor, [address of every rank's buffer]); ("barrier",)."""
+    """One rank's build as a generator.  Yields ("gather", array) -> [world, len] int64 numpy; ("text_async", block,
+    sizes) -> (the text buffer with this rank's block and its edges in place, wait function for the rest);
+    ("symm", nbytes) -> (uint8 tensor, [address of every rank's buffer]); ("barrier",)."""
     L = _lib.load()
     dev = block.device
     phases: dict = {}
@@ -131,7 +134,10 @@ def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: boo
     if n > (1 << 40):
         raise _lib.HkcsaError(_lib.ERANGE, f"text of {n} symbols exceeds 2^40")
     starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    text = yield ("text", block, sizes)
+    # The blocks travel while this rank already works on its own: histograms, cut points and the bucket exchange read
+    # the rank's own block only (+ the first bytes of the next block for the keys at its end and the last byte of the
+    # block before it), the whole text is first needed by the refinement rounds -- text_ready() makes the stream wait.
+    text, text_ready = yield ("text_async", block, sizes)
     begin, end = int(starts[rank]), int(starts[rank + 1])
     tick("text_allgather")
     # ---- 2. one prefix code and one set of cut points for everybody
@@ -198,6 +204,8 @@ def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: boo
     check(L.hkcsa_dsa_begin(state, C.byref(plan), _ptr(text), _ptr(keys), _ptr(ids64) if is_wide else _ptr(val_a),
                             _ptr(val_a), _ptr(val_b), M, cap, _ptr(scratch), nscratch, _stream()))
     tick("sort_round0")
+    text_ready()
+    tick("text_wait")
     slice_ptr = L.hkcsa_dsa_slice(state) or (val_a.data_ptr())
     off_slice = off_va if slice_ptr == val_a.data_ptr() else off_vb
     ext_done, dbl_done, prev_all = 0, 0, None
@@ -302,16 +310,28 @@ def _torch_run(prog, group, device):
                 x = req[1]
                 t = x.to(torch.int64) if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(device)
                 res = _all_gather_rows(t, world, group).cpu().numpy()
-            elif kind == "text":
+            elif kind == "text_async":
                 block, sizes = req[1], [int(v) for v in req[2]]
-                if len(set(sizes)) == 1:                        # equal blocks: the gathered buffer IS the text
-                    res = _all_gather_rows(block, world, group).reshape(-1)
+                if len(set(sizes)) == 1 and sizes[0] >= EDGE_HEAD + EDGE_TAIL and hasattr(dist, "all_gather_into_tensor"):
+                    # equal blocks: ONE in-place all-gather into the text buffer, left running on NCCL's stream.  The
+                    # edges (first bytes / last bytes of every block) go ahead in a small collective of their own.
+                    m = sizes[0]
+                    text = torch.empty(m * world, dtype=torch.uint8, device=device)
+                    own = text[rank * m:(rank + 1) * m]
+                    own.copy_(block)
+                    edges = _all_gather_rows(torch.cat([block[:EDGE_HEAD], block[m - EDGE_TAIL:]]), world, group)
+                    if rank + 1 < world:
+                        text[(rank + 1) * m:(rank + 1) * m + EDGE_HEAD] = edges[rank + 1, :EDGE_HEAD]
+                    if rank > 0:
+                        text[rank * m - EDGE_TAIL:rank * m] = edges[rank - 1, EDGE_HEAD:]
+                    work = dist.all_gather_into_tensor(text, own, group=group, async_op=True)
+                    res = (text, work.wait)
                 else:                                           # one collective on padded blocks, then compaction
                     width = max(sizes)
                     pad = torch.zeros(width, dtype=torch.uint8, device=device)
                     pad[: block.numel()] = block
                     allb = _all_gather_rows(pad, world, group)
-                    res = torch.cat([allb[r, : sizes[r]] for r in range(world)])
+                    res = (torch.cat([allb[r, : sizes[r]] for r in range(world)]), lambda: None)
             elif kind == "symm":
                 need = torch.tensor([int(req[1])], dtype=torch.int64, device=device)
                 dist.all_reduce(need, op=dist.ReduceOp.MAX, group=group)
@@ -374,9 +394,9 @@ def emulate_distributed_suffix_array(blocks, wide: bool | None = None, ext_round
             rows = [reqs[r][1].cpu().numpy() if isinstance(reqs[r][1], torch.Tensor) else np.asarray(reqs[r][1])
                     for r in live]
             res = [np.stack(rows).astype(np.int64)] * world
-        elif kind == "text":
+        elif kind == "text_async":
             full = torch.cat([reqs[r][1] for r in live])
-            res = [full] * world
+            res = [(full, lambda: None)] * world
         elif kind == "symm":
             need = max(int(reqs[r][1]) for r in live)
             bufs = [torch.empty(need, dtype=torch.uint8, device=dev) for _ in live]
