@@ -297,6 +297,21 @@ def _all_gather_rows(t: torch.Tensor, world: int, group) -> torch.Tensor:
     return torch.stack(parts)
 
 
+_SIDE_GROUPS: dict = {}
+
+
+def _side_group(group):
+    """A second communicator over the same ranks, for the text all-gather that runs beside the build: collectives of
+    one communicator execute in order, so the small all-gathers of the build (histograms, counts) would queue up
+    behind the text on the main one.  Created once per group (collectively: every rank gets here in the same order)."""
+    import torch.distributed as dist
+    key = id(group) if group is not None else 0
+    if key not in _SIDE_GROUPS:
+        ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
+        _SIDE_GROUPS[key] = dist.new_group(ranks=ranks)
+    return _SIDE_GROUPS[key]
+
+
 def _torch_run(prog, group, device):
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -324,7 +339,7 @@ def _torch_run(prog, group, device):
                         text[(rank + 1) * m:(rank + 1) * m + EDGE_HEAD] = edges[rank + 1, :EDGE_HEAD]
                     if rank > 0:
                         text[rank * m - EDGE_TAIL:rank * m] = edges[rank - 1, EDGE_HEAD:]
-                    work = dist.all_gather_into_tensor(text, own, group=group, async_op=True)
+                    work = dist.all_gather_into_tensor(text, own, group=_side_group(group), async_op=True)
                     res = (text, work.wait)
                 else:                                           # one collective on padded blocks, then compaction
                     width = max(sizes)
