@@ -782,21 +782,33 @@ seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict_
         __syncthreads();
         return;
     }
-    uint32_t lasthead = 0, keep = 0;
 #pragma unroll
     for (int e = 0; e < SEG_IPT; ++e) {
         head[e] = (f >> e) & 1u;
         single[e] = (f >> (SEG_IPT + e)) & 1u;
-        if (head[e]) lasthead = j0 + e + 1;
-        if (j0 + e < m && !single[e]) ++keep;
     }
-    // block-wide exclusive (max, sum) scan over threads
-    const uint32_t ih = warp_incl_max(lasthead);
-    uint32_t wk_total;
-    const uint32_t ek = warp_excl_sum(keep, wk_total);
-    uint32_t eh = __shfl_up_sync(0xffffffffu, ih, 1);
-    if (lane == 0) eh = 0;
-    if (lane == 31) { s_h[warp] = ih; s_k[warp] = wk_total; }
+    // last head and survivors of this thread's eight elements straight from the flag bits
+    const uint32_t h8 = f & 0xFFu, s8 = (f >> SEG_IPT) & 0xFFu;
+    const uint32_t vm = (j0 + SEG_IPT <= m) ? 0xFFu : (j0 < m ? (1u << (m - j0)) - 1u : 0u);
+    const uint32_t lasthead = h8 ? j0 + (32u - __clz(h8)) : 0u;
+    const uint32_t keep = __popc(~s8 & vm);
+    // block-wide exclusive (max, sum) scan over threads.  The last-head values grow with the lane, so the running
+    // maximum before a lane is the value of the nearest lower lane that has a head: one ballot and one shuffle; the
+    // survivor counts (<= 8) are summed bit by bit with four ballots.
+    const uint32_t lt = lanemask_lt();
+    const uint32_t hb = __ballot_sync(0xffffffffu, h8 != 0u);
+    const uint32_t lower = hb & lt;
+    uint32_t eh = __shfl_sync(0xffffffffu, lasthead, lower ? 31 - __clz(lower) : 0);
+    if (!lower) eh = 0;
+    uint32_t ek = 0, wk_total = 0;
+#pragma unroll
+    for (int bit = 0; bit < 4; ++bit) {
+        const uint32_t kb = __ballot_sync(0xffffffffu, (keep >> bit) & 1u);
+        ek += (uint32_t)__popc(kb & lt) << bit;
+        wk_total += (uint32_t)__popc(kb) << bit;
+    }
+    const uint32_t wh = __shfl_sync(0xffffffffu, lasthead, hb ? 31 - __clz(hb) : 0);     // the warp's last head
+    if (lane == 31) { s_h[warp] = hb ? wh : 0u; s_k[warp] = wk_total; }
     __syncthreads();
     uint32_t ph = carry_head[blockIdx.x], pk = carry_keep[blockIdx.x];
     for (uint32_t w = 0; w < warp; ++w) { ph = max(ph, s_h[w]); pk += s_k[w]; }
