@@ -76,7 +76,7 @@ class CompressedSuffixArray:
         self.epsilon = epsilon
         self._smap = engine.SymbolMap(text, extra="$") if isinstance(text, str) else None
         if self._smap is not None:
-            d_text = engine.to_device_u8(self._smap.encode(text), tail=self._smap.encode("$"))
+            d_text = engine.to_device_u8(self._smap.host_bytes(text), tail=self._smap.encode("$"))
             has_sentinel = "$" in text
         else:
             d_text = engine.to_device_u8(text, tail=b"$")

@@ -20,7 +20,7 @@ class EnhancedFMIndex:
         if isinstance(text, str):
             self._text0, self._text = text, None                     # self.text = text + "$" (:9), built on first access
             self._smap = engine.SymbolMap(text, extra="$")           # identity for latin-1 text
-            d_text = engine.to_device_u8(self._smap.encode(text), tail=self._smap.encode("$"))
+            d_text = engine.to_device_u8(self._smap.host_bytes(text), tail=self._smap.encode("$"))
         else:                                                        # bytes / uint8 array / tensor (extension)
             import torch
             d_text = engine.to_device_u8(text, tail=b"$")
@@ -131,6 +131,12 @@ class EnhancedFMIndex:
         above 255 on latin-1 text, or one that never occurs in a re-coded text) is a miss by definition
         (csa/enhanced_fm_index.py:27-28: unseen symbol -> rank 0 -> (-1, -1)): it is searched as the one-symbol
         pattern of a byte the text does not hold, or overridden on the host when every byte occurs."""
+        if self._smap is None or self._smap.identity:
+            try:                                     # every pattern a latin-1 str: packed without a Python loop
+                pat, off = self._E.pack_patterns(queries, self._idx.device)
+                return pat, off, []
+            except (TypeError, UnicodeEncodeError, ValueError):
+                pass
         enc, absent = [], []
         for k, q in enumerate(queries):
             if isinstance(q, str):

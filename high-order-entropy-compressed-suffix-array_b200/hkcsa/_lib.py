@@ -231,6 +231,8 @@ SIGNATURES = {
     "hkcsa_entropy_scratch_bytes": (_sz, [_u64]),
     "hkcsa_entropy_from_sa": (_i32, [_vp, _u64, _vp, _u32, C.POINTER(C.c_double), _vp, _sz, _vp]),
     "hkcsa_launch_count": (C.c_ulonglong, []),
+    "hkcsa_h2d_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "hkcsa_d2h_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "hkcsa_prof_enable": (_i32, [_i32]),
     "hkcsa_prof_enable_classes": (_i32, [_u32]),
     "hkcsa_prof_class_index": (_i32, [C.c_char_p]),

@@ -69,6 +69,8 @@ class SymbolMap:
     def __init__(self, text: str, extra: str = ""):
         self.back = None                      # identity
         self._cache = None                    # (text, its bytes): the constructor's probe is the encoding itself
+        if text.isascii():                    # O(1) flag: nothing to probe, nothing to encode (see host_bytes)
+            return
         try:
             self._cache = (text, text.encode("latin-1"))
         except UnicodeEncodeError:
@@ -96,6 +98,13 @@ class SymbolMap:
             return None
         return s.translate(self._fwd).encode("latin-1")
 
+    def host_bytes(self, s: str):
+        """What to_device_u8 is given for the text `s`: the str itself when it is ASCII under the identity map (its own
+        buffer is staged, no encoded copy), else encode(s)."""
+        if self.back is None and s.isascii():
+            return s
+        return self.encode(s)
+
     def decode(self, b: bytes) -> str:
         if self.back is None:
             return b.decode("latin-1")
@@ -105,37 +114,30 @@ class SymbolMap:
         return chr(byte) if self.back is None else self.back[byte]
 
 
-_PINNED: dict = {}
+_AsUTF8AndSize = C.pythonapi.PyUnicode_AsUTF8AndSize
+_AsUTF8AndSize.restype = C.c_void_p
+_AsUTF8AndSize.argtypes = [C.py_object, C.POINTER(C.c_ssize_t)]
 
 
-def _staged_h2d(arr: np.ndarray, device, tail: bytes = b"") -> torch.Tensor:
-    """Host bytes (+ an optional tail, e.g. the sentinel) -> device through a cached pinned staging buffer: one
-    memcpy into pinned memory and one asynchronous DMA, instead of a pageable copy (which the driver stages in
-    small chunks)."""
-    n = arr.size + len(tail)
-    key = torch.device(device).index
-    buf = _PINNED.get(key)
-    if buf is None or buf.numel() < n:
-        buf = torch.empty(max(n, 1 << 20), dtype=torch.uint8).pin_memory()
-        _PINNED[key] = buf
-    ev = _PINNED.get((key, "ev"))
-    if ev is not None:
-        ev.synchronize()                               # an earlier copy out of the staging buffer may be in flight
-    view = buf.numpy()
-    view[: arr.size] = arr
-    if tail:
-        view[arr.size:n] = np.frombuffer(tail, dtype=np.uint8)
-    out = torch.empty(n, dtype=torch.uint8, device=device)
-    out.copy_(buf[:n], non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record()
-    _PINNED[(key, "ev")] = ev
+def _staged_h2d(src, n: int, device, tail: bytes = b"") -> torch.Tensor:
+    """n pageable host bytes at `src` (an address, or an object ctypes takes for one) + an optional tail (e.g. the
+    sentinel) -> a fresh device tensor through hkcsa_h2d_staged: the library's pinned ring is filled by several host
+    threads while the DMA of the chunks already staged runs on the current stream.  Returns once the source has been
+    staged (it may be dropped); the copy completes in stream order."""
+    out = torch.empty(n + len(tail), dtype=torch.uint8, device=device)
+    L = _lib.load()
+    with torch.cuda.device(out.device):
+        if tail:                                           # first: its slot is long free when the bulk wants it
+            check(L.hkcsa_h2d_staged(out.data_ptr() + n, tail, len(tail), 1, _stream()))
+        if n:
+            check(L.hkcsa_h2d_staged(out.data_ptr(), src, n, 0, _stream()))
     return out
 
 
 def to_device_u8(data, device=None, tail: bytes = b"") -> torch.Tensor:
     """str (latin-1: utils/data_loader.py:4) / bytes / numpy / tensor -> contiguous uint8 CUDA tensor (`tail`
-    appended: the callers that add the '$' sentinel do not build a second host copy for it)."""
+    appended: the callers that add the '$' sentinel do not build a second host copy for it).  An ASCII str is staged
+    straight out of its own buffer (CPython keeps it at one byte per code point): no encoded copy is made."""
     device = device or _require_cuda()
     if isinstance(data, torch.Tensor):
         if data.dtype != torch.uint8:
@@ -145,6 +147,11 @@ def to_device_u8(data, device=None, tail: bytes = b"") -> torch.Tensor:
             d = torch.cat([d, torch.tensor(list(tail), dtype=torch.uint8, device=d.device)])
         return d
     if isinstance(data, str):
+        if data.isascii():
+            if len(data) + len(tail) == 0:
+                return torch.empty(0, dtype=torch.uint8, device=device)
+            size = C.c_ssize_t(0)
+            return _staged_h2d(_AsUTF8AndSize(data, C.byref(size)), len(data), device, tail)   # `data` outlives the call
         try:
             data = data.encode("latin-1")
         except UnicodeEncodeError:
@@ -155,7 +162,7 @@ def to_device_u8(data, device=None, tail: bytes = b"") -> torch.Tensor:
         arr = np.ascontiguousarray(data, dtype=np.uint8)
     if arr.size + len(tail) == 0:
         return torch.empty(0, dtype=torch.uint8, device=device)
-    return _staged_h2d(arr, device, tail)
+    return _staged_h2d(arr.ctypes.data, arr.size, device, tail)
 
 
 # ------------------------------------------------------------------ workload
@@ -526,15 +533,27 @@ def build_sampled_sa(sa: torch.Tensor, rate: int) -> SampledSA:
 
 
 def pack_patterns(patterns, device=None):
-    """list[str|bytes] -> (uint8[sum m], int64[P+1]) on the device."""
+    """list[str|bytes] -> (uint8[sum m], int64[P+1]) on the device.  A list of latin-1 str patterns (what the
+    reference's find_range takes, csa/enhanced_fm_index.py:21) is packed by ONE join + ONE encode and a C-level
+    len() map; anything else goes pattern by pattern."""
     device = device or _require_cuda()
-    enc = [p.encode("latin-1") if isinstance(p, str) else bytes(p) for p in patterns]
-    off = np.zeros(len(enc) + 1, dtype=np.int64)
-    if enc:
-        np.cumsum([len(e) for e in enc], out=off[1:])
-    flat = np.frombuffer(b"".join(enc), dtype=np.uint8)
-    d_flat = torch.from_numpy(flat.copy()).to(device) if flat.size else torch.empty(0, dtype=torch.uint8, device=device)
-    return d_flat, torch.from_numpy(off).to(device)
+    P = len(patterns)
+    flat = None
+    try:
+        joined = "".join(patterns)                      # TypeError unless every pattern is a str
+        flat = joined.encode("latin-1")                 # UnicodeEncodeError beyond latin-1: the slow path reports it
+        lens = np.fromiter(map(len, patterns), dtype=np.int64, count=P)
+    except (TypeError, UnicodeEncodeError):
+        flat = None
+    if flat is None:
+        enc = [p.encode("latin-1") if isinstance(p, str) else bytes(p) for p in patterns]
+        lens = np.fromiter(map(len, enc), dtype=np.int64, count=P)
+        flat = b"".join(enc)
+    off = np.zeros(P + 1, dtype=np.int64)
+    if P:
+        np.cumsum(lens, out=off[1:])
+    d_flat = to_device_u8(flat, device)
+    return d_flat, to_device_u8(off.view(np.uint8), device).view(torch.int64)
 
 
 @dataclass

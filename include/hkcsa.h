@@ -543,6 +543,22 @@ int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan,
                           const hkcsa_occ_plan *h_plan, const void *d_ssa_blob, const hkcsa_ssa_plan *h_ssa,
                           const uint32_t *d_rows, uint64_t m, uint32_t *d_out_pos, void *stream);
 
+/* ------------------------------------------------------------------------ */
+/* Host text in, index out: the reference's constructor takes a Python str   */
+/* (EnhancedFMIndex.__init__, csa/enhanced_fm_index.py:8-9; the corpus loader */
+/* returns one, utils/data_loader.py:4) whose bytes sit in PAGEABLE memory.   */
+/* hkcsa_h2d_staged copies nbytes from pageable h_src to d_dst through a      */
+/* library-owned pinned ring (64 MB, allocated on first use): `threads` host  */
+/* threads (0 = HKCSA_STAGE_THREADS or half the cores, at most 8) fill 4 MB   */
+/* slots and enqueue each slot's DMA on `stream` as soon as it is filled, so  */
+/* the host copy runs on several cores and overlaps the PCIe transfer.        */
+/* Returns when every byte has been staged (h_src may be released); the DMAs  */
+/* complete in stream order.  hkcsa_d2h_staged is the way back (index blobs,  */
+/* suffix array): returns when h_dst holds the data.                          */
+/* ------------------------------------------------------------------------ */
+int hkcsa_h2d_staged(void *d_dst, const void *h_src, size_t nbytes, int threads, void *stream);
+int hkcsa_d2h_staged(void *h_dst, const void *d_src, size_t nbytes, int threads, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
