@@ -132,7 +132,7 @@ class CompressedSuffixArray:
 
     def count_batch(self, patterns):
         lo, hi = self._idx.count_batch(*self._pack(patterns))
-        lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+        lo, hi = self._E.to_host(lo), self._E.to_host(hi)
         return np.where(lo >= 0, hi - lo + 1, 0)
 
     def locate_batch(self, patterns):

@@ -52,7 +52,7 @@ class EnhancedFMIndex:
     @property
     def bwt(self):
         if self._bwt is None:
-            raw = self._idx.bwt.cpu().numpy().tobytes()
+            raw = self._E.to_host(self._idx.bwt).tobytes()
             self._bwt = self._smap.decode(raw) if self._str else raw
         return self._bwt
 
@@ -100,7 +100,7 @@ class EnhancedFMIndex:
         """Inclusive SA ranges for many patterns at once: (lo, hi) int64 numpy arrays; (-1, -1) = miss."""
         pat, off, absent = self._pack(queries)
         lo, hi = self._idx.count_batch(pat, off)
-        lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+        lo, hi = self._E.to_host(lo), self._E.to_host(hi)
         if absent:                                   # a symbol the text cannot hold: (-1, -1) like :27-28
             lo[absent] = -1
             hi[absent] = -1

@@ -165,6 +165,24 @@ def to_device_u8(data, device=None, tail: bytes = b"") -> torch.Tensor:
     return _staged_h2d(arr.ctypes.data, arr.size, device, tail)
 
 
+_NP_OF = {torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16, torch.int32: np.int32,
+          torch.int64: np.int64, torch.float32: np.float32, torch.float64: np.float64}
+TO_HOST_STAGED_MIN = 8 << 20
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> numpy array in pageable memory.  From 8 MB on through hkcsa_d2h_staged (the pinned ring is
+    drained by several host threads while the next chunks' DMAs run); below that torch's own copy."""
+    nbytes = t.numel() * t.element_size()
+    if not t.is_cuda or nbytes < TO_HOST_STAGED_MIN or t.dtype not in _NP_OF:
+        return t.cpu().numpy()
+    t = t.contiguous()
+    out = np.empty(tuple(t.shape), dtype=_NP_OF[t.dtype])
+    with torch.cuda.device(t.device):
+        check(_lib.load().hkcsa_d2h_staged(out.ctypes.data, t.data_ptr(), nbytes, 0, _stream()))
+    return out
+
+
 # ------------------------------------------------------------------ workload
 def gen_text(kind: int, seed: int, n: int, device=None) -> torch.Tensor:
     device = device or _require_cuda()
@@ -697,16 +715,16 @@ class DeviceIndex:
             for l, vec in enumerate(self.coded_levels()):
                 if vec.coded_bits < self.wt.level_len(l):
                     parts[f"rrr_plan_{l}"] = np.frombuffer(bytes(vec.plan), dtype=np.uint8)
-                    parts[f"rrr_blob_{l}"] = vec.blob.cpu().numpy()
+                    parts[f"rrr_blob_{l}"] = to_host(vec.blob)
                 else:       # the code does not shrink this level: its 224 payload bits per rank block, headers dropped
                     a, b = int(self.wt.plan.off_blocks[l]), int(self.wt.plan.off_super[l])
                     words = self.wt.blob[a:b].cpu().numpy().view(np.uint32).reshape(-1, 8)
                     parts[f"raw_payload_{l}"] = np.ascontiguousarray(words[:, 1:])
         else:
-            parts["wt_blob"] = self.wt.blob.cpu().numpy()
+            parts["wt_blob"] = to_host(self.wt.blob)
         if self.ssa is not None:
             parts["ssa_plan"] = np.frombuffer(bytes(self.ssa.plan), dtype=np.uint8)
-            parts["ssa_blob"] = self.ssa.blob.cpu().numpy()
+            parts["ssa_blob"] = to_host(self.ssa.blob)
         with open(path, "wb") as f:
             np.savez(f, **parts)
 
@@ -716,7 +734,7 @@ class DeviceIndex:
         z = np.load(path)
         plan = WtPlan.from_buffer_copy(z["wt_plan"].tobytes())
         if "wt_blob" in z.files:
-            blob = torch.from_numpy(z["wt_blob"]).to(device)
+            blob = to_device_u8(z["wt_blob"], device)
         else:
             coded = []
             for l in range(int(plan.levels)):

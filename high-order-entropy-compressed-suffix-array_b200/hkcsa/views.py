@@ -47,7 +47,8 @@ class DeviceSequence(Sequence):
         return self.tensor.cpu().tolist()
 
     def numpy(self):
-        return self.tensor.cpu().numpy()
+        from . import engine
+        return engine.to_host(self.tensor)
 
     def __eq__(self, other):
         if isinstance(other, DeviceSequence):

@@ -108,3 +108,32 @@ def test_str_index_and_pattern_list_fast_path_match_oracle():
     keep = [k for k in range(50) if k != 4]
     assert np.array_equal(lo2[keep], olo[keep]) and np.array_equal(hi2[keep], ohi[keep])
     assert fm.text == text + "$" and len(fm.text) == n
+
+
+def test_to_host_matches_torch_copy():
+    import torch
+    from hkcsa import engine as E
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for dtype, n in ((torch.int32, 5_000_003), (torch.int64, 3_000_001), (torch.uint8, 40_000_007), (torch.int32, 100)):
+        t = torch.randint(0, 100, (n,), device="cuda", generator=g).to(dtype)
+        a = E.to_host(t)
+        assert a.dtype == t.cpu().numpy().dtype and np.array_equal(a, t.cpu().numpy())
+    t2 = torch.arange(6_000_000, device="cuda", dtype=torch.int32).view(2000, 3000).t()   # non-contiguous
+    assert np.array_equal(E.to_host(t2), t2.cpu().numpy())
+
+
+def test_save_load_round_trip_through_staged_copies(tmp_path):
+    """save() ships the blobs through hkcsa_d2h_staged (> 8 MB each): the loaded index answers like the built one."""
+    import torch
+    from hkcsa import engine as E
+    text = E.gen_text(E.ENG96, 9, 30_000_000)
+    text = torch.cat([text, torch.tensor([36], dtype=torch.uint8, device=text.device)])
+    idx = E.DeviceIndex(text, sa_sample_rate=32)
+    path = str(tmp_path / "idx.npz")
+    idx.save(path)
+    back = E.DeviceIndex.load(path)
+    pat, off = E.gen_patterns(5, 20_000, text[:-1], torch.unique(text[:-1]))
+    lo, hi = idx.count_batch(pat, off)
+    lo2, hi2 = back.count_batch(pat, off)
+    assert torch.equal(lo, lo2) and torch.equal(hi, hi2)
+    assert torch.equal(idx.wt.blob, back.wt.blob) and torch.equal(idx.ssa.blob, back.ssa.blob)
