@@ -431,15 +431,24 @@ static int dsa_refine(DsaState &S, cudaStream_t st)
     uint32_t *h_m = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(pinned_page()) + 2048);
     const uint32_t m = (uint32_t)S.m;
     const uint32_t tiles = (m + SEG_TILE - 1) / SEG_TILE;
-    seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(S.skey, m, S.agg_head, S.agg_keep, S.flags, ~0ULL, nullptr);
-    HK_LAUNCH_CHECK();
-    seg_scan_kernel<<<1, 1024, 0, st>>>(S.agg_head, S.agg_keep, tiles, S.counter);
-    HK_LAUNCH_CHECK();
+    {
+        prof::Scope ps(st, prof::SEG_REDUCE, (uint64_t)m * 8);
+        seg_reduce_kernel<<<tiles, SEG_THREADS, 0, st>>>(S.skey, m, S.agg_head, S.agg_keep, S.flags, ~0ULL, nullptr);
+        HK_LAUNCH_CHECK();
+    }
+    {
+        prof::Scope ps(st, prof::SEG_SCAN, (uint64_t)tiles * 16);
+        seg_scan_kernel<<<1, 1024, 0, st>>>(S.agg_head, S.agg_keep, tiles, S.counter);
+        HK_LAUNCH_CHECK();
+    }
     S.cpos = S.posbuf[S.pcur ^ 1];
     S.cidx = S.vfree;
-    seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(S.flags, S.sidx, S.pos, m, S.agg_head, S.agg_keep, S.sa, nullptr,
-                                                   S.cpos, S.cidx, S.grp, S.round != 0, false, nullptr, 0, nullptr);
-    HK_LAUNCH_CHECK();
+    {
+        prof::Scope ps(st, prof::SEG_APPLY, (uint64_t)m * 12);
+        seg_apply_kernel<<<tiles, SEG_THREADS, 0, st>>>(S.flags, S.sidx, S.pos, m, S.agg_head, S.agg_keep, S.sa, nullptr,
+                                                       S.cpos, S.cidx, S.grp, S.round != 0, false, nullptr, 0, nullptr);
+        HK_LAUNCH_CHECK();
+    }
     HK_CUDA(cudaMemcpyAsync(h_m, S.counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     HK_CUDA(cudaStreamSynchronize(st));
     S.m_sorted = m;

@@ -853,12 +853,6 @@ seg_apply_kernel(const uint16_t *__restrict__ flags, const uint32_t *__restrict_
 // (group start << 32 | number of its sub-group): equal keys = still tied within GS_DEPTH symbols.  The usual
 // seg_reduce / seg_scan / seg_apply then refine on these keys.  Groups above GS_MAX elements are left alone (one key
 // for the whole group): they go to the next regular round, whose depth therefore stays where it was.
-__global__ void group_key_init_kernel(const uint32_t *__restrict__ cgrp, uint32_t m, uint64_t *__restrict__ keys)
-{
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < m) keys[j] = (uint64_t)cgrp[j] << 32;
-}
-
 // -1 / 0 / +1: order of suffixes a and b beyond the `depth` symbols they share, 0 = tied within GS_DEPTH symbols
 __device__ __forceinline__ int suffix_cmp_from(const uint8_t *__restrict__ text, uint64_t n, uint64_t a, uint64_t b,
                                                uint64_t depth)
@@ -875,19 +869,14 @@ __device__ __forceinline__ int suffix_cmp_from(const uint8_t *__restrict__ text,
     return 0;
 }
 
+// One group of s <= GS_MAX elements starting at element j, ordered by ONE thread with symbol-by-symbol comparisons
+// (GS_DEPTH deep, end of text exact).  The general case; group_sort_kernel sends here only what its 16-byte windows
+// cannot decide.
 template <bool WIDE>
-__global__ void __launch_bounds__(256)
-group_sort_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp, uint32_t m,
-                  const uint8_t *__restrict__ text, uint64_t n, uint64_t depth, const uint64_t *__restrict__ ids64,
-                  uint64_t *__restrict__ keys)
+__device__ __forceinline__ void group_sort_serial(uint32_t *__restrict__ cidx, uint32_t j, uint32_t s, uint32_t g,
+                                               const uint8_t *__restrict__ text, uint64_t n, uint64_t depth,
+                                               const uint64_t *__restrict__ ids64, uint64_t *__restrict__ keys)
 {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const uint32_t g = cgrp[j];
-    if (j > 0 && cgrp[j - 1] == g) return;                      // not the first element of its group
-    uint32_t s = 1;
-    while (s <= GS_MAX && j + s < m && cgrp[j + s] == g) ++s;
-    if (s > GS_MAX || s < 2) return;                            // large group: keys stay (g << 32) for every member
     uint32_t v[GS_MAX];                                         // cidx entries (suffix ids, or ordinals when WIDE)
     uint64_t id[GS_MAX];
     for (uint32_t i = 0; i < s; ++i) {
@@ -914,15 +903,182 @@ group_sort_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp
     }
 }
 
+// out of line for group_sort_kernel: its rare groups must not cost the common path registers or a stack frame
+template <bool WIDE>
+__device__ __noinline__ void group_sort_serial_call(uint32_t *__restrict__ cidx, uint32_t j, uint32_t s, uint32_t g,
+                                                    const uint8_t *__restrict__ text, uint64_t n, uint64_t depth,
+                                                    const uint64_t *__restrict__ ids64, uint64_t *__restrict__ keys)
+{
+    group_sort_serial<WIDE>(cidx, j, s, g, text, n, depth, ids64, keys);
+}
+
+// the 16 symbols at text[p .. p + 16) as two big-endian words (integer order = symbol order); three aligned 8-byte
+// loads, all inside [p - 7, p + 24)
+__device__ __forceinline__ void window16_be(const uint8_t *__restrict__ text, uint64_t p, uint64_t &hi, uint64_t &lo)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(text) + p;
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(a & 7u) * 8u;
+    const uint64_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const uint64_t x0 = sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
+    const uint64_t x1 = sh ? (w1 >> sh) | (w2 << (64u - sh)) : w1;
+    hi = ((uint64_t)__byte_perm((uint32_t)x0, 0u, 0x0123) << 32) | __byte_perm((uint32_t)(x0 >> 32), 0u, 0x0123);
+    lo = ((uint64_t)__byte_perm((uint32_t)x1, 0u, 0x0123) << 32) | __byte_perm((uint32_t)(x1 >> 32), 0u, 0x0123);
+}
+
+// One thread per ELEMENT (the one-thread-per-group form left two thirds of the lanes idle behind serial chains of
+// dependent random loads and kept its arrays in local memory: 164 M elements took 8 ms, the distributed build's group
+// round 13-44 ms).  A CTA takes 1008 elements + 16 of look-ahead: (1) group ids into shared memory, every element
+// finds its group's start and size by scanning at most 16 neighbours; a group of 2..16 elements belongs to the CTA
+// holding its first element, larger groups keep one key (g << 32); (2) every member loads its suffix id and the 16
+// symbols beyond the shared depth as two big-endian words -- two dependent random loads per element, all elements in
+// flight at once; (3) place in the group = members with a smaller window, key = (g << 32 | that count).  Groups with
+// two equal windows (ties deeper than 16 symbols) or a window reaching the end of the text go to
+// group_sort_serial on the thread of their first element: the result is that of the serial form in every case.
+constexpr int GC_THREADS = 256;
+constexpr int GC_IPT = 4;
+constexpr int GC_SLOTS = GC_THREADS * GC_IPT;        // 1024 elements seen by a CTA
+constexpr int GC_HALO = GS_MAX;                      // look-ahead (and look-back for the group ids)
+constexpr int GC_STRIDE = GC_SLOTS - GC_HALO;        // elements owned by a CTA
+constexpr uint32_t GC_NOGROUP = 0xFFFFFFFFu;         // group ids are positions < 2^30
+
+template <bool WIDE>
+__global__ void __launch_bounds__(GC_THREADS)
+group_sort_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp, uint32_t m,
+                  const uint8_t *__restrict__ text, uint64_t n, uint64_t depth, const uint64_t *__restrict__ ids64,
+                  uint64_t *__restrict__ keys)
+{
+    __shared__ uint32_t s_grp[GC_SLOTS + 2 * GC_HALO];           // element base - GC_HALO + i
+    __shared__ uint64_t s_hi[GC_SLOTS], s_lo[GC_SLOTS];
+    __shared__ uint32_t s_v[GC_SLOTS];
+    __shared__ uint16_t s_meta[GC_SLOTS];                        // start slot (10 bits) | size - 1 (4 bits) | member (bit 15)
+    __shared__ uint8_t s_hard[GC_SLOTS];                         // this member's window cannot decide its place
+    const uint32_t tid = threadIdx.x;
+    const uint32_t base = blockIdx.x * (uint32_t)GC_STRIDE;
+    for (uint32_t i = tid; i < GC_SLOTS + 2 * GC_HALO; i += GC_THREADS) {
+        const int64_t e = (int64_t)base - GC_HALO + i;
+        s_grp[i] = (e >= 0 && e < (int64_t)m) ? cgrp[e] : GC_NOGROUP;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GC_IPT; ++k) {
+        const uint32_t slot = k * GC_THREADS + tid;
+        const uint32_t e = base + slot;
+        uint16_t meta = 0;
+        uint8_t hard = 0;
+        if (e < m) {
+            const uint32_t g = s_grp[GC_HALO + slot];
+            uint32_t back = 0, fwd = 0;
+            while (back < (uint32_t)GS_MAX && s_grp[GC_HALO + slot - 1 - back] == g) ++back;
+            while (back + fwd < (uint32_t)GS_MAX && s_grp[GC_HALO + slot + 1 + fwd] == g) ++fwd;
+            const uint32_t size = back + 1 + fwd;                // GS_MAX + 1 = "more than GS_MAX"
+            const int start = (int)slot - (int)back;
+            if (size < 2 || size > (uint32_t)GS_MAX) {
+                if (slot < (uint32_t)GC_STRIDE) keys[e] = (uint64_t)g << 32;      // left to the next regular round
+            } else if (start >= 0 && start < GC_STRIDE) {
+                const uint32_t v = cidx[e];
+                const uint64_t id = WIDE ? (ids64[v] & ((1ull << 56) - 1ull)) : (uint64_t)v;
+                const uint64_t p = id + depth;
+                uint64_t hi = 0, lo = 0;
+                if (p >= 8 && p + 24 <= n) window16_be(text, p, hi, lo);
+                else hard = 1;
+                s_v[slot] = v;
+                s_hi[slot] = hi;
+                s_lo[slot] = lo;
+                meta = (uint16_t)(0x8000u | ((size - 1) << 10) | (uint32_t)start);
+            }
+        }
+        s_meta[slot] = meta;
+        s_hard[slot] = hard;
+    }
+    __syncthreads();
+    // place among the members; a member whose window equals another member's marks the group as hard
+    uint32_t place[GC_IPT], less[GC_IPT];
+#pragma unroll
+    for (int k = 0; k < GC_IPT; ++k) {
+        const uint32_t slot = k * GC_THREADS + tid;
+        const uint32_t meta = s_meta[slot];
+        place[k] = less[k] = 0;
+        if (!(meta & 0x8000u)) continue;
+        const uint32_t start = meta & 0x3FFu, size = ((meta >> 10) & 0xFu) + 1;
+        const uint64_t hi = s_hi[slot], lo = s_lo[slot];
+        bool tie = false;
+        for (uint32_t i = 0; i < size; ++i) {
+            const uint32_t o = start + i;
+            if (o == slot) continue;
+            const uint64_t oh = s_hi[o], ol = s_lo[o];
+            const bool lt = oh < hi || (oh == hi && ol < lo);
+            const bool eq = oh == hi && ol == lo;
+            tie |= eq;
+            less[k] += lt;
+            place[k] += lt || (eq && o < slot);
+        }
+        if (tie) s_hard[slot] = 1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GC_IPT; ++k) {
+        const uint32_t slot = k * GC_THREADS + tid;
+        const uint32_t meta = s_meta[slot];
+        if (!(meta & 0x8000u)) continue;
+        const uint32_t start = meta & 0x3FFu, size = ((meta >> 10) & 0xFu) + 1;
+        bool hard = false;
+        for (uint32_t i = 0; i < size; ++i) hard |= (s_hard[start + i] != 0);
+        const uint32_t g = s_grp[GC_HALO + slot];
+        if (hard) {
+            if (slot == start) group_sort_serial_call<WIDE>(cidx, base + start, size, g, text, n, depth, ids64, keys);
+            continue;
+        }
+        const uint32_t out = base + start + place[k];
+        cidx[out] = s_v[slot];
+        keys[out] = ((uint64_t)g << 32) | less[k];
+    }
+}
+
+// Small working sets (one wave of CTAs: the kernel lasts as long as its longest chain of dependent loads, and a group
+// whose members share more than the guaranteed depth -- k-gram keys: 6 symbols guaranteed, ~21 shared -- ties inside
+// its first window): every key starts as (g << 32), the thread of a group's first element orders the group serially.
+__global__ void group_key_init_kernel(const uint32_t *__restrict__ cgrp, uint32_t m, uint64_t *__restrict__ keys)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) keys[j] = (uint64_t)cgrp[j] << 32;
+}
+template <bool WIDE>
+__global__ void __launch_bounds__(256)
+group_sort_heads_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp, uint32_t m,
+                        const uint8_t *__restrict__ text, uint64_t n, uint64_t depth,
+                        const uint64_t *__restrict__ ids64, uint64_t *__restrict__ keys)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t g = cgrp[j];
+    if (j > 0 && cgrp[j - 1] == g) return;                      // not the first element of its group
+    uint32_t s = 1;
+    while (s <= GS_MAX && j + s < m && cgrp[j + s] == g) ++s;
+    if (s > GS_MAX || s < 2) return;                            // large group: keys stay (g << 32) for every member
+    group_sort_serial<WIDE>(cidx, j, s, g, text, n, depth, ids64, keys);
+}
+
+constexpr uint32_t GC_MIN_M = 1u << 22;      // C2: 0.79 M survivors, serial form 0.089 ms against 0.112; C3: 5.1 M, 0.20 -> 0.12 ms
+
 cudaError_t group_local_keys(uint32_t *cidx, const uint32_t *cgrp, uint32_t m, const uint8_t *text, uint64_t n,
                              uint64_t depth, const uint64_t *ids64, uint64_t *keys, cudaStream_t st)
 {
     if (m == 0) return cudaSuccess;
-    const uint32_t blocks = (m + 255) / 256;
-    group_key_init_kernel<<<blocks, 256, 0, st>>>(cgrp, m, keys);
-    count_launch();
-    if (ids64) group_sort_kernel<true><<<blocks, 256, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
-    else group_sort_kernel<false><<<blocks, 256, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+    uint32_t min_m = GC_MIN_M;
+    if (const char *e = getenv("HKCSA_GC_MIN_M")) min_m = (uint32_t)strtoul(e, nullptr, 10);   // tests: 0 = always the element-parallel form
+    if (m < min_m) {
+        const uint32_t blocks = (m + 255) / 256;
+        group_key_init_kernel<<<blocks, 256, 0, st>>>(cgrp, m, keys);
+        count_launch();
+        if (ids64) group_sort_heads_kernel<true><<<blocks, 256, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+        else group_sort_heads_kernel<false><<<blocks, 256, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+        count_launch();
+        return cudaGetLastError();
+    }
+    const uint32_t blocks = (m + GC_STRIDE - 1) / GC_STRIDE;
+    if (ids64) group_sort_kernel<true><<<blocks, GC_THREADS, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+    else group_sort_kernel<false><<<blocks, GC_THREADS, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
     count_launch();
     return cudaGetLastError();
 }

@@ -484,6 +484,33 @@ def test_distributed_build_reference_benchmark_workload(E):
     _check_slices(_emulated_build(E, text, 4, False), text, False)
 
 
+@pytest.mark.parametrize("env", [{}, {"HKCSA_BITS0": "24"}, {"HKCSA_GRAM": "0", "HKCSA_BITS0": "16"}, {"HKCSA_BITS0": "40"}])
+@pytest.mark.parametrize("name", list(TEXTS))
+def test_sa_bwt_with_element_parallel_group_round(E, name, env, monkeypatch):
+    """HKCSA_GC_MIN_M=0: round 1 of the single-GPU builder through the element-parallel group kernel whatever the
+    number of survivors; narrow round-0 keys (HKCSA_BITS0) leave many groups, big ones included."""
+    monkeypatch.setenv("HKCSA_GC_MIN_M", "0")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    text = TEXTS[name]
+    sa, got = E.suffix_array_bwt(dev(E, text), E.SaStats())
+    want = O.build_suffix_array(text)
+    assert np.array_equal(host(sa).astype(np.uint32), want)
+    assert host(got).tobytes() == O.bwt_transform(text, want).tobytes()
+
+
+@pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "runs", "rand256_50k", "dna_1m_dollar", "rand2_100k", "fib"])
+@pytest.mark.parametrize("parts", [1, 3, 8])
+def test_distributed_build_with_element_parallel_group_round(E, name, parts, monkeypatch):
+    """HKCSA_GC_MIN_M=0: the group round's element-parallel kernel (working sets of 4 M suffixes and more take it) on
+    every working set -- groups across CTA boundaries, groups of more than 16, windows that tie or reach the end of
+    the text (handed to the serial form): same slices, 32- and 64-bit ids."""
+    monkeypatch.setenv("HKCSA_GC_MIN_M", "0")
+    text = TEXTS[name]
+    for wide in (False, True):
+        _check_slices(_emulated_build(E, text, parts, wide), text, wide)
+
+
 @pytest.mark.parametrize("ext", [0, 1, 3])
 def test_distributed_doubling_from_any_depth(E, ext):
     """Rank doubling may take over after any number of extension rounds (0: straight after round 0): suffixes that
