@@ -1059,7 +1059,7 @@ group_sort_heads_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict_
     group_sort_serial<WIDE>(cidx, j, s, g, text, n, depth, ids64, keys);
 }
 
-constexpr uint32_t GC_MIN_M = 1u << 22;      // C2: 0.79 M survivors, serial form 0.089 ms against 0.112; C3: 5.1 M, 0.20 -> 0.12 ms
+constexpr uint32_t GC_MIN_M = 1u << 25;      // serial / element-parallel: 0.79 M (C2) 0.089 / 0.112 ms, 5.1 M (C3) 0.198 / 0.230 ms, 164 M 10.2 / 8.1 ms
 
 cudaError_t group_local_keys(uint32_t *cidx, const uint32_t *cgrp, uint32_t m, const uint8_t *text, uint64_t n,
                              uint64_t depth, const uint64_t *ids64, uint64_t *keys, cudaStream_t st)

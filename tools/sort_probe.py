@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(ROOT, "high-order-entropy-compressed-suffix-arra
 import numpy as np, torch
 from hkcsa import engine as E
 
-n = 100_000_000
+n = int(float(os.environ.get("N", "1e8")))
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 cases = {
     "random 64-bit": torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g),
