@@ -22,13 +22,14 @@ constexpr int STAGE_SLOTS = 2;
 constexpr int STAGE_MAX_DEVICES = 16;
 
 struct Stage {
+    std::mutex mu;                                           // one staged copy at a time per device
     uint8_t *pin = nullptr;                                  // [threads][slots][chunk]
     cudaEvent_t ev[STAGE_MAX_THREADS][STAGE_SLOTS];
     bool busy[STAGE_MAX_THREADS][STAGE_SLOTS];
+    int events = 0;                                          // events created so far (a failed init resumes here)
     bool ready = false;
 };
 Stage g_stage[STAGE_MAX_DEVICES];
-std::mutex g_stage_mu;                                       // one staged copy at a time per process
 
 int stage_threads(size_t nbytes, int asked)
 {
@@ -46,15 +47,17 @@ int stage_threads(size_t nbytes, int asked)
 cudaError_t stage_init(Stage &s)
 {
     if (s.ready) return cudaSuccess;
-    cudaError_t e = cudaHostAlloc((void **)&s.pin, (size_t)STAGE_MAX_THREADS * STAGE_SLOTS * STAGE_CHUNK,
-                                  cudaHostAllocDefault);
-    if (e != cudaSuccess) return e;
-    for (int t = 0; t < STAGE_MAX_THREADS; ++t)
-        for (int k = 0; k < STAGE_SLOTS; ++k) {
-            e = cudaEventCreateWithFlags(&s.ev[t][k], cudaEventDisableTiming);
-            if (e != cudaSuccess) return e;
-            s.busy[t][k] = false;
-        }
+    cudaError_t e = cudaSuccess;
+    if (!s.pin) {
+        e = cudaHostAlloc((void **)&s.pin, (size_t)STAGE_MAX_THREADS * STAGE_SLOTS * STAGE_CHUNK, cudaHostAllocDefault);
+        if (e != cudaSuccess) { s.pin = nullptr; return e; }
+    }
+    for (; s.events < STAGE_MAX_THREADS * STAGE_SLOTS; ++s.events) {
+        const int t = s.events / STAGE_SLOTS, k = s.events % STAGE_SLOTS;
+        e = cudaEventCreateWithFlags(&s.ev[t][k], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        s.busy[t][k] = false;
+    }
     s.ready = true;
     return cudaSuccess;
 }
@@ -117,8 +120,8 @@ int staged_copy(uint8_t *d, uint8_t *h, size_t nbytes, bool to_device, int threa
     int dev = 0;
     HK_CUDA(cudaGetDevice(&dev));
     HK_REQUIRE(dev >= 0 && dev < STAGE_MAX_DEVICES, HKCSA_EINVAL, "device ordinal beyond the staging table");
-    std::lock_guard<std::mutex> lock(g_stage_mu);
     Stage &s = g_stage[dev];
+    std::lock_guard<std::mutex> lock(s.mu);
     HK_CUDA(stage_init(s));
     const int T = stage_threads(nbytes, threads);
     if (T == 1) {
