@@ -395,20 +395,23 @@ static constexpr size_t onesweep_smem()
     return fixed + elem * (size_t)THREADS * IPT;
 }
 
-__global__ void radix_hist_kernel(const uint64_t *__restrict__ keys, uint32_t n, int passes,
-                                  uint32_t *__restrict__ ghist)
+// PASSES known at compile time: one uniformity test per key (runs of one key: all-same texts) instead of one per
+// digit, the digits by shift + mask on the key's halves
+template <int PASSES>
+__global__ void __launch_bounds__(256)
+radix_hist_kernel(const uint64_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ ghist)
 {
     __shared__ uint32_t s_hist[8 * RADIX];
-    hist_zero(s_hist, passes);
+    hist_zero(s_hist, PASSES);
     __syncthreads();
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
         const bool valid = i < n;
         const uint64_t key = valid ? keys[i] : 0ULL;
-        hist_add_key(s_hist, key, passes, valid);
+        hist_add_key_unsorted<PASSES>(s_hist, key, valid);
     }
     __syncthreads();
-    hist_flush(s_hist, ghist, passes);
+    hist_flush(s_hist, ghist, PASSES);
 }
 
 // block p: exclusive scan of hist[p][0..255] -> base[p][0..255]
@@ -451,7 +454,13 @@ cudaError_t radix_histogram_u64(const uint64_t *d_keys, uint32_t n, int passes, 
     if (e != cudaSuccess) return e;
     if (n == 0) return cudaSuccess;
     int blocks = (int)std::min<uint64_t>((n + 1023) / 1024, (uint64_t)num_sms() * 8);
-    radix_hist_kernel<<<blocks, 256, 0, st>>>(d_keys, n, passes, s.hist);
+    prof::Scope ps(st, prof::RADIX_SCAN, (uint64_t)n * 8);
+    switch (passes) {
+#define HK_HIST(P) case P: radix_hist_kernel<P><<<blocks, 256, 0, st>>>(d_keys, n, s.hist); break;
+        HK_HIST(1) HK_HIST(2) HK_HIST(3) HK_HIST(4) HK_HIST(5) HK_HIST(6) HK_HIST(7)
+        default: radix_hist_kernel<8><<<blocks, 256, 0, st>>>(d_keys, n, s.hist); break;
+#undef HK_HIST
+    }
     count_launch();
     return cudaGetLastError();
 }
