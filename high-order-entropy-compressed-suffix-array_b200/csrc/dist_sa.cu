@@ -32,7 +32,7 @@ constexpr int DSA_BUCKET_BITS = 16;
 constexpr int DSA_MAX_WORLD = HKCSA_DSA_MAX_RANKS;
 // 64-bit suffix ids (n <= 2^40) travel with the BWT symbol of their suffix in the top byte: the source rank has
 // text[i - 1] at hand when it packs suffix i, so the owner's BWT slice needs no random gather over the whole text
-constexpr uint64_t DSA_ID_MASK = (1ull << 56) - 1ull;
+constexpr uint64_t DSA_ID_MASK = WIDE_ID_MASK;     // suffix_array.cuh: id in the low 40 bits, key extension above, BWT symbol on top
 
 struct DsaDest {                       // kernel parameter of the exchange
     uint64_t *keys[DSA_MAX_WORLD];     // receive arrays of every rank (peer-mapped)
@@ -59,7 +59,7 @@ template <int MODE, bool WIDE>
 __global__ void __launch_bounds__(PACK_THREADS, 4)
 dsa_pack_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin, uint64_t end, AlphaCode ac, int bits,
                 DsaDest dd, unsigned long long *__restrict__ counters, unsigned long long *__restrict__ bucket_hist,
-                uint32_t tile_stride)
+                uint32_t tile_stride, int xbits = 0)
 {
     using IdT = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
     __shared__ __align__(16) uint16_t s_off[PACK_TILE];
@@ -106,6 +106,7 @@ dsa_pack_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin, ui
     __syncthreads();
     uint64_t key[PACK_IPT];
     uint32_t ds[PACK_IPT];            // MODE 1: destination << 16 | slot among the tile's elements for that destination
+    uint16_t xk[MODE == 1 && WIDE ? PACK_IPT : 1];      // the WIDE_X_BITS code-stream bits that follow the key
     const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int e = 0; e < PACK_IPT; ++e) {
@@ -116,6 +117,15 @@ dsa_pack_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin, ui
         const uint32_t w0 = s_stream[wi], w1 = s_stream[wi + 1], w2 = s_stream[wi + 2];
         const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
         key[e] = (((uint64_t)hi << 32) | lo) >> (64 - bits);
+        if (MODE == 1 && WIDE) {
+            // 64-bit ids leave room: the next 16 bits of the same code stream travel in the id word, so the group
+            // round tells most tied suffixes apart without touching the text (xbits = 0: the look-ahead of the
+            // stream does not reach that far for 1-bit code words -- the field stays zero, everything ties)
+            const uint32_t ex = __funnelshift_l(s_stream[wi + 3], w2, sh);
+            const uint64_t rest = bits < 64 ? ((((uint64_t)hi << 32) | lo) << bits) | (((uint64_t)ex << 32) >> (64 - bits))
+                                            : ((uint64_t)ex << 32);
+            xk[e] = xbits ? (uint16_t)(rest >> (64 - WIDE_X_BITS)) : (uint16_t)0;
+        }
         const bool valid = g < end;
         const uint32_t bucket = (uint32_t)(key[e] >> (bits - DSA_BUCKET_BITS));
         if (MODE == 0) {
@@ -159,7 +169,7 @@ dsa_pack_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t begin, ui
             const uint32_t slot = s_first[dest] + (ds[e] & 0xFFFFu);
             s_keys[slot] = key[e];
             const uint64_t g = base + j;
-            if (WIDE) s_ids[slot] = (IdT)(g | ((uint64_t)text[g ? g - 1 : n - 1] << 56));
+            if (WIDE) s_ids[slot] = (IdT)(g | ((uint64_t)xk[e] << WIDE_ID_BITS) | ((uint64_t)text[g ? g - 1 : n - 1] << 56));
             else s_ids[slot] = (IdT)g;
         }
     }
@@ -617,8 +627,13 @@ extern "C" int hkcsa_dsa_pack_exchange(const uint8_t *d_text, const hkcsa_dsa_pl
     // algorithmic bytes: 1 B of text read, 8 B key + 4 / 8 B id stored (over NVLink for remote owners)
     prof::Scope ps(st, prof::SA_PACK0, (end - begin) * (p->wide ? 17 : 13));
     unsigned long long *cnt = reinterpret_cast<unsigned long long *>(d_counters);
+    // the stream of a tile reaches PACK_LOOK positions beyond it: 64 + WIDE_X_BITS bits exist for every position when
+    // no code word is shorter than two bits
+    int min_len = ac.len[256];                                  // past the end, then the bytes that occur
+    for (int c = 0; c < 256; ++c) if (p->fixed_code[c] && ac.len[c] < min_len) min_len = ac.len[c];
+    const int xbits = (min_len >= 2 && !getenv("HKCSA_DSA_NO_XBITS")) ? WIDE_X_BITS : 0;
     if (p->wide)
-        dsa_pack_kernel<1, true><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd, cnt, nullptr, 1);
+        dsa_pack_kernel<1, true><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd, cnt, nullptr, 1, xbits);
     else
         dsa_pack_kernel<1, false><<<(uint32_t)blocks, PACK_THREADS, 0, st>>>(d_text, p->n, begin, end, ac, (int)p->bits0, dd, cnt, nullptr, 1);
     HK_LAUNCH_CHECK();

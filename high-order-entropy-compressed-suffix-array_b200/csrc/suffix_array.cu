@@ -881,7 +881,7 @@ __device__ __forceinline__ void group_sort_serial(uint32_t *__restrict__ cidx, u
     uint64_t id[GS_MAX];
     for (uint32_t i = 0; i < s; ++i) {
         v[i] = cidx[j + i];
-        id[i] = WIDE ? (ids64[v[i]] & ((1ull << 56) - 1ull)) : (uint64_t)v[i];
+        id[i] = WIDE ? (ids64[v[i]] & WIDE_ID_MASK) : (uint64_t)v[i];
     }
     for (uint32_t i = 1; i < s; ++i) {                          // insertion sort: groups are tiny
         const uint32_t xv = v[i];
@@ -901,15 +901,6 @@ __device__ __forceinline__ void group_sort_serial(uint32_t *__restrict__ cidx, u
         cidx[j + i] = v[i];
         keys[j + i] = ((uint64_t)g << 32) | sub;
     }
-}
-
-// out of line for group_sort_kernel: its rare groups must not cost the common path registers or a stack frame
-template <bool WIDE>
-__device__ __noinline__ void group_sort_serial_call(uint32_t *__restrict__ cidx, uint32_t j, uint32_t s, uint32_t g,
-                                                    const uint8_t *__restrict__ text, uint64_t n, uint64_t depth,
-                                                    const uint64_t *__restrict__ ids64, uint64_t *__restrict__ keys)
-{
-    group_sort_serial<WIDE>(cidx, j, s, g, text, n, depth, ids64, keys);
 }
 
 // the 16 symbols at text[p .. p + 16) as two big-endian words (integer order = symbol order); three aligned 8-byte
@@ -941,9 +932,12 @@ constexpr int GC_SLOTS = GC_THREADS * GC_IPT;        // 1024 elements seen by a 
 constexpr int GC_HALO = GS_MAX;                      // look-ahead (and look-back for the group ids)
 constexpr int GC_STRIDE = GC_SLOTS - GC_HALO;        // elements owned by a CTA
 constexpr uint32_t GC_NOGROUP = 0xFFFFFFFFu;         // group ids are positions < 2^30
+constexpr uint32_t GC_MARK = 0xFFFFFFFFu;            // low key word of a group's first element: "order me serially"
+constexpr int GC_WORDS = (GC_SLOTS + 2 * GC_HALO) / 32;
+static_assert((GC_SLOTS + 2 * GC_HALO) % 32 == 0 && GC_HALO <= 32, "start bits are read one word back and one ahead");
 
 template <bool WIDE>
-__global__ void __launch_bounds__(GC_THREADS)
+__global__ void __launch_bounds__(GC_THREADS, 6)
 group_sort_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp, uint32_t m,
                   const uint8_t *__restrict__ text, uint64_t n, uint64_t depth, const uint64_t *__restrict__ ids64,
                   uint64_t *__restrict__ keys)
@@ -952,7 +946,9 @@ group_sort_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp
     __shared__ uint64_t s_hi[GC_SLOTS], s_lo[GC_SLOTS];
     __shared__ uint32_t s_v[GC_SLOTS];
     __shared__ uint16_t s_meta[GC_SLOTS];                        // start slot (10 bits) | size - 1 (4 bits) | member (bit 15)
+    __shared__ uint16_t s_x[WIDE ? GC_SLOTS : 1];                // WIDE: the key's extension bits out of the id word
     __shared__ uint8_t s_hard[GC_SLOTS];                         // this member's window cannot decide its place
+    __shared__ uint32_t s_headw[GC_WORDS + 2];                   // group-start bits of the positions in s_grp
     const uint32_t tid = threadIdx.x;
     const uint32_t base = blockIdx.x * (uint32_t)GC_STRIDE;
     for (uint32_t i = tid; i < GC_SLOTS + 2 * GC_HALO; i += GC_THREADS) {
@@ -960,35 +956,76 @@ group_sort_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp
         s_grp[i] = (e >= 0 && e < (int64_t)m) ? cgrp[e] : GC_NOGROUP;
     }
     __syncthreads();
-#pragma unroll
+    // one bit per position: "a group starts here" (position 0 counts as a start: whatever begins before the look-back
+    // is 16 or more away from every element this CTA decides on)
+    for (uint32_t i = tid; i < GC_SLOTS + 2 * GC_HALO; i += GC_THREADS) {
+        const uint32_t word = __ballot_sync(0xffffffffu, i == 0 || s_grp[i] != s_grp[i - 1]);
+        if ((tid & 31u) == 0) s_headw[i >> 5] = word;
+    }
+    if (tid == 0) s_headw[GC_WORDS] = s_headw[GC_WORDS + 1] = 0xFFFFFFFFu;     // past the end: every position a start
+    __syncthreads();
+#pragma unroll 2
     for (int k = 0; k < GC_IPT; ++k) {
         const uint32_t slot = k * GC_THREADS + tid;
         const uint32_t e = base + slot;
         uint16_t meta = 0;
-        uint8_t hard = 0;
         if (e < m) {
             const uint32_t g = s_grp[GC_HALO + slot];
-            uint32_t back = 0, fwd = 0;
-            while (back < (uint32_t)GS_MAX && s_grp[GC_HALO + slot - 1 - back] == g) ++back;
-            while (back + fwd < (uint32_t)GS_MAX && s_grp[GC_HALO + slot + 1 + fwd] == g) ++fwd;
-            const uint32_t size = back + 1 + fwd;                // GS_MAX + 1 = "more than GS_MAX"
-            const int start = (int)slot - (int)back;
+            // start of the group = the last start bit at or before this position, its end = the next one after it:
+            // two words of bits decide both (a group of up to 16 spans at most two words); farther = "more than 16"
+            const uint32_t pos = GC_HALO + slot, w = pos >> 5, b = pos & 31u;
+            const uint32_t le = 0xFFFFFFFFu >> (31u - b);                         // bits 0..b
+            const uint32_t cur = s_headw[w];
+            uint32_t st;
+            if (cur & le) st = (w << 5) + 31u - __clz(cur & le);
+            else { const uint32_t prev = s_headw[w - 1]; st = prev ? ((w - 1) << 5) + 31u - __clz(prev) : 0u; }
+            uint32_t nx;
+            if (cur & ~le) nx = (w << 5) + __ffs(cur & ~le) - 1u;
+            else { const uint32_t nxt = s_headw[w + 1]; nx = nxt ? ((w + 1) << 5) + __ffs(nxt) - 1u : pos + GS_MAX + 1u; }
+            const uint32_t size = min(nx - st, (uint32_t)GS_MAX + 1u);           // GS_MAX + 1 = "more than GS_MAX"
+            const int start = (int)st - GC_HALO;
             if (size < 2 || size > (uint32_t)GS_MAX) {
                 if (slot < (uint32_t)GC_STRIDE) keys[e] = (uint64_t)g << 32;      // left to the next regular round
             } else if (start >= 0 && start < GC_STRIDE) {
                 const uint32_t v = cidx[e];
-                const uint64_t id = WIDE ? (ids64[v] & ((1ull << 56) - 1ull)) : (uint64_t)v;
-                const uint64_t p = id + depth;
-                uint64_t hi = 0, lo = 0;
-                if (p >= 8 && p + 24 <= n) window16_be(text, p, hi, lo);
-                else hard = 1;
+                uint64_t id = v;
+                if (WIDE) {
+                    const uint64_t w = ids64[v];
+                    id = w & WIDE_ID_MASK;
+                    s_x[slot] = (uint16_t)(w >> WIDE_ID_BITS);
+                }
+                s_lo[slot] = id + depth;                         // where this member's window starts (until the window itself lands here)
                 s_v[slot] = v;
-                s_hi[slot] = hi;
-                s_lo[slot] = lo;
                 meta = (uint16_t)(0x8000u | ((size - 1) << 10) | (uint32_t)start);
             }
         }
         s_meta[slot] = meta;
+    }
+    __syncthreads();
+    // the window: 16 symbols beyond the shared depth -- for 64-bit ids only where the extension bits of the key
+    // (16 more bits of the code stream, carried in the id word) do not already tell this member from all the others
+#pragma unroll 2
+    for (int k = 0; k < GC_IPT; ++k) {
+        const uint32_t slot = k * GC_THREADS + tid;
+        const uint32_t meta = s_meta[slot];
+        uint8_t hard = 0;
+        if (meta & 0x8000u) {
+            bool need = true;
+            if (WIDE) {
+                const uint32_t start = meta & 0x3FFu, size = ((meta >> 10) & 0xFu) + 1;
+                const uint16_t x = s_x[slot];
+                need = false;
+                for (uint32_t i = 0; i < size; ++i) need |= (start + i != slot && s_x[start + i] == x);
+            }
+            uint64_t hi = 0, lo = 0;
+            if (need) {
+                const uint64_t p = s_lo[slot];
+                if (p >= 8 && p + 24 <= n) window16_be(text, p, hi, lo);
+                else hard = 1;
+            }
+            s_hi[slot] = hi;
+            s_lo[slot] = lo;
+        }
         s_hard[slot] = hard;
     }
     __syncthreads();
@@ -1002,13 +1039,15 @@ group_sort_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp
         if (!(meta & 0x8000u)) continue;
         const uint32_t start = meta & 0x3FFu, size = ((meta >> 10) & 0xFu) + 1;
         const uint64_t hi = s_hi[slot], lo = s_lo[slot];
+        const uint32_t x = WIDE ? s_x[slot] : 0u;
         bool tie = false;
         for (uint32_t i = 0; i < size; ++i) {
             const uint32_t o = start + i;
             if (o == slot) continue;
             const uint64_t oh = s_hi[o], ol = s_lo[o];
-            const bool lt = oh < hi || (oh == hi && ol < lo);
-            const bool eq = oh == hi && ol == lo;
+            const uint32_t ox = WIDE ? s_x[o] : 0u;
+            const bool eq = ox == x && oh == hi && ol == lo;
+            const bool lt = ox < x || (ox == x && (oh < hi || (oh == hi && ol < lo)));
             tie |= eq;
             less[k] += lt;
             place[k] += lt || (eq && o < slot);
@@ -1025,14 +1064,32 @@ group_sort_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp
         bool hard = false;
         for (uint32_t i = 0; i < size; ++i) hard |= (s_hard[start + i] != 0);
         const uint32_t g = s_grp[GC_HALO + slot];
-        if (hard) {
-            if (slot == start) group_sort_serial_call<WIDE>(cidx, base + start, size, g, text, n, depth, ids64, keys);
+        if (hard) {       // left to group_sort_marked_kernel: the first element's key carries the mark
+            keys[base + slot] = ((uint64_t)g << 32) | (slot == start ? GC_MARK : 0u);
             continue;
         }
         const uint32_t out = base + start + place[k];
         cidx[out] = s_v[slot];
         keys[out] = ((uint64_t)g << 32) | less[k];
     }
+}
+
+// second launch of the element-parallel form: the groups it marked (windows that tie or reach the end of the text)
+// ordered serially by the thread of their first element; everybody else reads one key and leaves
+template <bool WIDE>
+__global__ void __launch_bounds__(256)
+group_sort_marked_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict__ cgrp, uint32_t m,
+                         const uint8_t *__restrict__ text, uint64_t n, uint64_t depth,
+                         const uint64_t *__restrict__ ids64, uint64_t *__restrict__ keys)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint64_t k = keys[j];
+    if ((uint32_t)k != GC_MARK) return;
+    const uint32_t g = (uint32_t)(k >> 32);
+    uint32_t s = 1;
+    while (s < (uint32_t)GS_MAX && j + s < m && cgrp[j + s] == g) ++s;
+    group_sort_serial<WIDE>(cidx, j, s, g, text, n, depth, ids64, keys);
 }
 
 // Small working sets (one wave of CTAs: the kernel lasts as long as its longest chain of dependent loads, and a group
@@ -1077,9 +1134,15 @@ cudaError_t group_local_keys(uint32_t *cidx, const uint32_t *cgrp, uint32_t m, c
         return cudaGetLastError();
     }
     const uint32_t blocks = (m + GC_STRIDE - 1) / GC_STRIDE;
-    if (ids64) group_sort_kernel<true><<<blocks, GC_THREADS, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
-    else group_sort_kernel<false><<<blocks, GC_THREADS, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
-    count_launch();
+    const uint32_t blocks2 = (m + 255) / 256;
+    if (ids64) {
+        group_sort_kernel<true><<<blocks, GC_THREADS, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+        group_sort_marked_kernel<true><<<blocks2, 256, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+    } else {
+        group_sort_kernel<false><<<blocks, GC_THREADS, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+        group_sort_marked_kernel<false><<<blocks2, 256, 0, st>>>(cidx, cgrp, m, text, n, depth, ids64, keys);
+    }
+    count_launch(2);
     return cudaGetLastError();
 }
 

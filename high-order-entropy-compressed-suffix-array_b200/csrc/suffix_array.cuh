@@ -168,6 +168,14 @@ __device__ __forceinline__ void pack_emit8(uint32_t *s_stream, uint16_t *s_off8,
 
 cudaError_t byte_hist(const uint8_t *d_text, uint64_t n, uint64_t *d_hist, cudaStream_t st);
 
+// 64-bit suffix ids of the distributed build (texts beyond 4 GB, n <= 2^40): id in the low 40 bits, then WIDE_X_BITS
+// bits that continue the round-0 key (the code stream behind its 64 bits; 0 when the packer cannot provide them),
+// the BWT symbol in the top byte
+constexpr int WIDE_ID_BITS = 40;
+constexpr int WIDE_X_BITS = 16;
+constexpr uint64_t WIDE_ID_MASK = (1ull << WIDE_ID_BITS) - 1ull;
+static_assert(WIDE_ID_BITS + WIDE_X_BITS <= 56, "the top byte carries the BWT symbol");
+
 // ---------------------------------------------------------------- group-local refinement (suffix_array.cu)
 constexpr int GS_MAX = 16;       // groups up to this size are ordered by one thread
 constexpr int GS_DEPTH = 64;     // symbols compared beyond the depth the group shares
