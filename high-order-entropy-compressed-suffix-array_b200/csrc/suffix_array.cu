@@ -1116,14 +1116,16 @@ group_sort_heads_kernel(uint32_t *__restrict__ cidx, const uint32_t *__restrict_
     group_sort_serial<WIDE>(cidx, j, s, g, text, n, depth, ids64, keys);
 }
 
-constexpr uint32_t GC_MIN_M = 1u << 25;      // serial / element-parallel: 0.79 M (C2) 0.089 / 0.112 ms, 5.1 M (C3) 0.198 / 0.230 ms, 164 M 10.2 / 8.1 ms
+// serial / element-parallel: 0.79 M survivors (C2) 0.088 / 0.077 ms, 5.1 M (C3) 0.197 / 0.160 ms, 164 M 10.2 / 5.5 ms
+// (64-bit ids 13.0 / 5.5 ms): the element-parallel form everywhere; HKCSA_GC_MIN_M=<m> keeps the serial one below m
+constexpr uint32_t GC_MIN_M = 0;
 
 cudaError_t group_local_keys(uint32_t *cidx, const uint32_t *cgrp, uint32_t m, const uint8_t *text, uint64_t n,
                              uint64_t depth, const uint64_t *ids64, uint64_t *keys, cudaStream_t st)
 {
     if (m == 0) return cudaSuccess;
     uint32_t min_m = GC_MIN_M;
-    if (const char *e = getenv("HKCSA_GC_MIN_M")) min_m = (uint32_t)strtoul(e, nullptr, 10);   // tests: 0 = always the element-parallel form
+    if (const char *e = getenv("HKCSA_GC_MIN_M")) min_m = (uint32_t)strtoul(e, nullptr, 10);   // tests: a huge value = always the serial form
     if (m < min_m) {
         const uint32_t blocks = (m + 255) / 256;
         group_key_init_kernel<<<blocks, 256, 0, st>>>(cgrp, m, keys);

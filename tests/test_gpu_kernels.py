@@ -484,12 +484,17 @@ def test_distributed_build_reference_benchmark_workload(E):
     _check_slices(_emulated_build(E, text, 4, False), text, False)
 
 
+def name_hash(name):
+    return sum(name.encode()) % 2          # half of the texts through each form
+
+
 @pytest.mark.parametrize("env", [{}, {"HKCSA_BITS0": "24"}, {"HKCSA_GRAM": "0", "HKCSA_BITS0": "16"}, {"HKCSA_BITS0": "40"}])
 @pytest.mark.parametrize("name", list(TEXTS))
 def test_sa_bwt_with_element_parallel_group_round(E, name, env, monkeypatch):
-    """HKCSA_GC_MIN_M=0: round 1 of the single-GPU builder through the element-parallel group kernel whatever the
-    number of survivors; narrow round-0 keys (HKCSA_BITS0) leave many groups, big ones included."""
-    monkeypatch.setenv("HKCSA_GC_MIN_M", "0")
+    """Round 1 of the single-GPU builder through the element-parallel group kernel (the default) and through the serial
+    form (HKCSA_GC_MIN_M beyond any working set); narrow round-0 keys (HKCSA_BITS0) leave many groups, big ones
+    included."""
+    monkeypatch.setenv("HKCSA_GC_MIN_M", "0" if name_hash(name) else "4294967295")
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     text = TEXTS[name]
@@ -502,13 +507,16 @@ def test_sa_bwt_with_element_parallel_group_round(E, name, env, monkeypatch):
 @pytest.mark.parametrize("name", ["eng_300k", "dna_300k", "runs", "rand256_50k", "dna_1m_dollar", "rand2_100k", "fib"])
 @pytest.mark.parametrize("parts", [1, 3, 8])
 def test_distributed_build_with_element_parallel_group_round(E, name, parts, monkeypatch):
-    """HKCSA_GC_MIN_M=0: the group round's element-parallel kernel (working sets of 4 M suffixes and more take it) on
-    every working set -- groups across CTA boundaries, groups of more than 16, windows that tie or reach the end of
-    the text (handed to the serial form): same slices, 32- and 64-bit ids."""
-    monkeypatch.setenv("HKCSA_GC_MIN_M", "0")
+    """The group round's two forms give the same slices, 32- and 64-bit ids: the element-parallel kernel (default;
+    groups across CTA boundaries, groups of more than 16, windows that tie or reach the end of the text -- marked for
+    the serial second launch; 64-bit ids with and without the key extension bits) and the serial form."""
     text = TEXTS[name]
-    for wide in (False, True):
-        _check_slices(_emulated_build(E, text, parts, wide), text, wide)
+    for env in ({}, {"HKCSA_DSA_NO_XBITS": "1"}, {"HKCSA_GC_MIN_M": "4294967295"}):
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            for wide in (False, True):
+                _check_slices(_emulated_build(E, text, parts, wide), text, wide)
 
 
 @pytest.mark.parametrize("ext", [0, 1, 3])
