@@ -180,7 +180,7 @@ static_assert(WIDE_ID_BITS + WIDE_X_BITS <= 56, "the top byte carries the BWT sy
 constexpr int GS_MAX = 16;       // groups up to this size are ordered by one thread
 constexpr int GS_DEPTH = 64;     // symbols compared beyond the depth the group shares
 // keys[j] = (cgrp[j] << 32 | sub-group) with every group of at most GS_MAX elements reordered in place (cidx) by text
-// comparison from `depth` on; ids64 != nullptr: cidx holds ordinals into ids64 (low 56 bits = suffix id)
+// comparison from `depth` on; ids64 != nullptr: cidx holds ordinals into ids64 (WIDE_ID_MASK = suffix id, then the key extension bits)
 cudaError_t group_local_keys(uint32_t *cidx, const uint32_t *cgrp, uint32_t m, const uint8_t *text, uint64_t n,
                              uint64_t depth, const uint64_t *ids64, uint64_t *keys, cudaStream_t st);
 

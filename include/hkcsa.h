@@ -179,6 +179,9 @@ int hkcsa_dsa_dbl_sort(hkcsa_dsa_state *state, void *stream);
 /* wide ids: d_out[j] = id of the j-th suffix of the finished slice (uint64[M]); d_out_bwt (may be NULL) receives the  */
 /* BWT slice: with 64-bit ids the exchange carries text[i-1] in the top byte of every id (n <= 2^40 leaves it free), */
 /* so the slice's BWT costs no gather over the text                                                                   */
+/* Layout of a 64-bit id word in the receive arrays: bits 0-39 suffix id, bits 40-55 the 16 bits of the round-0    */
+/* code stream that follow the key (compared by the group round before it reads any text; 0 when a code word of one  */
+/* bit makes them unavailable), bits 56-63 text[i-1].                                                                 */
 int hkcsa_dsa_gather_ids64(const hkcsa_dsa_state *state, uint64_t *d_out, uint8_t *d_out_bwt, void *stream);
 /* bwt[j] = text[SA[j]-1] (text[n-1] when SA[j] == 0) for a slice of the suffix array */
 int hkcsa_bwt_slice(const uint8_t *d_text, uint64_t n, const uint32_t *d_sa_slice, uint64_t m,
