@@ -19,6 +19,7 @@ torch.distributed (`distributed_suffix_array`) and with the ranks emulated in on
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from dataclasses import dataclass, field
 
@@ -111,7 +112,7 @@ def _align(x: int, a: int = 256) -> int:
 def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: bool, ext_rounds_max: int,
                   group_round: bool = True, hist_stride: int | None = None):
     """One rank's build as a generator.  Yields ("gather", array) -> [world, len] int64 numpy; ("text_async", block,
-    sizes) -> (the text buffer with this rank's block and its edges in place, wait function for the rest);
+    sizes) -> (the text buffer with this rank's block and its edges in place, start and wait functions for the rest);
     ("symm", nbytes) -> (uint8 tensor, [address of every rank's buffer]); ("barrier",)."""
     L = _lib.load()
     dev = block.device
@@ -137,7 +138,12 @@ def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: boo
     # The blocks travel while this rank already works on its own: histograms, cut points and the bucket exchange read
     # the rank's own block only (+ the first bytes of the next block for the keys at its end and the last byte of the
     # block before it), the whole text is first needed by the refinement rounds -- text_ready() makes the stream wait.
-    text, text_ready = yield ("text_async", block, sizes)
+    # text_start() launches the collective: at once.  HKCSA_DSA_TEXT_LATE=1 holds it back until the bucket exchange is
+    # over, so that the two do not share the NVLink ingress -- measured on 4 GPUs x 1 GB: the exchange is no faster
+    # (15.9 ms either way: the packing bounds it), the round-0 sort beside the collective is slower (55.6 against 54.0 ms).
+    text, text_start, text_ready = yield ("text_async", block, sizes)
+    if os.environ.get("HKCSA_DSA_TEXT_LATE") != "1":
+        text_start()
     begin, end = int(starts[rank]), int(starts[rank + 1])
     tick("text_allgather")
     # ---- 2. one prefix code and one set of cut points for everybody
@@ -197,6 +203,7 @@ def _rank_program(rank: int, world: int, block: torch.Tensor, wide, profile: boo
                                     _u64arr(base), _ptr(d_counters), _stream()))
     yield ("barrier",)                                          # every pair has landed
     tick("pack_exchange")
+    text_start()
     # ---- 5. local sort + refinement
     state = C.create_string_buffer(L.hkcsa_dsa_state_bytes())
     nscratch = L.hkcsa_dsa_scratch_bytes(cap)
@@ -339,14 +346,23 @@ def _torch_run(prog, group, device):
                         text[(rank + 1) * m:(rank + 1) * m + EDGE_HEAD] = edges[rank + 1, :EDGE_HEAD]
                     if rank > 0:
                         text[rank * m - EDGE_TAIL:rank * m] = edges[rank - 1, EDGE_HEAD:]
-                    work = dist.all_gather_into_tensor(text, own, group=_side_group(group), async_op=True)
-                    res = (text, work.wait)
+                    pending = []
+
+                    def start(text=text, own=own, pending=pending):     # idempotent: the program may call it twice
+                        if not pending:
+                            pending.append(dist.all_gather_into_tensor(text, own, group=_side_group(group), async_op=True))
+
+                    def wait(pending=pending, start=start):
+                        start()
+                        pending[0].wait()
+
+                    res = (text, start, wait)
                 else:                                           # one collective on padded blocks, then compaction
                     width = max(sizes)
                     pad = torch.zeros(width, dtype=torch.uint8, device=device)
                     pad[: block.numel()] = block
                     allb = _all_gather_rows(pad, world, group)
-                    res = (torch.cat([allb[r, : sizes[r]] for r in range(world)]), lambda: None)
+                    res = (torch.cat([allb[r, : sizes[r]] for r in range(world)]), lambda: None, lambda: None)
             elif kind == "symm":
                 need = torch.tensor([int(req[1])], dtype=torch.int64, device=device)
                 dist.all_reduce(need, op=dist.ReduceOp.MAX, group=group)
@@ -411,7 +427,7 @@ def emulate_distributed_suffix_array(blocks, wide: bool | None = None, ext_round
             res = [np.stack(rows).astype(np.int64)] * world
         elif kind == "text_async":
             full = torch.cat([reqs[r][1] for r in live])
-            res = [(full, lambda: None)] * world
+            res = [(full, lambda: None, lambda: None)] * world
         elif kind == "symm":
             need = max(int(reqs[r][1]) for r in live)
             bufs = [torch.empty(need, dtype=torch.uint8, device=dev) for _ in live]

@@ -125,7 +125,8 @@ def _program_worker(rank, world, port, out):
             for name, cuts in (("ragged", cuts_ragged), ("equal", cuts_equal)):
                 block = torch.from_numpy(full[cuts[rank]:cuts[rank + 1]].copy())
                 sizes = (yield ("gather", np.array([block.numel()], dtype=np.int64)))[:, 0]
-                text, text_ready = yield ("text_async", block, sizes)
+                text, text_start, text_ready = yield ("text_async", block, sizes)
+                text_start()
                 text_ready()
                 got[name] = (sizes.tolist(), text.numpy().copy())
             hist = np.bincount(full[cuts_ragged[rank]:cuts_ragged[rank + 1]], minlength=256).astype(np.int64)
