@@ -550,11 +550,11 @@ def build_sampled_sa(sa: torch.Tensor, rate: int) -> SampledSA:
     return SampledSA(plan, blob)
 
 
-def pack_patterns(patterns, device=None):
-    """list[str|bytes] -> (uint8[sum m], int64[P+1]) on the device.  A list of latin-1 str patterns (what the
-    reference's find_range takes, csa/enhanced_fm_index.py:21) is packed by ONE join + ONE encode and a C-level
-    len() map; anything else goes pattern by pattern."""
-    device = device or _require_cuda()
+def pack_patterns_host(patterns):
+    """list[str|bytes] -> (bytes of all patterns back to back, int64[P+1] offsets), on the host.  A list of latin-1
+    str patterns (what the reference's find_range takes, csa/enhanced_fm_index.py:21) is packed by ONE join + ONE
+    encode and a C-level len() map; anything else goes pattern by pattern (a str beyond latin-1 raises
+    UnicodeEncodeError there: the caller decides what such a pattern means)."""
     P = len(patterns)
     flat = None
     try:
@@ -570,8 +570,14 @@ def pack_patterns(patterns, device=None):
     off = np.zeros(P + 1, dtype=np.int64)
     if P:
         np.cumsum(lens, out=off[1:])
-    d_flat = to_device_u8(flat, device)
-    return d_flat, to_device_u8(off.view(np.uint8), device).view(torch.int64)
+    return flat, off
+
+
+def pack_patterns(patterns, device=None):
+    """list[str|bytes] -> (uint8[sum m], int64[P+1]) on the device (pack_patterns_host + two staged copies)."""
+    device = device or _require_cuda()
+    flat, off = pack_patterns_host(patterns)
+    return to_device_u8(flat, device), to_device_u8(off.view(np.uint8), device).view(torch.int64)
 
 
 @dataclass

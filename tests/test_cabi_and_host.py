@@ -262,3 +262,39 @@ def test_distributed_build_plan_is_host_only():
     out = (C.c_double * 5)()
     assert L.hkcsa_entropy_from_sa(None, 10, None, 0, out, None, 0, None) == _lib.EINVAL       # k = 0 is the histogram's job
     assert L.hkcsa_entropy_from_sa(None, 3, None, 5, out, None, 0, None) == 0 and list(out) == [0.0] * 5   # n <= k -> 0
+
+
+def test_pack_patterns_host_fast_and_slow_paths_agree():
+    """One join + one encode for a list of latin-1 str patterns; bytes / mixed lists pattern by pattern: same CSR."""
+    from hkcsa import engine
+    pats = ["ana", "", "banana", "caf\xe9", "x" * 300]
+    flat, off = engine.pack_patterns_host(pats)
+    assert flat == "".join(pats).encode("latin-1") and off.tolist() == [0, 3, 3, 9, 13, 313] and off.dtype == np.int64
+    as_bytes = [p.encode("latin-1") for p in pats]
+    for variant in (as_bytes, [pats[0], as_bytes[1], bytearray(as_bytes[2]), pats[3], memoryview(as_bytes[4])]):
+        f2, o2 = engine.pack_patterns_host(variant)
+        assert f2 == flat and np.array_equal(o2, off)
+    f0, o0 = engine.pack_patterns_host([])
+    assert f0 == b"" and o0.tolist() == [0]
+    with pytest.raises(UnicodeEncodeError):              # beyond latin-1: the drop-in layer turns it into a miss
+        engine.pack_patterns_host(["ab", "sn\u2603w"])
+
+
+def test_symbol_map_ascii_latin1_and_wide_texts():
+    """ASCII text: nothing is encoded (host_bytes hands the str itself to the staged copy); latin-1: one encode;
+    beyond latin-1: order-preserving re-coding (the reference compares code points, csa/suffix_array.py:132)."""
+    from hkcsa import engine
+    text = "GATTACA" * 1000
+    m = engine.SymbolMap(text, extra="$")
+    assert m.identity and m.host_bytes(text) is text and m.encode("$") == b"$" and m.encode("\u2603") is None
+    lat = "caf\xe9" * 10
+    m2 = engine.SymbolMap(lat, extra="$")
+    assert m2.identity and m2.host_bytes(lat) == lat.encode("latin-1")
+    wide = "\u03b1\u03b2\u03b1\u03b3$"
+    m3 = engine.SymbolMap(wide, extra="$")
+    assert not m3.identity and m3.host_bytes(wide) == m3.encode(wide)
+    enc = m3.encode(wide)
+    assert [m3.symbol(b) for b in enc] == list(wide) and m3.decode(enc) == wide
+    assert sorted(set(enc)) == list(range(len(set(wide)))) and m3.encode("\u03b4") is None
+    order = sorted(set(wide))
+    assert [m3.encode(c)[0] for c in order] == list(range(len(order)))      # code points keep their order
