@@ -1,3 +1,5 @@
+# Round-end check on one GPU: the GPU test suite, smoke, the C2 / C1 / C3 bench lines and the ncu launch list of a C2 build
+# (outputs under gpurun_out/; the lines kept for the record are copied to profiles/).
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1

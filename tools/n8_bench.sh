@@ -1,3 +1,4 @@
+# bench.py on N GPUs of one node (default 8): the line incl. the dist_build record lands in gpurun_out/r2_bench_n$N.json
 set -x
 N=${1:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
