@@ -552,7 +552,7 @@ int hkcsa_locate_rows_occ(const void *d_wt_blob, const hkcsa_wt_plan *h_wt_plan,
 /* returns one, utils/data_loader.py:4) whose bytes sit in PAGEABLE memory.   */
 /* hkcsa_h2d_staged copies nbytes from pageable h_src to d_dst through a      */
 /* library-owned pinned ring (64 MB, allocated on first use): `threads` host  */
-/* threads (0 = HKCSA_STAGE_THREADS or half the cores, at most 8) fill 4 MB   */
+/* threads (0 = HKCSA_STAGE_THREADS or 4; at most 16) fill 2 MB               */
 /* slots and enqueue each slot's DMA on `stream` as soon as it is filled, so  */
 /* the host copy runs on several cores and overlaps the PCIe transfer.        */
 /* Returns when every byte has been staged (h_src may be released); the DMAs  */

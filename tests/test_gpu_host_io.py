@@ -10,7 +10,7 @@ import pytest
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
-CHUNK = 4 << 20
+CHUNK = 2 << 20
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -18,7 +18,7 @@ def _need_cuda(cuda):
     return cuda
 
 
-@pytest.mark.parametrize("threads", [1, 3, 8, 0])
+@pytest.mark.parametrize("threads", [1, 3, 16, 0])
 @pytest.mark.parametrize("n", [1, 17, CHUNK - 1, CHUNK, CHUNK + 1, 9 * CHUNK + 12345, 37_000_003])
 def test_staged_round_trip(n, threads):
     import torch
